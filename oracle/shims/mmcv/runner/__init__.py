@@ -1,0 +1,10 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY. Minimal stand-in for the un-vendored dependency named by the
+package path (mmcv-full==1.5.3 / mmdet==2.25.0, /root/reference/environment.yml:27-28); restates only the
+symbols imported at /root/reference/team_code_transfuser/model.py:20-30. parity unpinned (source absent)."""
+
+
+def force_fp32(apply_to=None, out_fp16=False):
+    """No-op when fp16_enabled is False (config.py:55), which is the only mode the reference uses."""
+    def wrap(func):
+        return func
+    return wrap

@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI in include/tfb200.h (libtfb200.so, hand-written sm_100a CUDA).
+
+There is deliberately NO fallback: if the library is missing or a kernel returns an error the call raises.
+Signatures are parsed from the header so the header stays the single source of truth for the boundary."""
+import ctypes
+import os
+import re
+
+import torch  # noqa: F401  (loads libcudart before libtfb200.so resolves it)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtfb200.so')
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'tfb200.h')
+
+_CTYPES = {
+    'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double,
+    'uint64_t': ctypes.c_uint64, 'unsigned int': ctypes.c_uint, 'tfb_stream_t': ctypes.c_void_p,
+}
+
+
+def parse_header(path=HEADER):
+    """Returns {name: (restype, [(ctype, argname)])} for every `TFB_EXPORT` declaration in the header."""
+    src = open(path).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    src = re.sub(r'//[^\n]*', '', src)
+    decls = {}
+    for m in re.finditer(r'TFB_EXPORT\s+(const char\s*\*|int)\s+(\w+)\s*\((.*?)\)\s*;', src, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        params = []
+        args = ' '.join(args.split())
+        if args and args != 'void':
+            for a in args.split(','):
+                a = a.strip()
+                pname = re.search(r'(\w+)$', a).group(1)
+                ptype = a[:len(a) - len(pname)].strip()
+                if '*' in ptype:
+                    params.append((ctypes.c_void_p, pname))
+                else:
+                    params.append((_CTYPES[ptype.replace('const ', '')], pname))
+        decls[name] = (ctypes.c_char_p if 'char' in ret else ctypes.c_int, params)
+    return decls
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError('transfuser_b200: %s is missing — run `python -c "import __graft_entry__ as g; g.build()"`; '
+                               'there is no CPU / eager fallback.' % LIB_PATH)
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.decls = parse_header()
+        self.fns = {}
+        for name, (ret, params) in self.decls.items():
+            fn = getattr(self.cdll, name)  # AttributeError if the header declares something the .so lacks
+            fn.restype = ret
+            fn.argtypes = [t for t, _ in params]
+            self.fns[name] = (fn, params)
+        self.launches = 0
+
+    def call(self, name, *args):
+        """Calls tfb_<name>; torch tensors become device pointers; the trailing stream argument is filled in."""
+        fn, params = self.fns[name]
+        conv = []
+        takes_stream = bool(params) and params[-1][1] == 'stream'
+        n_user = len(params) - (1 if takes_stream else 0)
+        if len(args) != n_user:
+            raise TypeError('%s expects %d arguments, got %d' % (name, n_user, len(args)))
+        for a, (t, pname) in zip(args, params):
+            if t is ctypes.c_void_p:
+                if a is None:
+                    conv.append(None)
+                elif isinstance(a, torch.Tensor):
+                    conv.append(a.data_ptr())
+                else:
+                    conv.append(int(a))
+            else:
+                conv.append(a)
+        if takes_stream:
+            conv.append(torch.cuda.current_stream().cuda_stream)
+        rc = fn(*conv)
+        self.launches += 1
+        if rc != 0:
+            raise RuntimeError('%s failed with code %d: %s' % (name, rc, self.cdll.tfb_last_error().decode()))
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _Lib()
+    return _LIB
+
+
+def call(name, *args):
+    return lib().call(name, *args)

@@ -1,0 +1,287 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[n]) (+ beta*C) (ReLU)
+// Operands fp32 in HBM, fed to the tensor cores as TF32 (kind::tf32, fp32 accumulate in TMEM), or bf16 (kind::f16).
+// All four transpose combinations are served without materialising a transpose: a K-contiguous operand is a
+// "K-major" UMMA operand, an M/N-contiguous operand is an "MN-major" one; both are staged by TMA into
+// 128B-swizzled shared memory and described to the MMA by a shared-memory matrix descriptor.
+//   forward  y = x W^T      : A K-major (x[M,K]),  B K-major (W[N,K])
+//   dgrad    dx = dy W      : A K-major (dy[M,N']), B MN-major (W[N',K'] read as [k][n])
+//   wgrad    dW = dy^T x    : A MN-major (dy[M',N] read as [k][m]), B MN-major (x[M',K] read as [k][n]); split-K + atomics
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-5 = epilogue
+// (TMEM -> registers -> global). One 128 x BN output tile per CTA, STAGES-deep mbarrier ring between TMA and MMA.
+// Replaces cuBLAS/cuDNN behind nn.Linear and 1x1 nn.Conv2d (transfuser.py:510-527,538-543; timm RegNet 1x1 convs).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kPerRow = 32;   // elements per 128-byte swizzle row
+  static constexpr int kUmmaK = 8;
+  static constexpr uint32_t kFmt = 2;  // TF32
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kPerRow = 64;
+  static constexpr int kUmmaK = 16;
+  static constexpr uint32_t kFmt = 1;  // BF16
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BM * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <typename T, int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ C,
+               int64_t ldc, int M, int N, int num_kb, int kb_per_split, const float* __restrict__ bias, float alpha, float beta,
+               int relu, int atomic_out) {
+  using E = Elem<T>;
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int BK = E::kPerRow;  // K elements per stage
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(num_kb, kb_begin + kb_per_split);
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        tc::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+        const int k0 = (kb_begin + i) * BK;
+        if (!A_MN) {
+          tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / E::kPerRow; ++j)
+            tc::tma_load_2d(&tma_a, &full_bar[s], sa + j * BK * 128, m0 + j * E::kPerRow, k0);
+        }
+        if (!B_MN) {
+          tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / E::kPerRow; ++j)
+            tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, n0 + j * E::kPerRow, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(E::kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BM, BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::fence_after_sync();
+        const uint32_t sa = tc::smem_u32(smem + s * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / E::kUmmaK; ++k) {
+          // K-major: advance 32 B inside the 128 B swizzle row; MN-major: advance kUmmaK rows of 128 B.
+          const uint32_t a_off = A_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
+          const uint32_t b_off = B_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
+          const uint64_t adesc = tc::make_smem_desc(sa + a_off, A_MN ? BK * 128 : 16, 1024);
+          const uint64_t bdesc = tc::make_smem_desc(sb + b_off, B_MN ? BK * 128 : 16, 1024);
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          if (sizeof(T) == 4) tc::umma_tf32(tmem_base, adesc, bdesc, idesc, acc);
+          else                tc::umma_f16(tmem_base, adesc, bdesc, idesc, acc);
+        }
+        tc::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+      }
+      tc::umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int q = warp & 3;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+    const int m = m0 + q * 32 + lane;
+    const bool add_bias = bias != nullptr && blockIdx.z == 0;
+    float* crow = C + (int64_t)m * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (m < M) {
+        const int n = n0 + c0;
+        if (n + 16 <= N && !atomic_out && beta == 0.f && ((reinterpret_cast<uintptr_t>(crow + n) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = alpha * v[j + 0] + (add_bias ? bias[n + j + 0] : 0.f);
+            o.y = alpha * v[j + 1] + (add_bias ? bias[n + j + 1] : 0.f);
+            o.z = alpha * v[j + 2] + (add_bias ? bias[n + j + 2] : 0.f);
+            o.w = alpha * v[j + 3] + (add_bias ? bias[n + j + 3] : 0.f);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(crow + n + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n + j < N) {
+              float o = alpha * v[j] + (add_bias ? bias[n + j] : 0.f);
+              if (atomic_out) {
+                atomicAdd(crow + n + j, o);
+              } else {
+                if (beta != 0.f) o += beta * crow[n + j];
+                if (relu) o = fmaxf(o, 0.f);
+                crow[n + j] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [rows][cols] matrix with leading dimension ld (elements); box = {box_cols, box_rows}.
+template <typename T>
+bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, Elem<T>::kTmaType, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <typename T, int BN, bool A_MN, bool B_MN>
+int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+              int relu, float alpha, float beta, int splits, cudaStream_t stream) {
+  using E = Elem<T>;
+  constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int BK = E::kPerRow;
+  CUtensorMap ma, mb;
+  bool ok;
+  if (!A_MN) ok = make_map_2d<T>(&ma, A, M, K, lda, BK, BM);              // A[m][k]
+  else       ok = make_map_2d<T>(&ma, A, K, M, lda, E::kPerRow, BK);      // A[k][m]
+  if (!ok) { tfb_set_last_error("cuTensorMapEncodeTiled(A) failed"); return TFB_ERR_DRIVER; }
+  if (!B_MN) ok = make_map_2d<T>(&mb, B, N, K, ldb, BK, BN);              // B[n][k]
+  else       ok = make_map_2d<T>(&mb, B, K, N, ldb, E::kPerRow, BK);      // B[k][n]
+  if (!ok) { tfb_set_last_error("cuTensorMapEncodeTiled(B) failed"); return TFB_ERR_DRIVER; }
+  const int num_kb = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > num_kb) splits = num_kb;
+  int kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;
+  const int atomic_out = splits > 1 ? 1 : 0;
+  if (atomic_out) {
+    if (relu) { tfb_set_last_error("split-K cannot fuse ReLU"); return TFB_ERR_ARG; }
+    if (beta == 0.f) {
+      if (cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream) != cudaSuccess) return TFB_ERR_DRIVER;
+    } else if (beta != 1.f) { tfb_set_last_error("split-K needs beta in {0,1}"); return TFB_ERR_ARG; }
+  }
+  auto kern = gemm_tc_kernel<T, BN, A_MN, B_MN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+      tfb_set_last_error("cudaFuncSetAttribute(smem) failed");
+      return TFB_ERR_DRIVER;
+    }
+    attr_done = true;
+  }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  kern<<<grid, 192, L::kTotal, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+template <typename T, int BN>
+int dispatch_major(int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
+                   int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream) {
+  // BLAS-style flags: op(A)[m][k] = transA ? A[k*lda+m] : A[m*lda+k];  op(B)[k][n] = transB ? B[n*ldb+k] : B[k*ldb+n]
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  if (!a_mn && !b_mn) return launch_tc<T, BN, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (!a_mn && b_mn)  return launch_tc<T, BN, false, true>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (a_mn && b_mn)   return launch_tc<T, BN, true, true>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return launch_tc<T, BN, true, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+}
+
+template <typename T>
+int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
+                int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream) {
+  TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
+  // TMA: 16-byte aligned bases and leading dimensions.
+  TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  TFB_REQUIRE((lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0);
+  if (N <= 64) return dispatch_major<T, 64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return dispatch_major<T, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+}
+
+}  // namespace
+
+TFB_API int tfb_gemm_tf32_tc(int transA, int transB, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                             int64_t ldb, float* C, int64_t ldc, const float* bias, int relu, float alpha, float beta,
+                             int splits, cudaStream_t stream) {
+  return gemm_tc_any<float>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+}
+
+TFB_API int tfb_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
+                             int64_t ldb, float* C, int64_t ldc, const float* bias, int relu, float alpha, float beta,
+                             int splits, cudaStream_t stream) {
+  return gemm_tc_any<__nv_bfloat16>(transA, transB, M, N, K, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, C, ldc,
+                                    bias, relu, alpha, beta, splits, stream);
+}
