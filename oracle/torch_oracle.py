@@ -1,0 +1,305 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY — never imported by the product path (only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may use it, and only as the checker / the CPU arm).
+
+CPU restatement, in stock fp32 PyTorch functional ops, of the reference's training hot path:
+  LidarCenterNet.forward            /root/reference/team_code_transfuser/model.py:733-805
+  TransfuserBackbone.forward        transfuser.py:120-211   (GPT 333-366, Block 545-549, SelfAttention 510-527)
+  SegDecoder / DepthDecoder         transfuser.py:239-246, 273-281
+  forward_gru                       model.py:611-646
+  LidarCenterNetHead.forward_single / get_targets / loss   model.py:127-147, 285-374, 149-248
+  timm 0.5.4 RegNetY-032 blocks and mmdet 2.25 losses: restated from their published definitions (sources are not in the
+  container; see oracle/shims/* — "parity unpinned" against the historical third-party packages).
+It is a *functional* restatement over a flat {reference state_dict name: tensor} mapping, so that it cannot share code
+(or bugs) with either the reference's nn.Module classes or the CUDA product.  It is pinned against the reference itself:
+tests/test_oracle.py runs the verbatim reference (oracle/ref_import.py) and this file on the same weights/inputs in the
+build container, and tests/golden/model_golden.npz holds reference outputs that this file must reproduce anywhere.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REGNET_DEPTHS = (2, 5, 13, 1)
+REGNET_WIDTHS = (72, 216, 576, 1512)
+GROUP_W = 24
+
+
+class Cfg:
+    """The subset of GlobalConfig (config.py) the hot path reads, with train.py's overrides (n_layer 4, train.py:56)."""
+    n_layer = 4
+    n_head = 4
+    img_vert_anchors, img_horz_anchors = 5, 22
+    lidar_vert_anchors, lidar_horz_anchors = 8, 8
+    embd_pdrop = attn_pdrop = resid_pdrop = 0.1
+    bev_resolution_height = bev_resolution_width = 160
+    lidar_resolution_height = lidar_resolution_width = 256
+    num_dir_bins = 12
+    pred_len = 4
+    lidar_pos_x = 1.3
+    ls_seg, ls_depth = 1.0, 10.0
+    deconv_scale_factor_1, deconv_scale_factor_2 = 8, 4
+    multitask = True
+
+
+def _bn(P, pre, x, train, act):
+    y = F.batch_norm(x, P[pre + 'running_mean'], P[pre + 'running_var'], P[pre + 'weight'], P[pre + 'bias'],
+                     training=train, momentum=0.1, eps=1e-5)
+    return F.relu(y) if act else y
+
+
+def _cba(P, pre, x, train, stride=1, groups=1, act=True, k=1):
+    y = F.conv2d(x, P[pre + 'conv.weight'], None, stride=stride, padding=k // 2, groups=groups)
+    return _bn(P, pre + 'bn.', y, train, act)
+
+
+def _bottleneck(P, pre, x, train, stride, has_ds):
+    width = P[pre + 'conv1.conv.weight'].shape[0]
+    y = _cba(P, pre + 'conv1.', x, train)
+    y = _cba(P, pre + 'conv2.', y, train, stride=stride, groups=width // GROUP_W, k=3)
+    s = y.mean((2, 3), keepdim=True)
+    s = F.relu(F.conv2d(s, P[pre + 'se.fc1.weight'], P[pre + 'se.fc1.bias']))
+    s = torch.sigmoid(F.conv2d(s, P[pre + 'se.fc2.weight'], P[pre + 'se.fc2.bias']))
+    y = y * s
+    y = _cba(P, pre + 'conv3.', y, train, act=False)
+    sc = _cba(P, pre + 'downsample.', x, train, stride=stride, act=False) if has_ds else x
+    return F.relu(y + sc)
+
+
+def _stage(P, pre, x, train, depth):
+    for i in range(depth):
+        x = _bottleneck(P, '%sb%d.' % (pre, i + 1), x, train, 2 if i == 0 else 1, i == 0)
+    return x
+
+
+def _gpt(P, pre, img, lid, cfg, train, drop):
+    bz, C = img.shape[0], img.shape[1]
+    ih, iw, lh, lw = img.shape[2], img.shape[3], lid.shape[2], lid.shape[3]
+    tok = torch.cat((img.permute(0, 2, 3, 1).reshape(bz, -1, C), lid.permute(0, 2, 3, 1).reshape(bz, -1, C)), dim=1)
+    x = drop(P[pre + 'pos_emb'] + tok, cfg.embd_pdrop)
+    T, nh = x.shape[1], cfg.n_head
+    for i in range(cfg.n_layer):
+        b = '%sblocks.%d.' % (pre, i)
+        h = F.layer_norm(x, (C,), P[b + 'ln1.weight'], P[b + 'ln1.bias'])
+        k = F.linear(h, P[b + 'attn.key.weight'], P[b + 'attn.key.bias']).view(bz, T, nh, C // nh).transpose(1, 2)
+        q = F.linear(h, P[b + 'attn.query.weight'], P[b + 'attn.query.bias']).view(bz, T, nh, C // nh).transpose(1, 2)
+        v = F.linear(h, P[b + 'attn.value.weight'], P[b + 'attn.value.bias']).view(bz, T, nh, C // nh).transpose(1, 2)
+        att = drop(F.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // nh)), dim=-1), cfg.attn_pdrop)
+        y = (att @ v).transpose(1, 2).reshape(bz, T, C)
+        x = x + drop(F.linear(y, P[b + 'attn.proj.weight'], P[b + 'attn.proj.bias']), cfg.resid_pdrop)
+        h = F.layer_norm(x, (C,), P[b + 'ln2.weight'], P[b + 'ln2.bias'])
+        h = F.relu(F.linear(h, P[b + 'mlp.0.weight'], P[b + 'mlp.0.bias']))
+        x = x + drop(F.linear(h, P[b + 'mlp.2.weight'], P[b + 'mlp.2.bias']), cfg.resid_pdrop)
+    x = F.layer_norm(x, (C,), P[pre + 'ln_f.weight'], P[pre + 'ln_f.bias'])
+    n_img = ih * iw
+    # token-major buffers re-interpreted as NCHW without permuting back (transfuser.py:363-364)
+    return x[:, :n_img, :].contiguous().view(bz, -1, ih, iw), x[:, n_img:, :].contiguous().view(bz, -1, lh, lw)
+
+
+def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', taps=None):
+    """TransfuserBackbone.forward (transfuser.py:120-211). `taps` (dict) collects per-stage activations."""
+    drop = drop or (lambda t, p: t)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((image / 255.0) - mean) / std
+    ie, le = pre + 'image_encoder.features.', pre + 'lidar_encoder._model.'
+    x = _bn(P, ie + 'stem.bn.', F.conv2d(x, P[ie + 'stem.conv.weight'], None, stride=2, padding=1), train, True)
+    l = _bn(P, le + 'stem.bn.', F.conv2d(lidar, P[le + 'conv1.weight'], None, stride=2, padding=1), train, True)
+    for s in range(4):
+        x = _stage(P, '%ss%d.' % (ie, s + 1), x, train, REGNET_DEPTHS[s])
+        l = _stage(P, '%ss%d.' % (le, s + 1), l, train, REGNET_DEPTHS[s])
+        xe = F.adaptive_avg_pool2d(x, (cfg.img_vert_anchors, cfg.img_horz_anchors))
+        lemb = F.adaptive_avg_pool2d(l, (cfg.lidar_vert_anchors, cfg.lidar_horz_anchors))
+        xo, lo = _gpt(P, '%stransformer%d.' % (pre, s + 1), xe, lemb, cfg, train, drop)
+        x = x + F.interpolate(xo, size=x.shape[2:], mode='bilinear', align_corners=False)
+        l = l + F.interpolate(lo, size=l.shape[2:], mode='bilinear', align_corners=False)
+        if taps is not None:
+            taps['img_s%d' % (s + 1)], taps['lid_s%d' % (s + 1)] = x, l
+    x = F.conv2d(x, P[pre + 'change_channel_conv_image.weight'], P[pre + 'change_channel_conv_image.bias'])
+    l = F.conv2d(l, P[pre + 'change_channel_conv_lidar.weight'], P[pre + 'change_channel_conv_lidar.bias'])
+    fused = x.mean((2, 3)) + l.mean((2, 3))
+    up = lambda t: F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+    p5 = F.relu(F.conv2d(l, P[pre + 'c5_conv.weight'], P[pre + 'c5_conv.bias']))
+    p4 = F.relu(F.conv2d(up(p5), P[pre + 'up_conv5.weight'], P[pre + 'up_conv5.bias']))
+    p3 = F.relu(F.conv2d(up(p4), P[pre + 'up_conv4.weight'], P[pre + 'up_conv4.bias']))
+    p2 = F.relu(F.conv2d(up(p3), P[pre + 'up_conv3.weight'], P[pre + 'up_conv3.bias']))
+    return (p2, p3, p4, p5), x, fused
+
+
+def _decoder(P, pre, x, cfg):
+    c = lambda t, n, act=True: (F.relu if act else (lambda z: z))(F.conv2d(t, P['%s%s.weight' % (pre, n)], P['%s%s.bias' % (pre, n)], padding=1))
+    x = c(c(x, 'deconv1.0'), 'deconv1.2')
+    x = F.interpolate(x, scale_factor=cfg.deconv_scale_factor_1, mode='bilinear', align_corners=False)
+    x = c(c(x, 'deconv2.0'), 'deconv2.2')
+    x = F.interpolate(x, scale_factor=cfg.deconv_scale_factor_2, mode='bilinear', align_corners=False)
+    return c(c(x, 'deconv3.0'), 'deconv3.2', act=False)
+
+
+def gru_waypoints(P, fused, target_point, cfg):
+    z = fused
+    for i in (0, 2, 4):
+        z = F.relu(F.linear(z, P['join.%d.weight' % i], P['join.%d.bias' % i]))
+    x = torch.zeros(z.shape[0], 2)
+    tp = target_point.clone()
+    tp[:, 1] *= -1
+    out = []
+    for _ in range(cfg.pred_len):
+        gi = F.linear(torch.cat([x, tp], dim=1), P['decoder.weight_ih'], P['decoder.bias_ih'])
+        gh = F.linear(z, P['decoder.weight_hh'], P['decoder.bias_hh'])
+        i_r, i_z, i_n = gi.chunk(3, 1)
+        h_r, h_z, h_n = gh.chunk(3, 1)
+        r, u = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        z = (1 - u) * n + u * z
+        x = F.linear(z, P['output.weight'], P['output.bias'])[:, :2] + x
+        out.append(x)
+    wp = torch.stack(out, dim=1)
+    return torch.cat((wp[:, :, :1] - cfg.lidar_pos_x, wp[:, :, 1:]), dim=2)
+
+
+def _gaussian_radius(h, w, mo=0.1):
+    r1 = ((h + w) - math.sqrt((h + w) ** 2 - 4 * (w * h * (1 - mo) / (1 + mo)))) / 2
+    r2 = (2 * (h + w) - math.sqrt((2 * (h + w)) ** 2 - 16 * ((1 - mo) * w * h))) / 8
+    a3, b3, c3 = 4 * mo, -2 * mo * (h + w), (mo - 1) * w * h
+    r3 = (b3 + math.sqrt(b3 ** 2 - 4 * a3 * c3)) / (2 * a3)
+    return min(r1, r2, r3)
+
+
+def centernet_targets(label, cfg, H=64, W=64):
+    """get_targets (model.py:285-374). Returns dict of target maps and avg_factor."""
+    B = label.shape[0]
+    ratio = float(W / cfg.lidar_resolution_width)
+    ratio_h = float(H / cfg.lidar_resolution_height)
+    heat = torch.zeros(B, 1, H, W)
+    t = {k: torch.zeros(B, c, H, W) for k, c in (('wh', 2), ('offset', 2), ('yaw_res', 1), ('velocity', 1), ('weight', 2))}
+    yaw_cls = torch.zeros(B, H, W, dtype=torch.long)
+    brake = torch.zeros(B, H, W, dtype=torch.long)
+    apc = 2 * np.pi / float(cfg.num_dir_bins)
+    for b in range(B):
+        for j in range(label.shape[1]):
+            box = label[b, j]
+            if float(box.sum()) == 0.:
+                continue
+            ct = box[:2] * ratio
+            x, y = int(ct[0]), int(ct[1])
+            bh, bw = box[3] * ratio_h, box[2] * ratio
+            r = max(2, int(_gaussian_radius(float(bh), float(bw))))
+            sig = (2 * r + 1) / 6
+            g = torch.arange(-r, r + 1, dtype=torch.float32)
+            k = (-(g.view(1, -1) ** 2 + g.view(-1, 1) ** 2) / (2 * sig * sig)).exp()
+            k[k < torch.finfo(torch.float32).eps * k.max()] = 0
+            le, ri, to, bo = min(x, r), min(W - x, r + 1), min(y, r), min(H - y, r + 1)
+            region = heat[b, 0, y - to:y + bo, x - le:x + ri]
+            heat[b, 0, y - to:y + bo, x - le:x + ri] = torch.maximum(region, k[r - to:r + bo, r - le:r + ri])
+            t['wh'][b, 0, y, x], t['wh'][b, 1, y, x] = bw, bh
+            ang = box[4] % (2 * np.pi)
+            sh = (ang + apc / 2) % (2 * np.pi)
+            cls = torch.div(sh, apc, rounding_mode='trunc')
+            yaw_cls[b, y, x] = cls.long()
+            t['yaw_res'][b, 0, y, x] = sh - (cls * apc + apc / 2)
+            t['velocity'][b, 0, y, x] = box[5]
+            brake[b, y, x] = box[6].long()
+            t['offset'][b, 0, y, x], t['offset'][b, 1, y, x] = ct[0] - x, ct[1] - y
+            t['weight'][b, :, y, x] = 1
+    t.update(heat=heat, yaw_cls=yaw_cls, brake=brake)
+    return t, max(1, int(heat.eq(1).sum()))
+
+
+def centernet_losses(preds, label, cfg):
+    """LidarCenterNetHead.loss (model.py:149-248) with mmdet's weighted-loss reduction (sum / avg_factor)."""
+    heat, wh, off, ycls, yres, vel, brk = preds
+    t, avg = centernet_targets(label, cfg, heat.shape[2], heat.shape[3])
+    eps = 1e-12
+    pos = t['heat'].eq(1)
+    focal = (-(heat + eps).log() * (1 - heat).pow(2) * pos - (1 - heat + eps).log() * heat.pow(2) * (1 - t['heat']).pow(4))
+    w2, w1 = t['weight'], t['weight'][:, :1]
+    out = {'loss_center_heatmap': focal.sum() / avg,
+           'loss_wh': 0.1 * ((wh - t['wh']).abs() * w2).sum() / (avg * 2),
+           'loss_offset': ((off - t['offset']).abs() * w2).sum() / (avg * 2)}
+    # CE maps are (B,H,W); the weight is (B,1,H,W): the product broadcasts to (B,B,H,W) (model.py:220-224, 235-239)
+    out['loss_yaw_class'] = (F.cross_entropy(ycls, t['yaw_cls'], reduction='none') * w1).sum() / avg
+    d = (yres - t['yaw_res']).abs()
+    out['loss_yaw_res'] = (torch.where(d < 1.0, 0.5 * d * d, d - 0.5) * w1).sum() / avg
+    out['loss_velocity'] = ((vel - t['velocity']).abs() * w1).sum() / avg
+    out['loss_brake'] = (F.cross_entropy(brk, t['brake'], reduction='none') * w1).sum() / avg
+    return out
+
+
+def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None):
+    """LidarCenterNet.forward (model.py:733-805): dict of the 11 losses. `P` maps reference state_dict names to tensors."""
+    lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
+    feats, img_grid, fused = backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
+    loss = {}
+    wp = gru_waypoints(P, fused, batch['target_point'], cfg)
+    head = lambda name, x: F.conv2d(F.relu(F.conv2d(x, P[name + '.0.weight'], P[name + '.0.bias'], padding=1)),
+                                    P[name + '.2.weight'], P[name + '.2.bias'])
+    pb = F.interpolate(head('pred_bev', feats[0]), (cfg.bev_resolution_height, cfg.bev_resolution_width), mode='bilinear', align_corners=True)
+    loss['loss_wp'] = (wp - batch['ego_waypoint']).abs().mean()
+    loss['loss_bev'] = F.cross_entropy(pb, batch['bev'], weight=torch.tensor([1., 1., 3.]))
+    names = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
+    preds = [head('head.' + n, feats[0]) for n in names]
+    preds[0] = preds[0].sigmoid()
+    loss.update(centernet_losses(preds, batch['label'], cfg))
+    if cfg.multitask:
+        seg = _decoder(P, 'seg_decoder.', img_grid, cfg)
+        depth = torch.sigmoid(_decoder(P, 'depth_decoder.', img_grid, cfg)).squeeze(1)
+        loss['loss_semantic'] = cfg.ls_seg * F.cross_entropy(seg, batch['semantic'])
+        loss['loss_depth'] = cfg.ls_depth * F.l1_loss(depth, batch['depth'])
+    if taps is not None:
+        taps.update(p2=feats[0], img_grid=img_grid, fused=fused, pred_wp=wp)
+    return loss
+
+
+# ------------------------------------------------------------------ deterministic synthetic data / weights
+def synthetic_batch(B, seed=0, n_boxes=None):
+    """Seeded synthetic batch of SURVEY.md §8(d)'s shape (CPU tensors, reference dtypes)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    r = lambda *s: torch.rand(*s, generator=g)
+    batch = dict(
+        rgb=torch.randint(0, 256, (B, 3, 160, 704), generator=g).float(),
+        lidar=(torch.randint(0, 6, (B, 2, 256, 256), generator=g).float() / 5) * (r(B, 2, 256, 256) < 0.1),
+        target_point_image=(r(B, 1, 256, 256) < 0.002).float(),
+        target_point=r(B, 2) * 20 - 10,
+        ego_vel=r(B, 1) * 8,
+        ego_waypoint=torch.randn(B, 4, 2, generator=g) * 3,
+        bev=torch.randint(0, 3, (B, 160, 160), generator=g),
+        semantic=torch.randint(0, 7, (B, 160, 704), generator=g),
+        depth=r(B, 160, 704),
+    )
+    label = torch.zeros(B, 20, 7)
+    for b in range(B):
+        k = int(torch.randint(0, 21, (1,), generator=g)) if n_boxes is None else n_boxes
+        if k:
+            label[b, :k, 0:2] = r(k, 2) * 253 + 1
+            label[b, :k, 2:4] = r(k, 2) * 32 + 8
+            label[b, :k, 4] = r(k) * 2 * math.pi - math.pi
+            label[b, :k, 5] = r(k) * 8
+            label[b, :k, 6] = (r(k) < 0.5).float()
+    batch['label'] = label
+    return batch
+
+
+def deterministic_state(named_shapes, seed=0):
+    """Machine-independent parameter values keyed by name (CPU generator): scaled normal weights, positive BN scales /
+    variances, so that every layer (including zero-initialised ones in the reference) carries signal in parity tests."""
+    import zlib
+    out = {}
+    for name, shape in named_shapes:
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
+        leaf = name.rsplit('.', 1)[-1]
+        if leaf == 'num_batches_tracked':
+            out[name] = torch.zeros((), dtype=torch.long)
+        elif leaf == 'running_var':
+            out[name] = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif leaf == 'running_mean':
+            out[name] = torch.randn(shape, generator=g) * 0.1
+        elif len(shape) <= 1 and leaf == 'weight':       # norm scales
+            out[name] = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif len(shape) <= 1:                             # biases
+            out[name] = torch.randn(shape, generator=g) * 0.05
+        elif leaf == 'pos_emb':
+            out[name] = torch.randn(shape, generator=g) * 0.1
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            out[name] = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+    return out

@@ -1,0 +1,266 @@
+"""Per-op parity of the CUDA kernels (forward and backward, through the C-ABI) against plain fp32 PyTorch ops.
+Tolerances: 1e-4 relative L2 for the exact-fp32 kernels (north_star: 1e-3), stated per test otherwise."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return torch.randn(*shape, device='cuda', generator=g) * scale
+
+
+def check_grads(mine_inputs, ref_inputs, mine_out, ref_out, tol=TOL, gseed=7):
+    g = rnd(*ref_out.shape, seed=gseed)
+    gm = nhwc(g) if (mine_out.dim() == 4 and mine_out.shape != ref_out.shape) else g.view_as(mine_out)
+    ref_g = torch.autograd.grad(ref_out, ref_inputs, g, allow_unused=True)
+    my_g = torch.autograd.grad(mine_out, mine_inputs, gm, allow_unused=True)
+    for i, (a, b) in enumerate(zip(my_g, ref_g)):
+        if a.dim() == 4 and a.shape != b.shape:
+            a = nchw(a)
+        assert rel(a.reshape(b.shape), b) < tol, ('grad', i, rel(a.reshape(b.shape), b))
+
+
+@pytest.mark.parametrize('cfg', [
+    # N, H, W, Cin, Cout, k, stride, groups, bias, relu
+    (2, 16, 24, 3, 32, 3, 2, 1, False, False),      # stem
+    (2, 12, 20, 72, 72, 3, 1, 3, False, False),     # grouped 3x3, group width 24
+    (2, 12, 20, 72, 72, 3, 2, 3, False, False),     # grouped, stride 2
+    (1, 10, 14, 216, 216, 3, 1, 9, False, False),
+    (2, 9, 11, 32, 72, 1, 2, 1, False, False),      # strided 1x1 shortcut
+    (2, 8, 8, 64, 64, 3, 1, 1, True, True),         # head 3x3 + bias + relu
+    (1, 5, 22, 512, 128, 3, 1, 1, True, True),      # decoder first layer
+    (2, 12, 16, 32, 7, 3, 1, 1, True, False),       # decoder last layer (Cout 7)
+    (2, 12, 16, 32, 1, 3, 1, 1, True, False),       # depth last layer (Cout 1)
+    (2, 7, 9, 72, 216, 1, 1, 1, False, False),      # 1x1 -> GEMM path
+    (2, 8, 8, 64, 12, 1, 1, 1, True, False),        # head 1x1 with bias
+])
+def test_conv2d(cfg):
+    from transfuser_b200 import ops
+    N, H, W, Cin, Cout, k, s, g, has_b, relu = cfg
+    x = rnd(N, Cin, H, W, seed=1).requires_grad_()
+    w = rnd(Cout, Cin // g, k, k, seed=2, scale=1.0 / math.sqrt(Cin // g * k * k)).requires_grad_()
+    b = rnd(Cout, seed=3).requires_grad_() if has_b else None
+    ref = F.conv2d(x, w, b, stride=s, padding=k // 2, groups=g)
+    ref = F.relu(ref) if relu else ref
+    xm = nhwc(x.detach()).requires_grad_()
+    wm = w.detach().clone().requires_grad_()
+    bm = b.detach().clone().requires_grad_() if has_b else None
+    out = ops.conv2d(xm, wm, bm, s, g, relu)
+    assert rel(nchw(out), ref) < TOL
+    check_grads([xm, wm] + ([bm] if has_b else []), [x, w] + ([b] if has_b else []), out, ref)
+
+
+@pytest.mark.parametrize('shape,relu', [((3, 10, 12, 72), True), ((2, 6, 7, 216), False), ((1, 5, 22, 1512), True)])
+def test_batchnorm_train(shape, relu):
+    from transfuser_b200 import ops
+    N, H, W, C = shape
+    x = (rnd(N, C, H, W, seed=4) * 2 + 0.5).requires_grad_()
+    bn = torch.nn.BatchNorm2d(C).cuda()
+    bn.weight.data = rnd(C, seed=5) * 0.3 + 1
+    bn.bias.data = rnd(C, seed=6) * 0.2
+    bn2 = torch.nn.BatchNorm2d(C).cuda()
+    bn2.load_state_dict(bn.state_dict())
+    ref = bn(x)
+    ref = F.relu(ref) if relu else ref
+    xm = nhwc(x.detach()).requires_grad_()
+    out = ops.batch_norm(xm, bn2, relu, True)
+    assert rel(nchw(out), ref) < TOL
+    assert rel(bn2.running_mean, bn.running_mean) < TOL and rel(bn2.running_var, bn.running_var) < TOL
+    check_grads([xm, bn2.weight, bn2.bias], [x, bn.weight, bn.bias], out, ref)
+
+
+def test_layernorm_linear_dropout():
+    from transfuser_b200 import ops
+    x = rnd(348, 216, seed=1).requires_grad_()
+    ln = torch.nn.LayerNorm(216).cuda()
+    ln.weight.data = rnd(216, seed=2) * 0.2 + 1
+    ln.bias.data = rnd(216, seed=3) * 0.1
+    lin = torch.nn.Linear(216, 864).cuda()
+    ref = F.relu(lin(ln(x)))
+    xm = x.detach().clone().requires_grad_()
+    ln2, lin2 = torch.nn.LayerNorm(216).cuda(), torch.nn.Linear(216, 864).cuda()
+    ln2.load_state_dict(ln.state_dict()); lin2.load_state_dict(lin.state_dict())
+    out = ops.linear(ops.layer_norm(xm, ln2), lin2.weight, lin2.bias, relu=True)
+    assert rel(out, ref) < TOL
+    check_grads([xm, ln2.weight, ln2.bias, lin2.weight, lin2.bias], [x, ln.weight, ln.bias, lin.weight, lin.bias], out, ref)
+    # dropout: keep-probability and scaling, same mask regenerated in backward
+    y = rnd(1 << 20, seed=9).abs().requires_grad_()
+    d = ops.DropoutFn.apply(y, 0.1, 1234)
+    kept = (d != 0).float().mean().item()
+    assert abs(kept - 0.9) < 5e-3
+    assert torch.allclose(d[d != 0], (y / 0.9)[d != 0], rtol=1e-6)
+    (gy,) = torch.autograd.grad(d.sum(), y)
+    assert torch.equal(gy != 0, d != 0)
+
+
+@pytest.mark.parametrize('C,nh', [(72, 4), (216, 4)])
+def test_attention(C, nh):
+    from transfuser_b200 import ops
+    B, T = 2, 174
+    h = rnd(B * T, C, seed=1).requires_grad_()
+    ws = [rnd(C, C, seed=10 + i, scale=1 / math.sqrt(C)).requires_grad_() for i in range(3)]
+    bs = [rnd(C, seed=20 + i, scale=0.1).requires_grad_() for i in range(3)]
+    q = F.linear(h, ws[0], bs[0]).view(B, T, nh, C // nh).transpose(1, 2)
+    k = F.linear(h, ws[1], bs[1]).view(B, T, nh, C // nh).transpose(1, 2)
+    v = F.linear(h, ws[2], bs[2]).view(B, T, nh, C // nh).transpose(1, 2)
+    att = F.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // nh)), dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(B * T, C)
+    hm = h.detach().clone().requires_grad_()
+    wm = [w.detach().clone().requires_grad_() for w in ws]
+    bm = [b.detach().clone().requires_grad_() for b in bs]
+    out = ops.AttentionFn.apply(hm, wm[0], bm[0], wm[1], bm[1], wm[2], bm[2], B, T, nh, 0.0, 1)
+    assert rel(out, ref) < TOL
+    g = rnd(B * T, C, seed=5)
+    rg = torch.autograd.grad(ref, [h] + ws + [bs[0], bs[2]], g)
+    mg = torch.autograd.grad(out, [hm] + wm + [bm[0], bm[2]], g)
+    for a, b_ in zip(mg, rg):
+        assert rel(a, b_) < TOL
+
+
+def test_se_add_pool():
+    from transfuser_b200 import ops
+    N, H, W, C, Cr = 3, 6, 9, 72, 8
+    x = rnd(N, C, H, W, seed=1).requires_grad_()
+    w1, b1 = rnd(Cr, C, 1, 1, seed=2, scale=0.2).requires_grad_(), rnd(Cr, seed=3, scale=0.1).requires_grad_()
+    w2, b2 = rnd(C, Cr, 1, 1, seed=4, scale=0.3).requires_grad_(), rnd(C, seed=5, scale=0.1).requires_grad_()
+    s = x.mean((2, 3), keepdim=True)
+    ref = x * torch.sigmoid(F.conv2d(F.relu(F.conv2d(s, w1, b1)), w2, b2))
+    xm = nhwc(x.detach()).requires_grad_()
+    ps = [t.detach().clone().requires_grad_() for t in (w1, b1, w2, b2)]
+    out = ops.SEFn.apply(xm, *ps)
+    assert rel(nchw(out), ref) < TOL
+    check_grads([xm] + ps, [x, w1, b1, w2, b2], out, ref)
+    # residual add + relu, global pool
+    a, b = rnd(N, H, W, C, seed=6).requires_grad_(), rnd(N, H, W, C, seed=7).requires_grad_()
+    am, bm = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    ref2, out2 = F.relu(a + b), ops.add(am, bm, relu=True)
+    assert rel(out2, ref2) < 1e-6
+    check_grads([am, bm], [a, b], out2, ref2)
+    ref3, out3 = a.mean((1, 2)), ops.PoolHWFn.apply(am)
+    assert rel(out3, ref3) < 1e-5
+    check_grads([am], [a], out3, ref3)
+
+
+@pytest.mark.parametrize('C,hw', [(72, ((40, 176), (64, 64))), (576, ((10, 44), (16, 16))), (1512, ((5, 22), (8, 8)))])
+def test_gpt_tokens_and_view_quirk(C, hw):
+    """Token build (adaptive avg pool + permute + pos_emb) and the reference's non-inverse `.view` on the way back
+    (transfuser.py:346-364), then bilinear upsample + add (transfuser.py:154-157)."""
+    from transfuser_b200 import ops
+    (Hi, Wi), (Hl, Wl) = hw
+    B = 2
+    img, lid = rnd(B, C, Hi, Wi, seed=1).requires_grad_(), rnd(B, C, Hl, Wl, seed=2).requires_grad_()
+    pos = rnd(1, 174, C, seed=3, scale=0.1).requires_grad_()
+    ie, le = F.adaptive_avg_pool2d(img, (5, 22)), F.adaptive_avg_pool2d(lid, (8, 8))
+    tok_ref = pos + torch.cat((ie.permute(0, 2, 3, 1).reshape(B, -1, C), le.permute(0, 2, 3, 1).reshape(B, -1, C)), dim=1)
+    im, lm, pm = nhwc(img.detach()).requires_grad_(), nhwc(lid.detach()).requires_grad_(), pos.detach().clone().requires_grad_()
+    tok = ops.TokensFn.apply(im, lm, pm, 5, 22, 8, 8, 0.0, 1)
+    assert rel(tok, tok_ref) < 1e-5
+    g = rnd(B, 174, C, seed=4)
+    for a, b in zip(torch.autograd.grad(tok, [im, lm, pm], g), torch.autograd.grad(tok_ref, [img, lid, pos], g)):
+        assert rel(nchw(a) if a.dim() == 4 and a.shape[-1] == C and a.shape != b.shape else a, b) < 1e-5
+    # view quirk + upsample + add
+    x = rnd(B, 174, C, seed=5).requires_grad_()
+    io = x[:, :110, :].contiguous().view(B, -1, 5, 22)
+    lo = x[:, 110:, :].contiguous().view(B, -1, 8, 8)
+    ref_i = img + F.interpolate(io, size=(Hi, Wi), mode='bilinear', align_corners=False)
+    ref_l = lid + F.interpolate(lo, size=(Hl, Wl), mode='bilinear', align_corners=False)
+    xm = x.detach().clone().requires_grad_()
+    oi, ol = ops.GptUpAddFn.apply(im, lm, xm, 5, 22, 8, 8)
+    assert rel(nchw(oi), ref_i) < 1e-5 and rel(nchw(ol), ref_l) < 1e-5
+    gi, gl = rnd(B, C, Hi, Wi, seed=6), rnd(B, C, Hl, Wl, seed=7)
+    rg = torch.autograd.grad([ref_i, ref_l], [x, img, lid], [gi, gl])
+    mg = torch.autograd.grad([oi, ol], [xm, im, lm], [nhwc(gi), nhwc(gl)])
+    assert rel(mg[0], rg[0]) < 1e-5 and rel(nchw(mg[1]), rg[1]) < 1e-5 and rel(nchw(mg[2]), rg[2]) < 1e-5
+
+
+@pytest.mark.parametrize('cfg', [(2, 8, 8, 64, 16, 16, False), (2, 64, 64, 3, 160, 160, True), (1, 5, 22, 64, 40, 176, False),
+                                 (1, 40, 176, 8, 160, 704, False)])
+def test_upsample(cfg):
+    from transfuser_b200 import ops
+    N, Hi, Wi, C, Ho, Wo, ac = cfg
+    x = rnd(N, C, Hi, Wi, seed=1).requires_grad_()
+    ref = F.interpolate(x, size=(Ho, Wo), mode='bilinear', align_corners=ac)
+    xm = nhwc(x.detach()).requires_grad_()
+    out = ops.upsample(xm, Ho, Wo, ac)
+    assert rel(nchw(out), ref) < 1e-5
+    check_grads([xm], [x], out, ref, tol=1e-5)
+
+
+def test_image_prep_and_layout():
+    from transfuser_b200 import ops
+    img = torch.randint(0, 256, (2, 3, 16, 24), device='cuda').float()
+    mean = torch.tensor([0.485, 0.456, 0.406], device='cuda').view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device='cuda').view(1, 3, 1, 1)
+    assert rel(nchw(ops.image_prep(img)), ((img / 255.0) - mean) / std) < 1e-6
+    x = rnd(2, 5, 7, 9, seed=1)
+    assert torch.equal(ops.nchw_to_nhwc(x), nhwc(x)) and torch.equal(ops.nhwc_to_nchw(nhwc(x)), x)
+
+
+def test_losses():
+    from transfuser_b200 import ops
+    # weighted CE (pred_bev) and plain CE (semantic)
+    logits = rnd(2, 3, 20, 24, seed=1).requires_grad_()
+    tgt = torch.randint(0, 3, (2, 20, 24), device='cuda')
+    w = torch.tensor([1., 1., 3.], device='cuda')
+    lm = nhwc(logits.detach()).requires_grad_()
+    ref, out = F.cross_entropy(logits, tgt, weight=w), ops.CrossEntropyFn.apply(lm, tgt, w, 'wsum', 1.0)
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    (g1,), (g2,) = torch.autograd.grad(out * 0.7, lm), torch.autograd.grad(ref * 0.7, logits)
+    assert rel(nchw(g1), g2) < 1e-5
+    logits = rnd(2, 7, 12, 16, seed=2).requires_grad_()
+    tgt = torch.randint(0, 7, (2, 12, 16), device='cuda')
+    lm = nhwc(logits.detach()).requires_grad_()
+    ref, out = 1.0 * F.cross_entropy(logits, tgt), ops.CrossEntropyFn.apply(lm, tgt, None, 'count', 1.0)
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    (g1,), (g2,) = torch.autograd.grad(out, lm), torch.autograd.grad(ref, logits)
+    assert rel(nchw(g1), g2) < 1e-5
+    # depth: 10 * l1(sigmoid(x), t)
+    x, t = rnd(2, 12, 16, seed=3).requires_grad_(), torch.rand(2, 12, 16, device='cuda')
+    xm = x.detach().clone().requires_grad_()
+    ref, out = 10.0 * F.l1_loss(torch.sigmoid(x), t), ops.L1Fn.apply(xm, t, True, 10.0)
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel(torch.autograd.grad(out, xm)[0], torch.autograd.grad(ref, x)[0]) < 1e-5
+
+
+def test_gru_waypoints():
+    from transfuser_b200 import ops
+    B = 5
+    cell, outl = torch.nn.GRUCell(4, 64).cuda(), torch.nn.Linear(64, 3).cuda()
+    z0, tp = rnd(B, 64, seed=1).requires_grad_(), rnd(B, 2, seed=2) * 5
+    z, x = z0, torch.zeros(B, 2, device='cuda')
+    tpn = tp.clone(); tpn[:, 1] *= -1
+    wps = []
+    for _ in range(4):
+        z = cell(torch.cat([x, tpn], dim=1), z)
+        x = outl(z)[:, :2] + x
+        wps.append(x)
+    ref = torch.stack(wps, dim=1)
+    ref = torch.cat((ref[:, :, :1] - 1.3, ref[:, :, 1:]), dim=2)
+    zm = z0.detach().clone().requires_grad_()
+    ps = [p.detach().clone().requires_grad_() for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias)]
+    out = ops.GRUFn.apply(zm, tp, *ps, 4, 1.3)
+    assert rel(out, ref) < 1e-5
+    g = rnd(B, 4, 2, seed=3)
+    rg = torch.autograd.grad(ref, [z0, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias], g)
+    mg = torch.autograd.grad(out, [zm] + ps, g)
+    for a, b in zip(mg, rg):
+        assert rel(a, b) < 1e-4

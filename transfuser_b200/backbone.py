@@ -1,0 +1,256 @@
+"""B200-native `TransfuserBackbone` — drop-in for /root/reference/team_code_transfuser/transfuser.py:7-211.
+
+Same constructor signature, same `forward(image, lidar, velocity) -> ((p2, p3, p4, p5), image_features_grid,
+fused_features)` contract (NCHW fp32 in / out), and the same parameter / buffer names and shapes as the reference
+(including the alias keys created by ImageCNN / LidarEncoder, transfuser.py:383-393, 475-486), so reference checkpoints
+load unchanged. The nn.Conv2d / nn.BatchNorm2d / nn.Linear / nn.LayerNorm objects below are *parameter containers only*:
+their forward is never called — every op runs through transfuser_b200.ops (hand-written sm_100a kernels, NHWC inside).
+
+The RegNetY-3.2GF definition (timm 0.5.4 `regnety_032`: stem 32, widths 72/216/576/1512, depths 2/5/13/1, group width 24,
+SE ratio 0.25) is restated from timm's published config; timm itself is not a dependency."""
+import torch
+from torch import nn
+
+from . import ops
+
+REGNETY_032 = dict(stem_width=32, widths=(72, 216, 576, 1512), depths=(2, 5, 13, 1), group_w=24, se_ratio=0.25)
+
+
+class _ConvBn(nn.Module):
+    """`conv` + `bn` (BatchNormAct2d in timm: the ReLU lives inside the norm layer)."""
+
+    def __init__(self, cin, cout, k=1, stride=1, groups=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, groups=groups, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+        self.stride, self.groups, self.act = stride, groups, act
+
+    def run(self, x):
+        y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups)
+        return ops.batch_norm(y, self.bn, self.act, self.bn.training)
+
+
+class _SE(nn.Module):
+    def __init__(self, channels, rd_channels):
+        super().__init__()
+        self.fc1 = nn.Conv2d(channels, rd_channels, 1, bias=True)
+        self.fc2 = nn.Conv2d(rd_channels, channels, 1, bias=True)
+
+    def run(self, x):
+        return ops.SEFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, cin, cout, stride, group_w, se_ratio):
+        super().__init__()
+        self.conv1 = _ConvBn(cin, cout, 1)
+        self.conv2 = _ConvBn(cout, cout, 3, stride=stride, groups=cout // group_w)
+        self.se = _SE(cout, int(round(cin * se_ratio)))
+        self.conv3 = _ConvBn(cout, cout, 1, act=False)
+        self.downsample = _ConvBn(cin, cout, 1, stride=stride, act=False) if (cin != cout or stride != 1) else None
+        nn.init.zeros_(self.conv3.bn.weight)  # timm zero_init_last_bn
+
+    def run(self, x):
+        y = self.conv3.run(self.se.run(self.conv2.run(self.conv1.run(x))))
+        sc = self.downsample.run(x) if self.downsample is not None else x
+        return ops.add(y, sc, relu=True)
+
+
+class _Stage(nn.Module):
+    def __init__(self, cin, cout, depth, group_w, se_ratio):
+        super().__init__()
+        for i in range(depth):
+            self.add_module('b%d' % (i + 1), _Bottleneck(cin if i == 0 else cout, cout, 2 if i == 0 else 1, group_w, se_ratio))
+
+    def run(self, x):
+        for blk in self.children():
+            x = blk.run(x)
+        return x
+
+
+class _RegNet(nn.Module):
+    """Parameter tree of timm's RegNet (names: stem.{conv,bn}, s1..s4.b{k}.{conv1,conv2,se,conv3,downsample})."""
+
+    def __init__(self, cfg=REGNETY_032, in_chans=3):
+        super().__init__()
+        self.stem = _ConvBn(in_chans, cfg['stem_width'], 3, stride=2)
+        self.feature_info = [dict(num_chs=cfg['stem_width'], reduction=2, module='stem')]
+        prev = cfg['stem_width']
+        for i, (w, d) in enumerate(zip(cfg['widths'], cfg['depths'])):
+            self.add_module('s%d' % (i + 1), _Stage(prev, w, d, cfg['group_w'], cfg['se_ratio']))
+            prev = w
+            self.feature_info.append(dict(num_chs=w, reduction=2 ** (i + 2), module='s%d' % (i + 1)))
+        self.num_features = prev
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+                nn.init.normal_(m.weight, 0.0, (2.0 / fan_out) ** 0.5)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+
+class ImageCNN(nn.Module):
+    """transfuser.py:369-416 (regnet branch): `features` + the alias attributes the reference's forward goes through."""
+
+    def __init__(self, architecture, normalize=True, out_features=512):
+        super().__init__()
+        if architecture != 'regnety_032':
+            raise RuntimeError('transfuser_b200 implements the regnety_032 trunk only (train.py:50-53 default), got %r' % (architecture,))
+        self.normalize = normalize
+        f = self.features = _RegNet()
+        f.conv1, f.bn1 = f.stem.conv, f.stem.bn
+        f.layer1, f.layer2, f.layer3, f.layer4 = f.s1, f.s2, f.s3, f.s4
+
+
+class LidarEncoder(nn.Module):
+    """transfuser.py:431-488: same trunk, new `conv1` with `in_channels`, `stem.conv` deleted."""
+
+    def __init__(self, architecture, in_channels=2, out_features=512):
+        super().__init__()
+        if architecture != 'regnety_032':
+            raise RuntimeError('transfuser_b200 implements the regnety_032 trunk only, got %r' % (architecture,))
+        m = self._model = _RegNet()
+        old = m.stem.conv
+        m.bn1 = m.stem.bn
+        m.layer1, m.layer2, m.layer3, m.layer4 = m.s1, m.s2, m.s3, m.s4
+        m.conv1 = nn.Conv2d(in_channels, old.out_channels, kernel_size=old.kernel_size, stride=old.stride, padding=old.padding, bias=False)
+        del m.stem.conv
+
+
+class SelfAttention(nn.Module):
+    def __init__(self, n_embd, n_head, attn_pdrop, resid_pdrop):
+        super().__init__()
+        assert n_embd % n_head == 0
+        self.key = nn.Linear(n_embd, n_embd)
+        self.query = nn.Linear(n_embd, n_embd)
+        self.value = nn.Linear(n_embd, n_embd)
+        self.proj = nn.Linear(n_embd, n_embd)
+        self.n_head, self.attn_pdrop, self.resid_pdrop = n_head, attn_pdrop, resid_pdrop
+
+
+class Block(nn.Module):
+    """transfuser.py:530-549: x + attn(ln1(x)); x + mlp(ln2(x)), ReLU MLP, three dropouts."""
+
+    def __init__(self, n_embd, n_head, block_exp, attn_pdrop, resid_pdrop):
+        super().__init__()
+        self.ln1 = nn.LayerNorm(n_embd)
+        self.ln2 = nn.LayerNorm(n_embd)
+        self.attn = SelfAttention(n_embd, n_head, attn_pdrop, resid_pdrop)
+        self.mlp = nn.Sequential(nn.Linear(n_embd, block_exp * n_embd), nn.ReLU(True), nn.Linear(block_exp * n_embd, n_embd),
+                                 nn.Dropout(resid_pdrop))
+
+    def run(self, x, B, T):
+        a, training = self.attn, self.training
+        h = ops.layer_norm(x, self.ln1)
+        p_att = a.attn_pdrop if training else 0.0
+        y = ops.AttentionFn.apply(h, a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
+                                  B, T, a.n_head, p_att, ops.next_seed())
+        y = ops.dropout(ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training)
+        x = ops.add(x, y)
+        h = ops.layer_norm(x, self.ln2)
+        h = ops.linear(h, self.mlp[0].weight, self.mlp[0].bias, relu=True)
+        h = ops.dropout(ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), a.resid_pdrop, training)
+        return ops.add(x, h)
+
+
+class GPT(nn.Module):
+    """transfuser.py:284-366."""
+
+    def __init__(self, n_embd, n_head, block_exp, n_layer, img_vert_anchors, img_horz_anchors, lidar_vert_anchors,
+                 lidar_horz_anchors, seq_len, embd_pdrop, attn_pdrop, resid_pdrop, config, use_velocity=True):
+        super().__init__()
+        if use_velocity:
+            raise RuntimeError('use_velocity=True is not implemented (train.py:54 default is 0)')
+        self.n_embd, self.seq_len, self.config, self.use_velocity = n_embd, 1, config, use_velocity
+        self.grid = (img_vert_anchors, img_horz_anchors, lidar_vert_anchors, lidar_horz_anchors)
+        self.pos_emb = nn.Parameter(torch.zeros(1, img_vert_anchors * img_horz_anchors + lidar_vert_anchors * lidar_horz_anchors, n_embd))
+        self.embd_pdrop = embd_pdrop
+        self.drop = nn.Dropout(embd_pdrop)
+        self.blocks = nn.Sequential(*[Block(n_embd, n_head, block_exp, attn_pdrop, resid_pdrop) for _ in range(n_layer)])
+        self.ln_f = nn.LayerNorm(n_embd)
+        self.block_size = self.seq_len
+        self.apply(self._init_weights)
+
+    def _init_weights(self, module):
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=self.config.gpt_linear_layer_init_mean, std=self.config.gpt_linear_layer_init_std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(self.config.gpt_layer_norm_init_weight)
+
+    def run(self, img, lid):
+        """img / lid: NHWC stage features -> the same features with the upsampled GPT output added."""
+        ghi, gwi, ghl, gwl = self.grid
+        B = img.shape[0]
+        T = ghi * gwi + ghl * gwl
+        p = self.embd_pdrop if self.training else 0.0
+        tok = ops.TokensFn.apply(img, lid, self.pos_emb, ghi, gwi, ghl, gwl, p, ops.next_seed())
+        x = tok.view(B * T, self.n_embd)
+        for blk in self.blocks:
+            x = blk.run(x, B, T)
+        x = ops.layer_norm(x, self.ln_f).view(B, T, self.n_embd)
+        return ops.GptUpAddFn.apply(img, lid, x, ghi, gwi, ghl, gwl)
+
+
+class TransfuserBackbone(nn.Module):
+    """Multi-scale fusion transformer for image + LiDAR feature fusion (transfuser.py:7-211)."""
+
+    def __init__(self, config, image_architecture='resnet34', lidar_architecture='resnet18', use_velocity=True):
+        super().__init__()
+        self.config = config
+        self.image_encoder = ImageCNN(architecture=image_architecture, normalize=True, out_features=config.perception_output_features)
+        if config.use_point_pillars:
+            raise RuntimeError('PointPillars LiDAR encoder is out of scope (config.py:42 default False)')
+        in_channels = 2 * config.lidar_seq_len + (1 if config.use_target_point_image else 0)
+        self.lidar_encoder = LidarEncoder(architecture=lidar_architecture, in_channels=in_channels, out_features=config.perception_output_features)
+        info = self.image_encoder.features.feature_info
+        for i in range(1, 5):
+            setattr(self, 'transformer%d' % i, GPT(
+                n_embd=info[i]['num_chs'], n_head=config.n_head, block_exp=config.block_exp, n_layer=config.n_layer,
+                img_vert_anchors=config.img_vert_anchors, img_horz_anchors=config.img_horz_anchors,
+                lidar_vert_anchors=config.lidar_vert_anchors, lidar_horz_anchors=config.lidar_horz_anchors, seq_len=config.seq_len,
+                embd_pdrop=config.embd_pdrop, attn_pdrop=config.attn_pdrop, resid_pdrop=config.resid_pdrop, config=config,
+                use_velocity=use_velocity))
+        c_last, c_out = info[4]['num_chs'], config.perception_output_features
+        self.change_channel_conv_image = nn.Conv2d(c_last, c_out, (1, 1))
+        self.change_channel_conv_lidar = nn.Conv2d(c_last, c_out, (1, 1))
+        channel = config.bev_features_chanels
+        self.up_conv5 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv4 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv3 = nn.Conv2d(channel, channel, (1, 1))
+        self.c5_conv = nn.Conv2d(c_out, channel, (1, 1))
+
+    def _bn_modules(self):
+        if not hasattr(self, '_bn_cache'):
+            object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
+        return self._bn_cache
+
+    def forward_nhwc(self, image, lidar):
+        """image: NCHW 0..255, lidar: NCHW -> (p2..p5 NHWC), image grid NHWC, fused [B,512]."""
+        if self.training:
+            torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+        ie, le = self.image_encoder.features, self.lidar_encoder._model
+        x = ops.image_prep(image) if self.image_encoder.normalize else ops.nchw_to_nhwc(image)
+        l = ops.nchw_to_nhwc(lidar)
+        x = ops.batch_norm(ops.conv2d(x, ie.stem.conv.weight, None, 2, 1), ie.stem.bn, True, ie.stem.bn.training)
+        l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
+        for i in range(1, 5):
+            x = getattr(ie, 's%d' % i).run(x)
+            l = getattr(le, 's%d' % i).run(l)
+            x, l = getattr(self, 'transformer%d' % i).run(x, l)
+        x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
+        l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
+        fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
+        f = self.config.bev_upsample_factor
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
+        p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
+        p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)
+        p2 = ops.conv2d(up(p3), self.up_conv3.weight, self.up_conv3.bias, relu=True)
+        return (p2, p3, p4, p5), x, fused
+
+    def forward(self, image, lidar, velocity):
+        feats, grid, fused = self.forward_nhwc(image, lidar)
+        return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused

@@ -1,0 +1,484 @@
+// HBM-bound NHWC elementwise / gather kernels of the TransFuser backbone, forward + backward:
+// residual add+ReLU, SE pooling / gating, input normalisation, layout transposes, adaptive-avg-pool token build,
+// the GPT-output "view quirk" + bilinear upsample + add, generic bilinear upsample, dropout, row softmax, bf16 cast.
+// Reference call sites: transfuser.py:129-130 (normalize_imagenet), 150-157 (avgpool, GPT, interpolate, add),
+// 346-364 (token build / output view), 519-522 (softmax, dropout); timm SEModule / Bottleneck add+ReLU.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                                       int64_t n, int relu) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float o = a[i] + b[i];
+    y[i] = relu ? fmaxf(o, 0.f) : o;
+  }
+}
+
+// MODE 0: dx = dy * (y > 0)   MODE 1: dx = dy * y * (1 - y)   MODE 2: y = sigmoid(x) (dy unused)
+template <int MODE>
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
+                                                  int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    if (MODE == 0) dx[i] = v > 0.f ? dy[i] : 0.f;
+    else if (MODE == 1) dx[i] = dy[i] * v * (1.f - v);
+    else dx[i] = 1.f / (1.f + expf(-v));
+  }
+}
+
+// out[n][c] = mean_p x[n][p][c] (MODE 0)  or  sum_p x[n][p][c] * z[n][p][c] (MODE 1: SE gate gradient)
+template <int MODE>
+__global__ void __launch_bounds__(256) pool_hw_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out,
+                                                      int HW, int C) {
+  __shared__ float sm[8][33];
+  const int n = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (c < C) {
+    const float* xp = x + (int64_t)n * HW * C + c;
+    const float* zp = MODE == 1 ? z + (int64_t)n * HW * C + c : nullptr;
+    for (int p = threadIdx.y; p < HW; p += 8) a += MODE == 0 ? xp[(int64_t)p * C] : xp[(int64_t)p * C] * zp[(int64_t)p * C];
+  }
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+    out[(int64_t)n * C + c] = MODE == 0 ? t / (float)HW : t;
+  }
+}
+
+// y[n][p][c] = x[n][p][c] * gate[n][c]  (+ add[n][c] * add_scale)
+__global__ void __launch_bounds__(256) scale_nc_kernel(const float* __restrict__ x, const float* __restrict__ gate,
+                                                       const float* __restrict__ add, float add_scale, float* __restrict__ y,
+                                                       int64_t total, int HW, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t n = i / ((int64_t)HW * C);
+    float v = x[i] * gate[n * C + c];
+    if (add) v = fmaf(add[n * C + c], add_scale, v);
+    y[i] = v;
+  }
+}
+
+// dx[n][p][c] (+)= d[n][c] * s
+__global__ void __launch_bounds__(256) bcast_nc_kernel(const float* __restrict__ d, float s, float* __restrict__ dx, int64_t total,
+                                                       int HW, int C, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t n = i / ((int64_t)HW * C);
+    const float v = d[n * C + c] * s;
+    dx[i] = accumulate ? dx[i] + v : v;
+  }
+}
+
+// NCHW uint8-range float image -> NHWC, ImageNet-normalised: ((x/255) - mean) / std   (transfuser.py:419-428)
+__global__ void __launch_bounds__(256) image_prep_kernel(const float* __restrict__ img, float* __restrict__ out, int64_t npix_total,
+                                                         int HW) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix_total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, p = i % HW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[i * 3 + c] = ((img[(n * 3 + c) * HW + p] / 255.0f) - mean[c]) / stdv[c];
+  }
+}
+
+// y[n][b][a] = x[n][a][b]
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int A, int B) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const float* xp = x + (int64_t)n * A * B;
+  float* yp = y + (int64_t)n * A * B;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int a = a0 + j, b = b0 + threadIdx.x;
+    tile[j][threadIdx.x] = (a < A && b < B) ? xp[(int64_t)a * B + b] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int b = b0 + j, a = a0 + threadIdx.x;
+    if (a < A && b < B) yp[(int64_t)b * A + a] = tile[threadIdx.x][j];
+  }
+}
+
+// tokens[n][t][c] = dropout(pos[t][c] + window_mean(feature)) ; t < gi: image grid (gh_i x gw_i), else lidar grid.
+__global__ void __launch_bounds__(256)
+tokens_fwd_kernel(const float* __restrict__ img, int Hi, int Wi, int ghi, int gwi, const float* __restrict__ lid, int Hl, int Wl,
+                  int ghl, int gwl, const float* __restrict__ pos, float* __restrict__ out, int N, int C, float p_drop,
+                  uint64_t seed) {
+  const int T = ghi * gwi + ghl * gwl;
+  const int64_t total = (int64_t)N * T * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % T);
+    const int n = (int)(i / ((int64_t)C * T));
+    const float* src; int H, W, gw, tt, gh;
+    if (t < ghi * gwi) { src = img; H = Hi; W = Wi; gh = ghi; gw = gwi; tt = t; }
+    else { src = lid; H = Hl; W = Wl; gh = ghl; gw = gwl; tt = t - ghi * gwi; }
+    const int wh = H / gh, ww = W / gw, gy = tt / gw, gx = tt % gw;
+    const float* sp = src + (((int64_t)n * H + gy * wh) * W + gx * ww) * C + c;
+    float s = 0.f;
+    for (int yy = 0; yy < wh; ++yy)
+      for (int xx = 0; xx < ww; ++xx) s += sp[((int64_t)yy * W + xx) * C];
+    const float v = pos[(int64_t)t * C + c] + s / (float)(wh * ww);
+    out[i] = v * tfb_dropout_scale(seed, (uint64_t)i, p_drop);
+  }
+}
+
+// gradient of the token build w.r.t. one feature map: d[n][y][x][c] (+)= g[n][t(y,x)][c] * drop / window
+__global__ void __launch_bounds__(256)
+tokens_bwd_feat_kernel(const float* __restrict__ g, float* __restrict__ d, int N, int H, int W, int gh, int gw, int t_off, int T, int C,
+                       float p_drop, uint64_t seed, int accumulate) {
+  const int64_t total = (int64_t)N * H * W * C;
+  const int wh = H / gh, ww = W / gw;
+  const float inv = 1.f / (float)(wh * ww);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int x = (int)((i / C) % W);
+    const int y = (int)((i / ((int64_t)C * W)) % H);
+    const int n = (int)(i / ((int64_t)C * W * H));
+    const int t = t_off + (y / wh) * gw + (x / ww);
+    const int64_t gi = ((int64_t)n * T + t) * C + c;
+    const float v = g[gi] * tfb_dropout_scale(seed, (uint64_t)gi, p_drop) * inv;
+    d[i] = accumulate ? d[i] + v : v;
+  }
+}
+
+// dpos[t][c] = sum_n g[n][t][c] * drop
+__global__ void __launch_bounds__(256) tokens_bwd_pos_kernel(const float* __restrict__ g, float* __restrict__ dpos, int N, int T, int C,
+                                                             float p_drop, uint64_t seed) {
+  const int64_t total = (int64_t)T * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const int64_t gi = (int64_t)n * total + i;
+      s += g[gi] * tfb_dropout_scale(seed, (uint64_t)gi, p_drop);
+    }
+    dpos[i] = s;
+  }
+}
+
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out, int align_corners) {
+  // PyTorch upsample_bilinear2d source index (area_pixel_compute_source_index)
+  float src;
+  if (align_corners) {
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = scale * (float)dst;
+  } else {
+    const float scale = (float)in / (float)out;
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  Lerp r;
+  r.i0 = (int)src;
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+// GPT output slab [gh*gw][C] of sample n, *viewed* as (C, gh, gw) without permuting (transfuser.py:363-364), bilinearly
+// upsampled (align_corners=False) to (H, W) and added to the NHWC feature map.
+// MODE 0: out = feat + up(view(tok))      MODE 1 (backward): dtok += up^T(dy)  (atomics; dtok zeroed by the caller)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gpt_up_add_kernel(const float* __restrict__ feat, float* __restrict__ tok, float* __restrict__ out, int N, int H, int W, int C, int gh,
+                  int gw, int t_off, int T) {
+  const int64_t total = (int64_t)N * H * W * C;
+  const int G = gh * gw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int x = (int)((i / C) % W);
+    const int y = (int)((i / ((int64_t)C * W)) % H);
+    const int n = (int)(i / ((int64_t)C * W * H));
+    const Lerp ly = lerp_coord(y, gh, H, 0), lx = lerp_coord(x, gw, W, 0);
+    float* slab = tok + ((int64_t)n * T + t_off) * C + (int64_t)c * G;
+    const int i00 = ly.i0 * gw + lx.i0, i01 = ly.i0 * gw + lx.i1, i10 = ly.i1 * gw + lx.i0, i11 = ly.i1 * gw + lx.i1;
+    if (MODE == 0) {
+      const float v = ly.l0 * (lx.l0 * slab[i00] + lx.l1 * slab[i01]) + ly.l1 * (lx.l0 * slab[i10] + lx.l1 * slab[i11]);
+      out[i] = feat[i] + v;
+    } else {
+      const float g = feat[i];  // dy
+      atomicAdd(slab + i00, ly.l0 * lx.l0 * g);
+      atomicAdd(slab + i01, ly.l0 * lx.l1 * g);
+      atomicAdd(slab + i10, ly.l1 * lx.l0 * g);
+      atomicAdd(slab + i11, ly.l1 * lx.l1 * g);
+    }
+  }
+}
+
+// generic NHWC bilinear upsample. MODE 0: y = up(x)   MODE 1: dx += up^T(dy) (atomics, dx zeroed by the launcher)
+template <int MODE>
+__global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi, int Ho,
+                                                       int Wo, int C, int align_corners) {
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int xo = (int)((i / C) % Wo);
+    const int yo = (int)((i / ((int64_t)C * Wo)) % Ho);
+    const int n = (int)(i / ((int64_t)C * Wo * Ho));
+    const Lerp ly = lerp_coord(yo, Hi, Ho, align_corners), lx = lerp_coord(xo, Wi, Wo, align_corners);
+    float* xp = x + (int64_t)n * Hi * Wi * C + c;
+    const int64_t o00 = ((int64_t)ly.i0 * Wi + lx.i0) * C, o01 = ((int64_t)ly.i0 * Wi + lx.i1) * C;
+    const int64_t o10 = ((int64_t)ly.i1 * Wi + lx.i0) * C, o11 = ((int64_t)ly.i1 * Wi + lx.i1) * C;
+    if (MODE == 0) {
+      y[i] = ly.l0 * (lx.l0 * xp[o00] + lx.l1 * xp[o01]) + ly.l1 * (lx.l0 * xp[o10] + lx.l1 * xp[o11]);
+    } else {
+      const float g = y[i];
+      atomicAdd(xp + o00, ly.l0 * lx.l0 * g);
+      atomicAdd(xp + o01, ly.l0 * lx.l1 * g);
+      atomicAdd(xp + o10, ly.l1 * lx.l0 * g);
+      atomicAdd(xp + o11, ly.l1 * lx.l1 * g);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
+                                                      uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * tfb_dropout_scale(seed, (uint64_t)i, p);
+}
+
+// one warp per row of length L: P = softmax(scale * S); Pd = dropout(P). P and Pd may alias S when p == 0.
+__global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ S, float* __restrict__ P, float* __restrict__ Pd,
+                                                          int64_t rows, int L, float scale, float p_drop, uint64_t seed) {
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* s = S + r * L;
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) m = fmaxf(m, s[j] * scale);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) sum += expf(s[j] * scale - m);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < L; j += 32) {
+    const float pv = expf(s[j] * scale - m) * inv;
+    P[r * L + j] = pv;
+    if (Pd != P) Pd[r * L + j] = pv * tfb_dropout_scale(seed, (uint64_t)(r * L + j), p_drop);
+  }
+}
+
+// dS = scale * P * (g - sum_j g_j P_j), g = dPd * dropout_scale
+__global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dPd, float* __restrict__ dS,
+                                                          int64_t rows, int L, float scale, float p_drop, uint64_t seed) {
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float g = dPd[r * L + j] * tfb_dropout_scale(seed, (uint64_t)(r * L + j), p_drop);
+    dot = fmaf(g, P[r * L + j], dot);
+  }
+  dot = warp_sum(dot);
+  for (int j = lane; j < L; j += 32) {
+    const float g = dPd[r * L + j] * tfb_dropout_scale(seed, (uint64_t)(r * L + j), p_drop);
+    dS[r * L + j] = scale * P[r * L + j] * (g - dot);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// y = x * (*s) * k  (device-resident scalar: no host sync)  /  y += ...
+__global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s, float k,
+                                                        float* __restrict__ y, int64_t n, int accumulate) {
+  const float f = (s ? *s : 1.f) * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = accumulate ? fmaf(x[i], f, y[i]) : x[i] * f;
+}
+
+}  // namespace
+
+TFB_API int tfb_add_relu(const float* a, const float* b, float* y, int64_t n, int relu, cudaStream_t stream) {
+  TFB_REQUIRE(a && b && y && n >= 0);
+  if (n == 0) return TFB_OK;
+  add_relu_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(a, b, y, n, relu);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, cudaStream_t stream) {
+  TFB_REQUIRE(y && dy && dx && n >= 0);
+  if (n == 0) return TFB_OK;
+  act_kernel<0><<<tfb_grid(n, 256), 256, 0, stream>>>(y, dy, dx, n);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_sigmoid_bwd(const float* y, const float* dy, float* dx, int64_t n, cudaStream_t stream) {
+  TFB_REQUIRE(y && dy && dx && n >= 0);
+  if (n == 0) return TFB_OK;
+  act_kernel<1><<<tfb_grid(n, 256), 256, 0, stream>>>(y, dy, dx, n);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_sigmoid_fwd(const float* x, float* y, int64_t n, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && n >= 0);
+  if (n == 0) return TFB_OK;
+  act_kernel<2><<<tfb_grid(n, 256), 256, 0, stream>>>(x, nullptr, y, n);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_pool_hw_fwd(const float* x, float* out, int N, int HW, int C, cudaStream_t stream) {
+  TFB_REQUIRE(x && out && N > 0 && HW > 0 && C > 0);
+  dim3 grid((C + 31) / 32, N), block(32, 8);
+  pool_hw_kernel<0><<<grid, block, 0, stream>>>(x, nullptr, out, HW, C);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_pool_hw_bwd(const float* dout, float* dx, int N, int HW, int C, int accumulate, cudaStream_t stream) {
+  TFB_REQUIRE(dout && dx && N > 0 && HW > 0 && C > 0);
+  const int64_t total = (int64_t)N * HW * C;
+  bcast_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(dout, 1.f / (float)HW, dx, total, HW, C, accumulate);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_se_scale_fwd(const float* x, const float* gate, float* y, int N, int HW, int C, cudaStream_t stream) {
+  TFB_REQUIRE(x && gate && y && N > 0 && HW > 0 && C > 0);
+  const int64_t total = (int64_t)N * HW * C;
+  scale_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_se_bwd_reduce(const float* x, const float* dy, float* dgate, int N, int HW, int C, cudaStream_t stream) {
+  TFB_REQUIRE(x && dy && dgate && N > 0 && HW > 0 && C > 0);
+  dim3 grid((C + 31) / 32, N), block(32, 8);
+  pool_hw_kernel<1><<<grid, block, 0, stream>>>(x, dy, dgate, HW, C);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_se_bwd_apply(const float* dy, const float* gate, const float* dpool, float* dx, int N, int HW, int C,
+                             cudaStream_t stream) {
+  TFB_REQUIRE(dy && gate && dpool && dx && N > 0 && HW > 0 && C > 0);
+  const int64_t total = (int64_t)N * HW * C;
+  scale_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_image_prep(const float* img_nchw, float* out_nhwc, int N, int H, int W, cudaStream_t stream) {
+  TFB_REQUIRE(img_nchw && out_nhwc && N > 0 && H > 0 && W > 0);
+  const int64_t npix = (int64_t)N * H * W;
+  image_prep_kernel<<<tfb_grid(npix, 256), 256, 0, stream>>>(img_nchw, out_nhwc, npix, H * W);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_transpose_last2(const float* x, float* y, int N, int A, int B, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && N > 0 && A > 0 && B > 0 && N <= 65535);
+  dim3 grid((B + 31) / 32, (A + 31) / 32, N), block(32, 8);
+  TFB_REQUIRE(grid.y <= 65535);
+  transpose_kernel<<<grid, block, 0, stream>>>(x, y, A, B);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_tokens_fwd(const float* img, int Hi, int Wi, int ghi, int gwi, const float* lid, int Hl, int Wl, int ghl, int gwl,
+                           const float* pos, float* out, int N, int C, float p_drop, uint64_t seed, cudaStream_t stream) {
+  TFB_REQUIRE(img && lid && pos && out && N > 0 && C > 0);
+  TFB_REQUIRE(Hi % ghi == 0 && Wi % gwi == 0 && Hl % ghl == 0 && Wl % gwl == 0);  // exact adaptive-avg-pool windows only
+  const int64_t total = (int64_t)N * (ghi * gwi + ghl * gwl) * C;
+  tokens_fwd_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos, out, N, C, p_drop, seed);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_tokens_bwd(const float* g, float* dimg, int Hi, int Wi, int ghi, int gwi, float* dlid, int Hl, int Wl, int ghl,
+                           int gwl, float* dpos, int N, int C, float p_drop, uint64_t seed, int accumulate_feat,
+                           cudaStream_t stream) {
+  TFB_REQUIRE(g && dimg && dlid && dpos && N > 0 && C > 0);
+  const int T = ghi * gwi + ghl * gwl;
+  const int64_t ti = (int64_t)N * Hi * Wi * C, tl = (int64_t)N * Hl * Wl * C;
+  tokens_bwd_feat_kernel<<<tfb_grid(ti, 256), 256, 0, stream>>>(g, dimg, N, Hi, Wi, ghi, gwi, 0, T, C, p_drop, seed, accumulate_feat);
+  TFB_CHECK_LAUNCH();
+  tokens_bwd_feat_kernel<<<tfb_grid(tl, 256), 256, 0, stream>>>(g, dlid, N, Hl, Wl, ghl, gwl, ghi * gwi, T, C, p_drop, seed, accumulate_feat);
+  TFB_CHECK_LAUNCH();
+  tokens_bwd_pos_kernel<<<tfb_grid((int64_t)T * C, 256), 256, 0, stream>>>(g, dpos, N, T, C, p_drop, seed);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_gpt_up_add_fwd(const float* feat, const float* tok, float* out, int N, int H, int W, int C, int gh, int gw, int t_off,
+                               int T, cudaStream_t stream) {
+  TFB_REQUIRE(feat && tok && out && N > 0);
+  const int64_t total = (int64_t)N * H * W * C;
+  gpt_up_add_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(feat, const_cast<float*>(tok), out, N, H, W, C, gh, gw, t_off, T);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_gpt_up_add_bwd(const float* dy, float* dtok, int N, int H, int W, int C, int gh, int gw, int t_off, int T,
+                               cudaStream_t stream) {
+  TFB_REQUIRE(dy && dtok && N > 0);
+  const int64_t total = (int64_t)N * H * W * C;
+  gpt_up_add_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dy, dtok, nullptr, N, H, W, C, gh, gw, t_off, T);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_upsample_bilinear_fwd(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                                      cudaStream_t stream) {
+  TFB_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  upsample_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(const_cast<float*>(x), y, N, Hi, Wi, Ho, Wo, C, align_corners);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_upsample_bilinear_bwd(const float* dy, float* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                                      cudaStream_t stream) {
+  TFB_REQUIRE(dy && dx && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
+  if (cudaMemsetAsync(dx, 0, (size_t)N * Hi * Wi * C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  upsample_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dx, const_cast<float*>(dy), N, Hi, Wi, Ho, Wo, C, align_corners);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f);
+  if (n == 0) return TFB_OK;
+  dropout_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, y, n, p, seed);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_softmax_fwd(const float* S, float* P, float* Pd, int64_t rows, int L, float scale, float p_drop, uint64_t seed,
+                            cudaStream_t stream) {
+  TFB_REQUIRE(S && P && Pd && rows > 0 && L > 0);
+  softmax_fwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(S, P, Pd, rows, L, scale, p_drop, seed);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_softmax_bwd(const float* P, const float* dPd, float* dS, int64_t rows, int L, float scale, float p_drop, uint64_t seed,
+                            cudaStream_t stream) {
+  TFB_REQUIRE(P && dPd && dS && rows > 0 && L > 0);
+  softmax_bwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(P, dPd, dS, rows, L, scale, p_drop, seed);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && n >= 0);
+  if (n == 0) return TFB_OK;
+  cast_bf16_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y, n);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+TFB_API int tfb_scale_dev(const float* x, const float* s_dev, float k, float* y, int64_t n, int accumulate, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && n >= 0);
+  if (n == 0) return TFB_OK;
+  scale_dev_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, s_dev, k, y, n, accumulate);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}

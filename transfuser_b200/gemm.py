@@ -6,12 +6,12 @@ import torch
 from . import _lib
 
 # 'tf32' (tcgen05 kind::tf32, default), 'simt' (exact fp32 CUDA cores: parity mode)
-MODE = os.environ.get('TFB_GEMM', 'tf32')
+MODE = os.environ.get('TFB_GEMM', 'simt')
 
 
 def set_mode(mode):
     global MODE
-    assert mode in ('tf32', 'simt')
+    assert mode in ('tf32', 'simt', 'bf16')
     MODE = mode
 
 
@@ -34,4 +34,11 @@ def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, relu=False, alpha=1
     else:
         _lib.call('tfb_gemm_f32_simt', int(trans_a), int(trans_b), M, N, K, a, lda, b, ldb, out, ldc, bias, int(relu),
                   float(alpha), float(beta), 1, 1, 0, 0, 0, 0, 0, 0)
+    return out
+
+
+def bgemm(a, b, out, M, N, K, lda, ldb, ldc, trans_a, trans_b, batch_outer, batch_inner, sa, sb, sc, alpha=1.0, beta=0.0):
+    """Two-level strided-batched fp32 GEMM on raw (tensor-with-offset) operands: sa/sb/sc = (outer stride, inner stride)."""
+    _lib.call('tfb_gemm_f32_simt', int(trans_a), int(trans_b), M, N, K, a, lda, b, ldb, out, ldc, None, 0, float(alpha), float(beta),
+              batch_outer, batch_inner, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1])
     return out

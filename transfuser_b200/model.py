@@ -1,0 +1,153 @@
+"""B200-native `LidarCenterNet` training forward — drop-in for /root/reference/team_code_transfuser/model.py:538-805.
+
+Same constructor and `forward(...) -> dict of the 11 scalar losses` contract (keys = config.detailed_losses), same
+parameter names (`_model.*`, `seg_decoder.*`, `depth_decoder.*`, `pred_bev.*`, `head.*_head.*`, `join.*`, `decoder.*`,
+`output.*`), so train.py's loop (`loss.backward()`, `optimizer.step()`, `state_dict()`) runs unchanged. The nn.* members
+are parameter containers; all compute goes through transfuser_b200.ops (hand-written sm_100a kernels).
+Inference-only members of the reference class (forward_ego, control_pid, visualisation) are out of scope this round."""
+import torch
+from torch import nn
+
+from . import ops
+from .backbone import TransfuserBackbone
+
+HEAD_NAMES = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
+HEAD_LOSSES = ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res', 'loss_velocity', 'loss_brake')
+
+
+def _conv_pair(cin, cmid, cout):
+    return nn.Sequential(nn.Conv2d(cin, cmid, kernel_size=3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(cmid, cout, kernel_size=1))
+
+
+def _run_pair(seq, x):
+    y = ops.conv2d(x, seq[0].weight, seq[0].bias, relu=True)
+    return ops.conv2d(y, seq[2].weight, seq[2].bias)
+
+
+class LidarCenterNetHead(nn.Module):
+    """Parameters of model.py:33-125 (seven conv3x3+ReLU+conv1x1 branches); targets + losses run in ops.CenterNetLossFn."""
+
+    def __init__(self, in_channel, feat_channel, num_classes, train_cfg=None):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_dir_bins = train_cfg.num_dir_bins
+        self.heatmap_head = _conv_pair(in_channel, feat_channel, num_classes)
+        self.wh_head = _conv_pair(in_channel, feat_channel, 2)
+        self.offset_head = _conv_pair(in_channel, feat_channel, 2)
+        self.yaw_class_head = _conv_pair(in_channel, feat_channel, self.num_dir_bins)
+        self.yaw_res_head = _conv_pair(in_channel, feat_channel, 1)
+        self.velocity_head = _conv_pair(in_channel, feat_channel, 1)
+        self.brake_head = _conv_pair(in_channel, feat_channel, 2)
+        self.train_cfg = train_cfg
+
+    def run(self, feat):
+        """feat NHWC -> [B, H, W, 21] raw predictions (heat logit | wh | offset | yaw class | yaw res | velocity | brake)."""
+        return torch.cat([_run_pair(getattr(self, n), feat) for n in HEAD_NAMES], dim=3)
+
+
+class _Decoder(nn.Module):
+    """SegDecoder / DepthDecoder parameter tree (transfuser.py:214-281)."""
+
+    def __init__(self, config, latent_dim, out_ch):
+        super().__init__()
+        self.config = config
+        c1, c2, c3 = config.deconv_channel_num_1, config.deconv_channel_num_2, config.deconv_channel_num_3
+        mk = lambda a, b, c, last_relu: nn.Sequential(*([nn.Conv2d(a, b, 3, 1, 1), nn.ReLU(True), nn.Conv2d(b, c, 3, 1, 1)] + ([nn.ReLU(True)] if last_relu else [])))
+        self.deconv1 = mk(latent_dim, c1, c2, True)
+        self.deconv2 = mk(c2, c3, c3, True)
+        self.deconv3 = mk(c3, c3, out_ch, False)
+
+    def run(self, x):
+        cfg = self.config
+        c = lambda seq, t, last_relu: ops.conv2d(ops.conv2d(t, seq[0].weight, seq[0].bias, relu=True), seq[2].weight, seq[2].bias, relu=last_relu)
+        x = c(self.deconv1, x, True)
+        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_1, x.shape[2] * cfg.deconv_scale_factor_1, False)
+        x = c(self.deconv2, x, True)
+        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_2, x.shape[2] * cfg.deconv_scale_factor_2, False)
+        return c(self.deconv3, x, False)
+
+
+class SegDecoder(_Decoder):
+    def __init__(self, config, latent_dim=512):
+        super().__init__(config, latent_dim, config.num_class)
+        self.latent_dim, self.num_class = latent_dim, config.num_class
+
+
+class DepthDecoder(_Decoder):
+    def __init__(self, config, latent_dim=512):
+        super().__init__(config, latent_dim, 1)
+        self.latent_dim = latent_dim
+
+
+class LidarCenterNet(nn.Module):
+    def __init__(self, config, device, backbone, image_architecture='resnet34', lidar_architecture='resnet18', use_velocity=True):
+        super().__init__()
+        self.device = device
+        self.config = config
+        self.pred_len = config.pred_len
+        self.use_target_point_image = config.use_target_point_image
+        self.gru_concat_target_point = config.gru_concat_target_point
+        self.use_point_pillars = config.use_point_pillars
+        if self.use_point_pillars:
+            raise RuntimeError('PointPillars is out of scope (config.py:42 default False)')
+        if not self.gru_concat_target_point:
+            raise RuntimeError('gru_concat_target_point=False is not implemented (config.py:31 default True)')
+        self.backbone = backbone
+        if backbone != 'transFuser':
+            raise RuntimeError('this round implements backbone="transFuser" only, got %r' % (backbone,))
+        self._model = TransfuserBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        if config.multitask:
+            self.seg_decoder = SegDecoder(config, config.perception_output_features).to(self.device)
+            self.depth_decoder = DepthDecoder(config, config.perception_output_features).to(self.device)
+        channel = config.channel
+        self.pred_bev = nn.Sequential(nn.Conv2d(channel, channel, kernel_size=(3, 3), stride=1, padding=(1, 1), bias=True),
+                                      nn.ReLU(inplace=True),
+                                      nn.Conv2d(channel, 3, kernel_size=(1, 1), stride=1, padding=0, bias=True)).to(self.device)
+        self.head = LidarCenterNetHead(channel, channel, 1, train_cfg=config).to(self.device)
+        self.i = 0
+        self.join = nn.Sequential(nn.Linear(512, 256), nn.ReLU(inplace=True), nn.Linear(256, 128), nn.ReLU(inplace=True),
+                                  nn.Linear(128, 64), nn.ReLU(inplace=True)).to(self.device)
+        self.decoder = nn.GRUCell(input_size=4, hidden_size=config.gru_hidden_size).to(self.device)
+        self.output = nn.Linear(config.gru_hidden_size, 3).to(self.device)
+        self.register_buffer('_bev_class_weight', torch.tensor([1., 1., 3.]), persistent=False)
+
+    def forward_gru(self, z, target_point):
+        for i in (0, 2, 4):
+            z = ops.linear(z, self.join[i].weight, self.join[i].bias, relu=True)
+        d = self.decoder
+        pred_wp = ops.GRUFn.apply(z, target_point, d.weight_ih, d.weight_hh, d.bias_ih, d.bias_hh, self.output.weight, self.output.bias,
+                                  self.pred_len, float(self.config.lidar_pos[0]))
+        return pred_wp, None, None, None, None
+
+    def forward(self, rgb, lidar_bev, ego_waypoint, target_point, target_point_image, ego_vel, bev, label, depth, semantic,
+                num_points=None, save_path=None, bev_points=None, cam_points=None):
+        cfg = self.config
+        loss = {}
+        if self.use_target_point_image:
+            lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
+        features, image_features_grid, fused_features = self._model.forward_nhwc(rgb, lidar_bev)
+        pred_wp, _, _, _, _ = self.forward_gru(fused_features, target_point)
+
+        pred_bev = _run_pair(self.pred_bev, features[0])
+        pred_bev = ops.upsample(pred_bev, cfg.bev_resolution_height, cfg.bev_resolution_width, True)
+        w = self._bev_class_weight.to(pred_bev.device)
+        loss['loss_wp'] = ops.L1Fn.apply(pred_wp, ego_waypoint, False, 1.0)
+        loss['loss_bev'] = ops.CrossEntropyFn.apply(pred_bev, bev, w, 'wsum', 1.0)
+
+        preds = self.head.run(features[0])
+        H, W = preds.shape[1], preds.shape[2]
+        head_losses = ops.CenterNetLossFn.apply(preds, label, float(W / cfg.lidar_resolution_width), float(H / cfg.lidar_resolution_height),
+                                               cfg.num_dir_bins)
+        for i, k in enumerate(HEAD_LOSSES):
+            loss[k] = head_losses[i]
+
+        if cfg.multitask:
+            pred_semantic = self.seg_decoder.run(image_features_grid)
+            pred_depth = self.depth_decoder.run(image_features_grid)
+            loss['loss_depth'] = ops.L1Fn.apply(pred_depth.view(pred_depth.shape[0], pred_depth.shape[1], pred_depth.shape[2]), depth, True, float(cfg.ls_depth))
+            loss['loss_semantic'] = ops.CrossEntropyFn.apply(pred_semantic, semantic, None, 'count', float(cfg.ls_seg))
+        else:
+            loss['loss_depth'] = torch.zeros_like(loss['loss_wp'])
+            loss['loss_semantic'] = torch.zeros_like(loss['loss_wp'])
+        self.i += 1
+        return loss

@@ -1,0 +1,596 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/tfb200.h): every forward AND backward below is a
+hand-written sm_100a kernel launch; torch supplies device memory, the current stream and the autograd graph only.
+
+Activations are NHWC fp32 ([N, H, W, C], contiguous); parameters keep the reference's PyTorch layouts so that the
+reference's state_dicts load unchanged."""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .gemm import bgemm, gemm
+
+call = _lib.call
+
+_SEED = [0x5EED0000]
+
+
+def manual_seed(seed):
+    _SEED[0] = int(seed) & 0x7FFFFFFFFFFF
+
+
+def next_seed():
+    _SEED[0] += 1
+    return _SEED[0]
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _colsum(x2d):
+    M, C = x2d.shape
+    out = torch.empty(C, dtype=torch.float32, device=x2d.device)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x2d.device)
+    call('tfb_colsum', x2d, M, C, out, ws)
+    return out
+
+
+def _relu_bwd(y, dy):
+    g = torch.empty_like(dy)
+    call('tfb_relu_bwd', y, dy, g, dy.numel())
+    return g
+
+
+# ------------------------------------------------------------------ dense layers (GEMM) and convolutions
+def _wgrad_splits(M, N, K):
+    """split-K factor for dW[N,K] = dy^T x with a long contraction (M rows): aim for >= 2 waves of 128x128 tiles."""
+    tiles = ((N + 127) // 128) * ((K + 127) // 128)
+    return max(1, min(64, (296 + tiles - 1) // tiles, M // 2048 if M >= 4096 else 1))
+
+
+class LinearFn(Function):
+    """y[M,N] = x[M,K] @ w[N,K]^T + b (ReLU). nn.Linear (transfuser.py:498-506, 538-543) and 1x1 nn.Conv2d as a GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        x = _c(x)
+        w2 = w.view(w.shape[0], -1)
+        y = torch.empty((x.shape[0], w2.shape[0]), dtype=torch.float32, device=x.device)
+        gemm(x, w2, y, trans_b=True, bias=bias, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy)
+        g = _relu_bwd(y, dy) if ctx.relu else dy
+        w2 = w.view(w.shape[0], -1)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(g, w2, dx, trans_b=False)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            gemm(g, x, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(x.shape[0], w2.shape[0], w2.shape[1]))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(g)
+        return dx, dw, db, None
+
+
+def linear(x, w, bias=None, relu=False):
+    lead = x.shape[:-1]
+    y = LinearFn.apply(x.reshape(-1, x.shape[-1]), w, bias, relu)
+    return y.view(*lead, y.shape[-1])
+
+
+class Conv2dFn(Function):
+    """NHWC conv, k in {1,3}, pad k//2, stride {1,2}, groups. 1x1/stride-1/groups-1 goes to LinearFn instead."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, groups, relu):
+        x = _c(x)
+        N, H, W, Cin = x.shape
+        Cout, ks = w.shape[0], w.shape[2]
+        Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
+        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+        call('tfb_conv2d_fwd', x, w, bias, y, N, H, W, Cin, Cout, ks, stride, groups, int(relu))
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (N, H, W, Cin, Cout, ks, stride, groups, relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        N, H, W, Cin, Cout, ks, stride, groups, relu, has_bias = ctx.cfg
+        dy = _c(dy)
+        g = _relu_bwd(y, dy) if relu else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+            call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
+        return dx, dw, db, None, None, None
+
+
+def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
+    if w.shape[2] == 1 and stride == 1 and groups == 1:
+        N, H, W, C = x.shape
+        return LinearFn.apply(x.reshape(-1, C), w, bias, relu).view(N, H, W, w.shape[0])
+    return Conv2dFn.apply(x, w, bias, stride, groups, relu)
+
+
+# ------------------------------------------------------------------ normalisation
+class BatchNormTrainFn(Function):
+    """BatchNorm2d in training mode (+ fused ReLU): batch statistics, running-stat update (momentum, unbiased var)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        x = _c(x)
+        C = x.shape[-1]
+        M = x.numel() // C
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws)
+        ctx.save_for_backward(x, weight, bias, mean, invstd)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, invstd = ctx.saved_tensors
+        dy = _c(dy)
+        C = x.shape[-1]
+        M = x.numel() // C
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(weight)
+        db = torch.empty_like(bias)
+        ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws)
+        return dx, dg, db, None, None, None, None, None
+
+
+def batch_norm(x, bn, relu, training):
+    """bn: an nn.BatchNorm2d used as a parameter/buffer container."""
+    if training:
+        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    invstd = torch.rsqrt(bn.running_var + bn.eps)
+    call('tfb_bn_apply', _c(x), y, x.numel() // C, C, bn.weight, bn.bias, bn.running_mean, invstd, int(relu))
+    return y
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _c(x)
+        C = x.shape[-1]
+        R = x.numel() // C
+        y = torch.empty_like(x)
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        call('tfb_layernorm_fwd', x, y, R, C, weight, bias, float(eps), mean, rstd)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(weight)
+        db = torch.empty_like(weight)
+        call('tfb_layernorm_bwd', x, dy, dx, R, C, weight, mean, rstd, dg, db, 0)
+        return dx, dg, db, None
+
+
+def layer_norm(x, ln):
+    return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+# ------------------------------------------------------------------ squeeze-excite, residual
+class SEFn(Function):
+    """timm SEModule: x * sigmoid(fc2(relu(fc1(mean_hw(x))))) — pooling, two tiny GEMMs and the gating, fwd + bwd."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _c(x)
+        N, H, W, C = x.shape
+        Cr = w1.shape[0]
+        dev = x.device
+        pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call('tfb_pool_hw_fwd', x, pooled, N, H * W, C)
+        h = torch.empty((N, Cr), dtype=torch.float32, device=dev)
+        gemm(pooled, w1.view(Cr, C), h, trans_b=True, bias=b1, relu=True, mode='simt')
+        s = torch.empty((N, C), dtype=torch.float32, device=dev)
+        gemm(h, w2.view(C, Cr), s, trans_b=True, bias=b2, mode='simt')
+        gate = torch.empty_like(s)
+        call('tfb_sigmoid_fwd', s, gate, s.numel())
+        y = torch.empty_like(x)
+        call('tfb_se_scale_fwd', x, gate, y, N, H * W, C)
+        ctx.save_for_backward(x, w1, w2, pooled, h, gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pooled, h, gate = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, C = x.shape
+        Cr = w1.shape[0]
+        dev = x.device
+        dgate = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call('tfb_se_bwd_reduce', x, dy, dgate, N, H * W, C)
+        ds = torch.empty_like(dgate)
+        call('tfb_sigmoid_bwd', gate, dgate, ds, ds.numel())
+        dw2 = torch.empty_like(w2)
+        gemm(ds, h, dw2.view(C, Cr), trans_a=True, mode='simt')
+        db2 = _colsum(ds)
+        dh = torch.empty((N, Cr), dtype=torch.float32, device=dev)
+        gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
+        dh = _relu_bwd(h, dh)
+        dw1 = torch.empty_like(w1)
+        gemm(dh, pooled, dw1.view(Cr, C), trans_a=True, mode='simt')
+        db1 = _colsum(dh)
+        dpool = torch.empty((N, C), dtype=torch.float32, device=dev)
+        gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
+        dx = torch.empty_like(x)
+        call('tfb_se_bwd_apply', dy, gate, dpool, dx, N, H * W, C)
+        return dx, dw1, db1, dw2, db2
+
+
+class AddFn(Function):
+    """y = a + b (ReLU optional): the Bottleneck shortcut (timm) and the GPT residuals (transfuser.py:546-547)."""
+
+    @staticmethod
+    def forward(ctx, a, b, relu):
+        a, b = _c(a), _c(b)
+        y = torch.empty_like(a)
+        call('tfb_add_relu', a, b, y, a.numel(), int(relu))
+        ctx.relu = relu
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        if ctx.relu:
+            (y,) = ctx.saved_tensors
+            dy = _relu_bwd(y, dy)
+        return dy, dy, None
+
+
+def add(a, b, relu=False):
+    return AddFn.apply(a, b, relu)
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call('tfb_dropout', x, y, x.numel(), float(p), seed)
+        ctx.p, ctx.seed = p, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), ctx.seed)
+        return dx, None, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, p, next_seed())
+
+
+# ------------------------------------------------------------------ attention (SelfAttention.forward, transfuser.py:510-527)
+class AttentionFn(Function):
+    """h[B*T, C] -> softmax(q k^T / sqrt(hs)) v for n_head heads, with the key/query/value projections inside.
+    The (b, head) products run as two-level strided-batched GEMMs straight on the packed [B*T, 3C] q|k|v buffer."""
+
+    @staticmethod
+    def forward(ctx, h, wq, bq, wk, bk, wv, bv, B, T, nh, p_drop, seed):
+        h = _c(h)
+        C = h.shape[1]
+        hs = C // nh
+        dev = h.device
+        qkv = torch.empty((B * T, 3 * C), dtype=torch.float32, device=dev)
+        gemm(h, wq, qkv[:, 0:C], trans_b=True, bias=bq)
+        gemm(h, wk, qkv[:, C:2 * C], trans_b=True, bias=bk)
+        gemm(h, wv, qkv[:, 2 * C:], trans_b=True, bias=bv)
+        S = torch.empty((B, nh, T, T), dtype=torch.float32, device=dev)
+        q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        bgemm(q, k, S, T, T, hs, 3 * C, 3 * C, T, False, True, B, nh, (T * 3 * C, hs), (T * 3 * C, hs), (nh * T * T, T * T))
+        scale = 1.0 / (hs ** 0.5)
+        Pd = torch.empty_like(S) if p_drop > 0 else S
+        call('tfb_softmax_fwd', S, S, Pd, B * nh * T, T, scale, float(p_drop), seed)
+        y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
+        bgemm(Pd, v, y, T, hs, T, T, 3 * C, C, False, False, B, nh, (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs))
+        ctx.save_for_backward(h, wq, wk, wv, qkv, S, Pd)
+        ctx.cfg = (B, T, nh, p_drop, seed, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, wq, wk, wv, qkv, P, Pd = ctx.saved_tensors
+        B, T, nh, p_drop, seed, scale = ctx.cfg
+        dy = _c(dy)
+        C = h.shape[1]
+        hs = C // nh
+        dev = h.device
+        q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv[:, 0:C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
+        sP, sQ, sY = (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs)
+        dP = torch.empty_like(P)
+        bgemm(dy, v, dP, T, T, hs, C, 3 * C, T, False, True, B, nh, sY, sQ, sP)          # dPd = dy v^T
+        bgemm(Pd, dy, dv, T, hs, T, T, C, 3 * C, True, False, B, nh, sP, sY, sQ)         # dv  = Pd^T dy
+        call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed)    # dS (in place)
+        bgemm(dP, k, dq, T, hs, T, T, 3 * C, 3 * C, False, False, B, nh, sP, sQ, sQ)     # dq  = dS k
+        bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
+        dh = torch.empty_like(h)
+        gemm(dq, wq, dh, trans_b=False)
+        gemm(dk, wk, dh, trans_b=False, beta=1.0)
+        gemm(dv, wv, dh, trans_b=False, beta=1.0)
+        grads = []
+        for d, w in ((dq, wq), (dk, wk), (dv, wv)):
+            dw = torch.empty_like(w)
+            gemm(d, h, dw, trans_a=True, splits=_wgrad_splits(h.shape[0], C, C))
+            grads += [dw, _colsum(d)]
+        return (dh, *grads, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------ GPT token build / output view + upsample + add
+class TokensFn(Function):
+    """AdaptiveAvgPool2d of both feature maps -> (B, T, C) tokens + pos_emb, dropout (transfuser.py:150-151, 346-357)."""
+
+    @staticmethod
+    def forward(ctx, img, lid, pos_emb, ghi, gwi, ghl, gwl, p_drop, seed):
+        img, lid = _c(img), _c(lid)
+        N, Hi, Wi, C = img.shape
+        _, Hl, Wl, _ = lid.shape
+        T = ghi * gwi + ghl * gwl
+        out = torch.empty((N, T, C), dtype=torch.float32, device=img.device)
+        call('tfb_tokens_fwd', img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos_emb, out, N, C, float(p_drop), seed)
+        ctx.cfg = (N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, p_drop, seed)
+        ctx.pos_shape = pos_emb.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, p_drop, seed = ctx.cfg
+        g = _c(g)
+        dimg = torch.empty((N, Hi, Wi, C), dtype=torch.float32, device=g.device)
+        dlid = torch.empty((N, Hl, Wl, C), dtype=torch.float32, device=g.device)
+        dpos = torch.empty(ctx.pos_shape, dtype=torch.float32, device=g.device)
+        call('tfb_tokens_bwd', g, dimg, Hi, Wi, ghi, gwi, dlid, Hl, Wl, ghl, gwl, dpos, N, C, float(p_drop), seed, 0)
+        return dimg, dlid, dpos, None, None, None, None, None, None
+
+
+class GptUpAddFn(Function):
+    """feat + bilinear_upsample(view(tokens)) for both branches; the token slab is *re-interpreted* as (C, gh, gw)
+    exactly like the reference's `.contiguous().view(...)` (transfuser.py:363-364, then 154-157)."""
+
+    @staticmethod
+    def forward(ctx, img, lid, tok, ghi, gwi, ghl, gwl):
+        img, lid, tok = _c(img), _c(lid), _c(tok)
+        N, Hi, Wi, C = img.shape
+        _, Hl, Wl, _ = lid.shape
+        T = tok.shape[1]
+        oi, ol = torch.empty_like(img), torch.empty_like(lid)
+        call('tfb_gpt_up_add_fwd', img, tok, oi, N, Hi, Wi, C, ghi, gwi, 0, T)
+        call('tfb_gpt_up_add_fwd', lid, tok, ol, N, Hl, Wl, C, ghl, gwl, ghi * gwi, T)
+        ctx.cfg = (N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, T)
+        return oi, ol
+
+    @staticmethod
+    def backward(ctx, di, dl):
+        N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, T = ctx.cfg
+        di, dl = _c(di), _c(dl)
+        dtok = torch.zeros((N, T, C), dtype=torch.float32, device=di.device)
+        call('tfb_gpt_up_add_bwd', di, dtok, N, Hi, Wi, C, ghi, gwi, 0, T)
+        call('tfb_gpt_up_add_bwd', dl, dtok, N, Hl, Wl, C, ghl, gwl, ghi * gwi, T)
+        return di, dl, dtok, None, None, None, None
+
+
+class UpsampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo, align_corners):
+        x = _c(x)
+        N, Hi, Wi, C = x.shape
+        y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
+        call('tfb_upsample_bilinear_fwd', x, y, N, Hi, Wi, Ho, Wo, C, int(align_corners))
+        ctx.cfg = (N, Hi, Wi, Ho, Wo, C, int(align_corners))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, Hi, Wi, Ho, Wo, C, ac = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty((N, Hi, Wi, C), dtype=torch.float32, device=dy.device)
+        call('tfb_upsample_bilinear_bwd', dy, dx, N, Hi, Wi, Ho, Wo, C, ac)
+        return dx, None, None, None
+
+
+def upsample(x, Ho, Wo, align_corners=False):
+    return UpsampleFn.apply(x, Ho, Wo, align_corners)
+
+
+class PoolHWFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, W, C = x.shape
+        out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        call('tfb_pool_hw_fwd', x, out, N, H * W, C)
+        ctx.shape = (N, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        N, H, W, C = ctx.shape
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=d.device)
+        call('tfb_pool_hw_bwd', _c(d), dx, N, H * W, C, 0)
+        return dx
+
+
+class TransposeFn(Function):
+    """[N, A, B] -> [N, B, A]; used as NCHW <-> NHWC at the module boundary (the reference's tensors are NCHW)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, A, B = x.shape
+        y = torch.empty((N, B, A), dtype=torch.float32, device=x.device)
+        call('tfb_transpose_last2', x, y, N, A, B)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        N, B, A = dy.shape
+        dx = torch.empty((N, A, B), dtype=torch.float32, device=dy.device)
+        call('tfb_transpose_last2', dy, dx, N, B, A)
+        return dx
+
+
+def nchw_to_nhwc(x):
+    N, C, H, W = x.shape
+    return TransposeFn.apply(x.reshape(N, C, H * W)).view(N, H, W, C)
+
+
+def nhwc_to_nchw(x):
+    N, H, W, C = x.shape
+    return TransposeFn.apply(x.reshape(N, H * W, C)).view(N, C, H, W)
+
+
+def image_prep(img_nchw):
+    """normalize_imagenet (transfuser.py:419-428) fused with the NCHW -> NHWC layout change. No gradient (input)."""
+    img = _c(img_nchw.detach())
+    N, _, H, W = img.shape
+    out = torch.empty((N, H, W, 3), dtype=torch.float32, device=img.device)
+    call('tfb_image_prep', img, out, N, H, W)
+    return out
+
+
+# ------------------------------------------------------------------ losses
+class CrossEntropyFn(Function):
+    """k * sum_m w_m nll_m / den over NHWC logits. den: 'wsum' (sum of weights: F.cross_entropy's weighted mean),
+    'count' (plain mean) — model.py:763, 786."""
+
+    @staticmethod
+    def forward(ctx, logits, target, class_w, den_mode, k):
+        logits, target = _c(logits), _c(target)
+        C = logits.shape[-1]
+        M = logits.numel() // C
+        acc = torch.empty(2, dtype=torch.float64, device=logits.device)
+        call('tfb_ce_fwd', logits, target, M, C, class_w, None, 1, acc)
+        out = torch.empty((), dtype=torch.float32, device=logits.device)
+        den = acc[1:] if den_mode == 'wsum' else None
+        kk = k if den_mode == 'wsum' else k / M
+        call('tfb_ratio', acc, den, 0.0, float(kk), out)
+        ctx.save_for_backward(logits, target, class_w, acc)
+        ctx.cfg = (M, C, den_mode, kk)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, class_w, acc = ctx.saved_tensors
+        M, C, den_mode, kk = ctx.cfg
+        d = torch.empty_like(logits)
+        den = acc[1:] if den_mode == 'wsum' else None
+        call('tfb_ce_bwd', logits, target, M, C, class_w, None, 1, _c(g), den, 0.0, float(kk), d)
+        return d, None, None, None, None
+
+
+class L1Fn(Function):
+    """k * mean(|f(x) - t|), f = sigmoid or identity (model.py:765, 788 with transfuser.py:279)."""
+
+    @staticmethod
+    def forward(ctx, x, t, sigmoid, k):
+        x, t = _c(x), _c(t)
+        acc = torch.empty(1, dtype=torch.float64, device=x.device)
+        call('tfb_l1_fwd', x, t, x.numel(), int(sigmoid), acc)
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        call('tfb_ratio', acc, None, 0.0, float(k) / x.numel(), out)
+        ctx.save_for_backward(x, t)
+        ctx.cfg = (int(sigmoid), float(k) / x.numel())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, t = ctx.saved_tensors
+        d = torch.empty_like(x)
+        call('tfb_l1_bwd', x, t, x.numel(), ctx.cfg[0], _c(g), ctx.cfg[1], d)
+        return d, None, None, None
+
+
+class CenterNetLossFn(Function):
+    """get_targets + the seven head losses (model.py:149-374) on pred[B,H,W,21] (heat logit | wh | offset | yaw class x12 |
+    yaw res | velocity | brake x2). Returns a [7] tensor in the order of the reference's loss dict."""
+
+    @staticmethod
+    def forward(ctx, pred, label, ratio_w, ratio_h, num_dir_bins):
+        pred, label = _c(pred), _c(label)
+        B, H, W, _ = pred.shape
+        dev = pred.device
+        tgt = torch.empty((B, 10, H, W), dtype=torch.float32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        call('tfb_centernet_targets', label, B, label.shape[1], tgt, H, W, float(ratio_w), float(ratio_h), num_dir_bins, count)
+        acc = torch.empty(7, dtype=torch.float64, device=dev)
+        out = torch.empty(7, dtype=torch.float32, device=dev)
+        call('tfb_centernet_loss_fwd', pred, tgt, B, H * W, count, acc, out)
+        ctx.save_for_backward(pred, tgt, count)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, tgt, count = ctx.saved_tensors
+        B, H, W, _ = pred.shape
+        d = torch.empty_like(pred)
+        call('tfb_centernet_loss_bwd', pred, tgt, B, H * W, count, _c(g), d)
+        return d, None, None, None, None
+
+
+class GRUFn(Function):
+    """forward_gru's autoregressive GRUCell loop (model.py:611-646) after the `join` MLP."""
+
+    @staticmethod
+    def forward(ctx, z0, target_point, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, x_shift):
+        z0, target_point = _c(z0), _c(target_point)
+        B = z0.shape[0]
+        wp = torch.empty((B, steps, 2), dtype=torch.float32, device=z0.device)
+        save = torch.empty((B, steps, 5 * 64 + 4), dtype=torch.float32, device=z0.device)
+        call('tfb_gru_fwd', z0, target_point, w_ih, w_hh, b_ih, b_hh, w_out, b_out, B, steps, float(x_shift), wp, save)
+        ctx.save_for_backward(save, w_ih, w_hh, w_out)
+        ctx.cfg = (B, steps)
+        return wp
+
+    @staticmethod
+    def backward(ctx, d):
+        save, w_ih, w_hh, w_out = ctx.saved_tensors
+        B, steps = ctx.cfg
+        dev = d.device
+        dz0 = torch.empty((B, 64), dtype=torch.float32, device=dev)
+        dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+        db_ih = torch.empty(192, dtype=torch.float32, device=dev)
+        db_hh = torch.empty(192, dtype=torch.float32, device=dev)
+        dw_out = torch.empty_like(w_out)
+        db_out = torch.empty(3, dtype=torch.float32, device=dev)
+        call('tfb_gru_bwd', _c(d), save, w_ih, w_hh, w_out, B, steps, dz0, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out)
+        return dz0, None, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out, None, None
