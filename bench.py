@@ -1,0 +1,259 @@
+"""bench.py — TransFuser training-step throughput (samples/s of RGB+LiDAR pairs) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3          # this repo's CUDA path (default)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                    # the reference's CPU PyTorch path (oracle port) on the host cores
+
+One "step" = BASELINE.json configs[1]: LidarCenterNet (TransFuser, RegNetY-3.2GF) forward + backward + AdamW on a batch of
+10 samples per GPU (160x704 RGB + 40k LiDAR points -> 2x256x256 BEV histogram on the GPU + target-point image), dropout on,
+all 11 losses, synthetic data, random-init weights. Prints ONE JSON line (rank 0)."""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_TRAIN = 230.3e9   # 3 x 76.8 GFLOP forward (2*MAC)
+METRIC = 'training samples/sec (RGB+LiDAR pairs)'
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_host_batch(B, seed, torch, np):
+    """Synthetic inputs of SURVEY.md §8(d) in PINNED host memory (the e2e arm copies them every step)."""
+    from oracle import bev_oracle, torch_oracle as O
+    b = O.synthetic_batch(B, seed=seed)
+    pts = np.stack([bev_oracle.synthetic_points(40000, 1000 * seed + i, np.float32, edge_cases=False) for i in range(B)])
+    b['points'] = torch.from_numpy(pts)
+    del b['lidar']
+    return {k: v.pin_memory() for k, v in b.items()}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from transfuser_b200 import LidarCenterNet, _lib, bev, gemm, ops, optim
+    from transfuser_b200.config import TrainConfig
+
+    rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    B = args.batch
+    cfg = TrainConfig()
+    torch.manual_seed(0)
+    ops.manual_seed(1234 + rank)
+    gemm.set_mode(args.gemm)
+    net = LidarCenterNet(cfg, dev, 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False).train()
+    fp = optim.flatten(net)
+    if args.gemm == 'bf16':
+        gemm.attach_bf16_weights(fp)
+    opt = optim.FusedAdamW(net.parameters(), lr=1e-4, grad_scale=1.0 / world)
+    reducer = optim.GradAllReducer(fp, n_chunks=8)
+    w = dict(zip(cfg.detailed_losses, cfg.detailed_losses_weights))
+    host = make_host_batch(B, seed=100 + rank, torch=torch, np=np)
+
+    def h2d():
+        return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+
+    def step(d):
+        lidar = bev.lidar_to_histogram_features_batched(d['points'])
+        opt.zero_grad()
+        losses = net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
+                     target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
+                     depth=d['depth'], semantic=d['semantic'])
+        loss = None
+        for k, v in losses.items():
+            loss = v * w[k] if loss is None else loss + v * w[k]
+        loss.backward()
+        opt.step(chunks=reducer.chunks())
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        dres = h2d()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.lib().launches
+        e0.record()
+        last = None
+        for _ in range(n):
+            d = h2d() if e2e else dres
+            loss = step(d)
+            if e2e:
+                last = float(loss.item())  # device -> host read of the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.lib().launches - l0, last
+
+    for _ in range(max(args.warmup, 3)):
+        step(h2d())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, _ = timed(args.steps, e2e=False)
+    ms_e2e, _, last_loss = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: per-entry-point CUDA-event timing over one extra step (rank 0) ----
+    roof = None
+    if rank == 0:
+        prof = _lib.Profiler()
+        _lib.lib().profiler = prof
+        step(h2d())
+        torch.cuda.synchronize()
+        _lib.lib().profiler = None
+        roof = prof.summary(peaks())
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    if rank == 0:
+        pk, how = peaks()
+        total = B * world
+        value = total * args.steps / (ms_dev / 1e3)
+        e2e_v = total * args.steps / (ms_e2e / 1e3)
+        line = {
+            'metric': METRIC, 'value': round(value, 3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': round(ms_dev / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.gemm == 'bf16' else 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'TransFuser RegNetY-3.2GF LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
+                                   '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU' % B,
+                       'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm,
+                       'l2': 'working set (672 MB weights + activations) exceeds the 126 MB L2; no explicit flush'},
+            'e2e': {'value': round(e2e_v, 3), 'unit': 'samples/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
+                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
+            'gpu_launches': launches, 'clocks': clocks,
+            'step_tensor_roofline': {'achieved_tflops': round(FLOP_PER_SAMPLE_TRAIN * value / 1e12, 2), 'peak_tflops': pk['bf16_tflops_sustained'],
+                                     'frac': round(FLOP_PER_SAMPLE_TRAIN * value / 1e12 / pk['bf16_tflops_sustained'], 4), 'of': how},
+            'roofline': roof,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_reference(steps=1, warmup=0, batch=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference(steps, warmup, batch):
+    """The reference's CPU PyTorch path (oracle port: oracle/torch_oracle.py, pinned to the verbatim reference) —
+    forward + backward + torch.optim.AdamW on the host cores, bounded sample of the same workload."""
+    import torch
+    from oracle import torch_oracle as O
+    from transfuser_b200 import LidarCenterNet
+    from transfuser_b200.config import TrainConfig
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = LidarCenterNet(TrainConfig(), 'cpu', 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False)  # parameter container only
+    P = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k and 'num_batches' not in k)
+         for k, v in net.state_dict().items()}
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4)
+    batch_d = O.synthetic_batch(batch, seed=7)
+    drop = lambda t, p: torch.nn.functional.dropout(t, p, True)
+    cfg = TrainConfig()
+    w = dict(zip(cfg.detailed_losses, cfg.detailed_losses_weights))
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        losses = O.forward(P, batch_d, O.Cfg, train=True, drop=drop)
+        sum(w[k] * v for k, v in losses.items()).backward()
+        opt.step()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.time()
+    for _ in range(steps):
+        one()
+    dt = time.time() - t0
+    return {'value': round(batch * steps / dt, 4), 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'ms_per_step': round(dt / steps * 1e3, 1),
+            'sample': '%d step(s) of batch %d (fwd+bwd+AdamW, fp32, %d torch threads)' % (steps, batch, torch.get_num_threads())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    cb = cpu_reference(steps=steps, warmup=warm, batch=2)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'samples/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)),
+            'steps': steps, 'warmup': warm, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'TransFuser RegNetY-3.2GF LidarCenterNet full train step (fwd+bwd+AdamW) on the host CPU, bounded sample: batch 2'},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=10, help='samples per GPU (BASELINE configs[1]: 10)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'simt'), choices=['simt', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

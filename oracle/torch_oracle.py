@@ -243,8 +243,8 @@ def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None):
     if cfg.multitask:
         seg = _decoder(P, 'seg_decoder.', img_grid, cfg)
         depth = torch.sigmoid(_decoder(P, 'depth_decoder.', img_grid, cfg)).squeeze(1)
-        loss['loss_semantic'] = cfg.ls_seg * F.cross_entropy(seg, batch['semantic'])
         loss['loss_depth'] = cfg.ls_depth * F.l1_loss(depth, batch['depth'])
+        loss['loss_semantic'] = cfg.ls_seg * F.cross_entropy(seg, batch['semantic'])
     if taps is not None:
         taps.update(p2=feats[0], img_grid=img_grid, fused=fused, pred_wp=wp)
     return loss

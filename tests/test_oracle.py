@@ -1,0 +1,91 @@
+"""CPU: the oracle restatement (oracle/torch_oracle.py) against (a) the committed fixture produced by the VERBATIM
+reference and (b) — in the build container, where /root/reference exists — the reference itself; plus the structural
+cross-check of the timm shim against torchvision's RegNetY-3.2GF and the C-ABI export check."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import, torch_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz')
+
+
+def _product_container():
+    from transfuser_b200 import LidarCenterNet
+    from transfuser_b200.config import TrainConfig
+    return LidarCenterNet(TrainConfig(), 'cpu', 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False)
+
+
+def test_oracle_reproduces_reference_golden():
+    from oracle.make_golden_model import BATCH, BATCH_SEED, GRAD_KEYS, WEIGHT_SEED
+    g = np.load(GOLD)
+    net = _product_container()  # parameter names / shapes only (the product's forward needs the GPU)
+    names = [(n, tuple(p.shape)) for n, p in list(net.named_parameters()) + list(net.named_buffers()) if not n.startswith('_bev')]
+    st = O.deterministic_state(names, seed=WEIGHT_SEED)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in st.items()}
+    # alias keys of the reference state_dict are not needed by the oracle (it reads stem./s1../conv1 names)
+
+    class C(O.Cfg):
+        embd_pdrop = attn_pdrop = resid_pdrop = 0.0
+    losses = O.forward(P, O.synthetic_batch(BATCH, seed=BATCH_SEED), C, train=True)
+    assert list(losses.keys()) == list(g['loss_names'])
+    for k, want in zip(g['loss_names'], g['losses']):
+        assert abs(float(losses[k]) - want) <= 1e-5 * max(abs(want), 1e-6), (k, float(losses[k]), want)
+    from transfuser_b200.config import TrainConfig
+    w = dict(zip(TrainConfig.detailed_losses, TrainConfig.detailed_losses_weights))
+    sum(w[k] * v for k, v in losses.items()).backward()
+    for k, want in zip(g['grad_keys'], g['grad_norms']):
+        assert abs(float(P[str(k)].grad.double().norm()) - want) <= 1e-3 * want, k
+    assert np.allclose(P['_model.image_encoder.features.stem.bn.running_mean'].detach().numpy(), g['stem_running_mean'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_oracle_and_state_dict_match_verbatim_reference():
+    from oracle.make_golden_model import reference_model
+    ref, cfg = reference_model()
+    mine = _product_container()
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)   # drop-in checkpoint contract
+    mine.load_state_dict(b, strict=True)
+    batch = O.synthetic_batch(1, seed=2)
+    P = {k: v.clone() for k, v in ref.state_dict().items()}
+
+    class C(O.Cfg):
+        embd_pdrop = attn_pdrop = resid_pdrop = 0.0
+    with torch.no_grad():
+        want = ref(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                   target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                   depth=batch['depth'], semantic=batch['semantic'])
+        got = O.forward(P, batch, C, train=True)
+    for k in want:
+        assert abs(float(want[k]) - float(got[k])) <= 1e-6 * max(abs(float(want[k])), 1e-6), k
+
+
+def test_timm_shim_matches_torchvision_regnet_structure():
+    """The un-vendored timm 0.5.4 `regnety_032` restatement has the stage widths / depths / group counts / SE sizes and the
+    parameter count of torchvision's independent RegNetY-3.2GF definition."""
+    import sys
+    sys.path.insert(0, ref_import.SHIMS)
+    import timm
+    import torchvision
+    shim = timm.create_model('regnety_032')
+    tv = torchvision.models.regnet_y_3_2gf(weights=None)
+    n_shim = sum(p.numel() for p in shim.parameters())
+    n_tv = sum(p.numel() for p in tv.parameters())
+    assert n_shim == n_tv, (n_shim, n_tv)
+    shapes_shim = sorted(tuple(p.shape) for p in shim.parameters())
+    shapes_tv = sorted(tuple(p.shape) for p in tv.parameters())
+    assert shapes_shim == shapes_tv
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from transfuser_b200 import _lib
+    decls = _lib.parse_header()
+    assert len(decls) >= 40
+    cdll = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in decls if not hasattr(cdll, n)]
+    assert not missing, missing
+    assert cdll.tfb_abi_version() == 1

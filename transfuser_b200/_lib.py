@@ -55,6 +55,7 @@ class _Lib:
             fn.argtypes = [t for t, _ in params]
             self.fns[name] = (fn, params)
         self.launches = 0
+        self.profiler = None
 
     def call(self, name, *args):
         """Calls tfb_<name>; torch tensors become device pointers; the trailing stream argument is filled in."""
@@ -76,7 +77,10 @@ class _Lib:
                 conv.append(a)
         if takes_stream:
             conv.append(torch.cuda.current_stream().cuda_stream)
-        rc = fn(*conv)
+        if self.profiler is not None:
+            rc = self.profiler.timed(name, args, lambda: fn(*conv))
+        else:
+            rc = fn(*conv)
         self.launches += 1
         if rc != 0:
             raise RuntimeError('%s failed with code %d: %s' % (name, rc, self.cdll.tfb_last_error().decode()))
@@ -94,3 +98,57 @@ def lib():
 
 def call(name, *args):
     return lib().call(name, *args)
+
+
+class Profiler:
+    """Per-entry-point CUDA-event timing (events recorded on the launching stream around every C-ABI call) plus the
+    algorithmic FLOPs / bytes of each call, used by bench.py for the live roofline of the dominant kernel."""
+
+    def __init__(self):
+        self.records = []
+
+    def timed(self, name, args, thunk):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = thunk()
+        e1.record()
+        self.records.append((name, self._work(name, args), e0, e1))
+        return rc
+
+    @staticmethod
+    def _work(name, a):
+        """(flops, bytes) — algorithmic: 2*MAC for contractions, every tensor argument touched once for the rest."""
+        if name.startswith('tfb_gemm'):
+            M, N, K = a[2], a[3], a[4]
+            nb = a[15] * a[16] if name.endswith('simt') else 1
+            return 2.0 * M * N * K * nb, 4.0 * nb * (M * K + N * K + M * N)
+        if name.startswith('tfb_conv2d'):
+            i0 = 3 if name.endswith('dgrad') else 4
+            N, H, W, Cin, Cout, ks, stride, groups = a[i0:i0 + 8]
+            Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
+            return 2.0 * N * Ho * Wo * Cout * (Cin // groups) * ks * ks, 4.0 * (N * H * W * Cin + N * Ho * Wo * Cout)
+        b = sum(t.numel() * t.element_size() for t in a if isinstance(t, torch.Tensor))
+        return 0.0, float(b)
+
+    def summary(self, peaks_and_how):
+        pk, how = peaks_and_how
+        torch.cuda.synchronize()
+        agg = {}
+        for name, (fl, by), e0, e1 in self.records:
+            d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += fl
+            d[2] += by
+            d[3] += 1
+        total = sum(v[0] for v in agg.values()) or 1.0
+        top = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        name, (ms, fl, by, n) = top[0]
+        tensor = fl > 0
+        if tensor:
+            ach, peak, unit = fl / (ms * 1e-3) / 1e12, pk['bf16_tflops_sustained'], 'TFLOP/s'
+        else:
+            ach, peak, unit = by / (ms * 1e-3) / 1e9, pk['hbm_gbs'], 'GB/s'
+        return {'kernel': name, 'bound': 'tensor' if tensor else 'hbm', 'achieved': round(ach, 3), 'peak': peak, 'unit': unit,
+                'frac': round(ach / peak, 5), 'traffic': None, 'of': how, 'launches': n, 'avg_ms': round(ms / n, 4),
+                'share_of_step': round(ms / total, 4),
+                'top5_ms': {k: round(v[0], 3) for k, v in top[:5]}, 'step_kernel_ms': round(total, 3)}

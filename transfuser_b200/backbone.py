@@ -111,7 +111,7 @@ class LidarEncoder(nn.Module):
             raise RuntimeError('transfuser_b200 implements the regnety_032 trunk only, got %r' % (architecture,))
         m = self._model = _RegNet()
         old = m.stem.conv
-        m.bn1 = m.stem.bn
+        m.conv1, m.bn1 = m.stem.conv, m.stem.bn   # same registration order as the reference (transfuser.py:446-453)
         m.layer1, m.layer2, m.layer3, m.layer4 = m.s1, m.s2, m.s3, m.s4
         m.conv1 = nn.Conv2d(in_channels, old.out_channels, kernel_size=old.kernel_size, stride=old.stride, padding=old.padding, bias=False)
         del m.stem.conv

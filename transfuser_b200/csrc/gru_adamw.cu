@@ -123,12 +123,12 @@ gru_bwd_kernel(const float* __restrict__ d_wp, const float* __restrict__ save, c
 }
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ p_bf16) {
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ p_bf16, int zero_grad) {
   const int64_t n4 = n / 4;
   const float step = lr / bc1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
     float4 Mv = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
     float* pp = &P.x; float* gg = &G.x; float* mm = &Mv.x; float* vv = &V.x;
 #pragma unroll
@@ -142,6 +142,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     reinterpret_cast<float4*>(p)[i] = P;
     reinterpret_cast<float4*>(m)[i] = Mv;
     reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p_bf16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(P.x, P.y), hi = __floats2bfloat162_rn(P.z, P.w);
       uint2 o;
@@ -157,6 +158,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float V = beta2 * v[i] + (1.f - beta2) * gr * gr;
     P -= step * Mv / (sqrtf(V) / bc2_sqrt + eps);
     p[i] = P; m[i] = Mv; v[i] = V;
+    if (zero_grad) g[i] = 0.f;
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(P);
   }
 }
@@ -187,14 +189,15 @@ TFB_API int tfb_gru_bwd(const float* d_wp, const float* save, const float* w_ih,
   return TFB_OK;
 }
 
-TFB_API int tfb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                           float weight_decay, int step, float grad_scale, void* p_bf16, cudaStream_t stream) {
+// zero_grad != 0: the gradient buffer is cleared in the same pass (saves the separate zero_grad() sweep).
+TFB_API int tfb_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int step, float grad_scale, void* p_bf16, int zero_grad, cudaStream_t stream) {
   TFB_REQUIRE(p && g && m && v && n >= 0 && step >= 1);
   if (n == 0) return TFB_OK;
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adamw_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale,
-                                                              (__nv_bfloat16*)p_bf16);
+                                                              (__nv_bfloat16*)p_bf16, zero_grad);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -12,7 +12,7 @@ namespace {
 // MODE 0: (sum x, sum x^2)            MODE 1: BN backward (sum g, sum g*xhat), g = dy * relu_mask
 template <int MODE>
 __global__ void __launch_bounds__(256)
-colreduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
+colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int relu) {
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -23,7 +23,7 @@ colreduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, int6
     if (MODE == 1) { mu = mean[c]; is = invstd[c]; ga = gamma[c]; be = beta[c]; }
     int cnt = 0;
     for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += (int64_t)gridDim.y * 8) {
-      const float v = x[r * C + c];
+      const float v = x[r * ldx + c];
       if (MODE == 0) {
         a0 += v; a1 = fmaf(v, v, a1);
       } else {
@@ -207,7 +207,7 @@ TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* 
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   const int slabs = (C + 31) / 32;
   dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
+  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
   TFB_CHECK_LAUNCH();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
   TFB_CHECK_LAUNCH();
@@ -234,7 +234,7 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   const int slabs = (C + 31) / 32;
   dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<1><<<grid, block, 0, stream>>>(x, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu);
+  colreduce_kernel<1><<<grid, block, 0, stream>>>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu);
   TFB_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<tfb_grid(M * C, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
                                                                 dgamma, dbeta);
@@ -243,12 +243,13 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
 }
 
 // out[c] = sum_r x[r][c]  (bias gradients of Linear / 1x1 conv layers)
-TFB_API int tfb_colsum(const float* x, int64_t M, int C, float* out, double* sums_ws, cudaStream_t stream) {
-  TFB_REQUIRE(x && out && sums_ws && M > 0 && C > 0);
+// x is [M, C] with row stride ldx (elements).
+TFB_API int tfb_colsum(const float* x, int64_t ldx, int64_t M, int C, float* out, double* sums_ws, cudaStream_t stream) {
+  TFB_REQUIRE(x && out && sums_ws && M > 0 && C > 0 && ldx >= C);
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   const int slabs = (C + 31) / 32;
   dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
+  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
   TFB_CHECK_LAUNCH();
   double_to_float_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, out, C);
   TFB_CHECK_LAUNCH();

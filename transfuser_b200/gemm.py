@@ -26,7 +26,7 @@ def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, relu=False, alpha=1
     M, N = out.shape
     K = a.shape[0] if trans_a else a.shape[1]
     lda, ldb, ldc = _ld(a), _ld(b), _ld(out)
-    use_tc = (mode != 'simt' and lda % 4 == 0 and ldb % 4 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+    use_tc = (mode == 'tf32' and not trans_a and trans_b and lda % 4 == 0 and ldb % 4 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
               and M >= 1 and N >= 8 and K >= 8)
     if use_tc:
         _lib.call('tfb_gemm_tf32_tc', int(trans_a), int(trans_b), M, N, K, a, lda, b, ldb, out, ldc, bias, int(relu),
@@ -41,4 +41,60 @@ def bgemm(a, b, out, M, N, K, lda, ldb, ldc, trans_a, trans_b, batch_outer, batc
     """Two-level strided-batched fp32 GEMM on raw (tensor-with-offset) operands: sa/sb/sc = (outer stride, inner stride)."""
     _lib.call('tfb_gemm_f32_simt', int(trans_a), int(trans_b), M, N, K, a, lda, b, ldb, out, ldc, None, 0, float(alpha), float(beta),
               batch_outer, batch_inner, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core mode: operands are bf16 copies (weights: maintained by the fused AdamW kernel inside the flat bf16 buffer;
+# activations: cast once by the producing op and kept for backward instead of the fp32 tensor), accumulation and outputs fp32.
+_FLAT = [None]
+_WCACHE = {}
+
+
+def attach_bf16_weights(flat_params):
+    """flat_params: transfuser_b200.optim.FlatParams. Creates / refreshes the bf16 mirror of the flat fp32 weight buffer."""
+    fp = flat_params
+    if fp.bf16 is None:
+        fp.bf16 = torch.empty(fp.total, dtype=torch.bfloat16, device=fp.flat.device)
+    _lib.call('tfb_cast_bf16', fp.flat, fp.bf16, fp.total)
+    _FLAT[0] = fp
+    return fp.bf16
+
+
+def to_bf16(x):
+    """fp32 contiguous CUDA tensor -> bf16 copy (one HBM pass: 4 B read + 2 B written per element)."""
+    assert x.is_contiguous() and x.dtype == torch.float32
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call('tfb_cast_bf16', x, y, x.numel())
+    return y
+
+
+def weight_bf16(w):
+    """bf16 view of a weight: straight out of the flat mirror when the parameter lives in the flat buffer, else a cached cast
+    (keyed on the tensor's in-place version counter)."""
+    fp = _FLAT[0]
+    if fp is not None:
+        off = (w.data_ptr() - fp.flat.data_ptr()) // 4
+        if 0 <= off < fp.total and w.is_contiguous():
+            return fp.bf16[off:off + w.numel()].view(w.shape)
+    key = id(w)
+    hit = _WCACHE.get(key)
+    if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+        return hit[2]
+    wb = to_bf16(w.detach().contiguous())
+    _WCACHE[key] = (w._version, w.data_ptr(), wb)
+    return wb
+
+
+def tc_ok(M, N, K, *lds):
+    """Shapes the tcgen05 bf16 kernel takes (TMA: 16-byte aligned leading dimensions); everything else runs on the SIMT kernel."""
+    return MODE == 'bf16' and M >= 32 and N >= 16 and K >= 16 and all(ld % 8 == 0 for ld in lds)
+
+
+def gemm_bf16(a, b, out, trans_a=False, trans_b=False, bias=None, relu=False, alpha=1.0, beta=0.0, splits=1):
+    """out[M,N] (fp32) = alpha * op(a) @ op(b) + beta*out (+bias) (relu); a, b bf16 2-D views with unit inner stride."""
+    M, N = out.shape
+    K = a.shape[0] if trans_a else a.shape[1]
+    _lib.call('tfb_gemm_bf16_tc', int(trans_a), int(trans_b), M, N, K, a, _ld(a), b, _ld(b), out, _ld(out), bias, int(relu),
+              float(alpha), float(beta), int(splits))
     return out

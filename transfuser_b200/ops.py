@@ -7,6 +7,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
+from . import gemm as G
 from .gemm import bgemm, gemm
 
 call = _lib.call
@@ -31,7 +32,8 @@ def _colsum(x2d):
     M, C = x2d.shape
     out = torch.empty(C, dtype=torch.float32, device=x2d.device)
     ws = torch.empty(2 * C, dtype=torch.float64, device=x2d.device)
-    call('tfb_colsum', x2d, M, C, out, ws)
+    assert x2d.stride(1) == 1
+    call('tfb_colsum', x2d, x2d.stride(0), M, C, out, ws)
     return out
 
 
@@ -49,31 +51,50 @@ def _wgrad_splits(M, N, K):
 
 
 class LinearFn(Function):
-    """y[M,N] = x[M,K] @ w[N,K]^T + b (ReLU). nn.Linear (transfuser.py:498-506, 538-543) and 1x1 nn.Conv2d as a GEMM."""
+    """y[M,N] = x[M,K] @ w[N,K]^T + b (ReLU). nn.Linear (transfuser.py:498-506, 538-543) and 1x1 nn.Conv2d as a GEMM.
+    bf16 mode: x is cast once (kept for backward instead of the fp32 tensor), the weight comes from the bf16 mirror, and
+    forward / dgrad / wgrad all run on the tcgen05 kernel (K-major / MN-major operand descriptors, no transposes)."""
 
     @staticmethod
     def forward(ctx, x, w, bias, relu):
         x = _c(x)
         w2 = w.view(w.shape[0], -1)
-        y = torch.empty((x.shape[0], w2.shape[0]), dtype=torch.float32, device=x.device)
-        gemm(x, w2, y, trans_b=True, bias=bias, relu=relu)
-        ctx.save_for_backward(x, w, y if relu else None)
+        M, K = x.shape
+        N = w2.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        ctx.tc = G.tc_ok(M, N, K, K, N)
+        if ctx.tc:
+            xs = G.to_bf16(x)
+            G.gemm_bf16(xs, G.weight_bf16(w2), y, trans_b=True, bias=bias, relu=relu)
+        else:
+            xs = x
+            gemm(x, w2, y, trans_b=True, bias=bias, relu=relu, mode='simt')
+        ctx.save_for_backward(xs, w, y if relu else None)
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        xs, w, y = ctx.saved_tensors
         dy = _c(dy)
         g = _relu_bwd(y, dy) if ctx.relu else dy
         w2 = w.view(w.shape[0], -1)
+        M, K = xs.shape
+        N = w2.shape[0]
         dx = dw = db = None
+        gb = G.to_bf16(g) if ctx.tc else None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            gemm(g, w2, dx, trans_b=False)
+            dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            if ctx.tc:
+                G.gemm_bf16(gb, G.weight_bf16(w2), dx, trans_b=False)
+            else:
+                gemm(g, w2, dx, trans_b=False, mode='simt')
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            gemm(g, x, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(x.shape[0], w2.shape[0], w2.shape[1]))
+            if ctx.tc:
+                G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
+            else:
+                gemm(g, xs, dw.view(w2.shape), trans_a=True, mode='simt')
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None
@@ -310,9 +331,13 @@ class AttentionFn(Function):
         hs = C // nh
         dev = h.device
         qkv = torch.empty((B * T, 3 * C), dtype=torch.float32, device=dev)
-        gemm(h, wq, qkv[:, 0:C], trans_b=True, bias=bq)
-        gemm(h, wk, qkv[:, C:2 * C], trans_b=True, bias=bk)
-        gemm(h, wv, qkv[:, 2 * C:], trans_b=True, bias=bv)
+        tc = G.tc_ok(B * T, C, C, C)
+        hs_ = G.to_bf16(h) if tc else h
+        for i, (w_, b_) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+            if tc:
+                G.gemm_bf16(hs_, G.weight_bf16(w_), qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_)
+            else:
+                gemm(h, w_, qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_, mode='simt')
         S = torch.empty((B, nh, T, T), dtype=torch.float32, device=dev)
         q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         bgemm(q, k, S, T, T, hs, 3 * C, 3 * C, T, False, True, B, nh, (T * 3 * C, hs), (T * 3 * C, hs), (nh * T * T, T * T))
@@ -321,14 +346,14 @@ class AttentionFn(Function):
         call('tfb_softmax_fwd', S, S, Pd, B * nh * T, T, scale, float(p_drop), seed)
         y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         bgemm(Pd, v, y, T, hs, T, T, 3 * C, C, False, False, B, nh, (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs))
-        ctx.save_for_backward(h, wq, wk, wv, qkv, S, Pd)
-        ctx.cfg = (B, T, nh, p_drop, seed, scale)
+        ctx.save_for_backward(hs_, wq, wk, wv, qkv, S, Pd)
+        ctx.cfg = (B, T, nh, p_drop, seed, scale, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         h, wq, wk, wv, qkv, P, Pd = ctx.saved_tensors
-        B, T, nh, p_drop, seed, scale = ctx.cfg
+        B, T, nh, p_drop, seed, scale, tc = ctx.cfg
         dy = _c(dy)
         C = h.shape[1]
         hs = C // nh
@@ -343,15 +368,22 @@ class AttentionFn(Function):
         call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed)    # dS (in place)
         bgemm(dP, k, dq, T, hs, T, T, 3 * C, 3 * C, False, False, B, nh, sP, sQ, sQ)     # dq  = dS k
         bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
-        dh = torch.empty_like(h)
-        gemm(dq, wq, dh, trans_b=False)
-        gemm(dk, wk, dh, trans_b=False, beta=1.0)
-        gemm(dv, wv, dh, trans_b=False, beta=1.0)
+        dh = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         grads = []
-        for d, w in ((dq, wq), (dk, wk), (dv, wv)):
-            dw = torch.empty_like(w)
-            gemm(d, h, dw, trans_a=True, splits=_wgrad_splits(h.shape[0], C, C))
-            grads += [dw, _colsum(d)]
+        if tc:
+            d16 = G.to_bf16(dqkv)
+            for i, w_ in enumerate((wq, wk, wv)):
+                G.gemm_bf16(d16[:, i * C:(i + 1) * C], G.weight_bf16(w_), dh, trans_b=False, beta=0.0 if i == 0 else 1.0)
+            for i, (d, w_) in enumerate(((dq, wq), (dk, wk), (dv, wv))):
+                dw = torch.empty_like(w_)
+                G.gemm_bf16(d16[:, i * C:(i + 1) * C], h, dw, trans_a=True, splits=_wgrad_splits(B * T, C, C))
+                grads += [dw, _colsum(d)]
+        else:
+            for i, (d, w_) in enumerate(((dq, wq), (dk, wk), (dv, wv))):
+                gemm(d, w_, dh, trans_b=False, beta=0.0 if i == 0 else 1.0, mode='simt')
+                dw = torch.empty_like(w_)
+                gemm(d, h, dw, trans_a=True, mode='simt')
+                grads += [dw, _colsum(d)]
         return (dh, *grads, None, None, None, None, None)
 
 

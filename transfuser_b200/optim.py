@@ -1,0 +1,142 @@
+"""Flat parameter / gradient storage + fused AdamW (csrc/gru_adamw.cu) + data-parallel gradient all-reduce.
+
+`flatten(model)` re-homes every parameter into ONE fp32 buffer (and gives every parameter a `.grad` view into ONE
+gradient buffer), which turns the optimizer step into a single HBM-bound kernel over 168 M elements and the DDP
+exchange into a few large NCCL all-reduces that are issued from autograd hooks while backward is still running
+(reference: torch.optim.AdamW + DistributedDataParallel, train.py:134,142,312-314)."""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+ALIGN = 64  # elements: keeps every parameter 256-byte aligned (TMA / float4 friendly)
+
+
+class FlatParams:
+    def __init__(self, model):
+        params, seen = [], set()
+        for p in model.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.params, self.offsets, self.total = params, offs, total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+            p._tfb_flat = (self, o)
+        self.bf16 = None
+
+    def ensure_grad_views(self):
+        """Re-attach the flat gradient views if a caller set .grad = None (train.py:305 uses set_to_none=True)."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+def flatten(model):
+    fp = FlatParams(model)
+    model._tfb_flat_params = fp
+    return fp
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction), one fused kernel per flat buffer.
+    The kernel also zeroes the gradient buffer it just consumed, so zero_grad() is free."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.grad_scale = grad_scale
+        self._step = 0
+        self._flat = None
+        self._m = self._v = None
+
+    def _flat_of(self):
+        if self._flat is None:
+            ps = [p for g in self.param_groups for p in g['params']]
+            owners = {id(getattr(p, '_tfb_flat', (None,))[0]) for p in ps}
+            if len(owners) != 1 or not hasattr(ps[0], '_tfb_flat'):
+                raise RuntimeError('FusedAdamW needs parameters flattened by transfuser_b200.optim.flatten(model)')
+            self._flat = ps[0]._tfb_flat[0]
+            self._m = torch.zeros_like(self._flat.flat)
+            self._v = torch.zeros_like(self._flat.flat)
+        return self._flat
+
+    def zero_grad(self, set_to_none=True):
+        fp = self._flat_of()
+        fp.ensure_grad_views()
+        if self._step == 0:
+            fp.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, chunks=None):
+        fp = self._flat_of()
+        g = self.param_groups[0]
+        self._step += 1
+        b1, b2 = g['betas']
+        spans = chunks or [(0, fp.total, None)]
+        for lo, hi, work in spans:
+            if work is not None:
+                work.wait()
+            bf = fp.bf16[lo:hi] if fp.bf16 is not None else None
+            _lib.call('tfb_adamw_step', fp.flat[lo:hi], fp.grad[lo:hi], self._m[lo:hi], self._v[lo:hi], hi - lo, float(g['lr']), float(b1),
+                      float(b2), float(g['eps']), float(g['weight_decay']), self._step, float(self.grad_scale), bf, 1)
+
+
+class GradAllReducer:
+    """Data-parallel exchange: SUM all-reduce of the flat gradient buffer in `n_chunks` spans. Each span is launched (async,
+    NCCL stream) from a post-accumulate-grad hook as soon as the last parameter of that span has its gradient, so the
+    exchange overlaps the rest of backward; FusedAdamW waits per span and folds the 1/world_size into its update."""
+
+    def __init__(self, fp, n_chunks=8):
+        self.fp = fp
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        per = (fp.total + n_chunks - 1) // n_chunks
+        per = (per + ALIGN - 1) // ALIGN * ALIGN
+        self.spans = [(lo, min(fp.total, lo + per)) for lo in range(0, fp.total, per)]
+        self.pending = [0] * len(self.spans)
+        self.counts = [0] * len(self.spans)
+        self.works = [None] * len(self.spans)
+        self.param_chunks = []
+        for p, o in zip(fp.params, fp.offsets):
+            first = o // per
+            last = (o + max(p.numel(), 1) - 1) // per
+            ids = list(range(first, last + 1))
+            self.param_chunks.append(ids)
+            for c in ids:
+                self.counts[c] += 1
+            if self.world > 1:
+                p.register_post_accumulate_grad_hook(self._make_hook(ids))
+        self.reset()
+
+    def reset(self):
+        self.pending = list(self.counts)
+        self.works = [None] * len(self.spans)
+
+    def _make_hook(self, ids):
+        def hook(_p):
+            for c in ids:
+                self.pending[c] -= 1
+                if self.pending[c] == 0:
+                    lo, hi = self.spans[c]
+                    self.works[c] = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+        return hook
+
+    def chunks(self):
+        """(lo, hi, work) spans for FusedAdamW.step; spans whose hook never fired (unused params) are reduced here."""
+        out = []
+        for c, (lo, hi) in enumerate(self.spans):
+            w = self.works[c]
+            if w is None and self.world > 1:
+                w = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+            out.append((lo, hi, w))
+        self.reset()
+        return out
