@@ -160,6 +160,11 @@ def run_b200(args):
         torch.cuda.synchronize()
         _lib.lib().profiler = None
         roof = prof.summary(peaks())
+        if os.path.isdir(os.path.join(ROOT, 'gpurun_out')):
+            det = sorted(prof.detail.items(), key=lambda kv: -kv[1][0])
+            with open(os.path.join(ROOT, 'gpurun_out', 'profile_detail_%s.txt' % args.gemm), 'w') as f:
+                for k, (ms, n, fl) in det:
+                    f.write('%9.3f ms  x%-4d %7.2f TF/s  %s\n' % (ms, n, (fl * n / (ms * 1e-3) / 1e12) if ms > 0 else 0.0, k))
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     if rank == 0:
         pk, how = peaks()

@@ -112,12 +112,32 @@ class Profiler:
         e0.record()
         rc = thunk()
         e1.record()
-        self.records.append((name, self._work(name, args), e0, e1))
+        self.records.append((name, self._work(name, args), e0, e1, self._key(name, args)))
         return rc
+
+    @staticmethod
+    def _key(name, a):
+        if name == 'tfb_gemm_small_m':
+            return '%s tb%d M%d N%d K%d' % (name, a[0], a[1], a[2], a[3])
+        if name == 'tfb_conv3x3_tc':
+            return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14])
+        if name.startswith('tfb_gemm'):
+            return '%s ta%d tb%d M%d N%d K%d%s' % (name, a[0], a[1], a[2], a[3], a[4], (' batch%dx%d' % (a[15], a[16])) if name.endswith('simt') else '')
+        if name.startswith('tfb_conv2d'):
+            i0 = 3 if name.endswith('dgrad') else 4
+            return '%s N%d H%d W%d Cin%d Cout%d k%d s%d g%d' % ((name,) + tuple(a[i0:i0 + 8]))
+        return name
 
     @staticmethod
     def _work(name, a):
         """(flops, bytes) — algorithmic: 2*MAC for contractions, every tensor argument touched once for the rest."""
+        if name == 'tfb_gemm_small_m':
+            return 2.0 * a[1] * a[2] * a[3], 4.0 * (a[1] * a[3] + a[2] * a[3] + a[1] * a[2])
+        if name == 'tfb_conv3x3_tc':
+            N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks = a[4:15]
+            # algorithmic (useful) MACs: each written channel contracts over its group's channels only
+            cin_eff = Cx if c_step == 0 else 24
+            return 2.0 * N * H * W * Cy * cin_eff * 9, 2.0 * N * H * W * Cx + 4.0 * N * H * W * Cy
         if name.startswith('tfb_gemm'):
             M, N, K = a[2], a[3], a[4]
             nb = a[15] * a[16] if name.endswith('simt') else 1
@@ -134,8 +154,12 @@ class Profiler:
         pk, how = peaks_and_how
         torch.cuda.synchronize()
         agg = {}
-        for name, (fl, by), e0, e1 in self.records:
+        self.detail = {}
+        for name, (fl, by), e0, e1, key in self.records:
             d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            dd = self.detail.setdefault(key, [0.0, 0, fl])
+            dd[0] += e0.elapsed_time(e1)
+            dd[1] += 1
             d[0] += e0.elapsed_time(e1)
             d[1] += fl
             d[2] += by

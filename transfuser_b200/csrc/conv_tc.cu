@@ -1,0 +1,223 @@
+// Implicit-GEMM 3x3 convolution (stride 1, pad 1, NHWC) on the tcgen05 tensor cores — no im2col buffer.
+// One CTA = one 8x16 spatial tile (128 output pixels = the UMMA M dimension) of one image x one block of output channels.
+// For each of the 9 taps and each input-channel chunk, TMA loads the tap-SHIFTED activation patch straight from the NHWC
+// bf16 tensor with a 4-D tensor map (box {KC channels, 16 w, 8 h, 1 n}; halo / image-border pixels are TMA out-of-bounds
+// zero fill = the conv's zero padding) into 128B/64B-swizzled shared memory, where it is already a K-major A operand;
+// the packed weights (K-major B operand, bf16, zero-padded, block-diagonal for grouped convs) come through a 2-D map.
+// All taps / chunks accumulate into ONE fp32 TMEM accumulator; the epilogue adds bias / ReLU and writes fp32 NHWC.
+// dgrad (stride 1) is the same kernel on dy with tap-flipped, transposed packed weights.
+// Grouped RegNetY convs (group width 24): two groups share one CTA (N = 48 output channels, 64-channel K window).
+// Replaces cuDNN behind the grouped 3x3 of timm's RegNetY blocks (transfuser.py:145-184) and the dense 3x3 of the
+// decoders / heads (transfuser.py:214-281; model.py:93-99, 581-585). Warp roles as in gemm_tc.cu.
+#include "common.cuh"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int TH = 8, TW = 16, BM = TH * TW;
+
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, int row_bytes) {
+  // K-major operand, rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); 8-row groups are row_bytes*8 apart.
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                                    // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(((uint32_t)row_bytes * 8) >> 4) << 32;     // SBO
+  d |= (uint64_t)1 << 46;                                    // descriptor version (Blackwell)
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;           // SWIZZLE_128B / SWIZZLE_64B
+  return d;
+}
+
+template <int KC, int NB, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, float* __restrict__ y,
+                  const float* __restrict__ bias, int H, int W, int Cout, int tiles_w, int tiles_h, int c_step, int nchunks,
+                  int nb_real, int relu) {
+  constexpr int ROWB = KC * 2;                 // bytes per smem row
+  constexpr int A_BYTES = BM * ROWB, B_BYTES = NB * ROWB, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; t /= tiles_h;
+  const int n = t;
+  const int gb = blockIdx.y;
+  const int h0 = th * TH, w0 = tw * TW;
+  const int iters = nchunks * 9;
+  constexpr uint32_t kTmemCols = NB <= 32 ? 32 : NB <= 64 ? 64 : 128;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_x);
+    tc::tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < iters; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        const int chunk = i / 9, tap = i % 9;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE;
+        tc::mbar_expect_tx(&full_bar[s], STAGE);
+        tc::tma_load_4d(&tma_x, &full_bar[s], sa, gb * c_step + chunk * KC, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n);
+        tc::tma_load_2d(&tma_w, &full_bar[s], sa + A_BYTES, 0, ((gb * nchunks + chunk) * 9 + tap) * NB);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(1u, 0u, 0u, BM, NB);  // bf16 x bf16 -> fp32, both K-major
+      for (int i = 0; i < iters; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::fence_after_sync();
+        const uint32_t sa = tc::smem_u32(smem + s * STAGE), sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)
+          tc::umma_f16(tmem_base, smem_desc_kmajor(sa + k * 32, ROWB), smem_desc_kmajor(sb + k * 32, ROWB), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        tc::umma_commit(&empty_bar[s]);
+      }
+      tc::umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+    const int r = q * 32 + lane;             // smem row = pixel (r / 16, r % 16) of the tile (W fastest in the TMA box)
+    const int h = h0 + r / TW, w = w0 + r % TW;
+    const bool pix_ok = h < H && w < W;
+    float* yp = y + (((int64_t)n * H + h) * W + w) * Cout + (int64_t)gb * nb_real;
+    const float* bp = bias ? bias + gb * nb_real : nullptr;
+    const int nvalid = min(nb_real, Cout - gb * nb_real);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NB; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (pix_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < nvalid) {
+            float o = v[j] + (bp ? bp[c0 + j] : 0.f);
+            if (relu) o = fmaxf(o, 0.f);
+            yp[c0 + j] = o;
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// out[gb][chunk][tap][j][kk] (bf16): the B operand rows for output channel j of block gb and reduction channel kk.
+// mode 0 (forward): value = w[co = gb*nb_real + j][ci - group(co)*Cig][tap],      ci = gb*c_step + chunk*KC + kk (same group only)
+// mode 1 (dgrad)  : value = w[co = gb*c_step + chunk*KC + kk][ci' - group*Cig][8 - tap], ci' = gb*nb_real + j (conv input channel)
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int groups, int mode, int NB, int KC,
+                    int c_step, int nchunks, int nb_real, int gblocks) {
+  const int Cig = Cin / groups, Cog = Cout / groups;
+  const int64_t total = (int64_t)gblocks * nchunks * 9 * NB * KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % KC);
+    const int j = (int)((i / KC) % NB);
+    const int tap = (int)((i / ((int64_t)KC * NB)) % 9);
+    const int chunk = (int)((i / ((int64_t)KC * NB * 9)) % nchunks);
+    const int gb = (int)(i / ((int64_t)KC * NB * 9 * nchunks));
+    float v = 0.f;
+    const int oc = gb * nb_real + j;            // channel of the tensor this kernel WRITES
+    const int rc = gb * c_step + chunk * KC + kk;  // channel of the tensor this kernel READS
+    if (j < nb_real) {
+      if (mode == 0) {
+        if (oc < Cout && rc < Cin) {
+          const int g = oc / Cog;
+          if (rc / Cig == g) v = w[((int64_t)oc * Cig + (rc - g * Cig)) * 9 + tap];
+        }
+      } else {
+        if (oc < Cin && rc < Cout) {
+          const int g = oc / Cig;
+          if (rc / Cog == g) v = w[((int64_t)rc * Cig + (oc - g * Cig)) * 9 + (8 - tap)];
+        }
+      }
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int KC, int NB>
+int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy, int c_step,
+                int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
+  constexpr int STAGES = NB <= 64 ? 6 : 4;
+  constexpr int STAGE = BM * KC * 2 + NB * KC * 2;
+  constexpr int SMEM = STAGES * STAGE + (2 * STAGES + 1) * 8 + 16 + 1024;
+  CUtensorMap mx, mw;
+  const uint64_t xd[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t xs[3] = {(uint64_t)Cx * 2, (uint64_t)W * Cx * 2, (uint64_t)H * W * Cx * 2};
+  const uint32_t xb[4] = {(uint32_t)KC, TW, TH, 1};
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (!tc::make_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x16, xd, xs, xb, swz)) {
+    tfb_set_last_error("cuTensorMapEncodeTiled(activation, 4-D) failed");
+    return TFB_ERR_DRIVER;
+  }
+  const uint64_t wd[2] = {(uint64_t)KC, (uint64_t)gblocks * nchunks * 9 * NB};
+  const uint64_t ws[1] = {(uint64_t)KC * 2};
+  const uint32_t wb[2] = {(uint32_t)KC, (uint32_t)NB};
+  if (!tc::make_map(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack, wd, ws, wb, swz)) {
+    tfb_set_last_error("cuTensorMapEncodeTiled(packed weights) failed");
+    return TFB_ERR_DRIVER;
+  }
+  auto kern = conv3x3_tc_kernel<KC, NB, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return TFB_ERR_DRIVER;
+    attr_done = true;
+  }
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  dim3 grid((unsigned)(tiles_w * tiles_h * N), gblocks);
+  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+}  // namespace
+
+// Packs fp32 PyTorch-layout 3x3 weights [Cout][Cin/groups][3][3] into the bf16 B-operand layout [gblocks][nchunks][9][NB][KC].
+TFB_API int tfb_conv3x3_pack_weights(const float* w, void* out_bf16, int Cout, int Cin, int groups, int mode, int NB, int KC,
+                                     int c_step, int nchunks, int nb_real, int gblocks, cudaStream_t stream) {
+  TFB_REQUIRE(w && out_bf16 && Cout > 0 && Cin > 0 && groups > 0 && (mode == 0 || mode == 1) && NB > 0 && KC > 0);
+  const int64_t total = (int64_t)gblocks * nchunks * 9 * NB * KC;
+  pack_weights_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(w, (__nv_bfloat16*)out_bf16, Cout, Cin, groups, mode, NB, KC, c_step,
+                                                               nchunks, nb_real, gblocks);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// y[N,H,W,Cy] (fp32) = conv3x3(x16[N,H,W,Cx] bf16, packed weights) (+bias) (ReLU). Block gb reads channels
+// [gb*c_step + chunk*KC, +KC) for chunk < nchunks and writes channels [gb*nb_real, +min(nb_real, Cy - gb*nb_real)).
+TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
+                           int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
+  TFB_REQUIRE(x16 && wpack && y && N > 0 && H > 0 && W > 0 && Cx > 0 && Cy > 0 && Cx % 8 == 0);
+  TFB_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0);
+#define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stream)
+  CASE(64, 16); CASE(64, 32); CASE(64, 48); CASE(64, 64); CASE(64, 128);
+  CASE(32, 16); CASE(32, 32);
+#undef CASE
+  tfb_set_last_error("tfb_conv3x3_tc: unsupported (KC, NB) tile");
+  return TFB_ERR_UNSUPPORTED;
+}

@@ -68,7 +68,10 @@ class LinearFn(Function):
             G.gemm_bf16(xs, G.weight_bf16(w2), y, trans_b=True, bias=bias, relu=relu)
         else:
             xs = x
-            gemm(x, w2, y, trans_b=True, bias=bias, relu=relu, mode='simt')
+            if M <= 16:
+                call('tfb_gemm_small_m', 1, M, N, K, x, K, w2, K, y, N, bias, 1 if relu else 0)
+            else:
+                gemm(x, w2, y, trans_b=True, bias=bias, relu=relu, mode='simt')
         ctx.save_for_backward(xs, w, y if relu else None)
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y
@@ -87,15 +90,21 @@ class LinearFn(Function):
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
             if ctx.tc:
                 G.gemm_bf16(gb, G.weight_bf16(w2), dx, trans_b=False)
+            elif M <= 16:
+                call('tfb_gemm_small_m', 0, M, K, N, g, N, w2, K, dx, K, None, 0)
             else:
                 gemm(g, w2, dx, trans_b=False, mode='simt')
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             if ctx.tc:
                 G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
+            elif M >= 4096:
+                # long contraction, narrow output (head 1x1 convs): the pixel-split direct-conv wgrad kernel (k = 1)
+                db = torch.empty(N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+                call('tfb_conv2d_wgrad', xs, g, dw, db, 1, M, 1, K, N, 1, 1, 1)
             else:
                 gemm(g, xs, dw.view(w2.shape), trans_a=True, mode='simt')
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and db is None:
             db = _colsum(g)
         return dx, dw, db, None
 
@@ -138,10 +147,82 @@ class Conv2dFn(Function):
         return dx, dw, db, None, None, None
 
 
+def _conv_tc_plan(c_read, c_write, groups):
+    """Tile plan of csrc/conv_tc.cu for a 3x3 stride-1 conv that READS a tensor with c_read channels and WRITES c_write
+    channels (forward: Cin -> Cout; dgrad: Cout -> Cin). Returns None when the shape must stay on the direct kernel."""
+    if c_read % 8 != 0:
+        return None                                  # TMA needs 16-byte channel rows
+    if groups > 1:
+        cg_r, cg_w = c_read // groups, c_write // groups
+        if cg_r != 24 or cg_w != 24:
+            return None
+        gblocks = (groups + 1) // 2                  # two 24-wide groups per CTA: N = 48, one 64-channel K window
+        return dict(NB=48, KC=64, c_step=48, nchunks=1, nb_real=48, gblocks=gblocks)
+    kc = 32 if c_read <= 32 else 64
+    nchunks = (c_read + kc - 1) // kc
+    nb = 16 if c_write <= 16 else 32 if c_write <= 32 else 64 if c_write <= 64 else 128
+    if kc == 32 and nb > 32:
+        kc, nchunks = 64, 1                          # (32-channel rows only exist for NB <= 32 tiles)
+        if c_read < 64:
+            return None
+    gblocks = (c_write + nb - 1) // nb
+    return dict(NB=nb, KC=kc, c_step=0, nchunks=nchunks, nb_real=nb if gblocks > 1 else c_write, gblocks=gblocks)
+
+
+def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
+    N, H, W, c_read = x16.shape
+    Cout, Cin = (w.shape[0], w.shape[1] * groups)
+    wp = torch.empty((plan['gblocks'], plan['nchunks'], 9, plan['NB'], plan['KC']), dtype=torch.bfloat16, device=x16.device)
+    call('tfb_conv3x3_pack_weights', w, wp, Cout, Cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
+         plan['gblocks'])
+    y = torch.empty((N, H, W, c_write), dtype=torch.float32, device=x16.device)
+    call('tfb_conv3x3_tc', x16, wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
+         plan['gblocks'], int(relu))
+    return y
+
+
+class Conv3x3TCFn(Function):
+    """3x3 / stride 1 conv in bf16 mode: forward and dgrad as implicit GEMMs on the tcgen05 tensor cores (csrc/conv_tc.cu:
+    TMA tap-shifted NHWC tiles, no im2col); wgrad on the fp32 direct kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, groups, relu):
+        x = _c(x)
+        Cout, Cin = w.shape[0], w.shape[1] * groups
+        y = _conv_tc_run(G.to_bf16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (groups, relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        groups, relu, has_bias = ctx.cfg
+        N, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        dy = _c(dy)
+        g = _relu_bwd(y, dy) if relu else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            plan = _conv_tc_plan(Cout, Cin, groups)
+            if plan is not None:
+                dx = _conv_tc_run(G.to_bf16(g), w, None, plan, 1, Cin, groups, False)
+            else:
+                dx = torch.empty_like(x)
+                call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, 3, 1, groups)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+            call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, 3, 1, groups)
+        return dx, dw, db, None, None
+
+
 def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
     if w.shape[2] == 1 and stride == 1 and groups == 1:
         N, H, W, C = x.shape
         return LinearFn.apply(x.reshape(-1, C), w, bias, relu).view(N, H, W, w.shape[0])
+    if G.MODE == 'bf16' and w.shape[2] == 3 and stride == 1 and _conv_tc_plan(w.shape[1] * groups, w.shape[0], groups) is not None:
+        return Conv3x3TCFn.apply(x, w, bias, groups, relu)
     return Conv2dFn.apply(x, w, bias, stride, groups, relu)
 
 
@@ -233,11 +314,15 @@ class SEFn(Function):
         pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
         call('tfb_pool_hw_fwd', x, pooled, N, H * W, C)
         h = torch.empty((N, Cr), dtype=torch.float32, device=dev)
-        gemm(pooled, w1.view(Cr, C), h, trans_b=True, bias=b1, relu=True, mode='simt')
-        s = torch.empty((N, C), dtype=torch.float32, device=dev)
-        gemm(h, w2.view(C, Cr), s, trans_b=True, bias=b2, mode='simt')
-        gate = torch.empty_like(s)
-        call('tfb_sigmoid_fwd', s, gate, s.numel())
+        gate = torch.empty((N, C), dtype=torch.float32, device=dev)
+        if N <= 16:
+            call('tfb_gemm_small_m', 1, N, Cr, C, pooled, C, w1, C, h, Cr, b1, 1)
+            call('tfb_gemm_small_m', 1, N, C, Cr, h, Cr, w2, Cr, gate, C, b2, 2)
+        else:
+            gemm(pooled, w1.view(Cr, C), h, trans_b=True, bias=b1, relu=True, mode='simt')
+            s = torch.empty((N, C), dtype=torch.float32, device=dev)
+            gemm(h, w2.view(C, Cr), s, trans_b=True, bias=b2, mode='simt')
+            call('tfb_sigmoid_fwd', s, gate, s.numel())
         y = torch.empty_like(x)
         call('tfb_se_scale_fwd', x, gate, y, N, H * W, C)
         ctx.save_for_backward(x, w1, w2, pooled, h, gate)
@@ -258,13 +343,19 @@ class SEFn(Function):
         gemm(ds, h, dw2.view(C, Cr), trans_a=True, mode='simt')
         db2 = _colsum(ds)
         dh = torch.empty((N, Cr), dtype=torch.float32, device=dev)
-        gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
+        if N <= 16:
+            call('tfb_gemm_small_m', 0, N, Cr, C, ds, C, w2, Cr, dh, Cr, None, 0)
+        else:
+            gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
         dh = _relu_bwd(h, dh)
         dw1 = torch.empty_like(w1)
         gemm(dh, pooled, dw1.view(Cr, C), trans_a=True, mode='simt')
         db1 = _colsum(dh)
         dpool = torch.empty((N, C), dtype=torch.float32, device=dev)
-        gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
+        if N <= 16:
+            call('tfb_gemm_small_m', 0, N, C, Cr, dh, Cr, w1, C, dpool, C, None, 0)
+        else:
+            gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
         dx = torch.empty_like(x)
         call('tfb_se_bwd_apply', dy, gate, dpool, dx, N, H * W, C)
         return dx, dw1, db1, dw2, db2
