@@ -76,6 +76,7 @@ def test_attention_bf16():
     (1, 40, 48, 32, 32, 1, True, True),        # 32-channel rows (SWIZZLE_64B tiles)
     (2, 23, 37, 32, 7, 1, True, False),        # ragged tile edges, Cout 7
     (1, 16, 32, 32, 1, 1, True, False),
+    (4, 40, 176, 32, 32, 1, True, False),      # long contraction: split-K wgrad
 ])
 def test_conv3x3_tensor_core(cfg):
     from transfuser_b200 import ops
@@ -97,7 +98,7 @@ def test_conv3x3_tensor_core(cfg):
     mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
     rg = torch.autograd.grad(ref, [x, w], go)
     assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < TOL
-    assert rel(mg[1], rg[1]) < 1e-4   # wgrad runs on the exact fp32 kernel
+    assert rel(mg[1], rg[1]) < TOL
 
 
 def test_full_model_bf16_close_to_fp32_mode():
@@ -124,3 +125,24 @@ def test_full_model_bf16_close_to_fp32_mode():
         a, b = outs['bf16'][k], outs['simt'][k]
         print('%-22s fp32 %.6f bf16 %.6f rel %.2e' % (k, b, a, abs(a - b) / max(abs(b), 1e-9)))
         assert abs(a - b) <= 3e-2 * max(abs(b), 0.05), (k, a, b)
+
+
+@pytest.mark.parametrize('cfg', [(2, 40, 48, 72, 72, 3), (2, 20, 24, 216, 216, 9), (2, 32, 44, 3, 32, 1)])
+def test_conv3x3_stride2_bf16_mode(cfg):
+    """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward / dgrad on the exact fp32 direct kernels, wgrad
+    through im2col + the batched tensor-core GEMM when the channel windows are 16-byte aligned."""
+    from transfuser_b200 import ops
+    N, H, W, Cin, Cout, g = cfg
+    gen = torch.Generator(device='cuda').manual_seed(Cin)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=gen).requires_grad_()
+    w = (torch.randn(Cout, Cin // g, 3, 3, device='cuda', generator=gen) / math.sqrt(Cin // g * 9)).requires_grad_()
+    ref = F.conv2d(x, w, None, stride=2, padding=1, groups=g)
+    xm = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_()
+    wm = w.detach().clone().requires_grad_()
+    out = ops.conv2d(xm, wm, None, 2, g, False)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-4
+    go = torch.randn_like(ref)
+    mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
+    rg = torch.autograd.grad(ref, [x, w], go)
+    assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < 1e-4
+    assert rel(mg[1], rg[1]) < TOL

@@ -119,6 +119,8 @@ class Profiler:
     def _key(name, a):
         if name == 'tfb_gemm_small_m':
             return '%s tb%d M%d N%d K%d' % (name, a[0], a[1], a[2], a[3])
+        if name == 'tfb_gemm_bf16_tc_wgrad_batched':
+            return '%s M%d N%d K%d batch%d splits%d' % (name, a[0], a[1], a[2], a[12], a[13])
         if name == 'tfb_conv3x3_tc':
             return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14])
         if name.startswith('tfb_gemm'):
@@ -133,6 +135,8 @@ class Profiler:
         """(flops, bytes) — algorithmic: 2*MAC for contractions, every tensor argument touched once for the rest."""
         if name == 'tfb_gemm_small_m':
             return 2.0 * a[1] * a[2] * a[3], 4.0 * (a[1] * a[3] + a[2] * a[3] + a[1] * a[2])
+        if name == 'tfb_gemm_bf16_tc_wgrad_batched':
+            return 2.0 * a[0] * a[1] * a[2] * a[12], 2.0 * a[2] * a[12] * (a[0] + a[1]) + 4.0 * a[0] * a[1] * a[12]
         if name == 'tfb_conv3x3_tc':
             N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks = a[4:15]
             # algorithmic (useful) MACs: each written channel contracts over its group's channels only

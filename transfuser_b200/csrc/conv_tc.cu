@@ -160,6 +160,35 @@ pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out
   }
 }
 
+// col[m][g][tap][c] (bf16) = x[n, ho*stride - 1 + tap/3, wo*stride - 1 + tap%3, g*Cg + c] (0 outside), m = (n, ho, wo): the im2col
+// matrix whose column windows are the B operands of the per-group wgrad GEMMs (dW_g = dy_g^T col_g). c fastest: coalesced.
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo, int stride,
+                 int groups) {
+  const int Cg = C / groups;
+  const int64_t total = (int64_t)N * Ho * Wo * C * 9;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cg);
+    const int tap = (int)((i / Cg) % 9);
+    const int g = (int)((i / ((int64_t)Cg * 9)) % groups);
+    const int64_t m = i / ((int64_t)C * 9);
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), n = (int)(m / ((int64_t)Wo * Ho));
+    const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((int64_t)n * H + hi) * W + wi) * C + g * Cg + c];
+    col[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dw[co][ci][tap] = dwp[co][tap][ci]  (GEMM output order -> PyTorch weight layout)
+__global__ void __launch_bounds__(256) permute_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cg) {
+  const int total = Cout * Cg * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % Cg, co = i / (9 * Cg);
+    dw[i] = dwp[(co * 9 + tap) * Cg + ci];
+  }
+}
+
 template <int KC, int NB>
 int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy, int c_step,
                 int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
@@ -220,4 +249,21 @@ TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias
 #undef CASE
   tfb_set_last_error("tfb_conv3x3_tc: unsupported (KC, NB) tile");
   return TFB_ERR_UNSUPPORTED;
+}
+
+// im2col for the tensor-core wgrad: x fp32 NHWC -> col bf16 [N*Ho*Wo][groups][9][C/groups] (stride 1 or 2, pad 1).
+TFB_API int tfb_im2col3x3_bf16(const float* x, void* col_bf16, int N, int H, int W, int C, int stride, int groups, cudaStream_t stream) {
+  TFB_REQUIRE(x && col_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2) && groups > 0 && C % groups == 0);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * C * 9;
+  im2col3x3_kernel<<<tfb_grid(total, 256, 16), 256, 0, stream>>>(x, (__nv_bfloat16*)col_bf16, N, H, W, C, Ho, Wo, stride, groups);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+TFB_API int tfb_conv3x3_permute_dw(const float* dwp, float* dw, int Cout, int Cg, cudaStream_t stream) {
+  TFB_REQUIRE(dwp && dw && Cout > 0 && Cg > 0);
+  permute_dw_kernel<<<tfb_grid((int64_t)Cout * Cg * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cg);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
 }

@@ -202,24 +202,37 @@ small_m_tb_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
   }
 }
 
-__global__ void __launch_bounds__(128)
+// !transB: block = 32 output columns x 8 K-slices; each thread accumulates its K slice for all rows, slices are reduced
+// through shared memory (B reads are coalesced over n; the K loop is 8x shorter than one-thread-per-column).
+__global__ void __launch_bounds__(256)
 small_m_nt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                   float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float red[8][16][33];
+  const int tx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   float acc[16];
 #pragma unroll
   for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float bv = B[(int64_t)k * ldb + n];
+  if (n < N) {
+#pragma unroll 4
+    for (int k = ky; k < K; k += 8) {
+      const float bv = B[(int64_t)k * ldb + n];
 #pragma unroll
-    for (int m = 0; m < 16; ++m)
-      if (m < M) acc[m] = fmaf(A[(int64_t)m * lda + k], bv, acc[m]);
+      for (int m = 0; m < 16; ++m)
+        if (m < M) acc[m] = fmaf(A[(int64_t)m * lda + k], bv, acc[m]);
+    }
   }
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    if (m < M) {
-      float v = acc[m];
+  for (int m = 0; m < 16; ++m) red[ky][m][tx] = acc[m];
+  __syncthreads();
+  // 256 threads finish the 16 x 32 outputs: thread -> (m = ky*2 + {0,1}, n = tx)
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm) {
+    const int m = ky * 2 + mm;
+    if (m < M && n < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v += red[j][m][tx];
       if (bias) v += bias[n];
       if (act == 1) v = fmaxf(v, 0.f);
       else if (act == 2) v = 1.f / (1.f + expf(-v));
@@ -234,7 +247,7 @@ TFB_API int tfb_gemm_small_m(int transB, int M, int N, int K, const float* A, in
                              int64_t ldc, const float* bias, int act, cudaStream_t stream) {
   TFB_REQUIRE(A && B && C && M >= 1 && M <= 16 && N >= 1 && K >= 1);
   if (transB) small_m_tb_kernel<<<(N + 7) / 8, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
-  else        small_m_nt_kernel<<<(N + 127) / 128, 128, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+  else        small_m_nt_kernel<<<(N + 31) / 32, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

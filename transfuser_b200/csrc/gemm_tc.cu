@@ -43,7 +43,7 @@ template <typename T, int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ C,
                int64_t ldc, int M, int N, int num_kb, int kb_per_split, const float* __restrict__ bias, float alpha, float beta,
-               int relu, int atomic_out) {
+               int relu, int atomic_out, int splits, int a_step, int b_step, int64_t c_bstride) {
   using E = Elem<T>;
   using L = SmemLayout<BN, STAGES>;
   constexpr int BK = E::kPerRow;  // K elements per stage
@@ -55,8 +55,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // grid.z = batch * splits. Batch b reads op(A) rows [b*a_step, +M) and op(B) columns [b*b_step, +N) of the SAME tensor maps
+  // (grouped-conv wgrad: one GEMM per channel group) and writes C + b*c_bstride.
+  const int bz = blockIdx.z / splits, sz = blockIdx.z % splits;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * kb_per_split;
+  const int am0 = m0 + bz * a_step, bn0 = n0 + bz * b_step;
+  C += (int64_t)bz * c_bstride;
+  const int kb_begin = sz * kb_per_split;
   const int kb_end = min(num_kb, kb_begin + kb_per_split);
   const int nkb = kb_end - kb_begin;  // >= 1 by construction
   constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -85,18 +90,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc::mbar_expect_tx(&full_bar[s], L::kStageBytes);
         const int k0 = (kb_begin + i) * BK;
         if (!A_MN) {
-          tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);
+          tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, am0);
         } else {
 #pragma unroll
           for (int j = 0; j < BM / E::kPerRow; ++j)
-            tc::tma_load_2d(&tma_a, &full_bar[s], sa + j * BK * 128, m0 + j * E::kPerRow, k0);
+            tc::tma_load_2d(&tma_a, &full_bar[s], sa + j * BK * 128, am0 + j * E::kPerRow, k0);
         }
         if (!B_MN) {
-          tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);
+          tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, bn0);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / E::kPerRow; ++j)
-            tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, n0 + j * E::kPerRow, k0);
+            tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, bn0 + j * E::kPerRow, k0);
         }
       }
     }
@@ -131,7 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc::mbar_wait(tmem_full_bar, 0);
     tc::fence_after_sync();
     const int m = m0 + q * 32 + lane;
-    const bool add_bias = bias != nullptr && blockIdx.z == 0;
+    const bool add_bias = bias != nullptr && sz == 0;
     float* crow = C + (int64_t)m * ldc;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -209,18 +214,20 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 
 template <typename T, int BN, bool A_MN, bool B_MN>
 int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
-              int relu, float alpha, float beta, int splits, cudaStream_t stream) {
+              int relu, float alpha, float beta, int splits, cudaStream_t stream, int nbatch = 1, int a_step = 0, int b_step = 0,
+              int64_t c_bstride = 0) {
   using E = Elem<T>;
   constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
   using L = SmemLayout<BN, STAGES>;
   constexpr int BK = E::kPerRow;
   CUtensorMap ma, mb;
   bool ok;
-  if (!A_MN) ok = make_map_2d<T>(&ma, A, M, K, lda, BK, BM);              // A[m][k]
-  else       ok = make_map_2d<T>(&ma, A, K, M, lda, E::kPerRow, BK);      // A[k][m]
+  const int64_t Mext = (int64_t)(nbatch - 1) * a_step + M, Next = (int64_t)(nbatch - 1) * b_step + N;   // extents of the shared maps
+  if (!A_MN) ok = make_map_2d<T>(&ma, A, Mext, K, lda, BK, BM);              // A[m][k]
+  else       ok = make_map_2d<T>(&ma, A, K, Mext, lda, E::kPerRow, BK);      // A[k][m]
   if (!ok) { tfb_set_last_error("cuTensorMapEncodeTiled(A) failed"); return TFB_ERR_DRIVER; }
-  if (!B_MN) ok = make_map_2d<T>(&mb, B, N, K, ldb, BK, BN);              // B[n][k]
-  else       ok = make_map_2d<T>(&mb, B, K, N, ldb, E::kPerRow, BK);      // B[k][n]
+  if (!B_MN) ok = make_map_2d<T>(&mb, B, Next, K, ldb, BK, BN);              // B[n][k]
+  else       ok = make_map_2d<T>(&mb, B, K, Next, ldb, E::kPerRow, BK);      // B[k][n]
   if (!ok) { tfb_set_last_error("cuTensorMapEncodeTiled(B) failed"); return TFB_ERR_DRIVER; }
   const int num_kb = (K + BK - 1) / BK;
   if (splits < 1) splits = 1;
@@ -231,7 +238,9 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
   if (atomic_out) {
     if (relu) { tfb_set_last_error("split-K cannot fuse ReLU"); return TFB_ERR_ARG; }
     if (beta == 0.f) {
-      if (cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream) != cudaSuccess) return TFB_ERR_DRIVER;
+      for (int b = 0; b < nbatch; ++b)
+        if (cudaMemset2DAsync(C + (int64_t)b * c_bstride, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream) != cudaSuccess)
+          return TFB_ERR_DRIVER;
     } else if (beta != 1.f) { tfb_set_last_error("split-K needs beta in {0,1}"); return TFB_ERR_ARG; }
   }
   auto kern = gemm_tc_kernel<T, BN, A_MN, B_MN, STAGES>;
@@ -243,8 +252,9 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
     }
     attr_done = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-  kern<<<grid, 192, L::kTotal, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out);
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * nbatch);
+  kern<<<grid, 192, L::kTotal, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
+                                         b_step, c_bstride);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -273,10 +283,30 @@ int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t
 
 }  // namespace
 
+// Batched split-K product for grouped-conv wgrad: for b < nbatch,
+//   C_b[M,N] (fp32, at C + b*c_bstride, row stride ldc) = A[:, b*a_step : +M]^T (bf16 [K, lda]) * B[:, b*b_step : +N] (bf16 [K, ldb])
+// i.e. the transA=1 / transB=0 case of tfb_gemm_bf16_tc with per-batch column windows of the same two matrices.
+TFB_API int tfb_gemm_bf16_tc_wgrad_batched(int M, int N, int K, const void* A, int64_t lda, int a_step, const void* B, int64_t ldb,
+                                           int b_step, float* C, int64_t ldc, int64_t c_bstride, int nbatch, int splits,
+                                           cudaStream_t stream) {
+  TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C && nbatch >= 1);
+  TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  TFB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_step % 8 == 0 && b_step % 8 == 0);
+  using T = __nv_bfloat16;
+  if (N <= 64) return launch_tc<T, 64, true, true>(M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
+  return launch_tc<T, 128, true, true>(M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
+}
+
+// TF32 operands straight from fp32 storage (kind::tf32). Only the K-major x K-major case (y = x W^T) is wired up: MN-major
+// TF32 operands need the 32-byte-atom swizzle. transA must be 0 and transB 1.
 TFB_API int tfb_gemm_tf32_tc(int transA, int transB, int M, int N, int K, const float* A, int64_t lda, const float* B,
                              int64_t ldb, float* C, int64_t ldc, const float* bias, int relu, float alpha, float beta,
                              int splits, cudaStream_t stream) {
-  return gemm_tc_any<float>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
+  if (transA || !transB) { tfb_set_last_error("tfb_gemm_tf32_tc: only transA=0, transB=1 is supported"); return TFB_ERR_UNSUPPORTED; }
+  TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && lda % 4 == 0 && ldb % 4 == 0);
+  if (N <= 64) return launch_tc<float, 64, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return launch_tc<float, 128, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
 }
 
 TFB_API int tfb_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,

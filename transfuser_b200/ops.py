@@ -141,9 +141,14 @@ class Conv2dFn(Function):
             dx = torch.empty_like(x)
             call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
-            call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
+            if G.MODE == 'bf16' and ks == 3 and Cout % 8 == 0:
+                dw = _conv_wgrad_tc(x, G.to_bf16(g), Cout, groups, stride)
+                if dw is not None and has_bias:
+                    db = _colsum(g.view(-1, Cout))
+            if dw is None:
+                dw = torch.empty_like(w)
+                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+                call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
         return dx, dw, db, None, None, None
 
 
@@ -181,6 +186,29 @@ def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
     return y
 
 
+def _conv_wgrad_tc(x, g16, Cout, groups, stride):
+    """dW of a 3x3 conv on the tensor cores: im2col(x) in bf16, then one split-K GEMM per channel group
+    (dW_g[Cog, 9*Cig] = dy_g^T col_g, batched over groups in a single launch), then the [co][tap][ci] -> [co][ci][tap] permute.
+    Returns None when the shape does not fit (channel windows must be 16-byte aligned)."""
+    N, H, W, Cin = x.shape
+    Cig, Cog = Cin // groups, Cout // groups
+    if Cout % 8 or (groups > 1 and (Cog % 8 or (9 * Cig) % 8)) or (9 * Cin) % 8:
+        return None
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    M = N * Ho * Wo
+    if M < 512:
+        return None
+    col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
+    call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
+    dwp = torch.empty((Cout, 9 * Cig), dtype=torch.float32, device=x.device)
+    ntiles = groups * ((9 * Cig + 127) // 128)
+    splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
+    call('tfb_gemm_bf16_tc_wgrad_batched', Cog, 9 * Cig, M, g16, Cout, Cog, col, 9 * Cin, 9 * Cig, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
+    dw = torch.empty((Cout, Cig, 3, 3), dtype=torch.float32, device=x.device)
+    call('tfb_conv3x3_permute_dw', dwp, dw, Cout, Cig)
+    return dw
+
+
 class Conv3x3TCFn(Function):
     """3x3 / stride 1 conv in bf16 mode: forward and dgrad as implicit GEMMs on the tcgen05 tensor cores (csrc/conv_tc.cu:
     TMA tap-shifted NHWC tiles, no im2col); wgrad on the fp32 direct kernel."""
@@ -203,17 +231,22 @@ class Conv3x3TCFn(Function):
         dy = _c(dy)
         g = _relu_bwd(y, dy) if relu else dy
         dx = dw = db = None
+        g16 = G.to_bf16(g) if Cout % 8 == 0 else None
         if ctx.needs_input_grad[0]:
             plan = _conv_tc_plan(Cout, Cin, groups)
             if plan is not None:
-                dx = _conv_tc_run(G.to_bf16(g), w, None, plan, 1, Cin, groups, False)
+                dx = _conv_tc_run(g16, w, None, plan, 1, Cin, groups, False)
             else:
                 dx = torch.empty_like(x)
                 call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, 3, 1, groups)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
-            call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, 3, 1, groups)
+            dw = _conv_wgrad_tc(x, g16, Cout, groups, 1) if g16 is not None else None
+            if dw is not None:
+                db = _colsum(g.view(-1, Cout)) if has_bias else None
+            else:
+                dw = torch.empty_like(w)
+                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+                call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, 3, 1, groups)
         return dx, dw, db, None, None
 
 
