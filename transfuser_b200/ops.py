@@ -32,8 +32,9 @@ def _colsum(x2d):
     M, C = x2d.shape
     out = torch.empty(C, dtype=torch.float32, device=x2d.device)
     ws = torch.empty(2 * C, dtype=torch.float64, device=x2d.device)
-    assert x2d.stride(1) == 1
-    call('tfb_colsum', x2d, x2d.stride(0), M, C, out, ws)
+    ld = C if x2d.is_contiguous() else x2d.stride(0)
+    assert x2d.is_contiguous() or x2d.stride(1) == 1
+    call('tfb_colsum', x2d, ld, M, C, out, ws)
     return out
 
 
@@ -192,7 +193,7 @@ def _conv_wgrad_tc(x, g16, Cout, groups, stride):
     Returns None when the shape does not fit (channel windows must be 16-byte aligned)."""
     N, H, W, Cin = x.shape
     Cig, Cog = Cin // groups, Cout // groups
-    if Cout % 8 or (groups > 1 and (Cog % 8 or (9 * Cig) % 8)) or (9 * Cin) % 8:
+    if Cig % 8 or (groups > 1 and Cog % 8):
         return None
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     M = N * Ho * Wo
@@ -200,10 +201,12 @@ def _conv_wgrad_tc(x, g16, Cout, groups, stride):
         return None
     col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
     call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
-    dwp = torch.empty((Cout, 9 * Cig), dtype=torch.float32, device=x.device)
+    ldg = g16.shape[-1]                      # >= Cout when dy was zero-padded to 8 channels
+    dwp = torch.empty((max(Cout, ldg) if groups == 1 else Cout, 9 * Cig), dtype=torch.float32, device=x.device)
     ntiles = groups * ((9 * Cig + 127) // 128)
     splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
-    call('tfb_gemm_bf16_tc_wgrad_batched', Cog, 9 * Cig, M, g16, Cout, Cog, col, 9 * Cin, 9 * Cig, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
+    call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else dwp.shape[0], 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
+         9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
     dw = torch.empty((Cout, Cig, 3, 3), dtype=torch.float32, device=x.device)
     call('tfb_conv3x3_permute_dw', dwp, dw, Cout, Cig)
     return dw
@@ -231,9 +234,15 @@ class Conv3x3TCFn(Function):
         dy = _c(dy)
         g = _relu_bwd(y, dy) if relu else dy
         dx = dw = db = None
-        g16 = G.to_bf16(g) if Cout % 8 == 0 else None
+        if Cout % 8 == 0:
+            g16 = G.to_bf16(g)
+        elif groups == 1 and Cin % 8 == 0:       # narrow dy (7 / 1 channels): zero-pad to 8 so the rows are TMA-loadable
+            g16 = torch.empty((N, H, W, 8), dtype=torch.bfloat16, device=g.device)
+            call('tfb_cast_bf16_pad', g, g16, N * H * W, Cout, 8)
+        else:
+            g16 = None
         if ctx.needs_input_grad[0]:
-            plan = _conv_tc_plan(Cout, Cin, groups)
+            plan = _conv_tc_plan(Cout, Cin, groups) if Cout % 8 == 0 else None
             if plan is not None:
                 dx = _conv_tc_run(g16, w, None, plan, 1, Cin, groups, False)
             else:
