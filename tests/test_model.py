@@ -113,4 +113,4 @@ def test_full_model_forward_backward_matches_oracle():
     sd = net.state_dict()
     worst = max((rel(sd[k], P[k]), k) for k in P if 'running' in k and ('.stem.' in k or '.s1.' in k or '.s4.' in k))
     assert worst[0] < 1e-4, worst
-    assert int(sd['_model.image_encoder.features.stem.bn.num_batches_tracked']) == 2
+    assert int(sd['_model.image_encoder.features.stem.bn.num_batches_tracked']) == 1

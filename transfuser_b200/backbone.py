@@ -231,6 +231,7 @@ class TransfuserBackbone(nn.Module):
         """image: NCHW 0..255, lidar: NCHW -> (p2..p5 NHWC), image grid NHWC, fused [B,512]."""
         if self.training:
             torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+            ops.tick(image.device)
         ie, le = self.image_encoder.features, self.lidar_encoder._model
         x = ops.image_prep(image) if self.image_encoder.normalize else ops.nchw_to_nhwc(image)
         l = ops.nchw_to_nhwc(lidar)

@@ -113,7 +113,8 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict_
 __global__ void __launch_bounds__(256)
 tokens_fwd_kernel(const float* __restrict__ img, int Hi, int Wi, int ghi, int gwi, const float* __restrict__ lid, int Hl, int Wl,
                   int ghl, int gwl, const float* __restrict__ pos, float* __restrict__ out, int N, int C, float p_drop,
-                  uint64_t seed) {
+                  const uint64_t* __restrict__ seed_dev, uint64_t seed_off) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   const int T = ghi * gwi + ghl * gwl;
   const int64_t total = (int64_t)N * T * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -136,7 +137,8 @@ tokens_fwd_kernel(const float* __restrict__ img, int Hi, int Wi, int ghi, int gw
 // gradient of the token build w.r.t. one feature map: d[n][y][x][c] (+)= g[n][t(y,x)][c] * drop / window
 __global__ void __launch_bounds__(256)
 tokens_bwd_feat_kernel(const float* __restrict__ g, float* __restrict__ d, int N, int H, int W, int gh, int gw, int t_off, int T, int C,
-                       float p_drop, uint64_t seed, int accumulate) {
+                       float p_drop, const uint64_t* __restrict__ seed_dev, uint64_t seed_off, int accumulate) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   const int64_t total = (int64_t)N * H * W * C;
   const int wh = H / gh, ww = W / gw;
   const float inv = 1.f / (float)(wh * ww);
@@ -154,7 +156,8 @@ tokens_bwd_feat_kernel(const float* __restrict__ g, float* __restrict__ d, int N
 
 // dpos[t][c] = sum_n g[n][t][c] * drop
 __global__ void __launch_bounds__(256) tokens_bwd_pos_kernel(const float* __restrict__ g, float* __restrict__ dpos, int N, int T, int C,
-                                                             float p_drop, uint64_t seed) {
+                                                             float p_drop, const uint64_t* __restrict__ seed_dev, uint64_t seed_off) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   const int64_t total = (int64_t)T * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -244,14 +247,17 @@ __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, fl
 }
 
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
-                                                      uint64_t seed) {
+                                                      const uint64_t* __restrict__ seed_dev, uint64_t seed_off) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = x[i] * tfb_dropout_scale(seed, (uint64_t)i, p);
 }
 
 // one warp per row of length L: P = softmax(scale * S); Pd = dropout(P). P and Pd may alias S when p == 0.
 __global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ S, float* __restrict__ P, float* __restrict__ Pd,
-                                                          int64_t rows, int L, float scale, float p_drop, uint64_t seed) {
+                                                          int64_t rows, int L, float scale, float p_drop, const uint64_t* __restrict__ seed_dev,
+                                                          uint64_t seed_off) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -272,7 +278,9 @@ __global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restric
 
 // dS = scale * P * (g - sum_j g_j P_j), g = dPd * dropout_scale
 __global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dPd, float* __restrict__ dS,
-                                                          int64_t rows, int L, float scale, float p_drop, uint64_t seed) {
+                                                          int64_t rows, int L, float scale, float p_drop, const uint64_t* __restrict__ seed_dev,
+                                                          uint64_t seed_off) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
   const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -392,25 +400,26 @@ TFB_API int tfb_transpose_last2(const float* x, float* y, int N, int A, int B, c
   return TFB_OK;
 }
 TFB_API int tfb_tokens_fwd(const float* img, int Hi, int Wi, int ghi, int gwi, const float* lid, int Hl, int Wl, int ghl, int gwl,
-                           const float* pos, float* out, int N, int C, float p_drop, uint64_t seed, cudaStream_t stream) {
+                           const float* pos, float* out, int N, int C, float p_drop, const uint64_t* seed_dev, uint64_t seed_off,
+                           cudaStream_t stream) {
   TFB_REQUIRE(img && lid && pos && out && N > 0 && C > 0);
   TFB_REQUIRE(Hi % ghi == 0 && Wi % gwi == 0 && Hl % ghl == 0 && Wl % gwl == 0);  // exact adaptive-avg-pool windows only
   const int64_t total = (int64_t)N * (ghi * gwi + ghl * gwl) * C;
-  tokens_fwd_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos, out, N, C, p_drop, seed);
+  tokens_fwd_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos, out, N, C, p_drop, seed_dev, seed_off);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 TFB_API int tfb_tokens_bwd(const float* g, float* dimg, int Hi, int Wi, int ghi, int gwi, float* dlid, int Hl, int Wl, int ghl,
-                           int gwl, float* dpos, int N, int C, float p_drop, uint64_t seed, int accumulate_feat,
+                           int gwl, float* dpos, int N, int C, float p_drop, const uint64_t* seed_dev, uint64_t seed_off, int accumulate_feat,
                            cudaStream_t stream) {
   TFB_REQUIRE(g && dimg && dlid && dpos && N > 0 && C > 0);
   const int T = ghi * gwi + ghl * gwl;
   const int64_t ti = (int64_t)N * Hi * Wi * C, tl = (int64_t)N * Hl * Wl * C;
-  tokens_bwd_feat_kernel<<<tfb_grid(ti, 256), 256, 0, stream>>>(g, dimg, N, Hi, Wi, ghi, gwi, 0, T, C, p_drop, seed, accumulate_feat);
+  tokens_bwd_feat_kernel<<<tfb_grid(ti, 256), 256, 0, stream>>>(g, dimg, N, Hi, Wi, ghi, gwi, 0, T, C, p_drop, seed_dev, seed_off, accumulate_feat);
   TFB_CHECK_LAUNCH();
-  tokens_bwd_feat_kernel<<<tfb_grid(tl, 256), 256, 0, stream>>>(g, dlid, N, Hl, Wl, ghl, gwl, ghi * gwi, T, C, p_drop, seed, accumulate_feat);
+  tokens_bwd_feat_kernel<<<tfb_grid(tl, 256), 256, 0, stream>>>(g, dlid, N, Hl, Wl, ghl, gwl, ghi * gwi, T, C, p_drop, seed_dev, seed_off, accumulate_feat);
   TFB_CHECK_LAUNCH();
-  tokens_bwd_pos_kernel<<<tfb_grid((int64_t)T * C, 256), 256, 0, stream>>>(g, dpos, N, T, C, p_drop, seed);
+  tokens_bwd_pos_kernel<<<tfb_grid((int64_t)T * C, 256), 256, 0, stream>>>(g, dpos, N, T, C, p_drop, seed_dev, seed_off);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -447,24 +456,26 @@ TFB_API int tfb_upsample_bilinear_bwd(const float* dy, float* dx, int N, int Hi,
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
-TFB_API int tfb_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, cudaStream_t stream) {
+// Dropout mask = f(*seed_dev + seed_off, element index): the base seed lives in device memory (advanced by tfb_step_tick once
+// per step, also inside a captured CUDA graph), seed_off identifies the call site; the backward regenerates the same mask.
+TFB_API int tfb_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* seed_dev, uint64_t seed_off, cudaStream_t stream) {
   TFB_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f);
   if (n == 0) return TFB_OK;
-  dropout_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, y, n, p, seed);
+  dropout_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, y, n, p, seed_dev, seed_off);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
-TFB_API int tfb_softmax_fwd(const float* S, float* P, float* Pd, int64_t rows, int L, float scale, float p_drop, uint64_t seed,
-                            cudaStream_t stream) {
+TFB_API int tfb_softmax_fwd(const float* S, float* P, float* Pd, int64_t rows, int L, float scale, float p_drop, const uint64_t* seed_dev,
+                            uint64_t seed_off, cudaStream_t stream) {
   TFB_REQUIRE(S && P && Pd && rows > 0 && L > 0);
-  softmax_fwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(S, P, Pd, rows, L, scale, p_drop, seed);
+  softmax_fwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(S, P, Pd, rows, L, scale, p_drop, seed_dev, seed_off);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
-TFB_API int tfb_softmax_bwd(const float* P, const float* dPd, float* dS, int64_t rows, int L, float scale, float p_drop, uint64_t seed,
-                            cudaStream_t stream) {
+TFB_API int tfb_softmax_bwd(const float* P, const float* dPd, float* dS, int64_t rows, int L, float scale, float p_drop, const uint64_t* seed_dev,
+                            uint64_t seed_off, cudaStream_t stream) {
   TFB_REQUIRE(P && dPd && dS && rows > 0 && L > 0);
-  softmax_bwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(P, dPd, dS, rows, L, scale, p_drop, seed);
+  softmax_bwd_kernel<<<(unsigned)ceil_div64(rows, 4), 128, 0, stream>>>(P, dPd, dS, rows, L, scale, p_drop, seed_dev, seed_off);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -124,7 +124,13 @@ gru_bwd_kernel(const float* __restrict__ d_wp, const float* __restrict__ save, c
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ p_bf16, int zero_grad) {
+             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ p_bf16, int zero_grad,
+             const int* __restrict__ step_dev) {
+  if (step_dev) {  // step count in device memory (CUDA-graph replay): bias corrections computed here
+    const double t = (double)(*step_dev);
+    bc1 = (float)(1.0 - pow((double)beta1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
   const int64_t n4 = n / 4;
   const float step = lr / bc1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -189,15 +195,31 @@ TFB_API int tfb_gru_bwd(const float* d_wp, const float* save, const float* w_ih,
   return TFB_OK;
 }
 
-// zero_grad != 0: the gradient buffer is cleared in the same pass (saves the separate zero_grad() sweep).
+// zero_grad != 0: the gradient buffer is cleared in the same pass. step_dev (optional): optimizer step count in device memory
+// (incremented by tfb_step_tick) — used instead of `step`, so a captured CUDA graph stays valid across replays.
 TFB_API int tfb_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                           float weight_decay, int step, float grad_scale, void* p_bf16, int zero_grad, cudaStream_t stream) {
-  TFB_REQUIRE(p && g && m && v && n >= 0 && step >= 1);
+                           float weight_decay, int step, const int* step_dev, float grad_scale, void* p_bf16, int zero_grad,
+                           cudaStream_t stream) {
+  TFB_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev));
   if (n == 0) return TFB_OK;
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adamw_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale,
-                                                              (__nv_bfloat16*)p_bf16, zero_grad);
+                                                              (__nv_bfloat16*)p_bf16, zero_grad, step_dev);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+namespace {
+__global__ void step_tick_kernel(unsigned long long* seed_dev, int* step_dev) {
+  if (seed_dev) *seed_dev += 0x9E3779B97F4A7C15ull;
+  if (step_dev) *step_dev += 1;
+}
+}  // namespace
+
+// Once per training step: advances the device-resident dropout base seed and / or the optimizer step counter.
+TFB_API int tfb_step_tick(uint64_t* seed_dev, int* step_dev, cudaStream_t stream) {
+  step_tick_kernel<<<1, 1, 0, stream>>>((unsigned long long*)seed_dev, step_dev);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

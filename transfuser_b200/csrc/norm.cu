@@ -50,6 +50,75 @@ colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
   }
 }
 
+// float4 variant (C % 4 == 0, 16-byte aligned rows): threadIdx.x -> one channel QUAD inside a 128-channel slab, two rows in
+// flight per iteration. Same MODE semantics as colreduce_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int relu) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < C) {
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f}, ga[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { mu[q] = mean[c + q]; is[q] = invstd[c + q]; ga[q] = gamma[c + q]; be[q] = beta[c + q]; }
+    }
+    int cnt = 0;
+    const int64_t step = (int64_t)gridDim.y * 8;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += 2 * step) {
+      const bool two = r + step < M;
+      const float4 v0 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      const float4 v1 = two ? *reinterpret_cast<const float4*>(x + (r + step) * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      if (MODE == 1) {
+        g0 = *reinterpret_cast<const float4*>(dy + r * C + c);
+        if (two) g1 = *reinterpret_cast<const float4*>(dy + (r + step) * C + c);
+      }
+      const float xv[2][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}};
+      const float gv[2][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (MODE == 0) {
+            a0[q] += xv[h][q]; a1[q] = fmaf(xv[h][q], xv[h][q], a1[q]);
+          } else {
+            const float xh = (xv[h][q] - mu[q]) * is[q];
+            float g = gv[h][q];
+            if (relu && !(fmaf(xh, ga[q], be[q]) > 0.f)) g = 0.f;
+            a0[q] += g; a1[q] = fmaf(g, xh, a1[q]);
+          }
+        }
+      }
+      if (++cnt == 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { d0[q] += a0[q]; d1[q] += a1[q]; a0[q] = a1[q] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { d0[q] += a0[q]; d1[q] += a1[q]; }
+  }
+  __shared__ double sd[8][32][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { sd[threadIdx.y][threadIdx.x][q] = d0[q]; sd[threadIdx.y][threadIdx.x][4 + q] = d1[q]; }
+  __syncthreads();
+  // 256 threads finish 32 quads x 8 values
+  const int tq = threadIdx.x, tv = threadIdx.y;   // value index 0..7 handled by row-phase thread tv
+  const int cc = (blockIdx.x * 32 + tq) * 4;
+  if (cc < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sd[j][tq][tv];
+    if (tv < 4) atomicAdd(&out[cc + tv], t);
+    else atomicAdd(&out[C + cc + tv - 4], t);
+  }
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, int C, float eps, float momentum,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var) {
@@ -189,6 +258,40 @@ __global__ void double_to_float_kernel(const double* __restrict__ in, float* __r
   if (i < n) out[i] = (float)in[i];
 }
 
+// Backward prologue of a dense layer, one pass over dy [M, C]:  g = relu ? dy * (y > 0) : dy;  optional outputs: g in fp32, g in
+// bf16 (operand of the tensor-core dgrad / wgrad GEMMs), and dbias[c] = sum_m g[m][c] (fp32 partials per thread, fp64 atomics).
+__global__ void __launch_bounds__(256)
+grad_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g32, __nv_bfloat16* __restrict__ g16,
+                 double* __restrict__ sums, int64_t M, int C) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (c < C) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += (int64_t)gridDim.y * 8) {
+      const int64_t i = r * C + c;
+      float g = dy[i];
+      if (y && !(y[i] > 0.f)) g = 0.f;
+      if (g32) g32[i] = g;
+      if (g16) g16[i] = __float2bfloat16_rn(g);
+      a += g;
+    }
+  }
+  if (sums) {
+    sm[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+      atomicAdd(&sums[c], (double)t);
+    }
+  }
+}
+
+template <int MODE>
+int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
+                     const float* gamma, const float* beta, int relu, cudaStream_t stream);
+
 int colreduce_splits(int64_t M, int slabs) {
   int64_t want = (4LL * tfb_num_sms() + slabs - 1) / slabs;
   int64_t maxs = ceil_div64(M, 8 * 16);  // at least 16 rows per thread
@@ -198,6 +301,23 @@ int colreduce_splits(int64_t M, int slabs) {
   return (int)want;
 }
 
+template <int MODE>
+int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
+                     const float* gamma, const float* beta, int relu, cudaStream_t stream) {
+  const bool vec = C % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!dy || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  dim3 block(32, 8);
+  if (vec) {
+    const int slabs = (C / 4 + 31) / 32;
+    dim3 grid(slabs, colreduce_splits(M, slabs));
+    colreduce4_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu);
+  } else {
+    const int slabs = (C + 31) / 32;
+    dim3 grid(slabs, colreduce_splits(M, slabs));
+    colreduce_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu);
+  }
+  return 0;
+}
+
 }  // namespace
 
 TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps,
@@ -205,9 +325,7 @@ TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* 
                        double* sums_ws, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && sums_ws && M > 0 && C > 0 && C % 4 == 0);
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  const int slabs = (C + 31) / 32;
-  dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
+  launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, stream);
   TFB_CHECK_LAUNCH();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
   TFB_CHECK_LAUNCH();
@@ -232,9 +350,7 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
                        cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0);
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  const int slabs = (C + 31) / 32;
-  dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<1><<<grid, block, 0, stream>>>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu);
+  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, stream);
   TFB_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<tfb_grid(M * C, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
                                                                 dgamma, dbeta);
@@ -247,12 +363,26 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
 TFB_API int tfb_colsum(const float* x, int64_t ldx, int64_t M, int C, float* out, double* sums_ws, cudaStream_t stream) {
   TFB_REQUIRE(x && out && sums_ws && M > 0 && C > 0 && ldx >= C);
   if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  const int slabs = (C + 31) / 32;
-  dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  colreduce_kernel<0><<<grid, block, 0, stream>>>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0);
+  launch_colreduce<0>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, stream);
   TFB_CHECK_LAUNCH();
   double_to_float_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, out, C);
   TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// See grad_prep_kernel. Any of y / g32 / g16_bf16 / dbias may be null; sums_ws (C doubles) is needed when dbias is given.
+TFB_API int tfb_grad_prep(const float* dy, const float* y, float* g32, void* g16_bf16, float* dbias, double* sums_ws, int64_t M, int C,
+                          cudaStream_t stream) {
+  TFB_REQUIRE(dy && M > 0 && C > 0 && (!dbias || sums_ws));
+  if (dbias && cudaMemsetAsync(sums_ws, 0, (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  const int slabs = (C + 31) / 32;
+  dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
+  grad_prep_kernel<<<grid, block, 0, stream>>>(dy, y, g32, (__nv_bfloat16*)g16_bf16, dbias ? sums_ws : nullptr, M, C);
+  TFB_CHECK_LAUNCH();
+  if (dbias) {
+    double_to_float_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, dbias, C);
+    TFB_CHECK_LAUNCH();
+  }
   return TFB_OK;
 }
 

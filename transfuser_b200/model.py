@@ -109,7 +109,7 @@ class LidarCenterNet(nn.Module):
                                   nn.Linear(128, 64), nn.ReLU(inplace=True)).to(self.device)
         self.decoder = nn.GRUCell(input_size=4, hidden_size=config.gru_hidden_size).to(self.device)
         self.output = nn.Linear(config.gru_hidden_size, 3).to(self.device)
-        self.register_buffer('_bev_class_weight', torch.tensor([1., 1., 3.]), persistent=False)
+        self.register_buffer('_bev_class_weight', torch.tensor([1., 1., 3.], device=self.device), persistent=False)
 
     def forward_gru(self, z, target_point):
         for i in (0, 2, 4):
@@ -130,7 +130,9 @@ class LidarCenterNet(nn.Module):
 
         pred_bev = _run_pair(self.pred_bev, features[0])
         pred_bev = ops.upsample(pred_bev, cfg.bev_resolution_height, cfg.bev_resolution_width, True)
-        w = self._bev_class_weight.to(pred_bev.device)
+        w = self._bev_class_weight
+        if w.device != pred_bev.device:
+            w = self._bev_class_weight = w.to(pred_bev.device)
         loss['loss_wp'] = ops.L1Fn.apply(pred_wp, ego_waypoint, False, 1.0)
         loss['loss_bev'] = ops.CrossEntropyFn.apply(pred_bev, bev, w, 'wsum', 1.0)
 

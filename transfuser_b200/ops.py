@@ -12,30 +12,75 @@ from .gemm import bgemm, gemm
 
 call = _lib.call
 
-_SEED = [0x5EED0000]
+# Dropout randomness = hash(device base seed + call-site offset, element index). The base seed is a device-resident uint64
+# advanced once per training step by `tick()` (a kernel, so it also advances inside a replayed CUDA graph); the offsets
+# below are plain Python ints that identify the call site.
+_SEED = {'off': 0, 'base': 0x5EED0000, 'dev': {}}
 
 
 def manual_seed(seed):
-    _SEED[0] = int(seed) & 0x7FFFFFFFFFFF
+    _SEED['base'] = int(seed) & 0x7FFFFFFFFFFF
+    _SEED['dev'].clear()
+
+
+def seed_state(device):
+    t = _SEED['dev'].get(device)
+    if t is None:
+        t = torch.tensor([_SEED['base']], dtype=torch.int64, device=device)
+        _SEED['dev'][device] = t
+    return t
+
+
+def tick(device):
+    """Advance the device-side dropout seed (call once per training step)."""
+    call('tfb_step_tick', seed_state(device), None)
+    _SEED['off'] = 0
 
 
 def next_seed():
-    _SEED[0] += 1
-    return _SEED[0]
+    _SEED['off'] += 0x10000000
+    return _SEED['off']
 
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _colsum(x2d):
+def _gbuf(p):
+    """Output buffer for the gradient of parameter `p`. When the model was flattened (optim.flatten) and p.grad is None
+    (zero_grad(set_to_none=True)), this is p's view of the flat gradient buffer: the backward kernel writes the gradient in
+    place, autograd adopts the tensor as p.grad without a copy, and the fused AdamW / all-reduce read the flat buffer."""
+    info = getattr(p, '_tfb_flat', None)
+    if info is not None and p.grad is None:
+        fp, off = info
+        return fp.grad[off:off + p.numel()].view(p.shape)
+    return torch.empty(p.shape, dtype=torch.float32, device=p.device)
+
+
+def _colsum(x2d, out=None):
     M, C = x2d.shape
-    out = torch.empty(C, dtype=torch.float32, device=x2d.device)
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=x2d.device)
     ws = torch.empty(2 * C, dtype=torch.float64, device=x2d.device)
     ld = C if x2d.is_contiguous() else x2d.stride(0)
     assert x2d.is_contiguous() or x2d.stride(1) == 1
     call('tfb_colsum', x2d, ld, M, C, out, ws)
     return out
+
+
+def _grad_prep(dy2d, y2d, want32, want16, bias_p):
+    """One pass over dy: ReLU mask (y2d given), fp32 / bf16 copies as requested, bias gradient. Returns (g32, g16, db)."""
+    M, C = dy2d.shape
+    dev = dy2d.device
+    g32 = torch.empty((M, C), dtype=torch.float32, device=dev) if (want32 and y2d is not None) else None
+    g16 = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want16 else None
+    db = _gbuf(bias_p) if bias_p is not None else None
+    ws = torch.empty(C, dtype=torch.float64, device=dev) if db is not None else None
+    if g32 is not None or g16 is not None or db is not None:
+        call('tfb_grad_prep', dy2d, y2d, g32, g16, db, ws, M, C)
+    if want32 and g32 is None:
+        g32 = dy2d
+    return g32, g16, db
 
 
 def _relu_bwd(y, dy):
@@ -73,20 +118,20 @@ class LinearFn(Function):
                 call('tfb_gemm_small_m', 1, M, N, K, x, K, w2, K, y, N, bias, 1 if relu else 0)
             else:
                 gemm(x, w2, y, trans_b=True, bias=bias, relu=relu, mode='simt')
-        ctx.save_for_backward(xs, w, y if relu else None)
+        ctx.save_for_backward(xs, w, y if relu else None, bias)
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xs, w, y = ctx.saved_tensors
+        xs, w, y, bias_p = ctx.saved_tensors
         dy = _c(dy)
-        g = _relu_bwd(y, dy) if ctx.relu else dy
         w2 = w.view(w.shape[0], -1)
         M, K = xs.shape
         N = w2.shape[0]
-        dx = dw = db = None
-        gb = G.to_bf16(g) if ctx.tc else None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        g, gb, db = _grad_prep(dy, y if ctx.relu else None, not ctx.tc, ctx.tc, bias_p if want_db else None)
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
             if ctx.tc:
@@ -96,17 +141,14 @@ class LinearFn(Function):
             else:
                 gemm(g, w2, dx, trans_b=False, mode='simt')
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
+            dw = _gbuf(w)
             if ctx.tc:
                 G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
             elif M >= 4096:
                 # long contraction, narrow output (head 1x1 convs): the pixel-split direct-conv wgrad kernel (k = 1)
-                db = torch.empty(N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-                call('tfb_conv2d_wgrad', xs, g, dw, db, 1, M, 1, K, N, 1, 1, 1)
+                call('tfb_conv2d_wgrad', xs, g, dw, None, 1, M, 1, K, N, 1, 1, 1)
             else:
                 gemm(g, xs, dw.view(w2.shape), trans_a=True, mode='simt')
-        if ctx.has_bias and ctx.needs_input_grad[2] and db is None:
-            db = _colsum(g)
         return dx, dw, db, None
 
 
@@ -127,13 +169,13 @@ class Conv2dFn(Function):
         Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
         call('tfb_conv2d_fwd', x, w, bias, y, N, H, W, Cin, Cout, ks, stride, groups, int(relu))
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.save_for_backward(x, w, y if relu else None, bias)
         ctx.cfg = (N, H, W, Cin, Cout, ks, stride, groups, relu, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, bias_p = ctx.saved_tensors
         N, H, W, Cin, Cout, ks, stride, groups, relu, has_bias = ctx.cfg
         dy = _c(dy)
         g = _relu_bwd(y, dy) if relu else dy
@@ -143,12 +185,12 @@ class Conv2dFn(Function):
             call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
         if ctx.needs_input_grad[1]:
             if G.MODE == 'bf16' and ks == 3 and Cout % 8 == 0:
-                dw = _conv_wgrad_tc(x, G.to_bf16(g), Cout, groups, stride)
+                dw = _conv_wgrad_tc(x, G.to_bf16(g), w, groups, stride)
                 if dw is not None and has_bias:
-                    db = _colsum(g.view(-1, Cout))
+                    db = _colsum(g.view(-1, Cout), _gbuf(bias_p))
             if dw is None:
-                dw = torch.empty_like(w)
-                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+                dw = _gbuf(w)
+                db = _gbuf(bias_p) if has_bias else None
                 call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
         return dx, dw, db, None, None, None
 
@@ -187,11 +229,12 @@ def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
     return y
 
 
-def _conv_wgrad_tc(x, g16, Cout, groups, stride):
+def _conv_wgrad_tc(x, g16, w, groups, stride):
     """dW of a 3x3 conv on the tensor cores: im2col(x) in bf16, then one split-K GEMM per channel group
     (dW_g[Cog, 9*Cig] = dy_g^T col_g, batched over groups in a single launch), then the [co][tap][ci] -> [co][ci][tap] permute.
     Returns None when the shape does not fit (channel windows must be 16-byte aligned)."""
     N, H, W, Cin = x.shape
+    Cout = w.shape[0]
     Cig, Cog = Cin // groups, Cout // groups
     if Cig % 8 or (groups > 1 and Cog % 8):
         return None
@@ -207,7 +250,7 @@ def _conv_wgrad_tc(x, g16, Cout, groups, stride):
     splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
     call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else dwp.shape[0], 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
          9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
-    dw = torch.empty((Cout, Cig, 3, 3), dtype=torch.float32, device=x.device)
+    dw = _gbuf(w)
     call('tfb_conv3x3_permute_dw', dwp, dw, Cout, Cig)
     return dw
 
@@ -221,40 +264,48 @@ class Conv3x3TCFn(Function):
         x = _c(x)
         Cout, Cin = w.shape[0], w.shape[1] * groups
         y = _conv_tc_run(G.to_bf16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu)
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.save_for_backward(x, w, y if relu else None, bias)
         ctx.cfg = (groups, relu, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, bias_p = ctx.saved_tensors
         groups, relu, has_bias = ctx.cfg
         N, H, W, Cin = x.shape
         Cout = w.shape[0]
         dy = _c(dy)
-        g = _relu_bwd(y, dy) if relu else dy
         dx = dw = db = None
         if Cout % 8 == 0:
-            g16 = G.to_bf16(g)
-        elif groups == 1 and Cin % 8 == 0:       # narrow dy (7 / 1 channels): zero-pad to 8 so the rows are TMA-loadable
-            g16 = torch.empty((N, H, W, 8), dtype=torch.bfloat16, device=g.device)
-            call('tfb_cast_bf16_pad', g, g16, N * H * W, Cout, 8)
+            # everything downstream runs on the tensor cores: only the bf16 copy of g (and the bias gradient) is produced
+            g, g16, db = _grad_prep(dy.view(-1, Cout), y.view(-1, Cout) if relu else None, False, True, bias_p if has_bias else None)
+            g16 = g16.view(N, H, W, Cout)
         else:
-            g16 = None
+            g = _relu_bwd(y, dy) if relu else dy
+            if groups == 1 and Cin % 8 == 0:     # narrow dy (7 / 1 channels): zero-pad to 8 so the rows are TMA-loadable
+                g16 = torch.empty((N, H, W, 8), dtype=torch.bfloat16, device=g.device)
+                call('tfb_cast_bf16_pad', g, g16, N * H * W, Cout, 8)
+            else:
+                g16 = None
         if ctx.needs_input_grad[0]:
             plan = _conv_tc_plan(Cout, Cin, groups) if Cout % 8 == 0 else None
             if plan is not None:
                 dx = _conv_tc_run(g16, w, None, plan, 1, Cin, groups, False)
             else:
+                if g is None:
+                    g = _relu_bwd(y, dy) if relu else dy
                 dx = torch.empty_like(x)
                 call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, 3, 1, groups)
         if ctx.needs_input_grad[1]:
-            dw = _conv_wgrad_tc(x, g16, Cout, groups, 1) if g16 is not None else None
+            dw = _conv_wgrad_tc(x, g16, w, groups, 1) if g16 is not None else None
             if dw is not None:
-                db = _colsum(g.view(-1, Cout)) if has_bias else None
+                if has_bias and db is None:
+                    db = _colsum(g.view(-1, Cout), _gbuf(bias_p))
             else:
-                dw = torch.empty_like(w)
-                db = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
+                if g is None:
+                    g = _relu_bwd(y, dy) if relu else dy
+                dw = _gbuf(w)
+                db = (_gbuf(bias_p) if db is None else db) if has_bias else None
                 call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, 3, 1, groups)
         return dx, dw, db, None, None
 
@@ -293,8 +344,8 @@ class BatchNormTrainFn(Function):
         C = x.shape[-1]
         M = x.numel() // C
         dx = torch.empty_like(x)
-        dg = torch.empty_like(weight)
-        db = torch.empty_like(bias)
+        dg = _gbuf(weight)
+        db = _gbuf(bias)
         ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws)
         return dx, dg, db, None, None, None, None, None
@@ -323,18 +374,18 @@ class LayerNormFn(Function):
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         call('tfb_layernorm_fwd', x, y, R, C, weight, bias, float(eps), mean, rstd)
-        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.save_for_backward(x, weight, mean, rstd, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean, rstd = ctx.saved_tensors
+        x, weight, mean, rstd, bias = ctx.saved_tensors
         dy = _c(dy)
         C = x.shape[-1]
         R = x.numel() // C
         dx = torch.empty_like(x)
-        dg = torch.empty_like(weight)
-        db = torch.empty_like(weight)
+        dg = _gbuf(weight)
+        db = _gbuf(bias)
         call('tfb_layernorm_bwd', x, dy, dx, R, C, weight, mean, rstd, dg, db, 0)
         return dx, dg, db, None
 
@@ -367,12 +418,12 @@ class SEFn(Function):
             call('tfb_sigmoid_fwd', s, gate, s.numel())
         y = torch.empty_like(x)
         call('tfb_se_scale_fwd', x, gate, y, N, H * W, C)
-        ctx.save_for_backward(x, w1, w2, pooled, h, gate)
+        ctx.save_for_backward(x, w1, w2, pooled, h, gate, b1, b2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w1, w2, pooled, h, gate = ctx.saved_tensors
+        x, w1, w2, pooled, h, gate, b1, b2 = ctx.saved_tensors
         dy = _c(dy)
         N, H, W, C = x.shape
         Cr = w1.shape[0]
@@ -381,18 +432,18 @@ class SEFn(Function):
         call('tfb_se_bwd_reduce', x, dy, dgate, N, H * W, C)
         ds = torch.empty_like(dgate)
         call('tfb_sigmoid_bwd', gate, dgate, ds, ds.numel())
-        dw2 = torch.empty_like(w2)
+        dw2 = _gbuf(w2)
         gemm(ds, h, dw2.view(C, Cr), trans_a=True, mode='simt')
-        db2 = _colsum(ds)
+        db2 = _colsum(ds, _gbuf(b2))
         dh = torch.empty((N, Cr), dtype=torch.float32, device=dev)
         if N <= 16:
             call('tfb_gemm_small_m', 0, N, Cr, C, ds, C, w2, Cr, dh, Cr, None, 0)
         else:
             gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
         dh = _relu_bwd(h, dh)
-        dw1 = torch.empty_like(w1)
+        dw1 = _gbuf(w1)
         gemm(dh, pooled, dw1.view(Cr, C), trans_a=True, mode='simt')
-        db1 = _colsum(dh)
+        db1 = _colsum(dh, _gbuf(b1))
         dpool = torch.empty((N, C), dtype=torch.float32, device=dev)
         if N <= 16:
             call('tfb_gemm_small_m', 0, N, C, Cr, dh, Cr, w1, C, dpool, C, None, 0)
@@ -434,7 +485,7 @@ class DropoutFn(Function):
     def forward(ctx, x, p, seed):
         x = _c(x)
         y = torch.empty_like(x)
-        call('tfb_dropout', x, y, x.numel(), float(p), seed)
+        call('tfb_dropout', x, y, x.numel(), float(p), seed_state(x.device), seed)
         ctx.p, ctx.seed = p, seed
         return y
 
@@ -442,7 +493,7 @@ class DropoutFn(Function):
     def backward(ctx, dy):
         dy = _c(dy)
         dx = torch.empty_like(dy)
-        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), ctx.seed)
+        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), seed_state(dy.device), ctx.seed)
         return dx, None, None
 
 
@@ -476,16 +527,16 @@ class AttentionFn(Function):
         bgemm(q, k, S, T, T, hs, 3 * C, 3 * C, T, False, True, B, nh, (T * 3 * C, hs), (T * 3 * C, hs), (nh * T * T, T * T))
         scale = 1.0 / (hs ** 0.5)
         Pd = torch.empty_like(S) if p_drop > 0 else S
-        call('tfb_softmax_fwd', S, S, Pd, B * nh * T, T, scale, float(p_drop), seed)
+        call('tfb_softmax_fwd', S, S, Pd, B * nh * T, T, scale, float(p_drop), seed_state(dev), seed)
         y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         bgemm(Pd, v, y, T, hs, T, T, 3 * C, C, False, False, B, nh, (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs))
-        ctx.save_for_backward(hs_, wq, wk, wv, qkv, S, Pd)
+        ctx.save_for_backward(hs_, wq, wk, wv, qkv, S, Pd, bq, bk, bv)
         ctx.cfg = (B, T, nh, p_drop, seed, scale, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        h, wq, wk, wv, qkv, P, Pd = ctx.saved_tensors
+        h, wq, wk, wv, qkv, P, Pd, bq, bk, bv = ctx.saved_tensors
         B, T, nh, p_drop, seed, scale, tc = ctx.cfg
         dy = _c(dy)
         C = h.shape[1]
@@ -498,7 +549,7 @@ class AttentionFn(Function):
         dP = torch.empty_like(P)
         bgemm(dy, v, dP, T, T, hs, C, 3 * C, T, False, True, B, nh, sY, sQ, sP)          # dPd = dy v^T
         bgemm(Pd, dy, dv, T, hs, T, T, C, 3 * C, True, False, B, nh, sP, sY, sQ)         # dv  = Pd^T dy
-        call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed)    # dS (in place)
+        call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed_state(dev), seed)    # dS (in place)
         bgemm(dP, k, dq, T, hs, T, T, 3 * C, 3 * C, False, False, B, nh, sP, sQ, sQ)     # dq  = dS k
         bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
         dh = torch.empty((B * T, C), dtype=torch.float32, device=dev)
@@ -507,16 +558,16 @@ class AttentionFn(Function):
             d16 = G.to_bf16(dqkv)
             for i, w_ in enumerate((wq, wk, wv)):
                 G.gemm_bf16(d16[:, i * C:(i + 1) * C], G.weight_bf16(w_), dh, trans_b=False, beta=0.0 if i == 0 else 1.0)
-            for i, (d, w_) in enumerate(((dq, wq), (dk, wk), (dv, wv))):
-                dw = torch.empty_like(w_)
+            for i, (d, w_, b_) in enumerate(((dq, wq, bq), (dk, wk, bk), (dv, wv, bv))):
+                dw = _gbuf(w_)
                 G.gemm_bf16(d16[:, i * C:(i + 1) * C], h, dw, trans_a=True, splits=_wgrad_splits(B * T, C, C))
-                grads += [dw, _colsum(d)]
+                grads += [dw, _colsum(d, _gbuf(b_))]
         else:
-            for i, (d, w_) in enumerate(((dq, wq), (dk, wk), (dv, wv))):
+            for i, (d, w_, b_) in enumerate(((dq, wq, bq), (dk, wk, bk), (dv, wv, bv))):
                 gemm(d, w_, dh, trans_b=False, beta=0.0 if i == 0 else 1.0, mode='simt')
-                dw = torch.empty_like(w_)
+                dw = _gbuf(w_)
                 gemm(d, h, dw, trans_a=True, mode='simt')
-                grads += [dw, _colsum(d)]
+                grads += [dw, _colsum(d, _gbuf(b_))]
         return (dh, *grads, None, None, None, None, None)
 
 
@@ -531,9 +582,9 @@ class TokensFn(Function):
         _, Hl, Wl, _ = lid.shape
         T = ghi * gwi + ghl * gwl
         out = torch.empty((N, T, C), dtype=torch.float32, device=img.device)
-        call('tfb_tokens_fwd', img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos_emb, out, N, C, float(p_drop), seed)
+        call('tfb_tokens_fwd', img, Hi, Wi, ghi, gwi, lid, Hl, Wl, ghl, gwl, pos_emb, out, N, C, float(p_drop), seed_state(img.device), seed)
         ctx.cfg = (N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, p_drop, seed)
-        ctx.pos_shape = pos_emb.shape
+        ctx.save_for_backward(pos_emb)
         return out
 
     @staticmethod
@@ -542,8 +593,8 @@ class TokensFn(Function):
         g = _c(g)
         dimg = torch.empty((N, Hi, Wi, C), dtype=torch.float32, device=g.device)
         dlid = torch.empty((N, Hl, Wl, C), dtype=torch.float32, device=g.device)
-        dpos = torch.empty(ctx.pos_shape, dtype=torch.float32, device=g.device)
-        call('tfb_tokens_bwd', g, dimg, Hi, Wi, ghi, gwi, dlid, Hl, Wl, ghl, gwl, dpos, N, C, float(p_drop), seed, 0)
+        dpos = _gbuf(ctx.saved_tensors[0])
+        call('tfb_tokens_bwd', g, dimg, Hi, Wi, ghi, gwi, dlid, Hl, Wl, ghl, gwl, dpos, N, C, float(p_drop), seed_state(g.device), seed, 0)
         return dimg, dlid, dpos, None, None, None, None, None, None
 
 
@@ -742,20 +793,16 @@ class GRUFn(Function):
         wp = torch.empty((B, steps, 2), dtype=torch.float32, device=z0.device)
         save = torch.empty((B, steps, 5 * 64 + 4), dtype=torch.float32, device=z0.device)
         call('tfb_gru_fwd', z0, target_point, w_ih, w_hh, b_ih, b_hh, w_out, b_out, B, steps, float(x_shift), wp, save)
-        ctx.save_for_backward(save, w_ih, w_hh, w_out)
+        ctx.save_for_backward(save, w_ih, w_hh, w_out, b_ih, b_hh, b_out)
         ctx.cfg = (B, steps)
         return wp
 
     @staticmethod
     def backward(ctx, d):
-        save, w_ih, w_hh, w_out = ctx.saved_tensors
+        save, w_ih, w_hh, w_out, b_ih, b_hh, b_out = ctx.saved_tensors
         B, steps = ctx.cfg
         dev = d.device
         dz0 = torch.empty((B, 64), dtype=torch.float32, device=dev)
-        dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
-        db_ih = torch.empty(192, dtype=torch.float32, device=dev)
-        db_hh = torch.empty(192, dtype=torch.float32, device=dev)
-        dw_out = torch.empty_like(w_out)
-        db_out = torch.empty(3, dtype=torch.float32, device=dev)
+        dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out = [_gbuf(t) for t in (w_ih, w_hh, b_ih, b_hh, w_out, b_out)]
         call('tfb_gru_bwd', _c(d), save, w_ih, w_hh, w_out, B, steps, dz0, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out)
         return dz0, None, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out, None, None

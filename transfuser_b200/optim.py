@@ -31,15 +31,26 @@ class FlatParams:
             n = p.numel()
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view(p.shape)
-            p.grad = self.grad[o:o + n].view(p.shape)
+            p.grad = None
             p._tfb_flat = (self, o)
         self.bf16 = None
 
-    def ensure_grad_views(self):
-        """Re-attach the flat gradient views if a caller set .grad = None (train.py:305 uses set_to_none=True)."""
+    def set_grads_to_none(self):
+        """zero_grad(set_to_none=True): with .grad None the backward kernels write each gradient straight into its span of
+        the flat buffer (ops._gbuf) and autograd adopts that view as p.grad — no accumulate / copy kernels."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_stragglers(self):
+        """Before the optimizer reads the flat gradient buffer: a parameter whose .grad is not its flat view (accumulated by
+        autograd into a fresh tensor) is copied in; a parameter that received no gradient is zeroed."""
+        base = self.grad.data_ptr()
         for p, o in zip(self.params, self.offsets):
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            g = p.grad
+            if g is None:
+                self.grad[o:o + p.numel()].zero_()
+            elif g.data_ptr() != base + 4 * o:
+                self.grad[o:o + p.numel()].copy_(g.reshape(-1))
 
 
 def flatten(model):
@@ -50,7 +61,8 @@ def flatten(model):
 
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (decoupled weight decay, bias correction), one fused kernel per flat buffer.
-    The kernel also zeroes the gradient buffer it just consumed, so zero_grad() is free."""
+    Gradients are written in place into the flat buffer by the backward kernels (ops._gbuf), so zero_grad() only drops the
+    .grad references and no buffer is cleared."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -58,6 +70,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self._flat = None
         self._m = self._v = None
+        self._step_dev = None
+        self.check_grads = True   # set False once the producer set is known to be complete (saves a Python sweep per step)
 
     def _flat_of(self):
         if self._flat is None:
@@ -68,19 +82,20 @@ class FusedAdamW(torch.optim.Optimizer):
             self._flat = ps[0]._tfb_flat[0]
             self._m = torch.zeros_like(self._flat.flat)
             self._v = torch.zeros_like(self._flat.flat)
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=self._flat.flat.device)
         return self._flat
 
     def zero_grad(self, set_to_none=True):
-        fp = self._flat_of()
-        fp.ensure_grad_views()
-        if self._step == 0:
-            fp.grad.zero_()
+        self._flat_of().set_grads_to_none()
 
     @torch.no_grad()
     def step(self, closure=None, chunks=None):
         fp = self._flat_of()
+        if self.check_grads:
+            fp.gather_stragglers()
         g = self.param_groups[0]
         self._step += 1
+        _lib.call('tfb_step_tick', None, self._step_dev)   # device-side step count: valid under CUDA-graph replay
         b1, b2 = g['betas']
         spans = chunks or [(0, fp.total, None)]
         for lo, hi, work in spans:
@@ -88,7 +103,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 work.wait()
             bf = fp.bf16[lo:hi] if fp.bf16 is not None else None
             _lib.call('tfb_adamw_step', fp.flat[lo:hi], fp.grad[lo:hi], self._m[lo:hi], self._v[lo:hi], hi - lo, float(g['lr']), float(b1),
-                      float(b2), float(g['eps']), float(g['weight_decay']), self._step, float(self.grad_scale), bf, 1)
+                      float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0)
 
 
 class GradAllReducer:
