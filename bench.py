@@ -77,8 +77,9 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from transfuser_b200 import LidarCenterNet, _lib, bev, gemm, ops, optim
+    from transfuser_b200 import _lib
     from transfuser_b200.config import TrainConfig
+    from transfuser_b200.trainer import Trainer
 
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -88,63 +89,20 @@ def run_b200(args):
     B = args.batch
     cfg = TrainConfig()
     torch.manual_seed(0)
-    ops.manual_seed(1234 + rank)
-    gemm.set_mode(args.gemm)
-    net = LidarCenterNet(cfg, dev, 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False).train()
-    fp = optim.flatten(net)
-    if args.gemm == 'bf16':
-        gemm.attach_bf16_weights(fp)
-    opt = optim.FusedAdamW(net.parameters(), lr=1e-4, grad_scale=1.0 / world)
-    reducer = optim.GradAllReducer(fp, n_chunks=8)
-    w = dict(zip(cfg.detailed_losses, cfg.detailed_losses_weights))
+    tr = Trainer(cfg, dev, gemm_mode=args.gemm, lr=1e-4, seed=rank)
     host = make_host_batch(B, seed=100 + rank, torch=torch, np=np)
 
     def h2d():
         return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
 
-    def step(d):
-        lidar = bev.lidar_to_histogram_features_batched(d['points'])
-        opt.zero_grad()
-        losses = net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
-                     target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
-                     depth=d['depth'], semantic=d['semantic'])
-        loss = None
-        for k, v in losses.items():
-            loss = v * w[k] if loss is None else loss + v * w[k]
-        loss.backward()
-        opt.step(chunks=reducer.chunks())
-        return loss
-
-    # ---- whole-step CUDA graph: fwd + bwd + (all-reduce) + AdamW captured once, replayed per step (dropout seed and
-    # optimizer step count live in device memory and are advanced by kernels inside the graph) ----
-    graph = {'g': None, 'loss': None, 'launches': 0, 'static': None, 'why': None}
-
-    def try_capture():
-        static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
-        for k in host:
-            static[k].copy_(host[k], non_blocking=True)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                step(static)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        opt.check_grads = False
-        g = torch.cuda.CUDAGraph()
-        l0 = _lib.lib().launches
-        with torch.cuda.graph(g):
-            loss = step(static)
-        graph.update(g=g, loss=loss, launches=_lib.lib().launches - l0, static=static)
+    step = tr.step
 
     def run_step(e2e):
-        if graph['g'] is None:
-            return step(h2d() if e2e else resident[0])
+        if tr.graph is None:
+            return tr.step(h2d() if e2e else resident[0])
         if e2e:
-            for k in host:
-                graph['static'][k].copy_(host[k], non_blocking=True)
-        graph['g'].replay()
-        return graph['loss']
+            tr.load(host)
+        return tr.replay()
 
     def barrier():
         torch.cuda.synchronize()
@@ -172,19 +130,15 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = graph['launches'] * n if graph['g'] is not None else _lib.lib().launches - l0
+        launches = tr.graph_launches * n if tr.graph is not None else _lib.lib().launches - l0
         return ms, launches, last
 
     for _ in range(max(args.warmup, 3)):
         step(h2d())
-    if args.graph:
-        try:
-            try_capture()
+    if args.graph and (world == 1 or args.graph >= 2):
+        if tr.capture(host):
             for _ in range(2):
                 run_step(True)
-        except Exception as e:  # noqa: keep the eager path if capture is not possible (reported in the JSON line)
-            graph.update(g=None, why=repr(e)[:200])
-            torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -218,7 +172,7 @@ def run_b200(args):
             'dtype': 'bf16' if args.gemm == 'bf16' else 'fp32', 'data': 'synthetic',
             'config': {'workload': 'TransFuser RegNetY-3.2GF LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
                                    '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU' % B,
-                       'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm, 'cuda_graph': graph['g'] is not None, 'cuda_graph_error': graph['why'],
+                       'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm, 'cuda_graph': tr.graph is not None, 'cuda_graph_error': tr.graph_error,
                        'l2': 'working set (672 MB weights + activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': round(e2e_v, 3), 'unit': 'samples/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
@@ -294,7 +248,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--graph', type=int, default=1, help='capture the whole step in a CUDA graph (falls back to eager if capture fails)')
+    ap.add_argument('--graph', type=int, default=1, help='1: capture the whole step in a CUDA graph on 1 GPU; 2: also with NCCL all-reduce inside (N > 1); 0: eager')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -1,0 +1,81 @@
+"""One data-parallel training step of the hot path — BEV histogram, LidarCenterNet forward, weighted loss sum, backward,
+gradient all-reduce, fused AdamW — as a reusable object, optionally captured into ONE CUDA graph and replayed.
+
+This is the body of the reference's `Engine.train()` loop (train.py:304-316) with the synchronising `.item()` calls moved
+out of the step; bench.py and the tests drive it."""
+import torch
+import torch.distributed as dist
+
+from . import _lib, bev, gemm, ops, optim
+from .model import LidarCenterNet
+
+INPUT_KEYS = ('rgb', 'points', 'target_point_image', 'target_point', 'ego_vel', 'ego_waypoint', 'bev', 'semantic', 'depth', 'label')
+
+
+class Trainer:
+    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=8):
+        self.cfg, self.device = cfg, device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        gemm.set_mode(gemm_mode)
+        ops.manual_seed(1234 + seed)
+        self.net = LidarCenterNet(cfg, device, 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False).train()
+        self.flat = optim.flatten(self.net)
+        if gemm_mode == 'bf16':
+            gemm.attach_bf16_weights(self.flat)
+        self.opt = optim.FusedAdamW(self.net.parameters(), lr=lr, grad_scale=1.0 / self.world)
+        self.reducer = optim.GradAllReducer(self.flat, n_chunks=n_chunks)
+        self.weights = dict(zip(cfg.detailed_losses, cfg.detailed_losses_weights))
+        self.graph = None
+        self.static = None
+        self.static_loss = None
+        self.graph_launches = 0
+        self.graph_error = None
+
+    def step(self, d):
+        """Eager step on device-resident inputs `d` (dict with INPUT_KEYS). Returns the weighted total loss (0-dim tensor)."""
+        lidar = bev.lidar_to_histogram_features_batched(d['points'])
+        self.opt.zero_grad()
+        losses = self.net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
+                          target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
+                          depth=d['depth'], semantic=d['semantic'])
+        loss = None
+        for k, v in losses.items():
+            loss = v * self.weights[k] if loss is None else loss + v * self.weights[k]
+        loss.backward()
+        self.opt.step(chunks=self.reducer.chunks())
+        return loss
+
+    def capture(self, example):
+        """Captures step() into a CUDA graph over static input buffers shaped like `example` (host or device tensors).
+        The dropout base seed and the optimizer step count live in device memory and are advanced by kernels inside the graph,
+        so every replay is a genuinely new step. Returns True on success (falls back to eager otherwise)."""
+        try:
+            self.static = {k: torch.empty(example[k].shape, dtype=example[k].dtype, device=self.device) for k in INPUT_KEYS}
+            self.load(example)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.step(self.static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.opt.check_grads = False
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.lib().launches
+            with torch.cuda.graph(g):
+                self.static_loss = self.step(self.static)
+            self.graph, self.graph_launches = g, _lib.lib().launches - l0
+            return True
+        except Exception as e:  # noqa: BLE001 — keep the eager path, report why
+            self.graph, self.graph_error = None, repr(e)[:300]
+            torch.cuda.synchronize()
+            return False
+
+    def load(self, batch):
+        """Copies a batch (pinned host or device tensors) into the static input buffers of the captured graph."""
+        for k in INPUT_KEYS:
+            self.static[k].copy_(batch[k], non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_loss
