@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _reset_numerics_mode():
+    """Every test starts in the exact-fp32 ('simt') GEMM mode; tests of the bf16 tensor-core mode switch it on themselves."""
+    try:
+        from transfuser_b200 import gemm
+    except Exception:
+        yield
+        return
+    gemm.set_mode('simt')
+    gemm._FLAT[0] = None
+    gemm._WCACHE.clear()
+    yield
+    gemm.set_mode('simt')
+    gemm._FLAT[0] = None
+    gemm._WCACHE.clear()
