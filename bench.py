@@ -148,12 +148,12 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel: per-entry-point CUDA-event timing over one extra step (rank 0) ----
     roof = None
+    prof = _lib.Profiler() if rank == 0 else None
+    _lib.lib().profiler = prof
+    step(h2d())                      # every rank runs it (it contains the gradient all-reduce); only rank 0 instruments
+    torch.cuda.synchronize()
+    _lib.lib().profiler = None
     if rank == 0:
-        prof = _lib.Profiler()
-        _lib.lib().profiler = prof
-        step(h2d())
-        torch.cuda.synchronize()
-        _lib.lib().profiler = None
         roof = prof.summary(peaks())
         if os.path.isdir(os.path.join(ROOT, 'gpurun_out')):
             det = sorted(prof.detail.items(), key=lambda kv: -kv[1][0])
