@@ -135,7 +135,7 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step(h2d())
-    if args.graph and (world == 1 or args.graph >= 2):
+    if args.graph:
         if tr.capture(host):
             for _ in range(2):
                 run_step(True)
@@ -185,8 +185,11 @@ def run_b200(args):
             line['cpu_baseline'] = cpu_reference(steps=1, warmup=0, batch=1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)   # skip process-group teardown: destroying a communicator that a live CUDA graph captured can block
 
 
 def cpu_reference(steps, warmup, batch):
@@ -248,7 +251,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--graph', type=int, default=1, help='1: capture the whole step in a CUDA graph on 1 GPU; 2: also with NCCL all-reduce inside (N > 1); 0: eager')
+    ap.add_argument('--graph', type=int, default=1, help='1: capture the whole step (incl. the NCCL gradient all-reduce when N > 1) in a CUDA graph; 0: eager')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
