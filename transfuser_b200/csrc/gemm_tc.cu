@@ -9,6 +9,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-5 = epilogue
 // (TMEM -> registers -> global). One 128 x BN output tile per CTA, STAGES-deep mbarrier ring between TMA and MMA.
 // Replaces cuBLAS/cuDNN behind nn.Linear and 1x1 nn.Conv2d (transfuser.py:510-527,538-543; timm RegNet 1x1 convs).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -36,14 +38,20 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int kStageOut = kBarOffset + 256;                              // 4 warps x 32 rows x 36 floats epilogue staging
+  static constexpr int kTotal = kStageOut + 4 * 32 * 36 * 4 + 1024;               // + alignment slack
 };
 
 template <typename T, int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ C,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ Cbase,
                int64_t ldc, int M, int N, int num_kb, int kb_per_split, const float* __restrict__ bias, float alpha, float beta,
-               int relu, int atomic_out, int splits, int a_step, int b_step, int64_t c_bstride) {
+               int relu, int atomic_out, int splits, int a_step, int b_step, int64_t c_bstride, int tiles_m, int tiles_n,
+               int total_tiles) {
+  // PERSISTENT: gridDim.x CTAs (<= one per SM) walk the tile list t = blockIdx.x, += gridDim.x. A tile is (m-tile, n-tile, z),
+  // z = batch * splits + split; m fastest so that concurrently running CTAs share the same B (weight) tile in L2.
+  // The TMEM accumulator is double buffered (2 x BN columns): the epilogue warps drain tile i while the MMA warp already
+  // accumulates tile i+1, and the TMA producer runs ahead across tile boundaries through the shared-memory ring.
   using E = Elem<T>;
   using L = SmemLayout<BN, STAGES>;
   constexpr int BK = E::kPerRow;  // K elements per stage
@@ -51,26 +59,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // grid.z = batch * splits. Batch b reads op(A) rows [b*a_step, +M) and op(B) columns [b*b_step, +N) of the SAME tensor maps
-  // (grouped-conv wgrad: one GEMM per channel group) and writes C + b*c_bstride.
-  const int bz = blockIdx.z / splits, sz = blockIdx.z % splits;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int am0 = m0 + bz * a_step, bn0 = n0 + bz * b_step;
-  C += (int64_t)bz * c_bstride;
-  const int kb_begin = sz * kb_per_split;
-  const int kb_end = min(num_kb, kb_begin + kb_per_split);
-  const int nkb = kb_end - kb_begin;  // >= 1 by construction
-  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 4); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -79,29 +80,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // decode tile t -> coordinates
+  auto decode = [&](int t, int& m0, int& n0, int& bz, int& sz, int& kb_begin, int& nkb) {
+    const int tm = t % tiles_m;
+    const int tn = (t / tiles_m) % tiles_n;
+    const int z = t / (tiles_m * tiles_n);
+    bz = z / splits; sz = z % splits;
+    m0 = tm * BM; n0 = tn * BN;
+    kb_begin = sz * kb_per_split;
+    nkb = min(num_kb, kb_begin + kb_per_split) - kb_begin;   // >= 1 by construction
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        tc::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sb = sa + L::kABytes;
-        tc::mbar_expect_tx(&full_bar[s], L::kStageBytes);
-        const int k0 = (kb_begin + i) * BK;
-        if (!A_MN) {
-          tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, am0);
-        } else {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, bz, sz, kb_begin, nkb;
+        decode(t, m0, n0, bz, sz, kb_begin, nkb);
+        const int am0 = m0 + bz * a_step, bn0 = n0 + bz * b_step;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          tc::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+          const int k0 = (kb_begin + i) * BK;
+          if (!A_MN) {
+            tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, am0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / E::kPerRow; ++j)
-            tc::tma_load_2d(&tma_a, &full_bar[s], sa + j * BK * 128, am0 + j * E::kPerRow, k0);
-        }
-        if (!B_MN) {
-          tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, bn0);
-        } else {
+            for (int j = 0; j < BM / E::kPerRow; ++j)
+              tc::tma_load_2d(&tma_a, &full_bar[s], sa + j * BK * 128, am0 + j * E::kPerRow, k0);
+          }
+          if (!B_MN) {
+            tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, bn0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / E::kPerRow; ++j)
-            tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, bn0 + j * E::kPerRow, k0);
+            for (int j = 0; j < BN / E::kPerRow; ++j)
+              tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, bn0 + j * E::kPerRow, k0);
+          }
         }
       }
     }
@@ -109,53 +127,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(E::kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BM, BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        tc::mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        int m0, n0, bz, sz, kb_begin, nkb;
+        decode(t, m0, n0, bz, sz, kb_begin, nkb);
+        const int as = lt & 1, aph = (lt >> 1) & 1;
+        tc::mbar_wait(&tmem_empty_bar[as], aph ^ 1);   // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
-        const uint32_t sa = tc::smem_u32(smem + s * L::kStageBytes);
-        const uint32_t sb = sa + L::kABytes;
+        const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + s * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / E::kUmmaK; ++k) {
-          // K-major: advance 32 B inside the 128 B swizzle row; MN-major: advance kUmmaK rows of 128 B.
-          const uint32_t a_off = A_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
-          const uint32_t b_off = B_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
-          const uint64_t adesc = tc::make_smem_desc(sa + a_off, A_MN ? BK * 128 : 16, 1024);
-          const uint64_t bdesc = tc::make_smem_desc(sb + b_off, B_MN ? BK * 128 : 16, 1024);
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          if (sizeof(T) == 4) tc::umma_tf32(tmem_base, adesc, bdesc, idesc, acc);
-          else                tc::umma_f16(tmem_base, adesc, bdesc, idesc, acc);
+          for (int k = 0; k < BK / E::kUmmaK; ++k) {
+            // K-major: advance 32 B inside the 128 B swizzle row; MN-major: advance kUmmaK rows of 128 B.
+            const uint32_t a_off = A_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
+            const uint32_t b_off = B_MN ? k * E::kUmmaK * 128 : k * E::kUmmaK * (int)sizeof(T);
+            const uint64_t adesc = tc::make_smem_desc(sa + a_off, A_MN ? BK * 128 : 16, 1024);
+            const uint64_t bdesc = tc::make_smem_desc(sb + b_off, B_MN ? BK * 128 : 16, 1024);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            if (sizeof(T) == 4) tc::umma_tf32(acc_addr, adesc, bdesc, idesc, acc);
+            else                tc::umma_f16(acc_addr, adesc, bdesc, idesc, acc);
+          }
+          tc::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        tc::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        tc::umma_commit(&tmem_full_bar[as]);  // accumulator complete
       }
-      tc::umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::fence_after_sync();
-    const int m = m0 + q * 32 + lane;
-    const bool add_bias = bias != nullptr && sz == 0;
-    float* crow = C + (int64_t)m * ldc;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      int m0, n0, bz, sz, kb_begin, nkb;
+      decode(t, m0, n0, bz, sz, kb_begin, nkb);
+      const int as = lt & 1, aph = (lt >> 1) & 1;
+      tc::mbar_wait(&tmem_full_bar[as], aph);
+      tc::fence_after_sync();
+      const int m = m0 + q * 32 + lane;
+      const bool add_bias = bias != nullptr && sz == 0;
+      float* crow = Cbase + (int64_t)bz * c_bstride + (int64_t)m * ldc;
+      const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols + ((uint32_t)(q * 32) << 16);
+      float* cwarp = Cbase + (int64_t)bz * c_bstride + (int64_t)(m0 + q * 32) * ldc;   // first row of this warp's 32-row band
+      const bool fast = !atomic_out && beta == 0.f && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(cwarp + n0) & 15) == 0);
+      if (fast) {
+        // coalesced path: 32-column chunks through this warp's padded smem staging buffer
+        float* stage = reinterpret_cast<float*>(smem + L::kStageOut) + q * (32 * 36);
+        const int rows_valid = M - (m0 + q * 32);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (m < M) {
-        const int n = n0 + c0;
-        if (n + 16 <= N && !atomic_out && beta == 0.f && ((reinterpret_cast<uintptr_t>(crow + n) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o;
-            o.x = alpha * v[j + 0] + (add_bias ? bias[n + j + 0] : 0.f);
-            o.y = alpha * v[j + 1] + (add_bias ? bias[n + j + 1] : 0.f);
-            o.z = alpha * v[j + 2] + (add_bias ? bias[n + j + 2] : 0.f);
-            o.w = alpha * v[j + 3] + (add_bias ? bias[n + j + 3] : 0.f);
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(crow + n + j) = o;
-          }
-        } else {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int cols_valid = N - (n0 + c0);
+          if (cols_valid <= 0) break;   // warp-uniform
+          tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage, cwarp + n0 + c0, ldc, rows_valid, cols_valid,
+                               add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane);
+        }
+      } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(acc_addr + (uint32_t)c0, v);
+        if (m < M) {
+          const int n = n0 + c0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (n + j < N) {
@@ -171,6 +206,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
+      }
+      // this warp is done reading the accumulator buffer: hand it back to the MMA warp (4 arrivals = 4 epilogue warps)
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);
     }
   }
   tc::fence_before_sync();
@@ -252,9 +292,12 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
     }
     attr_done = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * nbatch);
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int64_t total = (int64_t)tiles_m * tiles_n * splits * nbatch;
+  if (total > 0x7fffffff) { tfb_set_last_error("too many tiles"); return TFB_ERR_ARG; }
+  const int grid = (int)(total < tfb_num_sms() ? total : tfb_num_sms());
   kern<<<grid, 192, L::kTotal, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
-                                         b_step, c_bstride);
+                                         b_step, c_bstride, tiles_m, tiles_n, (int)total);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -278,6 +321,16 @@ int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
   TFB_REQUIRE((lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0);
   if (N <= 64) return dispatch_major<T, 64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  // 128x256 tiles when they still fill the chip (or when 128x128 would need a nearly empty second wave)
+  static int force_bn = -1;
+  if (force_bn < 0) { const char* e = getenv("TFB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+  const int64_t mt = (M + BM - 1) / BM;
+  const int64_t t128 = mt * ((N + 127) / 128) * (splits > 0 ? splits : 1), t256 = mt * ((N + 255) / 256) * (splits > 0 ? splits : 1);
+  const int sms = tfb_num_sms();
+  bool use256 = N >= 256 && (t256 >= sms || (t128 > sms && t128 < 2 * sms && t256 <= sms));
+  if (force_bn == 128) use256 = false;
+  if (force_bn == 256 && N >= 256) use256 = true;
+  if (use256) return dispatch_major<T, 256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
   return dispatch_major<T, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
 }
 

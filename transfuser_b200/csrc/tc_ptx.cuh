@@ -113,6 +113,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Same, without the wait: issue several loads back to back, then tmem_ld_wait() once.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue helper: one warp moves its 32 accumulator rows x 32 columns TMEM -> registers -> padded smem (row stride 36 floats:
+// conflict-free 16-byte accesses both ways) -> global memory with COALESCED 128-byte row segments (4 rows per instruction),
+// applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer. Rows >= rows_valid and columns
+// >= cols_valid are not written. Requires 16-byte aligned row starts (dst, ld % 4 == 0).
+__device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, float* dst, int64_t ld, int rows_valid, int cols_valid,
+                                                 const float* bias, float alpha, int relu, int lane) {
+  uint32_t r[32];
+  tmem_ld16_nowait(taddr, r);
+  tmem_ld16_nowait(taddr + 16, r + 16);
+  tmem_ld_wait();
+  float* srow = stage + lane * 36;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                       __uint_as_float(r[j + 3]));
+  __syncwarp();
+  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) {
+    bv.x = c4 + 0 < cols_valid ? bias[c4 + 0] : 0.f;
+    bv.y = c4 + 1 < cols_valid ? bias[c4 + 1] : 0.f;
+    bv.z = c4 + 2 < cols_valid ? bias[c4 + 2] : 0.f;
+    bv.w = c4 + 3 < cols_valid ? bias[c4 + 3] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + rsub;
+    float4 v = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+    v.x = fmaf(alpha, v.x, bv.x); v.y = fmaf(alpha, v.y, bv.y); v.z = fmaf(alpha, v.z, bv.z); v.w = fmaf(alpha, v.w, bv.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (row < rows_valid) {
+      float* p = dst + (int64_t)row * ld + c4;
+      if (c4 + 3 < cols_valid) {
+        *reinterpret_cast<float4*>(p) = v;
+      } else {
+        if (c4 + 0 < cols_valid) p[0] = v.x;
+        if (c4 + 1 < cols_valid) p[1] = v.y;
+        if (c4 + 2 < cols_valid) p[2] = v.z;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------- descriptors ----------------
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (Blackwell).
 //   K-major operand : rows of 128 B (the K extent of one stage), 8-row groups 1024 B apart -> SBO = 1024, LBO = 16 (ignored)
