@@ -29,34 +29,33 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, int row_byte
 }
 
 template <int KC, int NB, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, float* __restrict__ y,
                   const float* __restrict__ bias, int H, int W, int Cout, int tiles_w, int tiles_h, int c_step, int nchunks,
-                  int nb_real, int relu) {
+                  int nb_real, int relu, int gblocks, int total_tiles) {
+  // PERSISTENT: tile t = (spatial tile, channel block), channel block fastest (CTAs running together re-use the same activation
+  // patch out of L2); double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
   constexpr int ROWB = KC * 2;                 // bytes per smem row
   constexpr int A_BYTES = BM * ROWB, B_BYTES = NB * ROWB, STAGE = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stage_out = reinterpret_cast<float*>(smem + STAGES * STAGE + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int tw = t % tiles_w; t /= tiles_w;
-  const int th = t % tiles_h; t /= tiles_h;
-  const int n = t;
-  const int gb = blockIdx.y;
-  const int h0 = th * TH, w0 = tw * TW;
   const int iters = nchunks * 9;
-  constexpr uint32_t kTmemCols = NB <= 32 ? 32 : NB <= 64 ? 64 : 128;
+  constexpr uint32_t kAccCols = NB <= 32 ? 32 : NB <= 64 ? 64 : 128;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_x);
     tc::tma_prefetch_desc(&tma_w);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 4); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -65,57 +64,105 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  auto decode = [&](int t, int& gb, int& n, int& h0, int& w0) {
+    gb = t % gblocks;
+    int sp = t / gblocks;
+    const int tw = sp % tiles_w; sp /= tiles_w;
+    const int th = sp % tiles_h; sp /= tiles_h;
+    n = sp; h0 = th * TH; w0 = tw * TW;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < iters; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        const int chunk = i / 9, tap = i % 9;
-        tc::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE;
-        tc::mbar_expect_tx(&full_bar[s], STAGE);
-        tc::tma_load_4d(&tma_x, &full_bar[s], sa, gb * c_step + chunk * KC, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n);
-        tc::tma_load_2d(&tma_w, &full_bar[s], sa + A_BYTES, 0, ((gb * nchunks + chunk) * 9 + tap) * NB);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int gb, n, h0, w0;
+        decode(t, gb, n, h0, w0);
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          const int chunk = i / 9, tap = i % 9;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE;
+          tc::mbar_expect_tx(&full_bar[s], STAGE);
+          tc::tma_load_4d(&tma_x, &full_bar[s], sa, gb * c_step + chunk * KC, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n);
+          tc::tma_load_2d(&tma_w, &full_bar[s], sa + A_BYTES, 0, ((gb * nchunks + chunk) * 9 + tap) * NB);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(1u, 0u, 0u, BM, NB);  // bf16 x bf16 -> fp32, both K-major
-      for (int i = 0; i < iters; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        tc::mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int as = lt & 1, aph = (lt >> 1) & 1;
+        tc::mbar_wait(&tmem_empty_bar[as], aph ^ 1);
         tc::fence_after_sync();
-        const uint32_t sa = tc::smem_u32(smem + s * STAGE), sb = sa + A_BYTES;
+        const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + s * STAGE), sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k)
-          tc::umma_f16(tmem_base, smem_desc_kmajor(sa + k * 32, ROWB), smem_desc_kmajor(sb + k * 32, ROWB), idesc, (i > 0 || k > 0) ? 1u : 0u);
-        tc::umma_commit(&empty_bar[s]);
+          for (int k = 0; k < KC / 16; ++k)
+            tc::umma_f16(acc_addr, smem_desc_kmajor(sa + k * 32, ROWB), smem_desc_kmajor(sb + k * 32, ROWB), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);
+        }
+        tc::umma_commit(&tmem_full_bar[as]);
       }
-      tc::umma_commit(tmem_full_bar);
     }
   } else {
     const int q = warp & 3;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::fence_after_sync();
-    const int r = q * 32 + lane;             // smem row = pixel (r / 16, r % 16) of the tile (W fastest in the TMA box)
-    const int h = h0 + r / TW, w = w0 + r % TW;
-    const bool pix_ok = h < H && w < W;
-    float* yp = y + (((int64_t)n * H + h) * W + w) * Cout + (int64_t)gb * nb_real;
-    const float* bp = bias ? bias + gb * nb_real : nullptr;
-    const int nvalid = min(nb_real, Cout - gb * nb_real);
+    float* stage = stage_out + q * (32 * 36);
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      int gb, n, h0, w0;
+      decode(t, gb, n, h0, w0);
+      const int as = lt & 1, aph = (lt >> 1) & 1;
+      tc::mbar_wait(&tmem_full_bar[as], aph);
+      tc::fence_after_sync();
+      const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols + ((uint32_t)(q * 32) << 16);
+      const int nvalid = min(nb_real, Cout - gb * nb_real);
+      float* ytile = y + (int64_t)gb * nb_real;
+      const float* bp = bias ? bias + gb * nb_real : nullptr;
+      const bool fast = (Cout & 3) == 0 && ((gb * nb_real) & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+      if (fast) {
+        // accumulator row r of this warp's band = pixel (h0 + (q*32 + r) / 16, w0 + (q*32 + r) % 16)  (W fastest in the TMA box)
 #pragma unroll 1
-    for (int c0 = 0; c0 < NB; c0 += 16) {
-      float v[16];
-      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (pix_ok) {
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          const int cols_valid = nvalid - c0;
+          if (cols_valid <= 0) break;
+          tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
+                               [=](int row) -> float* {
+                                 const int r = q * 32 + row, h = h0 + r / TW, w = w0 + r % TW;
+                                 return (h < H && w < W) ? ytile + (((int64_t)n * H + h) * W + w) * Cout + c0 : nullptr;
+                               },
+                               cols_valid, bp ? bp + c0 : nullptr, 1.f, relu, lane);
+        }
+      } else {
+        const int r = q * 32 + lane;
+        const int h = h0 + r / TW, w = w0 + r % TW;
+        const bool pix_ok = h < H && w < W;
+        float* yp = ytile + (((int64_t)n * H + h) * W + w) * Cout;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(acc_addr + (uint32_t)c0, v);
+          if (pix_ok) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < nvalid) {
-            float o = v[j] + (bp ? bp[c0 + j] : 0.f);
-            if (relu) o = fmaxf(o, 0.f);
-            yp[c0 + j] = o;
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < nvalid) {
+                float o = v[j] + (bp ? bp[c0 + j] : 0.f);
+                if (relu) o = fmaxf(o, 0.f);
+                yp[c0 + j] = o;
+              }
+            }
           }
         }
       }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);
     }
   }
   tc::fence_before_sync();
@@ -212,7 +259,7 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
                 int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
   constexpr int STAGES = NB <= 64 ? 6 : 4;
   constexpr int STAGE = BM * KC * 2 + NB * KC * 2;
-  constexpr int SMEM = STAGES * STAGE + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * STAGE + 256 + 4 * 32 * 36 * 4 + 1024;   // ring + barriers/TMEM slot + epilogue staging + alignment slack
   CUtensorMap mx, mw;
   const uint64_t xd[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   const uint64_t xs[3] = {(uint64_t)Cx * 2, (uint64_t)W * Cx * 2, (uint64_t)H * W * Cx * 2};
@@ -236,8 +283,13 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
     attr_done = true;
   }
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
-  dim3 grid((unsigned)(tiles_w * tiles_h * N), gblocks);
-  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu);
+  const int64_t total = (int64_t)tiles_w * tiles_h * N * gblocks;
+  if (total > 0x7fffffff) { tfb_set_last_error("too many tiles"); return TFB_ERR_ARG; }
+  // NB <= 64 tiles use < 100 KB of shared memory: two persistent CTAs per SM hide each other's pipeline bubbles
+  const int per_sm = (SMEM <= 110 * 1024) ? 2 : 1;
+  const int64_t cap = (int64_t)tfb_num_sms() * per_sm;
+  const int grid = (int)(total < cap ? total : cap);
+  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu, gblocks, (int)total);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

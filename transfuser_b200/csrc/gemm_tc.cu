@@ -181,7 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int cols_valid = N - (n0 + c0);
           if (cols_valid <= 0) break;   // warp-uniform
-          tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage, cwarp + n0 + c0, ldc, rows_valid, cols_valid,
+          float* dst = cwarp + n0 + c0;
+          tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
+                               [=](int row) -> float* { return row < rows_valid ? dst + (int64_t)row * ldc : nullptr; }, cols_valid,
                                add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane);
         }
       } else {

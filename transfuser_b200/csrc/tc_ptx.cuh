@@ -126,10 +126,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // Epilogue helper: one warp moves its 32 accumulator rows x 32 columns TMEM -> registers -> padded smem (row stride 36 floats:
 // conflict-free 16-byte accesses both ways) -> global memory with COALESCED 128-byte row segments (4 rows per instruction),
-// applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer. Rows >= rows_valid and columns
-// >= cols_valid are not written. Requires 16-byte aligned row starts (dst, ld % 4 == 0).
-__device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, float* dst, int64_t ld, int rows_valid, int cols_valid,
-                                                 const float* bias, float alpha, int relu, int lane) {
+// applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer. `row_ptr(row)` returns the
+// 16-byte aligned destination of accumulator row `row` (0..31) or nullptr for rows that must not be written; columns
+// >= cols_valid are not written.
+template <class RowPtr>
+__device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, RowPtr row_ptr, int cols_valid, const float* bias,
+                                                 float alpha, int relu, int lane) {
   uint32_t r[32];
   tmem_ld16_nowait(taddr, r);
   tmem_ld16_nowait(taddr + 16, r + 16);
@@ -154,8 +156,9 @@ __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, f
     float4 v = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
     v.x = fmaf(alpha, v.x, bv.x); v.y = fmaf(alpha, v.y, bv.y); v.z = fmaf(alpha, v.z, bv.z); v.w = fmaf(alpha, v.w, bv.w);
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (row < rows_valid) {
-      float* p = dst + (int64_t)row * ld + c4;
+    float* p = row_ptr(row);
+    if (p != nullptr) {
+      p += c4;
       if (c4 + 3 < cols_valid) {
         *reinterpret_cast<float4*>(p) = v;
       } else {
