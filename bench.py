@@ -182,7 +182,7 @@ def run_b200(args):
             'roofline': roof,
         }
         if not args.no_cpu_baseline and world == 1:
-            line['cpu_baseline'] = cpu_reference(steps=1, warmup=0, batch=1)
+            line['cpu_baseline'] = cpu_baseline_subprocess()
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()
@@ -192,18 +192,36 @@ def run_b200(args):
         os._exit(0)   # skip process-group teardown: destroying a communicator that a live CUDA graph captured can block
 
 
-def cpu_reference(steps, warmup, batch):
+def effective_cores():
+    """Host cores this process may really use: CPU affinity capped by the cgroup CPU quota (a container can see 128 logical
+    CPUs while being throttled to a handful — spinning 128 OpenMP threads there is orders of magnitude slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def cpu_reference(steps, warmup, batch, budget_s=150.0):
     """The reference's CPU PyTorch path (oracle port: oracle/torch_oracle.py, pinned to the verbatim reference) —
-    forward + backward + torch.optim.AdamW on the host cores, bounded sample of the same workload."""
+    forward + backward + torch.optim.AdamW on the host cores, bounded sample of the same workload (stops early when the
+    time budget is used up; at least one timed step)."""
     import torch
     from oracle import torch_oracle as O
     from transfuser_b200 import LidarCenterNet
     from transfuser_b200.config import TrainConfig
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    net = LidarCenterNet(TrainConfig(), 'cpu', 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False)  # parameter container only
-    P = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k and 'num_batches' not in k)
-         for k, v in net.state_dict().items()}
+    cores = effective_cores()
+    threads = min(cores, 32)
+    torch.set_num_threads(threads)
+    t_start = time.time()
+    with torch.device('meta'):   # names / shapes only; values come from the seeded generator below
+        net = LidarCenterNet(TrainConfig(), 'meta', 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False)
+    names = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    P = {k: v.requires_grad_(v.dtype.is_floating_point and 'running' not in k and 'num_batches' not in k)
+         for k, v in O.deterministic_state(names, seed=3).items()}
     params = [v for v in P.values() if v.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4)
     batch_d = O.synthetic_batch(batch, seed=7)
@@ -218,13 +236,28 @@ def cpu_reference(steps, warmup, batch):
         opt.step()
 
     for _ in range(warmup):
+        if time.time() - t_start < budget_s * 0.4:
+            one()
+    done, t0 = 0, time.time()
+    while done < steps and (done == 0 or time.time() - t_start < budget_s):
         one()
-    t0 = time.time()
-    for _ in range(steps):
-        one()
+        done += 1
     dt = time.time() - t0
-    return {'value': round(batch * steps / dt, 4), 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'ms_per_step': round(dt / steps * 1e3, 1),
-            'sample': '%d step(s) of batch %d (fwd+bwd+AdamW, fp32, %d torch threads)' % (steps, batch, torch.get_num_threads())}
+    return {'value': round(batch * done / dt, 4), 'unit': 'samples/s', 'cores': threads, 'host_cores_visible': os.cpu_count(),
+            'host_cores_usable': cores, 'kind': 'port', 'ms_per_step': round(dt / done * 1e3, 1),
+            'sample': '%d step(s) of batch %d (fwd+bwd+AdamW, fp32, %d torch threads)' % (done, batch, threads)}
+
+
+def cpu_baseline_subprocess(timeout_s=300):
+    """Runs cpu_reference() in a child process (own OpenMP pool, hard timeout) so the GPU line is printed no matter what."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'cpu_baseline'], capture_output=True, text=True, timeout=timeout_s)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)
+        return {'value': None, 'error': (r.stderr or 'no output')[-300:]}
+    except subprocess.TimeoutExpired:
+        return {'value': None, 'error': 'cpu baseline exceeded %d s' % timeout_s}
 
 
 def run_reference(args):
@@ -248,12 +281,14 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=10, help='samples per GPU (BASELINE configs[1]: 10)')
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'cpu_baseline'])
     ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1: capture the whole step (incl. the NCCL gradient all-reduce when N > 1) in a CUDA graph; 0: eager')
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.impl == 'cpu_baseline':
+        print(json.dumps(cpu_reference(steps=2, warmup=0, batch=1, budget_s=120.0)), flush=True)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_b200(args)
