@@ -102,8 +102,8 @@ def test_conv3x3_tensor_core(cfg):
 
 
 def test_full_model_bf16_close_to_fp32_mode():
-    """Throughput mode vs parity mode on the same weights / inputs: every loss within 3% of max(|loss|, 0.05)
-    (bf16 operands, fp32 accumulate; the 0.05 floor covers the near-zero yaw-residual SmoothL1 term)."""
+    """Throughput mode vs parity mode on the same weights / inputs: every loss within 3% of max(|loss|, 0.1)
+    (bf16 operands, fp32 accumulate; the 0.1 floor covers the near-zero yaw-residual SmoothL1 term)."""
     import sys
     import os
     sys.path.insert(0, os.path.dirname(__file__))
@@ -124,13 +124,13 @@ def test_full_model_bf16_close_to_fp32_mode():
     for k in outs['simt']:
         a, b = outs['bf16'][k], outs['simt'][k]
         print('%-22s fp32 %.6f bf16 %.6f rel %.2e' % (k, b, a, abs(a - b) / max(abs(b), 1e-9)))
-        assert abs(a - b) <= 3e-2 * max(abs(b), 0.05), (k, a, b)
+        assert abs(a - b) <= 3e-2 * max(abs(b), 0.1), (k, a, b)
 
 
 @pytest.mark.parametrize('cfg', [(2, 40, 48, 72, 72, 3), (2, 20, 24, 216, 216, 9), (2, 32, 44, 3, 32, 1)])
 def test_conv3x3_stride2_bf16_mode(cfg):
-    """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward / dgrad on the exact fp32 direct kernels, wgrad
-    through im2col + the batched tensor-core GEMM when the channel windows are 16-byte aligned."""
+    """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward on the exact fp32 direct kernel; dgrad as the
+    stride-1 tensor-core dgrad of the zero-dilated dy; wgrad through im2col + the batched tensor-core GEMM."""
     from transfuser_b200 import ops
     N, H, W, Cin, Cout, g = cfg
     gen = torch.Generator(device='cuda').manual_seed(Cin)
@@ -144,5 +144,22 @@ def test_conv3x3_stride2_bf16_mode(cfg):
     go = torch.randn_like(ref)
     mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
     rg = torch.autograd.grad(ref, [x, w], go)
-    assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < 1e-4
+    assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < TOL   # grouped: zero-dilated dy through the tensor-core dgrad
     assert rel(mg[1], rg[1]) < TOL
+
+
+def test_conv1x1_stride2_bf16_mode():
+    """RegNet downsample shortcut (1x1, stride 2): subsample + tensor-core GEMM; backward through the zero-dilation."""
+    from transfuser_b200 import ops
+    gen = torch.Generator(device='cuda').manual_seed(9)
+    x = torch.randn(2, 72, 40, 48, device='cuda', generator=gen).requires_grad_()
+    w = (torch.randn(216, 72, 1, 1, device='cuda', generator=gen) / math.sqrt(72)).requires_grad_()
+    ref = F.conv2d(x, w, None, stride=2)
+    xm = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_()
+    wm = w.detach().clone().requires_grad_()
+    out = ops.conv2d(xm, wm, None, 2, 1, False)
+    assert out.shape == (2, 20, 24, 216) and rel(out.permute(0, 3, 1, 2), ref) < TOL
+    go = torch.randn_like(ref)
+    mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
+    rg = torch.autograd.grad(ref, [x, w], go)
+    assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < TOL and rel(mg[1], rg[1]) < TOL

@@ -315,7 +315,7 @@ TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0);
 #define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stream)
   CASE(64, 16); CASE(64, 32); CASE(64, 48); CASE(64, 64); CASE(64, 128);
-  CASE(32, 16); CASE(32, 32);
+  CASE(32, 16); CASE(32, 32); CASE(32, 64);
 #undef CASE
   tfb_set_last_error("tfb_conv3x3_tc: unsupported (KC, NB) tile");
   return TFB_ERR_UNSUPPORTED;

@@ -296,6 +296,29 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restric
   }
 }
 
+// Stride-2 sampling of an NHWC map and its transpose.
+// MODE 0: dst[n][ho][wo][c] = src[n][2ho][2wo][c]           (the input view of a 1x1 / stride-2 conv)
+// MODE 1: dst[n][h][w][c]   = (h, w both even) ? src[n][h/2][w/2][c] : 0   (zero-dilation: gradient of MODE 0, and the
+//         stride-1 equivalent input of a stride-2 conv's dgrad); TO = float or bf16.
+template <int MODE, typename TO>
+__global__ void __launch_bounds__(256) stride2_kernel(const float* __restrict__ src, TO* __restrict__ dst, int N, int H, int W, int Ho,
+                                                      int Wo, int C) {
+  const int64_t total = MODE == 0 ? (int64_t)N * Ho * Wo * C : (int64_t)N * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v;
+    if (MODE == 0) {
+      const int wo = (int)((i / C) % Wo), ho = (int)((i / ((int64_t)C * Wo)) % Ho), n = (int)(i / ((int64_t)C * Wo * Ho));
+      v = src[(((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + c];
+    } else {
+      const int w = (int)((i / C) % W), h = (int)((i / ((int64_t)C * W)) % H), n = (int)(i / ((int64_t)C * W * H));
+      v = ((h | w) & 1) == 0 && h / 2 < Ho && w / 2 < Wo ? src[(((int64_t)n * Ho + h / 2) * Wo + w / 2) * C + c] : 0.f;
+    }
+    if (sizeof(TO) == 4) reinterpret_cast<float*>(dst)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -490,6 +513,25 @@ TFB_API int tfb_scale_dev(const float* x, const float* s_dev, float k, float* y,
   TFB_REQUIRE(x && y && n >= 0);
   if (n == 0) return TFB_OK;
   scale_dev_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, s_dev, k, y, n, accumulate);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// xs[N,Ho,Wo,C] = x[N, ::2, ::2, C] with Ho = (H+1)/2, Wo = (W+1)/2.
+TFB_API int tfb_subsample2(const float* x, float* xs, int N, int H, int W, int C, cudaStream_t stream) {
+  TFB_REQUIRE(x && xs && N > 0 && H > 0 && W > 0 && C > 0);
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  stride2_kernel<0, float><<<tfb_grid((int64_t)N * Ho * Wo * C, 256), 256, 0, stream>>>(x, xs, N, H, W, Ho, Wo, C);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+// dst[N,H,W,C] = zero-dilated src[N,Ho,Wo,C] (values at even (h, w)); out_bf16 selects the output type.
+TFB_API int tfb_dilate2(const float* src, void* dst, int N, int H, int W, int C, int out_bf16, cudaStream_t stream) {
+  TFB_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0);
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int grid = tfb_grid((int64_t)N * H * W * C, 256);
+  if (out_bf16) stride2_kernel<1, __nv_bfloat16><<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, N, H, W, Ho, Wo, C);
+  else          stride2_kernel<1, float><<<grid, 256, 0, stream>>>(src, (float*)dst, N, H, W, Ho, Wo, C);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

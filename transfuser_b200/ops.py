@@ -181,8 +181,16 @@ class Conv2dFn(Function):
         g = _relu_bwd(y, dy) if relu else dy
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
+            plan = _conv_tc_plan(Cout, Cin, groups) if (G.MODE == 'bf16' and ks == 3 and stride == 2) else None
+            if plan is not None:
+                # stride-2 dgrad = stride-1 dgrad of the zero-dilated dy (tensor cores; 3/4 of the MMA work hits zeros, which is
+                # cheaper than the CUDA-core kernel)
+                up = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=g.device)
+                call('tfb_dilate2', g, up, N, H, W, Cout, 1)
+                dx = _conv_tc_run(up, w, None, plan, 1, Cin, groups, False)
+            else:
+                dx = torch.empty_like(x)
+                call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
         if ctx.needs_input_grad[1]:
             if G.MODE == 'bf16' and ks == 3 and Cout % 8 == 0:
                 dw = _conv_wgrad_tc(x, G.to_bf16(g), w, groups, stride)
@@ -209,10 +217,8 @@ def _conv_tc_plan(c_read, c_write, groups):
     kc = 32 if c_read <= 32 else 64
     nchunks = (c_read + kc - 1) // kc
     nb = 16 if c_write <= 16 else 32 if c_write <= 32 else 64 if c_write <= 64 else 128
-    if kc == 32 and nb > 32:
-        kc, nchunks = 64, 1                          # (32-channel rows only exist for NB <= 32 tiles)
-        if c_read < 64:
-            return None
+    if kc == 32 and nb > 64:
+        return None                                  # (32-channel rows exist for NB <= 64 tiles only)
     gblocks = (c_write + nb - 1) // nb
     return dict(NB=nb, KC=kc, c_step=0, nchunks=nchunks, nb_real=nb if gblocks > 1 else c_write, gblocks=gblocks)
 
@@ -310,7 +316,29 @@ class Conv3x3TCFn(Function):
         return dx, dw, db, None, None
 
 
+class Subsample2Fn(Function):
+    """x[:, ::2, ::2, :] — the input view of a 1x1 / stride-2 conv (RegNet downsample shortcut), so the conv itself is a GEMM."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, W, C = x.shape
+        xs = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), dtype=torch.float32, device=x.device)
+        call('tfb_subsample2', x, xs, N, H, W, C)
+        ctx.shape = (N, H, W, C)
+        return xs
+
+    @staticmethod
+    def backward(ctx, d):
+        N, H, W, C = ctx.shape
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=d.device)
+        call('tfb_dilate2', _c(d), dx, N, H, W, C, 0)
+        return dx
+
+
 def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
+    if w.shape[2] == 1 and stride == 2 and groups == 1 and G.MODE == 'bf16':
+        x, stride = Subsample2Fn.apply(x), 1
     if w.shape[2] == 1 and stride == 1 and groups == 1:
         N, H, W, C = x.shape
         return LinearFn.apply(x.reshape(-1, C), w, bias, relu).view(N, H, W, w.shape[0])
