@@ -280,9 +280,13 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
   if (atomic_out) {
     if (relu) { tfb_set_last_error("split-K cannot fuse ReLU"); return TFB_ERR_ARG; }
     if (beta == 0.f) {
-      for (int b = 0; b < nbatch; ++b)
-        if (cudaMemset2DAsync(C + (int64_t)b * c_bstride, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream) != cudaSuccess)
-          return TFB_ERR_DRIVER;
+      if (ldc == N && (nbatch == 1 || c_bstride == (int64_t)M * N)) {   // outputs are one contiguous block: a single memset
+        if (cudaMemsetAsync(C, 0, (size_t)nbatch * M * N * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+      } else {
+        for (int b = 0; b < nbatch; ++b)
+          if (cudaMemset2DAsync(C + (int64_t)b * c_bstride, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream) != cudaSuccess)
+            return TFB_ERR_DRIVER;
+      }
     } else if (beta != 1.f) { tfb_set_last_error("split-K needs beta in {0,1}"); return TFB_ERR_ARG; }
   }
   auto kern = gemm_tc_kernel<T, BN, A_MN, B_MN, STAGES>;
