@@ -126,6 +126,28 @@ def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', tap
     return (p2, p3, p4, p5), x, fused
 
 
+def backbone_late_fusion(P, image, lidar, cfg=Cfg, train=True, pre='_model.'):
+    """LateFusionBackbone.forward (late_fusion.py:72-111): independent trunks, 1x1 reduce, pooled sum, top-down on the LiDAR grid."""
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((image / 255.0) - mean) / std
+    ie, le = pre + 'image_encoder.features.', pre + 'lidar_encoder._model.'
+    x = _bn(P, ie + 'stem.bn.', F.conv2d(x, P[ie + 'stem.conv.weight'], None, stride=2, padding=1), train, True)
+    l = _bn(P, le + 'stem.bn.', F.conv2d(lidar, P[le + 'stem.conv.weight'], None, stride=2, padding=1), train, True)
+    for s in range(4):
+        x = _stage(P, '%ss%d.' % (ie, s + 1), x, train, REGNET_DEPTHS[s])
+        l = _stage(P, '%ss%d.' % (le, s + 1), l, train, REGNET_DEPTHS[s])
+    x = F.conv2d(x, P[pre + 'reduce_channels_conv_image.weight'], P[pre + 'reduce_channels_conv_image.bias'])
+    l = F.conv2d(l, P[pre + 'reduce_channels_conv_lidar.weight'], P[pre + 'reduce_channels_conv_lidar.bias'])
+    fused = x.mean((2, 3)) + l.mean((2, 3))
+    up = lambda t: F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+    p5 = F.relu(F.conv2d(l, P[pre + 'c5_conv.weight'], P[pre + 'c5_conv.bias']))
+    p4 = F.relu(F.conv2d(up(p5), P[pre + 'up_conv5.weight'], P[pre + 'up_conv5.bias']))
+    p3 = F.relu(F.conv2d(up(p4), P[pre + 'up_conv4.weight'], P[pre + 'up_conv4.bias']))
+    p2 = F.relu(F.conv2d(up(p3), P[pre + 'up_conv3.weight'], P[pre + 'up_conv3.bias']))
+    return (p2, p3, p4, p5), x, fused
+
+
 def _decoder(P, pre, x, cfg):
     c = lambda t, n, act=True: (F.relu if act else (lambda z: z))(F.conv2d(t, P['%s%s.weight' % (pre, n)], P['%s%s.bias' % (pre, n)], padding=1))
     x = c(c(x, 'deconv1.0'), 'deconv1.2')
@@ -225,10 +247,13 @@ def centernet_losses(preds, label, cfg):
     return out
 
 
-def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None):
+def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None, backbone_name='transFuser'):
     """LidarCenterNet.forward (model.py:733-805): dict of the 11 losses. `P` maps reference state_dict names to tensors."""
     lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
-    feats, img_grid, fused = backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
+    if backbone_name == 'late_fusion':
+        feats, img_grid, fused = backbone_late_fusion(P, batch['rgb'], lidar, cfg, train)
+    else:
+        feats, img_grid, fused = backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
     loss = {}
     wp = gru_waypoints(P, fused, batch['target_point'], cfg)
     head = lambda name, x: F.conv2d(F.relu(F.conv2d(x, P[name + '.0.weight'], P[name + '.0.bias'], padding=1)),

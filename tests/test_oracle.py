@@ -89,3 +89,29 @@ def test_c_abi_library_exports_every_declared_symbol():
     missing = [n for n in decls if not hasattr(cdll, n)]
     assert not missing, missing
     assert cdll.tfb_abi_version() == 1
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_late_fusion_oracle_and_state_dict_match_verbatim_reference():
+    """BASELINE config 5 (late_fusion.py): drop-in key set of the product module + oracle restatement vs the reference."""
+    m = ref_import.load()
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    torch.manual_seed(0)
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', 'late_fusion', 'regnety_032', 'regnety_032', use_velocity=False).train()
+    from transfuser_b200 import LidarCenterNet
+    from transfuser_b200.config import TrainConfig
+    mine = LidarCenterNet(TrainConfig(), 'cpu', 'late_fusion', 'regnety_032', 'regnety_032', use_velocity=False)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+    names = [(n, tuple(p.shape)) for n, p in list(ref.named_parameters()) + list(ref.named_buffers())]
+    ref.load_state_dict(O.deterministic_state(names, seed=6), strict=False)
+    batch = O.synthetic_batch(1, seed=4)
+    P = {k: v.clone() for k, v in ref.state_dict().items()}
+    with torch.no_grad():
+        want = ref(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                   target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                   depth=batch['depth'], semantic=batch['semantic'])
+        got = O.forward(P, batch, O.Cfg, train=True, backbone_name='late_fusion')
+    for k in want:
+        assert abs(float(want[k]) - float(got[k])) <= 1e-6 * max(abs(float(want[k])), 1e-6), k

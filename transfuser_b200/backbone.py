@@ -235,7 +235,7 @@ class TransfuserBackbone(nn.Module):
         ie, le = self.image_encoder.features, self.lidar_encoder._model
         x = ops.image_prep(image) if self.image_encoder.normalize else ops.nchw_to_nhwc(image)
         l = ops.nchw_to_nhwc(lidar)
-        x = ops.batch_norm(ops.conv2d(x, ie.stem.conv.weight, None, 2, 1), ie.stem.bn, True, ie.stem.bn.training)
+        x = ie.stem.run(x)
         l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
         for i in range(1, 5):
             x = getattr(ie, 's%d' % i).run(x)
@@ -243,6 +243,79 @@ class TransfuserBackbone(nn.Module):
             x, l = getattr(self, 'transformer%d' % i).run(x, l)
         x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
+        fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
+        f = self.config.bev_upsample_factor
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
+        p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
+        p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)
+        p2 = ops.conv2d(up(p3), self.up_conv3.weight, self.up_conv3.bias, relu=True)
+        return (p2, p3, p4, p5), x, fused
+
+    def forward(self, image, lidar, velocity):
+        feats, grid, fused = self.forward_nhwc(image, lidar)
+        return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused
+
+
+class _PlainEncoder(nn.Module):
+    """late_fusion.py:114-163: the timm trunk used whole (stem -> s1..s4); classifier parts replaced by empty Sequentials."""
+
+    def __init__(self, architecture, attr, in_chans=3, normalize=True):
+        super().__init__()
+        if architecture != 'regnety_032':
+            raise RuntimeError('transfuser_b200 implements the regnety_032 trunk only, got %r' % (architecture,))
+        self.normalize = normalize
+        net = _RegNet(in_chans=in_chans)
+        net.fc, net.classifier, net.global_pool, net.head = nn.Sequential(), nn.Sequential(), nn.Sequential(), nn.Sequential()
+        setattr(self, attr, net)
+        object.__setattr__(self, '_net', net)
+
+    def run(self, x):
+        net = self._net
+        x = net.stem.run(x)
+        for i in range(1, 5):
+            x = getattr(net, 's%d' % i).run(x)
+        return x
+
+
+class LateFusionBackbone(nn.Module):
+    """B200-native drop-in for /root/reference/team_code_transfuser/late_fusion.py:5-111 (BASELINE config 5): two independent
+    RegNetY trunks, 1x1 channel reduction, global pools summed, FPN top-down on the LiDAR grid. Same parameter names."""
+
+    def __init__(self, config, image_architecture='resnet34', lidar_architecture='resnet18', use_velocity=0):
+        super().__init__()
+        self.config = config
+        if config.use_point_pillars:
+            raise RuntimeError('PointPillars LiDAR encoder is out of scope (config.py:42 default False)')
+        if use_velocity:
+            raise RuntimeError('use_velocity=True is not implemented (train.py:54 default is 0)')
+        in_channels = 2 * config.lidar_seq_len + (1 if config.use_target_point_image else 0)
+        self.image_encoder = _PlainEncoder(image_architecture, 'features', 3, normalize=True)
+        self.lidar_encoder = _PlainEncoder(lidar_architecture, '_model', in_channels, normalize=False)
+        self.norm_after_pool_img = nn.Sequential()
+        self.norm_after_pool_lidar = nn.Sequential()
+        self.use_velocity = use_velocity
+        channel, c_out, c_last = config.bev_features_chanels, config.perception_output_features, REGNETY_032['widths'][-1]
+        self.reduce_channels_conv_image = nn.Conv2d(c_last, c_out, (1, 1))
+        self.reduce_channels_conv_lidar = nn.Conv2d(c_last, c_out, (1, 1))
+        self.up_conv5 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv4 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv3 = nn.Conv2d(channel, channel, (1, 1))
+        self.c5_conv = nn.Conv2d(c_out, channel, (1, 1))
+
+    def _bn_modules(self):
+        if not hasattr(self, '_bn_cache'):
+            object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
+        return self._bn_cache
+
+    def forward_nhwc(self, image, lidar):
+        if self.training:
+            torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+            ops.tick(image.device)
+        x = self.image_encoder.run(ops.image_prep(image))
+        l = self.lidar_encoder.run(ops.nchw_to_nhwc(lidar))
+        x = ops.conv2d(x, self.reduce_channels_conv_image.weight, self.reduce_channels_conv_image.bias)
+        l = ops.conv2d(l, self.reduce_channels_conv_lidar.weight, self.reduce_channels_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
         f = self.config.bev_upsample_factor
         up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)

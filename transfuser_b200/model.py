@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .backbone import TransfuserBackbone
+from .backbone import LateFusionBackbone, TransfuserBackbone
 
 HEAD_NAMES = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
 HEAD_LOSSES = ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res', 'loss_velocity', 'loss_brake')
@@ -93,9 +93,12 @@ class LidarCenterNet(nn.Module):
         if not self.gru_concat_target_point:
             raise RuntimeError('gru_concat_target_point=False is not implemented (config.py:31 default True)')
         self.backbone = backbone
-        if backbone != 'transFuser':
-            raise RuntimeError('this round implements backbone="transFuser" only, got %r' % (backbone,))
-        self._model = TransfuserBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        if backbone == 'transFuser':
+            self._model = TransfuserBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        elif backbone == 'late_fusion':
+            self._model = LateFusionBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        else:
+            raise RuntimeError('implemented backbones: "transFuser", "late_fusion"; got %r' % (backbone,))
         if config.multitask:
             self.seg_decoder = SegDecoder(config, config.perception_output_features).to(self.device)
             self.depth_decoder = DepthDecoder(config, config.perception_output_features).to(self.device)
