@@ -34,38 +34,60 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
   }
 }
 
-// out[n][c] = mean_p x[n][p][c] (MODE 0)  or  sum_p x[n][p][c] * z[n][p][c] (MODE 1: SE gate gradient)
+// out[n][c] (+)= scale * sum_p x[n][p][c] (MODE 0)  or  sum_p x[n][p][c] * z[n][p][c] (MODE 1: SE gate gradient)
+// block (32 channel quads, 8 row phases); grid (quad slabs, n, HW splits); partial sums leave through fp32 atomics (out zeroed).
 template <int MODE>
 __global__ void __launch_bounds__(256) pool_hw_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out,
-                                                      int HW, int C) {
-  __shared__ float sm[8][33];
-  const int n = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
-  float a = 0.f;
+                                                      int HW, int C, float scale) {
+  __shared__ float4 sm[8][33];
+  const int n = blockIdx.y, c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C) {
     const float* xp = x + (int64_t)n * HW * C + c;
     const float* zp = MODE == 1 ? z + (int64_t)n * HW * C + c : nullptr;
-    for (int p = threadIdx.y; p < HW; p += 8) a += MODE == 0 ? xp[(int64_t)p * C] : xp[(int64_t)p * C] * zp[(int64_t)p * C];
+    for (int p = blockIdx.z * 8 + threadIdx.y; p < HW; p += gridDim.z * 8) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + (int64_t)p * C);
+      if (MODE == 0) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      else {
+        const float4 w = *reinterpret_cast<const float4*>(zp + (int64_t)p * C);
+        a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+      }
+    }
   }
   sm[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    float t = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
-    out[(int64_t)n * C + c] = MODE == 0 ? t / (float)HW : t;
+    for (int j = 0; j < 8; ++j) { const float4 v = sm[j][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    float* o = out + (int64_t)n * C + c;
+    atomicAdd(o + 0, t.x * scale); atomicAdd(o + 1, t.y * scale); atomicAdd(o + 2, t.z * scale); atomicAdd(o + 3, t.w * scale);
   }
 }
 
-// y[n][p][c] = x[n][p][c] * gate[n][c]  (+ add[n][c] * add_scale)
+// y[n][p][c] = x[n][p][c] * gate[n][c]  (+ add[n][c] * add_scale); VEC = 4 when C % 4 == 0 (16-byte accesses)
+template <int VEC>
 __global__ void __launch_bounds__(256) scale_nc_kernel(const float* __restrict__ x, const float* __restrict__ gate,
                                                        const float* __restrict__ add, float add_scale, float* __restrict__ y,
                                                        int64_t total, int HW, int C) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int64_t n = i / ((int64_t)HW * C);
-    float v = x[i] * gate[n * C + c];
-    if (add) v = fmaf(add[n * C + c], add_scale, v);
-    y[i] = v;
+  const int Cv = C / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / VEC; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv) * VEC;
+    const int64_t n = i / ((int64_t)HW * Cv);
+    if (VEC == 4) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      const float4 g = *reinterpret_cast<const float4*>(gate + n * C + c);
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+      if (add) {
+        const float4 a = *reinterpret_cast<const float4*>(add + n * C + c);
+        v.x = fmaf(a.x, add_scale, v.x); v.y = fmaf(a.y, add_scale, v.y); v.z = fmaf(a.z, add_scale, v.z); v.w = fmaf(a.w, add_scale, v.w);
+      }
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      float v = x[i] * gate[n * C + c];
+      if (add) v = fmaf(add[n * C + c], add_scale, v);
+      y[i] = v;
+    }
   }
 }
 
@@ -373,8 +395,12 @@ TFB_API int tfb_sigmoid_fwd(const float* x, float* y, int64_t n, cudaStream_t st
 }
 TFB_API int tfb_pool_hw_fwd(const float* x, float* out, int N, int HW, int C, cudaStream_t stream) {
   TFB_REQUIRE(x && out && N > 0 && HW > 0 && C > 0);
-  dim3 grid((C + 31) / 32, N), block(32, 8);
-  pool_hw_kernel<0><<<grid, block, 0, stream>>>(x, nullptr, out, HW, C);
+  TFB_REQUIRE(C % 4 == 0);
+  if (cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  int splits = (HW + 255) / 256;
+  if (splits > 32) splits = 32;
+  dim3 grid((C / 4 + 31) / 32, N, splits), block(32, 8);
+  pool_hw_kernel<0><<<grid, block, 0, stream>>>(x, nullptr, out, HW, C, 1.f / (float)HW);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -388,14 +414,19 @@ TFB_API int tfb_pool_hw_bwd(const float* dout, float* dx, int N, int HW, int C, 
 TFB_API int tfb_se_scale_fwd(const float* x, const float* gate, float* y, int N, int HW, int C, cudaStream_t stream) {
   TFB_REQUIRE(x && gate && y && N > 0 && HW > 0 && C > 0);
   const int64_t total = (int64_t)N * HW * C;
-  scale_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
+  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
+  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 TFB_API int tfb_se_bwd_reduce(const float* x, const float* dy, float* dgate, int N, int HW, int C, cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dgate && N > 0 && HW > 0 && C > 0);
-  dim3 grid((C + 31) / 32, N), block(32, 8);
-  pool_hw_kernel<1><<<grid, block, 0, stream>>>(x, dy, dgate, HW, C);
+  TFB_REQUIRE(C % 4 == 0);
+  if (cudaMemsetAsync(dgate, 0, (size_t)N * C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  int splits = (HW + 255) / 256;
+  if (splits > 32) splits = 32;
+  dim3 grid((C / 4 + 31) / 32, N, splits), block(32, 8);
+  pool_hw_kernel<1><<<grid, block, 0, stream>>>(x, dy, dgate, HW, C, 1.f);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -403,7 +434,8 @@ TFB_API int tfb_se_bwd_apply(const float* dy, const float* gate, const float* dp
                              cudaStream_t stream) {
   TFB_REQUIRE(dy && gate && dpool && dx && N > 0 && HW > 0 && C > 0);
   const int64_t total = (int64_t)N * HW * C;
-  scale_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
+  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
+  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
