@@ -7,6 +7,64 @@
 
 namespace {
 
+// "Last block finalises" epilogue of the column reductions. The workspace `sums` (doubles) is ZERO on entry to every kernel
+// that uses it and is zeroed again here by the last block, together with the arrival counter stored right behind it, so no
+// memset / convert / finalize launches are needed and one workspace serves every layer on a stream.
+//   kind 0: nothing (no reduction output requested)
+//   kind 1: BatchNorm forward  -> save_mean, save_invstd, running statistics        (sums = [sum x | sum x^2])
+//   kind 2: BatchNorm backward -> dgamma = sum g*xhat, dbeta = sum g                 (sums = [sum g | sum g*xhat])
+//   kind 3: column sum         -> out[c] = sum                                        (sums = [sum])
+struct Finalize {
+  int kind;
+  int nsums;             // doubles in use (C or 2C); the counter lives at sums[nsums]
+  int64_t M;
+  float eps, momentum;
+  float* o0;             // save_mean | dbeta  | out
+  float* o1;             // save_invstd | dgamma
+  float* running_mean;
+  float* running_var;
+};
+
+__device__ __forceinline__ void finalize_last_block(double* sums, int C, const Finalize& f) {
+  if (f.kind == 0) return;
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  if (tid == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(sums + f.nsums);
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    is_last = ticket == gridDim.x * gridDim.y * gridDim.z - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = tid; c < C; c += nthr) {
+    const double s0 = __ldcg(sums + c);
+    const double s1 = f.nsums > C ? __ldcg(sums + C + c) : 0.0;
+    if (f.kind == 1) {
+      const double mean = s0 / (double)f.M;
+      double var = s1 / (double)f.M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      f.o0[c] = (float)mean;
+      f.o1[c] = (float)(1.0 / sqrt(var + (double)f.eps));
+      if (f.running_mean) {
+        const double unbiased = f.M > 1 ? var * (double)f.M / (double)(f.M - 1) : var;
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)mean;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+      }
+    } else if (f.kind == 2) {
+      f.o0[c] = (float)s0;
+      f.o1[c] = (float)s1;
+    } else {
+      f.o0[c] = (float)s0;
+    }
+    sums[c] = 0.0;
+    if (f.nsums > C) sums[C + c] = 0.0;
+  }
+  if (tid == 0) *reinterpret_cast<unsigned int*>(sums + f.nsums) = 0u;
+}
+
 // ---------------- per-channel column reductions over a [M, C] matrix ----------------
 // block (32, 8): threadIdx.x -> channel inside a 32-wide slab, threadIdx.y -> row phase. grid (slabs, row splits).
 // MODE 0: (sum x, sum x^2)            MODE 1: BN backward (sum g, sum g*xhat), g = dy * relu_mask
@@ -14,7 +72,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int relu) {
+                 const float* __restrict__ beta, int relu, Finalize fin) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
   double d0 = 0.0, d1 = 0.0;
@@ -46,8 +104,9 @@ colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) { t0 += sd0[j][threadIdx.x]; t1 += sd1[j][threadIdx.x]; }
     atomicAdd(&out[c], t0);
-    atomicAdd(&out[C + c], t1);
+    if (fin.nsums > C) atomicAdd(&out[C + c], t1);
   }
+  finalize_last_block(out, C, fin);
 }
 
 // float4 variant (C % 4 == 0, 16-byte aligned rows): threadIdx.x -> one channel QUAD inside a 128-channel slab, two rows in
@@ -56,7 +115,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int relu) {
+                  const float* __restrict__ beta, int relu, Finalize fin) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
   double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
@@ -115,25 +174,9 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += sd[j][tq][tv];
     if (tv < 4) atomicAdd(&out[cc + tv], t);
-    else atomicAdd(&out[C + cc + tv - 4], t);
+    else if (fin.nsums > C) atomicAdd(&out[C + cc + tv - 4], t);
   }
-}
-
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t M, int C, float eps, float momentum,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mean = sums[c] / (double)M;
-  double var = sums[C + c] / (double)M - mean * mean;
-  if (var < 0.0) var = 0.0;
-  save_mean[c] = (float)mean;
-  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-  }
+  finalize_last_block(out, C, fin);
 }
 
 // y = (x - mean) * invstd * gamma + beta (ReLU); 4 channels per thread (C % 4 == 0).
@@ -162,8 +205,8 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t tota
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t M, int C,
                     const double* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta) {
+                    const float* __restrict__ gamma, const float* __restrict__ beta, int relu, const float* __restrict__ dgamma,
+                    const float* __restrict__ dbeta) {
   const int C4 = C / 4;
   const int64_t total4 = M * C4;
   const double invM = 1.0 / (double)M;
@@ -184,16 +227,10 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
       const float xh = (xs[q] - mus[q]) * iss[q];
       float g = gs[q];
       if (relu && !(fmaf(xh, gas[q], bes[q]) > 0.f)) g = 0.f;
-      const float mg = (float)(sums[c + q] * invM), mgx = (float)(sums[C + c + q] * invM);
+      const float mg = (float)((double)dbeta[c + q] * invM), mgx = (float)((double)dgamma[c + q] * invM);
       o[q] = gas[q] * iss[q] * (g - mg - xh * mgx);
     }
     reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] = (float)sums[C + c];
-      dbeta[c] = (float)sums[c];
-    }
   }
 }
 
@@ -268,16 +305,11 @@ ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
   }
 }
 
-__global__ void double_to_float_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
-}
-
 // Backward prologue of a dense layer, one pass over dy [M, C]:  g = relu ? dy * (y > 0) : dy;  optional outputs: g in fp32, g in
 // bf16 (operand of the tensor-core dgrad / wgrad GEMMs), and dbias[c] = sum_m g[m][c] (fp32 partials per thread, fp64 atomics).
 __global__ void __launch_bounds__(256)
 grad_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g32, __nv_bfloat16* __restrict__ g16,
-                 double* __restrict__ sums, int64_t M, int C) {
+                 double* __restrict__ sums, int64_t M, int C, Finalize fin) {
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -300,12 +332,13 @@ grad_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, floa
       for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
       atomicAdd(&sums[c], (double)t);
     }
+    finalize_last_block(sums, C, fin);
   }
 }
 
 template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
-                     const float* gamma, const float* beta, int relu, cudaStream_t stream);
+                     const float* gamma, const float* beta, int relu, Finalize fin, cudaStream_t stream);
 
 int colreduce_splits(int64_t M, int slabs) {
   int64_t want = (4LL * tfb_num_sms() + slabs - 1) / slabs;
@@ -318,31 +351,30 @@ int colreduce_splits(int64_t M, int slabs) {
 
 template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
-                     const float* gamma, const float* beta, int relu, cudaStream_t stream) {
+                     const float* gamma, const float* beta, int relu, Finalize fin, cudaStream_t stream) {
   const bool vec = C % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!dy || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
   dim3 block(32, 8);
   if (vec) {
     const int slabs = (C / 4 + 31) / 32;
     dim3 grid(slabs, colreduce_splits(M, slabs));
-    colreduce4_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu);
+    colreduce4_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, fin);
   } else {
     const int slabs = (C + 31) / 32;
     dim3 grid(slabs, colreduce_splits(M, slabs));
-    colreduce_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu);
+    colreduce_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, fin);
   }
   return 0;
 }
 
 }  // namespace
 
+// sums_ws: (2*C + 1) doubles, ZERO on entry, left zero on exit (shared by all layers of a stream; no memset launches).
 TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps,
                        float momentum, int relu, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                        double* sums_ws, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && sums_ws && M > 0 && C > 0 && C % 4 == 0);
-  if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, stream);
-  TFB_CHECK_LAUNCH();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
+  Finalize fin = {1, 2 * C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var};
+  launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, fin, stream);
   TFB_CHECK_LAUNCH();
   const int64_t total4 = M * C / 4;
   bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu);
@@ -360,12 +392,13 @@ TFB_API int tfb_bn_apply(const float* x, float* y, int64_t M, int C, const float
   return TFB_OK;
 }
 
+// sums_ws: as for tfb_bn_fwd.
 TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
                        const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
                        cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0 && C % 4 == 0);
-  if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, stream);
+  Finalize fin = {2, 2 * C, M, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
+  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, fin, stream);
   TFB_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<tfb_grid(M * C / 4, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
                                                                 dgamma, dbeta);
@@ -377,10 +410,8 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
 // x is [M, C] with row stride ldx (elements).
 TFB_API int tfb_colsum(const float* x, int64_t ldx, int64_t M, int C, float* out, double* sums_ws, cudaStream_t stream) {
   TFB_REQUIRE(x && out && sums_ws && M > 0 && C > 0 && ldx >= C);
-  if (cudaMemsetAsync(sums_ws, 0, 2 * (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  launch_colreduce<0>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, stream);
-  TFB_CHECK_LAUNCH();
-  double_to_float_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, out, C);
+  Finalize fin = {3, C, M, 0.f, 0.f, out, nullptr, nullptr, nullptr};
+  launch_colreduce<0>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, fin, stream);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -389,15 +420,11 @@ TFB_API int tfb_colsum(const float* x, int64_t ldx, int64_t M, int C, float* out
 TFB_API int tfb_grad_prep(const float* dy, const float* y, float* g32, void* g16_bf16, float* dbias, double* sums_ws, int64_t M, int C,
                           cudaStream_t stream) {
   TFB_REQUIRE(dy && M > 0 && C > 0 && (!dbias || sums_ws));
-  if (dbias && cudaMemsetAsync(sums_ws, 0, (size_t)C * sizeof(double), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   const int slabs = (C + 31) / 32;
   dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
-  grad_prep_kernel<<<grid, block, 0, stream>>>(dy, y, g32, (__nv_bfloat16*)g16_bf16, dbias ? sums_ws : nullptr, M, C);
+  Finalize fin = {dbias ? 3 : 0, C, M, 0.f, 0.f, dbias, nullptr, nullptr, nullptr};
+  grad_prep_kernel<<<grid, block, 0, stream>>>(dy, y, g32, (__nv_bfloat16*)g16_bf16, dbias ? sums_ws : nullptr, M, C, fin);
   TFB_CHECK_LAUNCH();
-  if (dbias) {
-    double_to_float_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums_ws, dbias, C);
-    TFB_CHECK_LAUNCH();
-  }
   return TFB_OK;
 }
 

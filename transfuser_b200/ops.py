@@ -46,6 +46,19 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_WS = {}
+
+
+def _ws(device):
+    """The per-device reduction workspace (fp64 sums + arrival counter) shared by every BatchNorm / bias-gradient reduction:
+    the kernels require it to be zero on entry and leave it zero on exit (last-block finalisation), so it is zeroed only once."""
+    t = _WS.get(device)
+    if t is None:
+        t = torch.zeros(2 * 8192 + 8, dtype=torch.float64, device=device)
+        _WS[device] = t
+    return t
+
+
 def _gbuf(p):
     """Output buffer for the gradient of parameter `p`. When the model was flattened (optim.flatten) and p.grad is None
     (zero_grad(set_to_none=True)), this is p's view of the flat gradient buffer: the backward kernel writes the gradient in
@@ -61,7 +74,7 @@ def _colsum(x2d, out=None):
     M, C = x2d.shape
     if out is None:
         out = torch.empty(C, dtype=torch.float32, device=x2d.device)
-    ws = torch.empty(2 * C, dtype=torch.float64, device=x2d.device)
+    ws = _ws(x2d.device)
     ld = C if x2d.is_contiguous() else x2d.stride(0)
     assert x2d.is_contiguous() or x2d.stride(1) == 1
     call('tfb_colsum', x2d, ld, M, C, out, ws)
@@ -75,7 +88,7 @@ def _grad_prep(dy2d, y2d, want32, want16, bias_p):
     g32 = torch.empty((M, C), dtype=torch.float32, device=dev) if (want32 and y2d is not None) else None
     g16 = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want16 else None
     db = _gbuf(bias_p) if bias_p is not None else None
-    ws = torch.empty(C, dtype=torch.float64, device=dev) if db is not None else None
+    ws = _ws(dev) if db is not None else None
     if g32 is not None or g16 is not None or db is not None:
         call('tfb_grad_prep', dy2d, y2d, g32, g16, db, ws, M, C)
     if want32 and g32 is None:
@@ -359,7 +372,7 @@ class BatchNormTrainFn(Function):
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        ws = _ws(x.device)
         call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.relu = relu
@@ -374,7 +387,7 @@ class BatchNormTrainFn(Function):
         dx = torch.empty_like(x)
         dg = _gbuf(weight)
         db = _gbuf(bias)
-        ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        ws = _ws(x.device)
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws)
         return dx, dg, db, None, None, None, None, None
 
