@@ -8,6 +8,8 @@ their forward is never called — every op runs through transfuser_b200.ops (han
 
 The RegNetY-3.2GF definition (timm 0.5.4 `regnety_032`: stem 32, widths 72/216/576/1512, depths 2/5/13/1, group width 24,
 SE ratio 0.25) is restated from timm's published config; timm itself is not a dependency."""
+import os
+
 import torch
 from torch import nn
 
@@ -221,6 +223,7 @@ class TransfuserBackbone(nn.Module):
         self.up_conv4 = nn.Conv2d(channel, channel, (1, 1))
         self.up_conv3 = nn.Conv2d(channel, channel, (1, 1))
         self.c5_conv = nn.Conv2d(c_out, channel, (1, 1))
+        self.two_streams = ops.TWO_STREAMS
 
     def _bn_modules(self):
         if not hasattr(self, '_bn_cache'):
@@ -235,12 +238,33 @@ class TransfuserBackbone(nn.Module):
         ie, le = self.image_encoder.features, self.lidar_encoder._model
         x = ops.image_prep(image) if self.image_encoder.normalize else ops.nchw_to_nhwc(image)
         l = ops.nchw_to_nhwc(lidar)
-        x = ie.stem.run(x)
-        l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
-        for i in range(1, 5):
-            x = getattr(ie, 's%d' % i).run(x)
-            l = getattr(le, 's%d' % i).run(l)
-            x, l = getattr(self, 'transformer%d' % i).run(x, l)
+        if not self.two_streams:
+            x = ie.stem.run(x)
+            l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
+            for i in range(1, 5):
+                x = getattr(ie, 's%d' % i).run(x)
+                l = getattr(le, 's%d' % i).run(l)
+                x, l = getattr(self, 'transformer%d' % i).run(x, l)
+        else:
+            # The two trunks are independent between fusion points: the LiDAR trunk runs on a second stream (forward here,
+            # backward automatically — autograd replays each node on its forward stream), so its small kernels fill the SMs the
+            # image trunk leaves idle. Joins before each GPT; forks after it. Captured into the step's CUDA graph as branches.
+            main = torch.cuda.current_stream()
+            side = ops.side_stream(image.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
+            x = ie.stem.run(x)
+            for i in range(1, 5):
+                with torch.cuda.stream(side):
+                    l = getattr(le, 's%d' % i).run(l)
+                x = getattr(ie, 's%d' % i).run(x)
+                main.wait_stream(side)
+                l.record_stream(main)
+                x, l = getattr(self, 'transformer%d' % i).run(x, l)
+                if i < 4:
+                    side.wait_stream(main)
+                    l.record_stream(side)
         x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
@@ -312,8 +336,18 @@ class LateFusionBackbone(nn.Module):
         if self.training:
             torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
             ops.tick(image.device)
-        x = self.image_encoder.run(ops.image_prep(image))
-        l = self.lidar_encoder.run(ops.nchw_to_nhwc(lidar))
+        if ops.TWO_STREAMS:
+            main, side = torch.cuda.current_stream(), ops.side_stream(image.device)
+            l = ops.nchw_to_nhwc(lidar)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                l = self.lidar_encoder.run(l)
+            x = self.image_encoder.run(ops.image_prep(image))
+            main.wait_stream(side)
+            l.record_stream(main)
+        else:
+            x = self.image_encoder.run(ops.image_prep(image))
+            l = self.lidar_encoder.run(ops.nchw_to_nhwc(lidar))
         x = ops.conv2d(x, self.reduce_channels_conv_image.weight, self.reduce_channels_conv_image.bias)
         l = ops.conv2d(l, self.reduce_channels_conv_lidar.weight, self.reduce_channels_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))

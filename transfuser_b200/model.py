@@ -129,6 +129,17 @@ class LidarCenterNet(nn.Module):
         if self.use_target_point_image:
             lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
         features, image_features_grid, fused_features = self._model.forward_nhwc(rgb, lidar_bev)
+        two = ops.TWO_STREAMS and cfg.multitask
+        if two:
+            # auxiliary decoders (image grid -> 160x704 maps) on the second stream, concurrently with the BEV-side heads
+            main, side = torch.cuda.current_stream(), ops.side_stream(rgb.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                pred_semantic = self.seg_decoder.run(image_features_grid)
+                pred_depth = self.depth_decoder.run(image_features_grid)
+                loss_depth = ops.L1Fn.apply(pred_depth.view(pred_depth.shape[0], pred_depth.shape[1], pred_depth.shape[2]), depth, True, float(cfg.ls_depth))
+                loss_semantic = ops.CrossEntropyFn.apply(pred_semantic, semantic, None, 'count', float(cfg.ls_seg))
+
         pred_wp, _, _, _, _ = self.forward_gru(fused_features, target_point)
 
         pred_bev = _run_pair(self.pred_bev, features[0])
@@ -146,7 +157,12 @@ class LidarCenterNet(nn.Module):
         for i, k in enumerate(HEAD_LOSSES):
             loss[k] = head_losses[i]
 
-        if cfg.multitask:
+        if two:
+            main.wait_stream(side)
+            loss_depth.record_stream(main)
+            loss_semantic.record_stream(main)
+            loss['loss_depth'], loss['loss_semantic'] = loss_depth, loss_semantic
+        elif cfg.multitask:
             pred_semantic = self.seg_decoder.run(image_features_grid)
             pred_depth = self.depth_decoder.run(image_features_grid)
             loss['loss_depth'] = ops.L1Fn.apply(pred_depth.view(pred_depth.shape[0], pred_depth.shape[1], pred_depth.shape[2]), depth, True, float(cfg.ls_depth))

@@ -3,6 +3,8 @@ hand-written sm_100a kernel launch; torch supplies device memory, the current st
 
 Activations are NHWC fp32 ([N, H, W, C], contiguous); parameters keep the reference's PyTorch layouts so that the
 reference's state_dicts load unchanged."""
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -47,15 +49,39 @@ def _c(t):
 
 
 _WS = {}
+_SIDE = {}
+TWO_STREAMS = os.environ.get('TFB_TWO_STREAMS', '1') == '1'
+
+
+def side_stream(device):
+    """The second CUDA stream on which independent branches of the step run (LiDAR trunk, auxiliary decoders)."""
+    device = torch.device(device)
+    s = _SIDE.get(device)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE[device] = s
+    return s
+
+
+def join_side_streams():
+    """Make the current stream wait for all work queued on the side streams (used before NCCL calls issued from autograd hooks)."""
+    if not _SIDE:
+        return
+    cur = torch.cuda.current_stream()
+    for s in _SIDE.values():
+        if s.device == cur.device:
+            cur.wait_stream(s)
+
 
 
 def _ws(device):
     """The per-device reduction workspace (fp64 sums + arrival counter) shared by every BatchNorm / bias-gradient reduction:
     the kernels require it to be zero on entry and leave it zero on exit (last-block finalisation), so it is zeroed only once."""
-    t = _WS.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)   # one workspace per stream: kernels of a stream run in order
+    t = _WS.get(key)
     if t is None:
         t = torch.zeros(2 * 8192 + 8, dtype=torch.float64, device=device)
-        _WS[device] = t
+        _WS[key] = t
     return t
 
 

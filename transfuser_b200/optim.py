@@ -8,6 +8,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import ops as ops_mod
 
 ALIGN = 64  # elements: keeps every parameter 256-byte aligned (TMA / float4 friendly)
 
@@ -142,6 +143,7 @@ class GradAllReducer:
                 self.pending[c] -= 1
                 if self.pending[c] == 0:
                     lo, hi = self.spans[c]
+                    ops_mod.join_side_streams()   # gradients of the LiDAR branch / decoders are produced on the second stream
                     self.works[c] = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
         return hook
 
@@ -151,6 +153,7 @@ class GradAllReducer:
         for c, (lo, hi) in enumerate(self.spans):
             w = self.works[c]
             if w is None and self.world > 1:
+                ops_mod.join_side_streams()
                 w = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
             out.append((lo, hi, w))
         self.reset()
