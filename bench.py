@@ -84,6 +84,7 @@ def run_b200(args):
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's version / debug banner must not land on stdout (one JSON line)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     B = args.batch
