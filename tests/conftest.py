@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box via gpurun)')
 
 
+@pytest.fixture(scope='session', autouse=True)
+def _built_library():
+    """The C-ABI library is a build product (git-ignored): build it once per session if it is not there yet
+    (nvcc cross-compiles sm_100a without a GPU)."""
+    from transfuser_b200 import build as b
+    if not os.path.isfile(b.LIB):
+        b.build(verbose=False)
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
