@@ -79,7 +79,13 @@ def test_full_model_forward_backward_matches_oracle():
 
     net = net.cuda().train()
     cb = {k: v.cuda() for k, v in batch.items()}
-    feats, grid, fused = net._model.forward_nhwc(cb['rgb'], torch.cat((cb['lidar'], cb['target_point_image']), dim=1))
+    mine = {}
+    feats, grid, fused = net._model.forward_nhwc(cb['rgb'], torch.cat((cb['lidar'], cb['target_point_image']), dim=1), taps=mine)
+    torch.cuda.synchronize()
+    for k in sorted(mine):   # per-stage activations after each GPT fusion (north_star: per-layer activations within 1e-3 rel)
+        e = rel(mine[k].permute(0, 3, 1, 2), taps[k])
+        print('activation %-8s rel err %.2e' % (k, e))
+        assert e < 1e-3, (k, e)
     assert rel(feats[0].permute(0, 3, 1, 2), taps['p2']) < 1e-3
     assert rel(grid.permute(0, 3, 1, 2), taps['img_grid']) < 1e-3 and rel(fused, taps['fused']) < 1e-3
     net.load_state_dict({k: v.detach().float() for k, v in build().state_dict().items()}, strict=False)  # undo the BN stat update

@@ -230,8 +230,9 @@ class TransfuserBackbone(nn.Module):
             object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
         return self._bn_cache
 
-    def forward_nhwc(self, image, lidar):
-        """image: NCHW 0..255, lidar: NCHW -> (p2..p5 NHWC), image grid NHWC, fused [B,512]."""
+    def forward_nhwc(self, image, lidar, taps=None):
+        """image: NCHW 0..255, lidar: NCHW -> (p2..p5 NHWC), image grid NHWC, fused [B,512]. `taps` (optional dict) receives the
+        per-stage fused feature maps (NHWC) for layer-by-layer parity checks."""
         if self.training:
             torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
             ops.tick(image.device)
@@ -245,6 +246,8 @@ class TransfuserBackbone(nn.Module):
                 x = getattr(ie, 's%d' % i).run(x)
                 l = getattr(le, 's%d' % i).run(l)
                 x, l = getattr(self, 'transformer%d' % i).run(x, l)
+                if taps is not None:
+                    taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
         else:
             # The two trunks are independent between fusion points: the LiDAR trunk runs on a second stream (forward here,
             # backward automatically — autograd replays each node on its forward stream), so its small kernels fill the SMs the
@@ -262,6 +265,8 @@ class TransfuserBackbone(nn.Module):
                 main.wait_stream(side)
                 l.record_stream(main)
                 x, l = getattr(self, 'transformer%d' % i).run(x, l)
+                if taps is not None:
+                    taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
                 if i < 4:
                     side.wait_stream(main)
                     l.record_stream(side)
