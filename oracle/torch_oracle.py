@@ -148,6 +148,75 @@ def backbone_late_fusion(P, image, lidar, cfg=Cfg, train=True, pre='_model.'):
     return (p2, p3, p4, p5), x, fused
 
 
+def _gather_sum(emb, pts):
+    """Sum of the 5 correspondences per cell (geometric_fusion.py:145-148): emb [B,C,h,w], pts [B,H,W,5,2] int64 (x, y) -> [B,C,H,W].
+    The reference indexes B x B and takes the diagonal; per-sample advanced indexing is the same selection."""
+    B, C = emb.shape[:2]
+    H, W = pts.shape[1], pts.shape[2]
+    e = emb.permute(0, 2, 3, 1)
+    bi = torch.arange(B).view(B, 1)
+    g = e[bi, pts[..., 1].reshape(B, -1), pts[..., 0].reshape(B, -1)]          # [B, H*W*5, C]
+    return g.view(B, H, W, 5, C).sum(3).permute(0, 3, 1, 2)
+
+
+def _proj3(P, pre, x):
+    """image/lidar_projection{i}: 3 x (Linear + ReLU) over the channel dim (geometric_fusion.py:66-74)."""
+    x = x.permute(0, 2, 3, 1)
+    for j in (0, 2, 4):
+        x = F.relu(F.linear(x, P['%s%d.weight' % (pre, j)], P['%s%d.bias' % (pre, j)]))
+    return x.permute(0, 3, 1, 2)
+
+
+def backbone_geometric_fusion(P, image, lidar, bev_points, img_points, cfg=Cfg, train=True, pre='_model.'):
+    """GeometricFusionBackbone.forward (geometric_fusion.py:98-296), n_scale 4, use_velocity False. Per scale: 1x1 embed to
+    n_embd, pool to the anchor grids, gather-sum 5 projected correspondences from the other modality, 3-layer MLP,
+    bilinear x(8,4,2,1), 1x1 back to the trunk width, residual add. Scale 4's image branch gathers from the scale-3
+    LiDAR embedding (geometric_fusion.py:277, reproduced)."""
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((image / 255.0) - mean) / std
+    ie, le = pre + 'image_encoder.features.', pre + 'lidar_encoder._model.'
+    x = _bn(P, ie + 'stem.bn.', F.conv2d(x, P[ie + 'stem.conv.weight'], None, stride=2, padding=1), train, True)
+    l = _bn(P, le + 'bn1.', F.conv2d(lidar, P[le + 'conv1.weight'], None, stride=2, padding=1), train, True)
+    c1 = lambda t, n: F.conv2d(t, P[pre + n + '.weight'], P[pre + n + '.bias'])
+    prev_lidar_embd = None
+    for s in range(4):
+        i = s + 1
+        x = _stage(P, '%ss%d.' % (ie, i), x, train, REGNET_DEPTHS[s])
+        l = _stage(P, '%ss%d.' % (le, i), l, train, REGNET_DEPTHS[s])
+        xe = F.adaptive_avg_pool2d(c1(x, 'image_conv%d' % i), (cfg.img_vert_anchors, cfg.img_horz_anchors))
+        lemb = F.adaptive_avg_pool2d(c1(l, 'lidar_conv%d' % i), (cfg.lidar_vert_anchors, cfg.lidar_horz_anchors))
+        bev_enc = _proj3(P, '%simage_projection%d.' % (pre, i), _gather_sum(xe, bev_points))
+        img_enc = _proj3(P, '%slidar_projection%d.' % (pre, i), _gather_sum(prev_lidar_embd if i == 4 else lemb, img_points))
+        if i < 4:
+            sf = 2 ** (3 - s)
+            bev_enc = F.interpolate(bev_enc, scale_factor=sf, mode='bilinear', align_corners=False)
+            img_enc = F.interpolate(img_enc, scale_factor=sf, mode='bilinear', align_corners=False)
+        l = l + c1(bev_enc, 'lidar_deconv%d' % i)
+        x = x + c1(img_enc, 'image_deconv%d' % i)
+        prev_lidar_embd = lemb
+    x = c1(x, 'change_channel_conv_image')
+    l = c1(l, 'change_channel_conv_lidar')
+    fused = x.mean((2, 3)) + l.mean((2, 3))
+    up = lambda t: F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+    p5 = F.relu(c1(l, 'c5_conv'))
+    p4 = F.relu(c1(up(p5), 'up_conv5'))
+    p3 = F.relu(c1(up(p4), 'up_conv4'))
+    p2 = F.relu(c1(up(p3), 'up_conv3'))
+    return (p2, p3, p4, p5), x, fused
+
+
+def synthetic_correspondences(B, seed=0, cfg=Cfg):
+    """Seeded int64 LiDAR<->camera correspondence indices of data.py:632-673's shape: bev_points [B,8,8,5,2] index the
+    5x22 image anchor grid (x<22, y<5), cam_points [B,5,22,5,2] index the 8x8 BEV anchor grid."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    ri = lambda hi, *s: torch.randint(0, hi, s, generator=g)
+    lh, lw, ih, iw = cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, cfg.img_vert_anchors, cfg.img_horz_anchors
+    bev = torch.stack((ri(iw, B, lh, lw, 5), ri(ih, B, lh, lw, 5)), -1)
+    cam = torch.stack((ri(lw, B, ih, iw, 5), ri(lh, B, ih, iw, 5)), -1)
+    return bev, cam
+
+
 def _decoder(P, pre, x, cfg):
     c = lambda t, n, act=True: (F.relu if act else (lambda z: z))(F.conv2d(t, P['%s%s.weight' % (pre, n)], P['%s%s.bias' % (pre, n)], padding=1))
     x = c(c(x, 'deconv1.0'), 'deconv1.2')
@@ -252,6 +321,8 @@ def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None, backbone_name='
     lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
     if backbone_name == 'late_fusion':
         feats, img_grid, fused = backbone_late_fusion(P, batch['rgb'], lidar, cfg, train)
+    elif backbone_name == 'geometric_fusion':
+        feats, img_grid, fused = backbone_geometric_fusion(P, batch['rgb'], lidar, batch['bev_points'], batch['cam_points'], cfg, train)
     else:
         feats, img_grid, fused = backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
     loss = {}

@@ -115,3 +115,28 @@ def test_late_fusion_oracle_and_state_dict_match_verbatim_reference():
         got = O.forward(P, batch, O.Cfg, train=True, backbone_name='late_fusion')
     for k in want:
         assert abs(float(want[k]) - float(got[k])) <= 1e-6 * max(abs(float(want[k])), 1e-6), k
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_geometric_fusion_oracle_matches_verbatim_reference():
+    """BASELINE config 4 (geometric_fusion.py): oracle restatement vs the reference module, batch 2 so that the
+    reference's B x B gather + diagonal (geometric_fusion.py:145-147) is exercised with distinct per-sample indices."""
+    m = ref_import.load()
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    torch.manual_seed(0)
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', 'geometric_fusion', 'regnety_032', 'regnety_032', use_velocity=False).train()
+    names = [(n, tuple(p.shape)) for n, p in list(ref.named_parameters()) + list(ref.named_buffers())]
+    ref.load_state_dict(O.deterministic_state(names, seed=8), strict=False)
+    batch = O.synthetic_batch(2, seed=5)
+    batch['bev_points'], batch['cam_points'] = O.synthetic_correspondences(2, seed=5)
+    P = {k: v.clone() for k, v in ref.state_dict().items()}
+    with torch.no_grad():
+        want = ref(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                   target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                   depth=batch['depth'], semantic=batch['semantic'], bev_points=batch['bev_points'], cam_points=batch['cam_points'])
+        got = O.forward(P, batch, O.Cfg, train=True, backbone_name='geometric_fusion')
+    assert set(want) == set(got)
+    for k in want:
+        # fp32: the gather-sum adds the 5 correspondences in a different order than the reference's diagonal/permute/sum
+        assert abs(float(want[k]) - float(got[k])) <= 1e-4 * max(abs(float(want[k])), 1e-3), (k, float(want[k]), float(got[k]))
