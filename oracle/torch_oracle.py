@@ -316,26 +316,38 @@ def centernet_losses(preds, label, cfg):
     return out
 
 
-def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None, backbone_name='transFuser'):
-    """LidarCenterNet.forward (model.py:733-805): dict of the 11 losses. `P` maps reference state_dict names to tensors."""
+HEAD_NAMES = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
+
+
+def _run_backbone(P, batch, cfg, train, drop, taps, backbone_name):
     lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
     if backbone_name == 'late_fusion':
-        feats, img_grid, fused = backbone_late_fusion(P, batch['rgb'], lidar, cfg, train)
-    elif backbone_name == 'geometric_fusion':
-        feats, img_grid, fused = backbone_geometric_fusion(P, batch['rgb'], lidar, batch['bev_points'], batch['cam_points'], cfg, train)
-    else:
-        feats, img_grid, fused = backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
+        return backbone_late_fusion(P, batch['rgb'], lidar, cfg, train)
+    if backbone_name == 'geometric_fusion':
+        return backbone_geometric_fusion(P, batch['rgb'], lidar, batch['bev_points'], batch['cam_points'], cfg, train)
+    return backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
+
+
+def _conv_pair(P, name, x):
+    return F.conv2d(F.relu(F.conv2d(x, P[name + '.0.weight'], P[name + '.0.bias'], padding=1)), P[name + '.2.weight'], P[name + '.2.bias'])
+
+
+def head_preds(P, feat):
+    """LidarCenterNetHead.forward_single (model.py:101-125): seven conv3x3+ReLU+conv1x1 branches, sigmoid on the heatmap."""
+    preds = [_conv_pair(P, 'head.' + n, feat) for n in HEAD_NAMES]
+    preds[0] = preds[0].sigmoid()
+    return preds
+
+
+def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None, backbone_name='transFuser'):
+    """LidarCenterNet.forward (model.py:733-805): dict of the 11 losses. `P` maps reference state_dict names to tensors."""
+    feats, img_grid, fused = _run_backbone(P, batch, cfg, train, drop, taps, backbone_name)
     loss = {}
     wp = gru_waypoints(P, fused, batch['target_point'], cfg)
-    head = lambda name, x: F.conv2d(F.relu(F.conv2d(x, P[name + '.0.weight'], P[name + '.0.bias'], padding=1)),
-                                    P[name + '.2.weight'], P[name + '.2.bias'])
-    pb = F.interpolate(head('pred_bev', feats[0]), (cfg.bev_resolution_height, cfg.bev_resolution_width), mode='bilinear', align_corners=True)
+    pb = F.interpolate(_conv_pair(P, 'pred_bev', feats[0]), (cfg.bev_resolution_height, cfg.bev_resolution_width), mode='bilinear', align_corners=True)
     loss['loss_wp'] = (wp - batch['ego_waypoint']).abs().mean()
     loss['loss_bev'] = F.cross_entropy(pb, batch['bev'], weight=torch.tensor([1., 1., 3.]))
-    names = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
-    preds = [head('head.' + n, feats[0]) for n in names]
-    preds[0] = preds[0].sigmoid()
-    loss.update(centernet_losses(preds, batch['label'], cfg))
+    loss.update(centernet_losses(head_preds(P, feats[0]), batch['label'], cfg))
     if cfg.multitask:
         seg = _decoder(P, 'seg_decoder.', img_grid, cfg)
         depth = torch.sigmoid(_decoder(P, 'depth_decoder.', img_grid, cfg)).squeeze(1)
@@ -344,6 +356,58 @@ def forward(P, batch, cfg=Cfg, train=True, drop=None, taps=None, backbone_name='
     if taps is not None:
         taps.update(p2=feats[0], img_grid=img_grid, fused=fused, pred_wp=wp)
     return loss
+
+
+# ------------------------------------------------------------------ inference: CenterNet decode + forward_ego
+def decode_heatmap(preds, num_dir_bins=12, k=100, kernel=3, ratio=4.0, stable=False):
+    """LidarCenterNetHead.decode_heatmap (model.py:436-497) with mmdet 2.25.0's get_local_maximum / get_topk_from_heatmap /
+    transpose_and_gather_feat folded in. preds: the 7 NCHW maps of head_preds (heatmap already a probability).
+    Returns boxes [B,k,8] = (x, y, w, h in LiDAR-BEV pixels, yaw, velocity, brake class, score) sorted by score, labels [B,k].
+    torch.topk leaves the order of equal scores unspecified; `stable=True` fixes it (equal scores by ascending cell index,
+    the CUDA kernel's rule) and is otherwise the same computation."""
+    heat, wh, off, yaw_cls, yaw_res, vel, brake = preds
+    B, _, H, W = heat.shape
+    peak = F.max_pool2d(heat, kernel, stride=1, padding=(kernel - 1) // 2) == heat
+    kept = (heat * peak.float()).view(B, -1)
+    if stable:
+        score, flat = torch.sort(kept, dim=1, descending=True, stable=True)
+        score, flat = score[:, :k], flat[:, :k]
+    else:
+        score, flat = torch.topk(kept, k)
+    labels, cell = flat // (H * W), flat % (H * W)
+    ys, xs = (cell // W).float(), (cell % W).float()
+    at = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, t.shape[1]).gather(1, cell.unsqueeze(2).expand(-1, -1, t.shape[1]))
+    wh, off = at(wh), at(off)
+    yaw = at(yaw_cls).argmax(-1).float() * (2 * np.pi / float(num_dir_bins)) + at(yaw_res).squeeze(2)   # class2angle, model.py:269-283
+    yaw = torch.where(yaw > np.pi, yaw - 2 * np.pi, yaw)
+    geom = torch.stack([xs + off[..., 0], ys + off[..., 1], wh[..., 0], wh[..., 1]], dim=2) * ratio
+    rest = torch.stack([yaw, at(vel)[..., 0], at(brake).argmax(-1).float(), score], dim=2)
+    return torch.cat((geom, rest), dim=2), labels
+
+
+def bbox_local_metric(bbox, pixels_per_meter=8.0, bounding_box_divisor=2.0, lidar_pos=(1.3, 0.0, 2.5)):
+    """LidarCenterNet.get_bbox_local_metric (model.py:810-844): one decoded row -> (6x3 array: 4 corners, centre, velocity
+    tip in the ego frame, metres; brake; confidence). The BEV-pixel -> LiDAR map is the inverse of utils.py:29-37's T = 8*[[0,-1,16],[-1,0,32]]."""
+    x, y, w, h, yaw, speed, brake, confidence = bbox
+    w = w / bounding_box_divisor / pixels_per_meter
+    h = h / bounding_box_divisor / pixels_per_meter
+    T = np.array([[0, -1, 16], [-1, 0, 32], [0, 0, 1]], dtype=np.float32)
+    T[:2, :] *= 8
+    c = np.linalg.inv(T) @ np.array([x, y, 1.0]) + np.array(lidar_pos)
+    c[1] = -c[1]
+    pts = np.array([[-h, -w, 1], [-h, w, 1], [h, w, 1], [h, -w, 1], [0, 0, 1], [0, h * speed * 0.5, 1]])
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    return pts @ R.T + np.array([c[0], c[1], 0]), brake, confidence
+
+
+def forward_ego(P, batch, cfg=Cfg, backbone_name='transFuser', bb_confidence_threshold=0.3):
+    """LidarCenterNet.forward_ego (model.py:685-731) in eval mode: (pred_wp, list of 6x3 boxes of sample 0 above threshold)."""
+    feats, _, fused = _run_backbone(P, batch, cfg, False, None, None, backbone_name)
+    wp = gru_waypoints(P, fused, batch['target_point'], cfg)
+    boxes, _ = decode_heatmap(head_preds(P, feats[0]), cfg.num_dir_bins)
+    b0 = boxes[0]
+    b0 = b0[b0[:, -1] > bb_confidence_threshold]
+    return wp, [bbox_local_metric(r) for r in b0.detach().cpu().numpy()], boxes
 
 
 # ------------------------------------------------------------------ deterministic synthetic data / weights

@@ -140,3 +140,55 @@ def test_geometric_fusion_oracle_matches_verbatim_reference():
     for k in want:
         # fp32: the gather-sum adds the 5 correspondences in a different order than the reference's diagonal/permute/sum
         assert abs(float(want[k]) - float(got[k])) <= 1e-4 * max(abs(float(want[k])), 1e-3), (k, float(want[k]), float(got[k]))
+
+
+def _ref_eval_model(m, backbone, seed):
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    cfg.n_layer = 4
+    torch.manual_seed(0)
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', backbone, 'regnety_032', 'regnety_032', use_velocity=False)
+    names = [(n, tuple(p.shape)) for n, p in list(ref.named_parameters()) + list(ref.named_buffers())]
+    ref.load_state_dict(O.deterministic_state(names, seed=seed), strict=False)
+    return ref.eval()
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_decode_heatmap_oracle_matches_reference_head():
+    """model.py:376-497 (get_bboxes / decode_heatmap) on seeded maps with plateaus, saturated peaks and border maxima."""
+    m = ref_import.load()
+    ref = _ref_eval_model(m, 'transFuser', 3)
+    g = torch.Generator().manual_seed(21)
+    for case in range(3):
+        B = 2
+        heat = torch.rand(B, 1, 64, 64, generator=g)
+        if case == 1:
+            heat = (heat * 8).round() / 8            # plateaus: equal neighbours are all kept by (hmax == heat)
+        if case == 2:
+            heat = heat * (heat > 0.995)             # fewer than k peaks: the tail of the top-k is zeros
+        preds = [heat] + [torch.randn(B, c, 64, 64, generator=g) for c in (2, 2, 12, 1, 1, 2)]
+        want = ref.head.get_bboxes(*[[p] for p in preds])
+        got_boxes, got_labels = O.decode_heatmap(preds, 12)
+        for b in range(B):
+            wb, wl = want[b]
+            keep = wb[:, -1] > 0                     # rows with score 0 are an arbitrary choice among equal zeros
+            if case != 1:                            # (ties between equal positive scores are ordered arbitrarily by topk)
+                assert torch.equal(wb[keep], got_boxes[b][keep]) and torch.equal(wl[keep], got_labels[b][keep])
+            else:
+                assert torch.equal(wb[:, -1], got_boxes[b][:, -1])
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_forward_ego_oracle_matches_verbatim_reference():
+    """model.py:685-731 in eval mode (running-stat BN, no dropout): waypoints, decoded boxes, ego-frame box corners."""
+    m = ref_import.load()
+    ref = _ref_eval_model(m, 'transFuser', 9)
+    batch = O.synthetic_batch(1, seed=6)
+    P = {k: v.clone() for k, v in ref.state_dict().items()}
+    with torch.no_grad():
+        wp, boxes = ref.forward_ego(batch['rgb'], batch['lidar'], batch['target_point'], batch['target_point_image'], batch['ego_vel'])
+        got_wp, got_boxes, raw = O.forward_ego(P, batch, O.Cfg)
+    assert torch.allclose(wp, got_wp, rtol=1e-5, atol=1e-5)
+    assert len(boxes) == len(got_boxes) and len(boxes) > 0, (len(boxes), len(got_boxes), float(raw[0, 0, -1]))
+    for (a, abrake, aconf), (b, bbrake, bconf) in zip(boxes, got_boxes):
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5) and abrake == bbrake and abs(aconf - bconf) < 1e-6

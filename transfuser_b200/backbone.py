@@ -367,3 +367,122 @@ class LateFusionBackbone(nn.Module):
     def forward(self, image, lidar, velocity):
         feats, grid, fused = self.forward_nhwc(image, lidar)
         return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused
+
+
+class _GeoLidarEncoder(nn.Module):
+    """geometric_fusion.py:353-403: like transfuser.py's LidarEncoder, but the whole `stem` is deleted after aliasing, so the
+    stem's parameters live under `conv1` / `bn1` only."""
+
+    def __init__(self, architecture, in_channels=2):
+        super().__init__()
+        if architecture != 'regnety_032':
+            raise RuntimeError('transfuser_b200 implements the regnety_032 trunk only, got %r' % (architecture,))
+        m = self._model = _RegNet()
+        old = m.stem.conv
+        m.conv1, m.bn1 = m.stem.conv, m.stem.bn
+        m.layer1, m.layer2, m.layer3, m.layer4 = m.s1, m.s2, m.s3, m.s4
+        m.conv1 = nn.Conv2d(in_channels, old.out_channels, kernel_size=old.kernel_size, stride=old.stride, padding=old.padding, bias=False)
+        del m.stem
+
+
+def _mlp3(hid):
+    return nn.Sequential(nn.Linear(hid, hid), nn.ReLU(True), nn.Linear(hid, hid), nn.ReLU(True), nn.Linear(hid, hid), nn.ReLU(True))
+
+
+class GeometricFusionBackbone(nn.Module):
+    """B200-native drop-in for /root/reference/team_code_transfuser/geometric_fusion.py:7-296 (BASELINE config 4): at each of
+    the 4 trunk scales, features of one modality are pooled to its anchor grid, gathered at 5 projected correspondences per
+    cell of the other modality's grid, summed, passed through a 3-layer MLP and added back at full resolution.
+
+    Same parameter names / shapes as the reference. Two exact-in-real-arithmetic reassociations keep the work on the
+    anchor grids instead of the full maps (both ops are linear, bilinear weights sum to 1):
+      avgpool(conv1x1(x))           -> conv1x1(avgpool(x))          (geometric_fusion.py:132-135)
+      conv1x1(interpolate(enc))     -> interpolate(conv1x1(enc))    (geometric_fusion.py:150-151)
+    so the 512-channel embeddings only ever exist as [B,5,22,512] / [B,8,8,512]. fp32 rounding differs at the 1e-6 level.
+    The scale-4 image branch gathers from the scale-3 LiDAR embedding, as the reference does (geometric_fusion.py:277)."""
+
+    def __init__(self, config, image_architecture='resnet34', lidar_architecture='resnet18', use_velocity=0):
+        super().__init__()
+        self.config = config
+        if config.use_point_pillars:
+            raise RuntimeError('PointPillars LiDAR encoder is out of scope (config.py:42 default False)')
+        if use_velocity:
+            raise RuntimeError('use_velocity=True is not implemented (train.py:54 default is 0)')
+        if config.n_scale != 4:
+            raise RuntimeError('n_scale=%r is not implemented (config.py default 4)' % (config.n_scale,))
+        self.use_velocity = use_velocity
+        in_channels = 2 * config.lidar_seq_len + (1 if config.use_target_point_image else 0)
+        self.image_encoder = ImageCNN(architecture=image_architecture, normalize=True)
+        self.lidar_encoder = _GeoLidarEncoder(architecture=lidar_architecture, in_channels=in_channels)
+        widths, hid = REGNETY_032['widths'], config.n_embd
+        for stem in ('image_conv', 'image_deconv', 'lidar_conv', 'lidar_deconv'):
+            for i in range(4):
+                cin, cout = (hid, widths[i]) if 'deconv' in stem else (widths[i], hid)
+                setattr(self, '%s%d' % (stem, i + 1), nn.Conv2d(cin, cout, 1))
+        for stem in ('image_projection', 'lidar_projection'):
+            for i in range(4):
+                setattr(self, '%s%d' % (stem, i + 1), _mlp3(hid))
+        c_out = config.perception_output_features
+        self.change_channel_conv_image = nn.Conv2d(widths[-1], c_out, (1, 1))
+        self.change_channel_conv_lidar = nn.Conv2d(widths[-1], c_out, (1, 1))
+        channel = config.bev_features_chanels
+        self.up_conv5 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv4 = nn.Conv2d(channel, channel, (1, 1))
+        self.up_conv3 = nn.Conv2d(channel, channel, (1, 1))
+        self.c5_conv = nn.Conv2d(c_out, channel, (1, 1))
+
+    def _bn_modules(self):
+        if not hasattr(self, '_bn_cache'):
+            object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
+        return self._bn_cache
+
+    @staticmethod
+    def _project(mlp, x):
+        for j in (0, 2, 4):
+            x = ops.linear(x, mlp[j].weight, mlp[j].bias, relu=True)
+        return x
+
+    def forward_nhwc(self, image, lidar, bev_points, img_points):
+        """image NCHW 0..255, lidar NCHW, bev_points [B,8,8,5,2] / img_points [B,5,22,5,2] int64 (x, y) correspondences."""
+        cfg = self.config
+        if self.training:
+            torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
+            ops.tick(image.device)
+        ie, le = self.image_encoder.features, self.lidar_encoder._model
+        x = ie.stem.run(ops.image_prep(image))
+        l = ops.batch_norm(ops.conv2d(ops.nchw_to_nhwc(lidar), le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
+        ih, iw, lh, lw = cfg.img_vert_anchors, cfg.img_horz_anchors, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors
+        prev_lidar_embd = None
+        for i in range(1, 5):
+            x = getattr(ie, 's%d' % i).run(x)
+            l = getattr(le, 's%d' % i).run(l)
+            ic, lc = getattr(self, 'image_conv%d' % i), getattr(self, 'lidar_conv%d' % i)
+            img_embd = ops.linear(ops.avgpool_grid(x, ih, iw), ic.weight, ic.bias)          # [B,5,22,512]
+            # scale 4's LiDAR embedding is never read (the image branch gathers from scale 3's, geometric_fusion.py:277)
+            lidar_embd = ops.linear(ops.avgpool_grid(l, lh, lw), lc.weight, lc.bias) if i < 4 else None   # [B,8,8,512]
+            bev_enc = self._project(getattr(self, 'image_projection%d' % i), ops.gather_sum(img_embd, bev_points))
+            img_enc = self._project(getattr(self, 'lidar_projection%d' % i),
+                                    ops.gather_sum(prev_lidar_embd if i == 4 else lidar_embd, img_points))
+            ld, idc = getattr(self, 'lidar_deconv%d' % i), getattr(self, 'image_deconv%d' % i)
+            dl = ops.linear(bev_enc, ld.weight, ld.bias)                                    # [B,8,8,C_i]
+            dx = ops.linear(img_enc, idc.weight, idc.bias)                                  # [B,5,22,C_i]
+            if i < 4:
+                dl = ops.upsample(dl, l.shape[1], l.shape[2], False)
+                dx = ops.upsample(dx, x.shape[1], x.shape[2], False)
+            l = ops.add(l, dl)
+            x = ops.add(x, dx)
+            prev_lidar_embd = lidar_embd
+        x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
+        l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
+        fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
+        f = cfg.bev_upsample_factor
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
+        p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
+        p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)
+        p2 = ops.conv2d(up(p3), self.up_conv3.weight, self.up_conv3.bias, relu=True)
+        return (p2, p3, p4, p5), x, fused
+
+    def forward(self, image, lidar, velocity, bev_points, img_points):
+        feats, grid, fused = self.forward_nhwc(image, lidar, bev_points, img_points)
+        return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused

@@ -20,6 +20,12 @@ class TrainConfig:
     use_point_pillars = False
     max_lidar_points = 40000
     backbone = 'transFuser'
+    # inference-side box decode (config.py:16, 39, 58-62)
+    pixels_per_meter = 8.0
+    bb_confidence_threshold = 0.3
+    top_k_center_keypoints = 100
+    center_net_max_pooling_kernel = 3
+    bounding_box_divisor = 2.0
     # CenterNet (config.py:52-60)
     num_dir_bins = 12
     fp16_enabled = False
@@ -48,8 +54,10 @@ class TrainConfig:
     deconv_scale_factor_1 = 8
     deconv_scale_factor_2 = 4
     # GPT (config.py:174-185; n_layer 4 per train.py:56)
+    n_embd = 512
     block_exp = 4
     n_layer = 4
+    n_scale = 4
     n_head = 4
     embd_pdrop = 0.1
     resid_pdrop = 0.1

@@ -4,12 +4,14 @@ Same constructor and `forward(...) -> dict of the 11 scalar losses` contract (ke
 parameter names (`_model.*`, `seg_decoder.*`, `depth_decoder.*`, `pred_bev.*`, `head.*_head.*`, `join.*`, `decoder.*`,
 `output.*`), so train.py's loop (`loss.backward()`, `optimizer.step()`, `state_dict()`) runs unchanged. The nn.* members
 are parameter containers; all compute goes through transfuser_b200.ops (hand-written sm_100a kernels).
-Inference-only members of the reference class (forward_ego, control_pid, visualisation) are out of scope this round."""
+`forward_ego` (model.py:685-731: waypoints + decoded boxes for the driving agent) runs the same kernels in eval mode plus the
+one-launch CenterNet decode; the agent-side control / visualisation members (control_pid, visualize_model_io) are out of scope."""
+import numpy as np
 import torch
 from torch import nn
 
 from . import ops
-from .backbone import LateFusionBackbone, TransfuserBackbone
+from .backbone import GeometricFusionBackbone, LateFusionBackbone, TransfuserBackbone
 
 HEAD_NAMES = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
 HEAD_LOSSES = ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res', 'loss_velocity', 'loss_brake')
@@ -43,6 +45,16 @@ class LidarCenterNetHead(nn.Module):
     def run(self, feat):
         """feat NHWC -> [B, H, W, 21] raw predictions (heat logit | wh | offset | yaw class | yaw res | velocity | brake)."""
         return torch.cat([_run_pair(getattr(self, n), feat) for n in HEAD_NAMES], dim=3)
+
+    def get_bboxes_nhwc(self, preds):
+        """model.py:376-497 (get_bboxes with with_nms=False -> decode_heatmap) on the raw NHWC head output of `run`:
+        list over the batch of (boxes [k,8] = x, y, w, h, yaw, velocity, brake, score; labels [k])."""
+        cfg = self.train_cfg
+        kernel = getattr(cfg, 'center_net_max_pooling_kernel', 3)
+        if kernel != 3:
+            raise RuntimeError('center_net_max_pooling_kernel=%r is not implemented (config.py:59 default 3)' % (kernel,))
+        boxes, labels = ops.centernet_decode(preds, self.num_dir_bins, getattr(cfg, 'top_k_center_keypoints', 100), 4.0)
+        return [(boxes[b], labels[b]) for b in range(boxes.shape[0])]
 
 
 class _Decoder(nn.Module):
@@ -97,8 +109,10 @@ class LidarCenterNet(nn.Module):
             self._model = TransfuserBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
         elif backbone == 'late_fusion':
             self._model = LateFusionBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        elif backbone == 'geometric_fusion':
+            self._model = GeometricFusionBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
         else:
-            raise RuntimeError('implemented backbones: "transFuser", "late_fusion"; got %r' % (backbone,))
+            raise RuntimeError('implemented backbones: "transFuser", "late_fusion", "geometric_fusion"; got %r' % (backbone,))
         if config.multitask:
             self.seg_decoder = SegDecoder(config, config.perception_output_features).to(self.device)
             self.depth_decoder = DepthDecoder(config, config.perception_output_features).to(self.device)
@@ -122,13 +136,55 @@ class LidarCenterNet(nn.Module):
                                   self.pred_len, float(self.config.lidar_pos[0]))
         return pred_wp, None, None, None, None
 
+    def _run_backbone(self, rgb, lidar_bev, bev_points, cam_points):
+        if self.backbone == 'geometric_fusion':
+            if bev_points is None or cam_points is None:
+                raise RuntimeError('the geometric_fusion backbone needs bev_points and cam_points (train.py:281-288)')
+            return self._model.forward_nhwc(rgb, lidar_bev, bev_points, cam_points)
+        return self._model.forward_nhwc(rgb, lidar_bev)
+
+    def get_bbox_local_metric(self, bbox):
+        """model.py:810-842: one decoded row (x, y, w, h, yaw, speed, brake, confidence; LiDAR-BEV pixels) -> (6x3 array: the
+        4 corners, centre and velocity tip in the ego frame in metres; brake; confidence). Host numpy, as in the reference."""
+        cfg = self.config
+        x, y, w, h, yaw, speed, brake, confidence = bbox
+        scale = cfg.bounding_box_divisor * cfg.pixels_per_meter
+        w, h = w / scale, h / scale
+        # inverse of utils.py:29-37's LiDAR -> BEV-image map  p = 8 * [[0,-1,16],[-1,0,32]] @ (X, Y, 1)
+        ppm = 8.0
+        cx = (32.0 * ppm - y) / ppm + cfg.lidar_pos[0]
+        cy = -((16.0 * ppm - x) / ppm + cfg.lidar_pos[1])
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        local = np.array([[-h, -w], [-h, w], [h, w], [h, -w], [0.0, 0.0], [0.0, h * speed * 0.5]], dtype=np.float64)
+        out = np.ones((6, 3), dtype=np.float64)
+        out[:, 0] = c * local[:, 0] - s_ * local[:, 1] + cx
+        out[:, 1] = s_ * local[:, 0] + c * local[:, 1] + cy
+        return out, brake, confidence
+
+    @torch.no_grad()
+    def forward_ego(self, rgb, lidar_bev, target_point, target_point_image, ego_vel, bev_points=None, cam_points=None, save_path=None,
+                    expert_waypoints=None, stuck_detector=0, forced_move=False, num_points=None, rgb_back=None, debug=False):
+        """model.py:685-731: (pred_wp [B,4,2], list of (corners, brake, confidence) for sample 0's boxes above
+        config.bb_confidence_threshold). Debug visualisation (model.py:720-728) is not implemented."""
+        if debug and save_path is not None:
+            raise RuntimeError('forward_ego(debug=True) visualisation is out of scope')
+        if self.use_target_point_image:
+            lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
+        features, _, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points)
+        pred_wp, _, _, _, _ = self.forward_gru(fused_features, target_point)
+        bboxes, _ = self.head.get_bboxes_nhwc(self.head.run(features[0]))[0]
+        bboxes = bboxes[bboxes[:, -1] > self.config.bb_confidence_threshold]
+        rotated_bboxes = [self.get_bbox_local_metric(b) for b in bboxes.cpu().numpy()]
+        self.i += 1
+        return pred_wp, rotated_bboxes
+
     def forward(self, rgb, lidar_bev, ego_waypoint, target_point, target_point_image, ego_vel, bev, label, depth, semantic,
                 num_points=None, save_path=None, bev_points=None, cam_points=None):
         cfg = self.config
         loss = {}
         if self.use_target_point_image:
             lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
-        features, image_features_grid, fused_features = self._model.forward_nhwc(rgb, lidar_bev)
+        features, image_features_grid, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points)
         two = ops.TWO_STREAMS and cfg.multitask
         if two:
             # auxiliary decoders (image grid -> 160x704 maps) on the second stream, concurrently with the BEV-side heads

@@ -714,6 +714,74 @@ def upsample(x, Ho, Wo, align_corners=False):
     return UpsampleFn.apply(x, Ho, Wo, align_corners)
 
 
+class AvgPoolGridFn(Function):
+    """AdaptiveAvgPool2d((gh, gw)) on NHWC maps whose sides divide evenly (geometric_fusion.py:19-20)."""
+
+    @staticmethod
+    def forward(ctx, x, gh, gw):
+        x = _c(x)
+        N, H, W, C = x.shape
+        out = torch.empty((N, gh, gw, C), dtype=torch.float32, device=x.device)
+        call('tfb_avgpool_grid_fwd', x, out, N, H, W, C, gh, gw)
+        ctx.cfg = (N, H, W, C, gh, gw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, C, gh, gw = ctx.cfg
+        dout = _c(dout)
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dout.device)
+        call('tfb_avgpool_grid_bwd', dout, dx, N, H, W, C, gh, gw, 0)
+        return dx, None, None
+
+
+def avgpool_grid(x, gh, gw):
+    return AvgPoolGridFn.apply(x, gh, gw)
+
+
+class GatherSumFn(Function):
+    """out[b,Y,X,:] = sum_j emb[b, pts[b,Y,X,j,1], pts[b,Y,X,j,0], :] — the B x B advanced index + diagonal + sum of
+    geometric_fusion.py:145-148 as one gather; backward scatters with float atomics."""
+
+    @staticmethod
+    def forward(ctx, emb, pts):
+        emb, pts = _c(emb), _c(pts)
+        if pts.dtype != torch.int64 or pts.dim() != 5 or pts.shape[-1] != 2 or pts.shape[0] != emb.shape[0]:
+            raise RuntimeError('correspondences must be int64 [B, H, W, P, 2], got %s %s' % (pts.dtype, tuple(pts.shape)))
+        B, h, w, C = emb.shape
+        _, H, W, P, _ = pts.shape
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=emb.device)
+        call('tfb_gather_sum_fwd', emb, pts, out, B, h, w, C, H * W, P)
+        ctx.save_for_backward(pts)
+        ctx.cfg = (B, h, w, C, H * W, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pts, = ctx.saved_tensors
+        B, h, w, C, M, P = ctx.cfg
+        dout = _c(dout)
+        demb = torch.empty((B, h, w, C), dtype=torch.float32, device=dout.device)
+        call('tfb_gather_sum_bwd', dout, pts, demb, B, h, w, C, M, P)
+        return demb, None
+
+
+def gather_sum(emb, pts):
+    return GatherSumFn.apply(emb, pts)
+
+
+def centernet_decode(preds, num_dir_bins, k=100, ratio=4.0):
+    """preds: raw head output [B,H,W,9+num_dir_bins] (NHWC). Returns (boxes [B,k,8], labels [B,k] int64), model.py:436-497."""
+    preds = _c(preds)
+    B, H, W, C = preds.shape
+    if C != 9 + num_dir_bins:
+        raise RuntimeError('head output has %d channels, expected %d' % (C, 9 + num_dir_bins))
+    boxes = torch.empty((B, k, 8), dtype=torch.float32, device=preds.device)
+    labels = torch.empty((B, k), dtype=torch.int32, device=preds.device)
+    call('tfb_centernet_decode', preds, B, H, W, num_dir_bins, k, float(ratio), boxes, labels)
+    return boxes, labels.long()
+
+
 class PoolHWFn(Function):
     @staticmethod
     def forward(ctx, x):
