@@ -96,7 +96,7 @@ def _gpt(P, pre, img, lid, cfg, train, drop):
     return x[:, :n_img, :].contiguous().view(bz, -1, ih, iw), x[:, n_img:, :].contiguous().view(bz, -1, lh, lw)
 
 
-def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', taps=None):
+def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', taps=None, lidar_bn='stem.bn.'):
     """TransfuserBackbone.forward (transfuser.py:120-211). `taps` (dict) collects per-stage activations."""
     drop = drop or (lambda t, p: t)
     mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
@@ -104,7 +104,7 @@ def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', tap
     x = ((image / 255.0) - mean) / std
     ie, le = pre + 'image_encoder.features.', pre + 'lidar_encoder._model.'
     x = _bn(P, ie + 'stem.bn.', F.conv2d(x, P[ie + 'stem.conv.weight'], None, stride=2, padding=1), train, True)
-    l = _bn(P, le + 'stem.bn.', F.conv2d(lidar, P[le + 'conv1.weight'], None, stride=2, padding=1), train, True)
+    l = _bn(P, le + lidar_bn, F.conv2d(lidar, P[le + 'conv1.weight'], None, stride=2, padding=1), train, True)
     for s in range(4):
         x = _stage(P, '%ss%d.' % (ie, s + 1), x, train, REGNET_DEPTHS[s])
         l = _stage(P, '%ss%d.' % (le, s + 1), l, train, REGNET_DEPTHS[s])
@@ -124,6 +124,17 @@ def backbone(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.', tap
     p3 = F.relu(F.conv2d(up(p4), P[pre + 'up_conv4.weight'], P[pre + 'up_conv4.bias']))
     p2 = F.relu(F.conv2d(up(p3), P[pre + 'up_conv3.weight'], P[pre + 'up_conv3.bias']))
     return (p2, p3, p4, p5), x, fused
+
+
+def backbone_latent_tf(P, image, lidar, cfg=Cfg, train=True, drop=None, pre='_model.'):
+    """latentTFBackbone.forward (latentTF.py:118-217): the TransFuser architecture with the two LiDAR histogram channels replaced
+    by a fixed positional grid in [-1, 1] (channel 0 varies top-down, channel 1 left-right, latentTF.py:132-137); the target
+    point channel is kept. Its LidarEncoder deletes the whole stem, so the stem BN is keyed `bn1` (latentTF.py:195-196)."""
+    H, W = lidar.shape[2], lidar.shape[3]
+    rows = torch.linspace(-1, 1, cfg.lidar_resolution_width).view(1, 1, H, 1).expand(lidar.shape[0], 1, H, W)
+    cols = torch.linspace(-1, 1, cfg.lidar_resolution_height).view(1, 1, 1, W).expand(lidar.shape[0], 1, H, W)
+    lidar = torch.cat((rows.to(lidar.dtype), cols.to(lidar.dtype), lidar[:, 2:]), dim=1)
+    return backbone(P, image, lidar, cfg, train, drop, pre, lidar_bn='bn1.')
 
 
 def backbone_late_fusion(P, image, lidar, cfg=Cfg, train=True, pre='_model.'):
@@ -325,6 +336,8 @@ def _run_backbone(P, batch, cfg, train, drop, taps, backbone_name):
         return backbone_late_fusion(P, batch['rgb'], lidar, cfg, train)
     if backbone_name == 'geometric_fusion':
         return backbone_geometric_fusion(P, batch['rgb'], lidar, batch['bev_points'], batch['cam_points'], cfg, train)
+    if backbone_name == 'latentTF':
+        return backbone_latent_tf(P, batch['rgb'], lidar, cfg, train, drop)
     return backbone(P, batch['rgb'], lidar, cfg, train, drop, taps=taps)
 
 

@@ -67,6 +67,26 @@ def torch_ops(monkeypatch):
         std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
         return _nhwc(((img / 255.0) - mean) / std)
 
+    def tokens(img, lid, pos_emb, ghi, gwi, ghl, gwl, p, seed):
+        B, C = img.shape[0], img.shape[3]
+        pool = lambda t, gh, gw: _nhwc(F.adaptive_avg_pool2d(_nchw(t), (gh, gw))).reshape(B, gh * gw, C)
+        return torch.cat((pool(img, ghi, gwi), pool(lid, ghl, gwl)), dim=1) + pos_emb
+
+    def attention(h, wq, bq, wk, bk, wv, bv, B, T, nh, p, seed):
+        C = h.shape[1]
+        split = lambda w, b: F.linear(h, w, b).view(B, T, nh, C // nh).transpose(1, 2)
+        q, k, v = split(wq, bq), split(wk, bk), split(wv, bv)
+        att = F.softmax((q @ k.transpose(-2, -1)) * (1.0 / (C // nh) ** 0.5), dim=-1)
+        return (att @ v).transpose(1, 2).reshape(B * T, C)
+
+    def gpt_up_add(img, lid, x, ghi, gwi, ghl, gwl):
+        B, n_img = x.shape[0], ghi * gwi
+        # transfuser.py:363-364: token-major buffers re-interpreted as NCHW without permuting back
+        xi = x[:, :n_img].contiguous().view(B, -1, ghi, gwi)
+        xl = x[:, n_img:].contiguous().view(B, -1, ghl, gwl)
+        up = lambda t, ref: _nhwc(F.interpolate(t, size=ref.shape[1:3], mode='bilinear', align_corners=False))
+        return img + up(xi, img), lid + up(xl, lid)
+
     class _Apply:
         def __init__(self, fn):
             self.apply = fn
@@ -87,6 +107,12 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'GRUFn', _Apply(gru))
     monkeypatch.setattr(ops, 'centernet_decode', decode)
     monkeypatch.setattr(ops, 'TWO_STREAMS', False)
+    monkeypatch.setattr(ops, 'TokensFn', _Apply(tokens))
+    monkeypatch.setattr(ops, 'AttentionFn', _Apply(attention))
+    monkeypatch.setattr(ops, 'GptUpAddFn', _Apply(gpt_up_add))
+    monkeypatch.setattr(ops, 'layer_norm', lambda x, ln: F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps))
+    monkeypatch.setattr(ops, 'dropout', lambda x, p, training: x)       # the tests run with all dropout probabilities at 0
+    monkeypatch.setattr(ops, 'next_seed', lambda: 0)
     return ops
 
 
@@ -103,7 +129,7 @@ def fp64():
 def _build(backbone, seed):
     from transfuser_b200 import LidarCenterNet
     from transfuser_b200.config import TrainConfig
-    net = LidarCenterNet(TrainConfig(), 'cpu', backbone, 'regnety_032', 'regnety_032', use_velocity=False)
+    net = LidarCenterNet(TrainConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0), 'cpu', backbone, 'regnety_032', 'regnety_032', use_velocity=False)
     names = [(n, tuple(p.shape)) for n, p in list(net.named_parameters()) + list(net.named_buffers()) if not n.startswith('_bev')]
     net.load_state_dict(O.deterministic_state(names, seed=seed), strict=False)
     return net.double()
@@ -150,7 +176,25 @@ def test_late_fusion_module_wiring(torch_ops, fp64):
     assert _rel(feats[0], want_feats[0]) < 1e-9 and _rel(grid, want_grid) < 1e-9 and _rel(fused, want_fused) < 1e-9
 
 
-@pytest.mark.parametrize('backbone', ['late_fusion', 'geometric_fusion'])
+@pytest.mark.parametrize('backbone', ['transFuser', 'latentTF'])
+@pytest.mark.parametrize('train', [True, False])
+def test_transfuser_family_module_wiring(torch_ops, fp64, backbone, train):
+    """TransfuserBackbone / latentTFBackbone (single-stream schedule) vs the oracle, incl. the per-stage taps."""
+    net = _build(backbone, 4)
+    net.train(train)
+    batch = _batch(2, 11)
+    lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
+    P = {k: v.clone() for k, v in net.state_dict().items()}
+    fn = O.backbone if backbone == 'transFuser' else O.backbone_latent_tf
+    with torch.no_grad():
+        want_feats, want_grid, want_fused = fn(P, batch['rgb'], lidar.clone(), O.Cfg, train)
+        feats, grid, fused = net._model(batch['rgb'], lidar, batch['ego_vel'])
+    for a, b in zip(feats, want_feats):
+        assert a.shape == b.shape and _rel(a, b) < 1e-9, _rel(a, b)
+    assert _rel(grid, want_grid) < 1e-9 and _rel(fused, want_fused) < 1e-9
+
+
+@pytest.mark.parametrize('backbone', ['late_fusion', 'geometric_fusion', 'latentTF'])
 def test_forward_ego_wiring(torch_ops, fp64, backbone):
     """LidarCenterNet.forward_ego (eval): waypoints, thresholded boxes of sample 0, host box geometry vs oracle.forward_ego."""
     net = _build(backbone, 9).eval()

@@ -192,3 +192,30 @@ def test_forward_ego_oracle_matches_verbatim_reference():
     assert len(boxes) == len(got_boxes) and len(boxes) > 0, (len(boxes), len(got_boxes), float(raw[0, 0, -1]))
     for (a, abrake, aconf), (b, bbrake, bconf) in zip(boxes, got_boxes):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-5) and abrake == bbrake and abs(aconf - bconf) < 1e-6
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_latent_tf_oracle_matches_verbatim_reference():
+    """latentTF.py (positional grid instead of the LiDAR histogram): the 11 training losses, eval mode for the dropouts."""
+    m = ref_import.load()
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    cfg.n_layer = 4
+    torch.manual_seed(0)
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', 'latentTF', 'regnety_032', 'regnety_032', use_velocity=False)
+    names = [(n, tuple(p.shape)) for n, p in list(ref.named_parameters()) + list(ref.named_buffers())]
+    ref.load_state_dict(O.deterministic_state(names, seed=12), strict=False)
+    for mode in (True, False):
+        ref.train(mode)
+        for mod in ref.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        batch = O.synthetic_batch(2, seed=7)
+        P = {k: v.clone() for k, v in ref.state_dict().items()}
+        with torch.no_grad():
+            want = ref(batch['rgb'].clone(), batch['lidar'].clone(), ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                       target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                       depth=batch['depth'], semantic=batch['semantic'])
+            got = O.forward(P, batch, O.Cfg, train=mode, backbone_name='latentTF')
+        for k in want:
+            assert abs(float(want[k]) - float(got[k])) <= 1e-5 * max(abs(float(want[k])), 1e-3), (mode, k, float(want[k]), float(got[k]))

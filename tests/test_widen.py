@@ -39,6 +39,20 @@ def test_geometric_fusion_state_dict_matches_reference():
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
+def test_latent_tf_state_dict_matches_reference():
+    m = ref_import.load()
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    cfg.n_layer = 4
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', 'latentTF', 'regnety_032', 'regnety_032', use_velocity=False)
+    from transfuser_b200 import LidarCenterNet
+    from transfuser_b200.config import TrainConfig
+    mine = LidarCenterNet(TrainConfig(), 'cpu', 'latentTF', 'regnety_032', 'regnety_032', use_velocity=False)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference checkout not present (GPU box)')
 def test_bbox_local_metric_matches_reference():
     """model.py:810-842 (host numpy in the reference too) on seeded decoded rows."""
     m = ref_import.load()
@@ -192,6 +206,32 @@ def test_geometric_fusion_forward_backward_matches_oracle():
     # gradient in the reference; the same parameters (and only those) stay without gradient here
     assert {n for n, p in named.items() if p.grad is None} == {n for n in named if P[n].grad is None} == {
         '_model.lidar_conv4.weight', '_model.lidar_conv4.bias'}
+
+
+@pytest.mark.gpu
+@FIRST_RUN
+def test_latent_tf_forward_backward_matches_oracle():
+    """latentTF.py: same kernels as the TransFuser path, positional grid instead of the LiDAR histogram."""
+    net, C = _build('latentTF', 12)
+    batch = O.synthetic_batch(2, seed=7)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in net.state_dict().items()}
+
+    class OC(O.Cfg):
+        embd_pdrop = attn_pdrop = resid_pdrop = 0.0
+    ref = O.forward(P, batch, OC, train=True, backbone_name='latentTF')
+    w = dict(zip(C.detailed_losses, C.detailed_losses_weights))
+    sum(w[k] * ref[k] for k in ref).backward()
+    net = net.cuda().train()
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = net(cb['rgb'], cb['lidar'], ego_waypoint=cb['ego_waypoint'], target_point=cb['target_point'],
+              target_point_image=cb['target_point_image'], ego_vel=cb['ego_vel'], bev=cb['bev'], label=cb['label'],
+              depth=cb['depth'], semantic=cb['semantic'])
+    for k in ref:
+        assert abs(out[k].item() - ref[k].item()) <= 1e-3 * max(abs(ref[k].item()), 1e-6), (k, out[k].item(), ref[k].item())
+    sum(w[k] * out[k] for k in out).backward()
+    e = np.array([rel(p.grad, P[n].grad) for n, p in net.named_parameters() if not n.endswith('attn.key.bias')])
+    print('latentTF: median grad rel err vs fp32 oracle %.2e, p95 %.2e' % (np.median(e), np.percentile(e, 95)))
+    assert np.median(e) < 5e-2 and all(torch.isfinite(p.grad).all() for p in net.parameters())
 
 
 @pytest.mark.gpu

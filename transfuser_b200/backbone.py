@@ -206,7 +206,7 @@ class TransfuserBackbone(nn.Module):
         if config.use_point_pillars:
             raise RuntimeError('PointPillars LiDAR encoder is out of scope (config.py:42 default False)')
         in_channels = 2 * config.lidar_seq_len + (1 if config.use_target_point_image else 0)
-        self.lidar_encoder = LidarEncoder(architecture=lidar_architecture, in_channels=in_channels, out_features=config.perception_output_features)
+        self.lidar_encoder = self._make_lidar_encoder(lidar_architecture, in_channels)
         info = self.image_encoder.features.feature_info
         for i in range(1, 5):
             setattr(self, 'transformer%d' % i, GPT(
@@ -225,6 +225,9 @@ class TransfuserBackbone(nn.Module):
         self.c5_conv = nn.Conv2d(c_out, channel, (1, 1))
         self.two_streams = ops.TWO_STREAMS
 
+    def _make_lidar_encoder(self, architecture, in_channels):
+        return LidarEncoder(architecture=architecture, in_channels=in_channels, out_features=self.config.perception_output_features)
+
     def _bn_modules(self):
         if not hasattr(self, '_bn_cache'):
             object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
@@ -241,7 +244,7 @@ class TransfuserBackbone(nn.Module):
         l = ops.nchw_to_nhwc(lidar)
         if not self.two_streams:
             x = ie.stem.run(x)
-            l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
+            l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
             for i in range(1, 5):
                 x = getattr(ie, 's%d' % i).run(x)
                 l = getattr(le, 's%d' % i).run(l)
@@ -256,7 +259,7 @@ class TransfuserBackbone(nn.Module):
             side = ops.side_stream(image.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.stem.bn, True, le.stem.bn.training)
+                l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
             x = ie.stem.run(x)
             for i in range(1, 5):
                 with torch.cuda.stream(side):
@@ -486,3 +489,28 @@ class GeometricFusionBackbone(nn.Module):
     def forward(self, image, lidar, velocity, bev_points, img_points):
         feats, grid, fused = self.forward_nhwc(image, lidar, bev_points, img_points)
         return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused
+
+
+class latentTFBackbone(TransfuserBackbone):
+    """B200-native drop-in for /root/reference/team_code_transfuser/latentTF.py:8-217: the TransFuser architecture with the two
+    LiDAR histogram channels replaced by a fixed positional grid in [-1, 1] (latentTF.py:132-137; the target-point channel is
+    kept). Same kernels and schedule as TransfuserBackbone; the only differences are the input assembly and the parameter
+    names of the LiDAR stem (its encoder deletes the whole `stem`, latentTF.py:195-196)."""
+
+    def _make_lidar_encoder(self, architecture, in_channels):
+        return _GeoLidarEncoder(architecture=architecture, in_channels=in_channels)
+
+    def _grid(self, lidar):
+        key = (lidar.device, lidar.dtype, lidar.shape[2], lidar.shape[3])
+        if getattr(self, '_grid_key', None) != key:
+            cfg = self.config
+            rows = torch.linspace(-1, 1, cfg.lidar_resolution_width, device=lidar.device, dtype=lidar.dtype)
+            cols = torch.linspace(-1, 1, cfg.lidar_resolution_height, device=lidar.device, dtype=lidar.dtype)
+            g = torch.stack((rows.view(-1, 1).expand(lidar.shape[2], lidar.shape[3]), cols.view(1, -1).expand(lidar.shape[2], lidar.shape[3])))
+            object.__setattr__(self, '_grid_buf', g.unsqueeze(0).contiguous())
+            object.__setattr__(self, '_grid_key', key)
+        return self._grid_buf
+
+    def forward_nhwc(self, image, lidar, taps=None):
+        lidar = torch.cat((self._grid(lidar).expand(lidar.shape[0], -1, -1, -1), lidar[:, 2:]), dim=1)
+        return super().forward_nhwc(image, lidar, taps)

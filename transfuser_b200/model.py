@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .backbone import GeometricFusionBackbone, LateFusionBackbone, TransfuserBackbone
+from .backbone import GeometricFusionBackbone, LateFusionBackbone, TransfuserBackbone, latentTFBackbone
 
 HEAD_NAMES = ('heatmap_head', 'wh_head', 'offset_head', 'yaw_class_head', 'yaw_res_head', 'velocity_head', 'brake_head')
 HEAD_LOSSES = ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res', 'loss_velocity', 'loss_brake')
@@ -111,8 +111,10 @@ class LidarCenterNet(nn.Module):
             self._model = LateFusionBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
         elif backbone == 'geometric_fusion':
             self._model = GeometricFusionBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
+        elif backbone == 'latentTF':
+            self._model = latentTFBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)
         else:
-            raise RuntimeError('implemented backbones: "transFuser", "late_fusion", "geometric_fusion"; got %r' % (backbone,))
+            raise RuntimeError('implemented backbones: "transFuser", "late_fusion", "geometric_fusion", "latentTF"; got %r' % (backbone,))
         if config.multitask:
             self.seg_decoder = SegDecoder(config, config.perception_output_features).to(self.device)
             self.depth_decoder = DepthDecoder(config, config.perception_output_features).to(self.device)
