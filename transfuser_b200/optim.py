@@ -107,6 +107,61 @@ class FusedAdamW(torch.optim.Optimizer):
                       float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0)
 
 
+    # ---- torch.optim.AdamW-compatible (de)serialisation: the reference saves / resumes optimizer_%d.pth (train.py:183, 384)
+    def state_dict(self):
+        """Same structure as torch.optim.AdamW.state_dict(): per-parameter {'step', 'exp_avg', 'exp_avg_sq'} in parameter
+        order, so a reference run can resume from it (and vice versa). Every parameter shares the fused step count."""
+        fp = self._flat_of()
+        ps = [p for g in self.param_groups for p in g['params']]
+        off = {id(p): o for p, o in zip(fp.params, fp.offsets)}
+        state = {}
+        if self._step > 0:
+            for i, p in enumerate(ps):
+                o, n = off[id(p)], p.numel()
+                state[i] = dict(step=torch.tensor(float(self._step)),
+                                exp_avg=self._m[o:o + n].view(p.shape).clone(), exp_avg_sq=self._v[o:o + n].view(p.shape).clone())
+        groups, start = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != 'params'}
+            d.setdefault('amsgrad', False)
+            d['params'] = list(range(start, start + len(g['params'])))
+            start += len(g['params'])
+            groups.append(d)
+        return dict(state=state, param_groups=groups)
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        fp = self._flat_of()
+        ps = [p for g in self.param_groups for p in g['params']]
+        saved = [i for g in state_dict['param_groups'] for i in g['params']]
+        if len(saved) != len(ps):
+            raise ValueError('optimizer state has %d parameters, the model has %d' % (len(saved), len(ps)))
+        off = {id(p): o for p, o in zip(fp.params, fp.offsets)}
+        self._m.zero_()
+        self._v.zero_()
+        steps = set()
+        for idx, p in zip(saved, ps):
+            st = state_dict['state'].get(idx)
+            if st is None:
+                continue                       # never received a gradient in the saved run: moments stay zero
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError('optimizer state %d has shape %s, parameter has %s' % (idx, tuple(st['exp_avg'].shape), tuple(p.shape)))
+            o, n = off[id(p)], p.numel()
+            self._m[o:o + n].copy_(st['exp_avg'].reshape(-1))
+            self._v[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(st['step']))
+        if len(steps) > 1:
+            raise ValueError('per-parameter step counts differ (%s): the fused optimizer keeps one step count' % sorted(steps))
+        self._step = steps.pop() if steps else 0
+        self._step_dev.fill_(self._step)
+        for g, sg in zip(self.param_groups, state_dict['param_groups']):
+            for k in ('lr', 'betas', 'eps', 'weight_decay'):
+                if k in sg:
+                    g[k] = tuple(sg[k]) if k == 'betas' else sg[k]
+            if sg.get('amsgrad', False):
+                raise ValueError('amsgrad=True is not implemented (train.py:142 uses the default)')
+
+
 class GradAllReducer:
     """Data-parallel exchange: SUM all-reduce of the flat gradient buffer in `n_chunks` spans. Each span is launched (async,
     NCCL stream) from a post-accumulate-grad hook as soon as the last parameter of that span has its gradient, so the
