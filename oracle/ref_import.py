@@ -40,3 +40,30 @@ def load_histogram_fn():
     ns = {'np': np}
     exec('\n'.join(src[start:end]), ns)
     return ns['lidar_to_histogram_features']
+
+
+def load_data_fns(names):
+    """Functions of data.py exec'd one by one from the file's own text (data.py as a module needs ujson / skimage, which are
+    not in the image): the reference's utils.py is imported verbatim for the transforms, cv2 is the real OpenCV, and `np` is
+    numpy plus the `np.float` alias that data.py:630 still uses (removed in numpy 1.24)."""
+    import ast
+    import types
+    import cv2
+    import numpy as np
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    utils = importlib.import_module('utils')
+    npx = types.ModuleType('np_with_float_alias')
+    npx.__dict__.update(np.__dict__)
+    npx.float = float
+    text = open(os.path.join(REF_ROOT, 'data.py')).read()
+    ns = {'np': npx, 'cv2': cv2}
+    ns.update({k: getattr(utils, k) for k in dir(utils) if k.startswith('get_')})
+    wanted = set(names)
+    for node in ast.parse(text).body:
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF_ROOT, 'data.py'), 'exec'), ns)
+    missing = wanted - set(ns)
+    if missing:
+        raise RuntimeError('not found in data.py: %s' % sorted(missing))
+    return {k: ns[k] for k in names}

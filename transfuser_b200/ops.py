@@ -831,7 +831,10 @@ def nhwc_to_nchw(x):
 
 
 def image_prep(img_nchw):
-    """normalize_imagenet (transfuser.py:419-428) fused with the NCHW -> NHWC layout change. No gradient (input)."""
+    """normalize_imagenet (transfuser.py:419-428) fused with the NCHW -> NHWC layout change. No gradient (input).
+    A tensor produced by pipeline.InputPipeline.prepare(normalized_nhwc=True) is already in that form and passes through."""
+    if getattr(img_nchw, '_tfb_nhwc_normalized', False):
+        return img_nchw
     img = _c(img_nchw.detach())
     N, _, H, W = img.shape
     out = torch.empty((N, H, W, 3), dtype=torch.float32, device=img.device)

@@ -1,0 +1,106 @@
+"""GPU input pipeline: the device side of CARLA_Data.__getitem__
+(/root/reference/team_code_transfuser/data.py:103-356) for a whole batch, fed with compact inputs.
+
+The reference prepares every sample on CPU workers (numpy / OpenCV) and ships expanded tensors: fp32 RGB (1.35 MB), fp32
+LiDAR histogram + target map (0.79 MB), float depth and int64 semantics (0.45 + 0.90 MB) per sample. Here the host ships
+what is on disk — uint8 frames, raw points, one 4x4 pose transform, the target point — and three launches build the model
+inputs in HBM (csrc/input_prep.cu, csrc/bev_hist.cu):
+
+    batch = InputPipeline(config, device).prepare(raw)      # raw: dict of pinned host / device tensors, see prepare()
+    losses = model(batch['rgb'], batch['lidar'], target_point_image=batch['target_point_image'], ...)
+
+Host-side pieces that stay numpy, as in the reference (tiny, per sample): the pose algebra of align() (data.py:413-431) and
+the augmentation draw. JPEG/PNG decoding, label parsing and the BEV-label rotation (skimage) are not part of this module."""
+import numpy as np
+import torch
+
+from . import _lib
+
+LIDAR_TO_VEHICLE = np.array([[0., 1., 0., 1.3], [-1., 0., 0., 0.0], [0., 0., 1., 2.5], [0., 0., 0., 1.]])   # utils.py:14-24
+
+
+def align_transform(ego_matrix_0, ego_matrix_1, degree=0.0):
+    """4x4 float64 matrix of align() (data.py:413-431): LiDAR frame of measurement 0 -> LiDAR frame of measurement 1, followed
+    by the augmentation rotation by `degree`."""
+    m0, m1 = np.asarray(ego_matrix_0, dtype=np.float64), np.asarray(ego_matrix_1, dtype=np.float64)
+    T = np.linalg.inv(LIDAR_TO_VEHICLE) @ np.linalg.inv(m1) @ m0 @ LIDAR_TO_VEHICLE
+    rad = np.deg2rad(degree)
+    c, s = np.cos(rad), np.sin(rad)
+    return np.array([[c, s, 0, 0], [-s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]) @ T
+
+
+def crop_shift_pixels(degree, img_width, scale):
+    """data.py:219: horizontal crop shift that accompanies an augmentation yaw of `degree` (truncated like int())."""
+    return int(degree / 60 * img_width / scale)
+
+
+class InputPipeline:
+    def __init__(self, config, device, crop=(160, 704)):
+        self.device = torch.device(device)
+        self.crop = tuple(crop)
+        conv = getattr(config, 'converter', None)
+        lut = np.zeros(256, dtype=np.uint8)
+        if conv is not None:
+            lut[:len(conv)] = np.uint8(conv)
+        self.has_lut = conv is not None
+        self.lut = torch.from_numpy(lut).to(self.device)
+
+    def _dev(self, t, dtype):
+        t = torch.as_tensor(t)
+        if t.dtype != dtype:
+            raise TypeError('expected %s, got %s' % (dtype, t.dtype))
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    def prepare(self, raw, normalized_nhwc=False):
+        """raw (host or device tensors):
+             rgb [B,H,W,3] uint8 (RGB), optional depth [B,H,W,3] uint8, seg [B,H,W] uint8, crop_shift [B] int32 (host values),
+             points [B,N,4] float32 (padded), optional n_valid [B] int32, transforms [B,4,4] float64 (align_transform),
+             target_point [B,2] float64.
+           Returns rgb [B,3,h,w] float32 0..255 (or, with normalized_nhwc, the normalised NHWC tensor the backbone consumes
+           directly), lidar [B,2,256,256], target_point_image [B,1,256,256], target_point [B,2] float32, and depth [B,h,w] /
+           semantic [B,h,w] int64 when their sources are given."""
+        if self.device.type != 'cuda':
+            raise RuntimeError('InputPipeline needs a CUDA device (no CPU fallback)')
+        out = {}
+        rgb = self._dev(raw['rgb'], torch.uint8)
+        B, H, W, _ = rgb.shape
+        ch, cw = self.crop
+        shift_host = torch.as_tensor(raw.get('crop_shift', torch.zeros(B, dtype=torch.int32))).to('cpu', torch.int32)
+        x0 = W // 2 - cw // 2 + shift_host
+        if ch > H or cw > W or int(x0.min()) < 0 or int(x0.max()) + cw > W:
+            raise ValueError('crop %s with shifts %s leaves the %dx%d frame' % (self.crop, shift_host.tolist(), H, W))
+        shift = shift_host.to(self.device, non_blocking=True)
+        depth = self._dev(raw['depth'], torch.uint8) if raw.get('depth') is not None else None
+        seg = self._dev(raw['seg'], torch.uint8) if raw.get('seg') is not None else None
+        if seg is not None and not self.has_lut:
+            raise RuntimeError('config.converter is needed to map the semantic classes (data.py:36)')
+        rgb_out = None if normalized_nhwc else torch.empty((B, 3, ch, cw), dtype=torch.float32, device=self.device)
+        rgb_norm = torch.empty((B, ch, cw, 3), dtype=torch.float32, device=self.device) if normalized_nhwc else None
+        depth_out = torch.empty((B, ch, cw), dtype=torch.float32, device=self.device) if depth is not None else None
+        seg_out = torch.empty((B, ch, cw), dtype=torch.int64, device=self.device) if seg is not None else None
+        _lib.call('tfb_camera_prep', rgb, depth, seg, shift, self.lut, B, H, W, ch, cw, rgb_out, rgb_norm, depth_out, seg_out)
+        if normalized_nhwc:
+            rgb_norm._tfb_nhwc_normalized = True       # ops.image_prep passes such a tensor through untouched
+        out['rgb'] = rgb_norm if normalized_nhwc else rgb_out
+        if depth_out is not None:
+            out['depth'] = depth_out
+        if seg_out is not None:
+            out['semantic'] = seg_out
+
+        points = torch.as_tensor(raw['points'])
+        if points.dim() != 3 or points.shape[2] != 4 or points.dtype not in (torch.float32, torch.float64):
+            raise ValueError('points must be [B, N, 4] float32/float64')
+        points = points.to(self.device, non_blocking=True).contiguous()
+        T = self._dev(torch.as_tensor(raw['transforms']).reshape(B, 16), torch.float64)
+        n_valid = self._dev(raw['n_valid'], torch.int32) if raw.get('n_valid') is not None else None
+        counts = torch.empty((B, 2, 256, 256), dtype=torch.int32, device=self.device)
+        lidar = torch.empty((B, 2, 256, 256), dtype=torch.float32, device=self.device)
+        _lib.call('tfb_bev_histogram_aligned', points, 1 if points.dtype == torch.float64 else 0, T, n_valid, B, points.shape[1], counts, lidar)
+        out['lidar'] = lidar
+
+        tp = self._dev(raw['target_point'], torch.float64)
+        tpi = torch.empty((B, 1, 256, 256), dtype=torch.float32, device=self.device)
+        _lib.call('tfb_draw_target_point', tp, B, tpi)
+        out['target_point_image'] = tpi
+        out['target_point'] = tp.float()
+        return out
