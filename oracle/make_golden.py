@@ -47,7 +47,7 @@ def make_pipeline():
     crop, H, W = (32, 176), 40, 240                      # a small frame keeps the (incompressible, random) fixture small
     for seed in (0, 1):
         f = PO.synthetic_frame(seed, H=H, W=W)
-        shift = f['degree'] / 60 * W / 1
+        shift = f['degree'] / 60 * (W // 3) / 1          # data.py:219 with img_width = one camera's width
         pts = fn['align'](f['points'], dict(ego_matrix=f['ego_matrix_0']), dict(ego_matrix=f['ego_matrix_1']), degree=f['degree'])
         out['lidar_%d' % seed] = fn['lidar_to_histogram_features'](pts)
         out['rgb_%d' % seed] = fn['crop_image_cv2'](f['rgb'], crop=crop, crop_shift=shift).astype(np.float32)

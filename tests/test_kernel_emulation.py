@@ -1,0 +1,216 @@
+"""The simple CUDA kernels added for SURVEY.md §8f (decode, geometric-fusion gather / pool, input preparation), executed
+UNCHANGED on the CPU through tests/cuda_emul/cuda_emul.h (OS threads + barriers standing in for a thread block) and compared
+with the oracle / plain torch ops. This is how their indexing and arithmetic were checked in a container without a GPU; the
+`-m gpu` tests remain the parity tests proper. Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bev_oracle
+from oracle import pipeline_oracle as PO
+from oracle import torch_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), 'transfuser_b200', 'csrc')
+OUT = os.path.join(HERE, 'cuda_emul', '_build')
+
+DRIVERS = {
+    'geometric.cu': r'''
+extern "C" void run_avgpool_fwd(const float* x, float* out, int N, int H, int W, int C, int gh, int gw, int vec) {
+  if (vec == 4) emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_fwd_kernel<4>(x, out, N, H, W, C, gh, gw); });
+  else emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_fwd_kernel<1>(x, out, N, H, W, C, gh, gw); });
+}
+extern "C" void run_avgpool_bwd(const float* dout, float* dx, int N, int H, int W, int C, int gh, int gw, int acc, int vec) {
+  if (vec == 4) emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_bwd_kernel<4>(dout, dx, N, H, W, C, gh, gw, acc); });
+  else emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_bwd_kernel<1>(dout, dx, N, H, W, C, gh, gw, acc); });
+}
+extern "C" void run_gather_fwd(const float* emb, const int64_t* pts, float* out, int B, int h, int w, int C, int M, int P) {
+  emul_launch(dim3(2), dim3(64), [=] { gather_sum_fwd_kernel(emb, pts, out, B, h, w, C, M, P); });
+}
+extern "C" void run_gather_bwd(const float* dout, const int64_t* pts, float* demb, int B, int h, int w, int C, int M, int P) {
+  emul_launch(dim3(2), dim3(64), [=] { gather_sum_bwd_kernel(dout, pts, demb, B, h, w, C, M, P); });
+}
+''',
+    'decode.cu': r'''
+extern "C" void run_decode(const float* preds, int B, int H, int W, int nb, int k, int npad, float ratio, float apc, float* boxes, int* labels) {
+  emul_launch(dim3(B), dim3(kDecodeThreads), [=] { centernet_decode_kernel(preds, H, W, nb, k, npad, ratio, apc, boxes, labels); });
+}
+''',
+    'input_prep.cu': r'''
+extern "C" void run_draw(const double* tp, int B, float* out) {
+  emul_launch(dim3(4, B), dim3(64), [=] { draw_target_point_kernel(tp, out); });
+}
+extern "C" void run_camera(const uint8_t* rgb, const uint8_t* depth, const uint8_t* seg, const int* shift, const uint8_t* lut, int B, int H, int W,
+                           int ch, int cw, float* rgb_nchw, float* rgb_norm, float* depth_out, int64_t* seg_out) {
+  emul_launch(dim3(3), dim3(64), [=] { camera_prep_kernel(rgb, depth, seg, shift, lut, B, H, W, ch, cw, rgb_nchw, rgb_norm, depth_out, seg_out); });
+}
+''',
+    'bev_hist.cu': r'''
+extern "C" void run_aligned(const float* pts, const double* T, const int* n_valid, int batch, int n_max, unsigned* counts, float* out) {
+  emul_launch(dim3(2, batch), dim3(64), [=] { bev_scatter_aligned_kernel<float>(pts, T, n_valid, n_max, counts); });
+  emul_launch(dim3(kGrid / 32, kGrid / 32, batch * 2), dim3(32, 8), [=] { bev_finalize_kernel(counts, out, batch); });
+}
+''',
+}
+
+
+def _emulated(cu):
+    """Kernel part of csrc/<cu> (above its C-ABI entry points) + the emulation header + a driver, built with g++."""
+    os.makedirs(OUT, exist_ok=True)
+    text = open(os.path.join(CSRC, cu)).read()
+    body = text[:text.index('}  // namespace') + len('}  // namespace')]
+    body = body.replace('#include "common.cuh"', '#include "../cuda_emul.h"')
+    assert '<<<' not in body
+    src = os.path.join(OUT, cu.replace('.cu', '_emul.cpp'))
+    lib = os.path.join(OUT, cu.replace('.cu', '_emul.so'))
+    full = body + '\nusing namespace std;\n' + DRIVERS[cu]
+    if not (os.path.exists(src) and open(src).read() == full and os.path.exists(lib)):
+        open(src, 'w').write(full)
+        r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes',
+                            src, '-o', lib], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    return ctypes.CDLL(lib)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('shape,grid', [((2, 8, 16, 24), (4, 3)), ((1, 6, 10, 44), (5, 22)), ((2, 4, 8, 8), (8, 8))])
+def test_avgpool_grid_kernels(shape, grid):
+    lib = _emulated('geometric.cu')
+    N, C, H, W = shape
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1), requires_grad=True)
+    want = F.adaptive_avg_pool2d(x, grid)
+    xm = _nhwc(x.detach())
+    out = torch.empty(N, grid[0], grid[1], C)
+    vec = 4 if C % 4 == 0 else 1
+    lib.run_avgpool_fwd(_p(xm), _p(out), N, H, W, C, grid[0], grid[1], vec)
+    assert torch.equal(out.permute(0, 3, 1, 2), want.detach())          # same accumulation order as ATen's CPU kernel
+    go = torch.randn(*want.shape, generator=torch.Generator().manual_seed(2))
+    gw, = torch.autograd.grad(want, x, go)
+    dx = torch.empty(N, H, W, C)
+    gon = _nhwc(go)                                    # keep the operand alive across the ctypes call
+    lib.run_avgpool_bwd(_p(gon), _p(dx), N, H, W, C, grid[0], grid[1], 0, vec)
+    assert torch.allclose(dx.permute(0, 3, 1, 2), gw, rtol=0, atol=1e-7)
+    base = torch.randn(N, H, W, C, generator=torch.Generator().manual_seed(3))
+    acc = base.clone()
+    lib.run_avgpool_bwd(_p(gon), _p(acc), N, H, W, C, grid[0], grid[1], 1, vec)
+    assert torch.allclose(acc, base + dx, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('B,hw,HW,C', [(2, (5, 22), (8, 8), 16), (3, (8, 8), (5, 22), 8), (1, (4, 4), (2, 3), 4)])
+def test_gather_sum_kernels(B, hw, HW, C):
+    lib = _emulated('geometric.cu')
+    g = torch.Generator().manual_seed(B * 7 + C)
+    emb = torch.randn(B, C, *hw, generator=g, requires_grad=True)
+    pts = torch.stack((torch.randint(0, hw[1], (B, *HW, 5), generator=g), torch.randint(0, hw[0], (B, *HW, 5), generator=g)), -1)
+    pts[:, 0, 0] = 0
+    pts[0, 0, 1, 0] = torch.tensor([-1, -1])            # python-style negative index = last column / row
+    flat = pts.view(-1, 2)
+    t = emb.permute(0, 2, 3, 1).contiguous()[:, flat[:, 1], flat[:, 0]].view(B, B, *HW, 5, -1)       # geometric_fusion.py:145
+    want = torch.diagonal(t, 0).permute(4, 3, 0, 1, 2).contiguous().sum(-1)
+    em = _nhwc(emb.detach())
+    out = torch.empty(B, HW[0], HW[1], C)
+    lib.run_gather_fwd(_p(em), _p(pts), _p(out), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    assert torch.allclose(out.permute(0, 3, 1, 2), want.detach(), rtol=0, atol=1e-6)
+    go = torch.randn(*want.shape, generator=g)
+    gw, = torch.autograd.grad(want, emb, go)
+    demb = torch.zeros(B, hw[0], hw[1], C)               # the entry point memsets before the launch
+    gon = _nhwc(go)
+    lib.run_gather_bwd(_p(gon), _p(pts), _p(demb), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    assert torch.allclose(demb.permute(0, 3, 1, 2), gw, rtol=1e-5, atol=1e-5)
+    # out-of-range correspondences are skipped
+    bad = pts.clone()
+    bad[0, 0, 0, 0] = torch.tensor([hw[1], 0])
+    out2 = torch.empty_like(out)
+    lib.run_gather_fwd(_p(em), _p(bad), _p(out2), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    assert torch.allclose(out2[0, 0, 0], out[0, 0, 0] - em[0, pts[0, 0, 0, 0, 1], pts[0, 0, 0, 0, 0]], atol=1e-5)
+
+
+@pytest.mark.parametrize('case,H,W', [(0, 64, 64), (1, 64, 64), (2, 64, 64), (3, 64, 64), (0, 24, 40)])
+def test_centernet_decode_kernel(case, H, W):
+    lib = _emulated('decode.cu')
+    g = torch.Generator().manual_seed(40 + case)
+    B = 2
+    heat_logit = torch.randn(B, 1, H, W, generator=g) * 2
+    if case == 1:
+        heat_logit = (heat_logit * 2).round() / 2
+    if case == 2:
+        heat_logit = heat_logit - 8 * (torch.rand(B, 1, H, W, generator=g) < 0.999)
+    if case == 3:
+        heat_logit[:, :, 0, :] = 30.0
+    rest = [torch.randn(B, c, H, W, generator=g) for c in (2, 2, 12, 1, 1, 2)]
+    want, want_labels = O.decode_heatmap([heat_logit.sigmoid()] + rest, 12, stable=True)
+    raw = _nhwc(torch.cat([heat_logit] + rest, dim=1))
+    boxes = torch.empty(B, 100, 8)
+    labels = torch.empty(B, 100, dtype=torch.int32)
+    npad = 2
+    while npad < H * W:
+        npad <<= 1
+    lib.run_decode(_p(raw), B, H, W, 12, 100, npad, ctypes.c_float(4.0), ctypes.c_float(np.float32(2.0 * np.pi / 12)), _p(boxes), _p(labels))
+    assert torch.equal(labels.long(), want_labels)
+    assert torch.equal(boxes[..., 6], want[..., 6])
+    assert torch.allclose(boxes, want, rtol=1e-6, atol=1e-5), (boxes - want).abs().amax(dim=(0, 1))
+
+
+def test_target_point_kernel():
+    lib = _emulated('input_prep.cu')
+    pts = [(x, y) for x in (-16.2, -16.0, 15.9, 16.0, 16.1, 0.3) for y in (-1.4, -1.3, 30.6, 30.7, 30.8, 7.77)] + [(1e12, -1e12), (float('nan'), 0.0)]
+    tp = torch.tensor(pts, dtype=torch.float64)
+    out = torch.empty(len(pts), 1, 256, 256)
+    lib.run_draw(_p(tp), len(pts), _p(out))
+    for i, p in enumerate(pts):
+        assert np.array_equal(out[i].numpy(), PO.draw_target_point(np.array(p)).astype(np.float32)), p
+
+
+def test_camera_prep_kernel():
+    lib = _emulated('input_prep.cu')
+    conv = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
+    H, W, crop = 40, 240, (32, 176)
+    fs = [PO.synthetic_frame(s, H=H, W=W) for s in (0, 1, 2)]
+    for f, deg in zip(fs, (5.0, -7.9, 0.0)):            # |shift| <= (240 - 176) / 2: the product's host check rejects more
+        f['degree'] = deg
+    shifts = [int(f['degree'] / 60 * W) for f in fs]
+    B = len(fs)
+    rgb, depth = (torch.from_numpy(np.stack([f[k] for f in fs])) for k in ('rgb', 'depth'))
+    seg = torch.from_numpy(np.stack([f['seg'] for f in fs]))
+    lut = torch.zeros(256, dtype=torch.uint8)
+    lut[:len(conv)] = torch.tensor(conv, dtype=torch.uint8)
+    o_rgb, o_norm = torch.empty(B, 3, *crop), torch.empty(B, *crop, 3)
+    o_depth, o_seg = torch.empty(B, *crop), torch.empty(B, *crop, dtype=torch.int64)
+    shift_t = torch.tensor(shifts, dtype=torch.int32)
+    lib.run_camera(_p(rgb), _p(depth), _p(seg), _p(shift_t), _p(lut), B, H, W, crop[0], crop[1],
+                   _p(o_rgb), _p(o_norm), _p(o_depth), _p(o_seg))
+    for b, f in enumerate(fs):
+        c = PO.crop_rgb(f['rgb'], crop, shifts[b])
+        assert np.array_equal(o_rgb[b].numpy(), c.astype(np.float32))
+        assert np.array_equal(o_norm[b].numpy(), PO.normalize_nhwc(c))
+        assert np.array_equal(o_depth[b].numpy(), PO.depth_from_rgb(PO.crop_rgb(f['depth'], crop, shifts[b])).astype(np.float32))
+        assert np.array_equal(o_seg[b].numpy(), PO.seg_classes(f['seg'], conv, crop, shifts[b]).astype(np.int64))
+
+
+def test_aligned_histogram_kernel():
+    lib = _emulated('bev_hist.cu')
+    fs = [PO.synthetic_frame(s, n_points=1500) for s in (0, 1)]
+    fs[1]['degree'] = 0.0
+    pts = torch.from_numpy(np.stack([f['points'] for f in fs]))
+    Ts = [PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree']) for f in fs]
+    T = torch.from_numpy(np.stack(Ts)).reshape(2, 16).contiguous()
+    n_valid = torch.tensor([1500, 1200], dtype=torch.int32)
+    counts = torch.zeros(2, 2, 256, 256, dtype=torch.int32)       # the entry point memsets before the launch
+    out = torch.empty(2, 2, 256, 256)
+    lib.run_aligned(_p(pts), _p(T), _p(n_valid), 2, 1500, _p(counts), _p(out))
+    for b, f in enumerate(fs):
+        n = int(n_valid[b])
+        want = bev_oracle.lidar_to_histogram_features(PO.align_points(f['points'][:n], Ts[b]))
+        assert np.array_equal(out[b].numpy(), want)

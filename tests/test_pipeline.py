@@ -15,7 +15,7 @@ FIRST_RUN = pytest.mark.xfail(strict=False, reason='written after the round-1 GP
 CONVERTER = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]    # any 23-entry map to 7 classes
 
 
-def _oracle_sample(f, crop=(160, 704), scale=1, img_width=960):
+def _oracle_sample(f, crop=(160, 704), scale=1, img_width=320):
     shift = int(f['degree'] / 60 * img_width / scale)
     T = PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree'])
     rgb = PO.crop_rgb(f['rgb'], crop, shift)
@@ -31,7 +31,7 @@ def test_pipeline_oracle_matches_reference_functions():
     fn = ref_import.load_data_fns(['align', 'draw_target_point', 'crop_image_cv2', 'crop_seg', 'get_depth', 'lidar_to_histogram_features'])
     for seed in range(6):
         f = PO.synthetic_frame(seed)
-        shift = f['degree'] / 60 * 960 / 1                                   # data.py:219 (float; the crops apply int())
+        shift = f['degree'] / 60 * 320 / 1                                   # data.py:219, config.img_width 320 (float; the crops apply int())
         want_pts = fn['align'](f['points'], dict(ego_matrix=f['ego_matrix_0']), dict(ego_matrix=f['ego_matrix_1']), degree=f['degree'])
         T = PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree'])
         got_pts = PO.align_points(f['points'], T)
@@ -52,7 +52,7 @@ def test_pipeline_oracle_matches_reference_functions():
 def test_pipeline_oracle_matches_golden():
     g = np.load(GOLD)
     for seed in (0, 1):
-        o = _oracle_sample(PO.synthetic_frame(seed, H=40, W=240), crop=(32, 176), img_width=240)
+        o = _oracle_sample(PO.synthetic_frame(seed, H=40, W=240), crop=(32, 176), img_width=80)
         for k in ('rgb', 'depth', 'semantic', 'lidar', 'target_point_image'):
             assert np.array_equal(o[k], g['%s_%d' % (k, seed)]), (k, seed)
 
@@ -68,7 +68,7 @@ def test_product_pose_algebra_matches_reference():
         want = fn['align'](f['points'], dict(ego_matrix=f['ego_matrix_0']), dict(ego_matrix=f['ego_matrix_1']), degree=f['degree'])
         assert np.allclose(PO.align_points(f['points'], T), want, rtol=0, atol=1e-9)
         assert np.array_equal(bev_oracle.lidar_to_histogram_features(PO.align_points(f['points'], T)), bev_oracle.lidar_to_histogram_features(want))
-    assert pipeline.crop_shift_pixels(-13.7, 960, 1) == int(-13.7 / 60 * 960 / 1)
+    assert pipeline.crop_shift_pixels(-13.7, 320, 1) == int(-13.7 / 60 * 320 / 1)
 
 
 def test_pipeline_rejects_bad_inputs_on_host():
@@ -83,7 +83,7 @@ def _raw_batch(seeds):
     fs = [PO.synthetic_frame(s) for s in seeds]
     raw = dict(rgb=torch.from_numpy(np.stack([f['rgb'] for f in fs])), depth=torch.from_numpy(np.stack([f['depth'] for f in fs])),
                seg=torch.from_numpy(np.stack([f['seg'] for f in fs])),
-               crop_shift=torch.tensor([pipeline.crop_shift_pixels(f['degree'], 960, 1) for f in fs], dtype=torch.int32),
+               crop_shift=torch.tensor([pipeline.crop_shift_pixels(f['degree'], 320, 1) for f in fs], dtype=torch.int32),
                points=torch.from_numpy(np.stack([f['points'] for f in fs])),
                transforms=torch.from_numpy(np.stack([pipeline.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree']) for f in fs])),
                target_point=torch.from_numpy(np.stack([f['target_point'] for f in fs])))
