@@ -126,3 +126,20 @@ def test_reference_ddp_checkpoint_loads_strict_into_product_model():
     state_dict = {k[7:]: v for k, v in state_dict.items()}                  # submission_agent.py:95
     res = ref.load_state_dict(state_dict, strict=False)
     assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_parameters_without_gradient_are_left_to_the_optimizer_untouched():
+    """torch.optim.AdamW skips parameters whose .grad is None (config 4's lidar_conv4 never gets one): the fused optimizer's
+    launch spans exclude them."""
+    assert optim.subtract_spans(0, 1000, []) == [(0, 1000)]
+    assert optim.subtract_spans(0, 1000, [(0, 64)]) == [(64, 1000)]
+    assert optim.subtract_spans(0, 1000, [(128, 64), (960, 64)]) == [(0, 128), (192, 960)]
+    assert optim.subtract_spans(512, 1024, [(128, 64), (448, 128), (1000, 64)]) == [(576, 1000)]
+    assert optim.subtract_spans(0, 64, [(0, 64)]) == []
+    net = _Tiny()
+    fp = optim.flatten(net)
+    net.b.weight.grad = torch.ones_like(net.b.weight)
+    spans = fp.gather_stragglers()
+    got = {o for o, _ in spans}
+    want = {o for p, o in zip(fp.params, fp.offsets) if p is not net.b.weight}
+    assert got == want and all(n % optim.ALIGN == 0 for _, n in spans)

@@ -44,20 +44,39 @@ class FlatParams:
 
     def gather_stragglers(self):
         """Before the optimizer reads the flat gradient buffer: a parameter whose .grad is not its flat view (accumulated by
-        autograd into a fresh tensor) is copied in; a parameter that received no gradient is zeroed."""
+        autograd into a fresh tensor) is copied in; a parameter that received no gradient is zeroed. Returns the (offset,
+        padded length) spans of the parameters without a gradient: torch.optim.AdamW leaves those untouched (no weight decay,
+        no moment update), so the fused optimizer skips them too."""
         base = self.grad.data_ptr()
+        no_grad = []
         for p, o in zip(self.params, self.offsets):
             g = p.grad
             if g is None:
                 self.grad[o:o + p.numel()].zero_()
+                no_grad.append((o, (p.numel() + ALIGN - 1) // ALIGN * ALIGN))
             elif g.data_ptr() != base + 4 * o:
                 self.grad[o:o + p.numel()].copy_(g.reshape(-1))
+        return no_grad
 
 
 def flatten(model):
     fp = FlatParams(model)
     model._tfb_flat_params = fp
     return fp
+
+
+def subtract_spans(lo, hi, holes):
+    """[lo, hi) minus the (offset, length) `holes` (sorted, disjoint) -> list of (lo, hi) pieces."""
+    out = []
+    for o, n in holes:
+        if o + n <= lo or o >= hi:
+            continue
+        if o > lo:
+            out.append((lo, o))
+        lo = max(lo, o + n)
+    if lo < hi:
+        out.append((lo, hi))
+    return out
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -73,6 +92,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._m = self._v = None
         self._step_dev = None
         self.check_grads = True   # set False once the producer set is known to be complete (saves a Python sweep per step)
+        self._no_grad_spans = []  # parameters that never receive a gradient (as found by the last checked step)
 
     def _flat_of(self):
         if self._flat is None:
@@ -93,7 +113,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None, chunks=None):
         fp = self._flat_of()
         if self.check_grads:
-            fp.gather_stragglers()
+            self._no_grad_spans = fp.gather_stragglers()
         g = self.param_groups[0]
         self._step += 1
         _lib.call('tfb_step_tick', None, self._step_dev)   # device-side step count: valid under CUDA-graph replay
@@ -102,9 +122,10 @@ class FusedAdamW(torch.optim.Optimizer):
         for lo, hi, work in spans:
             if work is not None:
                 work.wait()
-            bf = fp.bf16[lo:hi] if fp.bf16 is not None else None
-            _lib.call('tfb_adamw_step', fp.flat[lo:hi], fp.grad[lo:hi], self._m[lo:hi], self._v[lo:hi], hi - lo, float(g['lr']), float(b1),
-                      float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0)
+            for a, b in (subtract_spans(lo, hi, self._no_grad_spans) if self._no_grad_spans else [(lo, hi)]):
+                bf = fp.bf16[a:b] if fp.bf16 is not None else None
+                _lib.call('tfb_adamw_step', fp.flat[a:b], fp.grad[a:b], self._m[a:b], self._v[a:b], b - a, float(g['lr']), float(b1),
+                          float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0)
 
 
     # ---- torch.optim.AdamW-compatible (de)serialisation: the reference saves / resumes optimizer_%d.pth (train.py:183, 384)
