@@ -27,8 +27,11 @@ for ta, tb, M, N, K, splits, tag in SHAPES:
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts[2:])[len(ts[2:]) // 2]
-    line = '%-18s ta%d tb%d M%6d N%5d K%5d  %8.1f us  %7.1f TF/s' % (tag, ta, tb, M, N, K, t * 1e3, 2.0 * M * N * K / (t * 1e-3) / 1e12)
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float())     # same bf16 operands, fp32 product
+    err = ((c - ref).norm() / ref.norm()).item()
+    line = '%-18s ta%d tb%d M%6d N%5d K%5d  %8.1f us  %7.1f TF/s  rel err %.1e%s' % (
+        tag, ta, tb, M, N, K, t * 1e3, 2.0 * M * N * K / (t * 1e-3) / 1e12, err, '' if err < 1e-3 else '  <-- WRONG')
     print(line, flush=True)
     out.append(line)
 os.makedirs('gpurun_out', exist_ok=True)
-open('gpurun_out/gemm_bench_%s.txt' % os.environ.get('TFB_GEMM_BN', 'auto'), 'w').write('\n'.join(out) + '\n')
+open('gpurun_out/gemm_bench_%s.txt' % (os.environ.get('TFB_GEMM_BN') or ('model' + os.environ['TFB_GEMM_TILE_MODEL'] if 'TFB_GEMM_TILE_MODEL' in os.environ else 'auto')), 'w').write('\n'.join(out) + '\n')

@@ -333,6 +333,28 @@ int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t
   const int64_t mt = (M + BM - 1) / BM;
   const int64_t t128 = mt * ((N + 127) / 128) * (splits > 0 ? splits : 1), t256 = mt * ((N + 255) / 256) * (splits > 0 ? splits : 1);
   const int sms = tfb_num_sms();
+  // Experiment switches (not the default path): TFB_GEMM_BN=64|192 forces those tile widths; TFB_GEMM_TILE_MODEL=<c> picks the
+  // width in {64,128,192,256} that minimises waves(BN) * (BN + c): full waves of the persistent grid times a per-tile cost of
+  // BN columns plus a fixed overhead of c column-equivalents (M = 1740 token GEMMs lose up to half a wave to quantisation).
+  static int model_c = -2;
+  if (model_c == -2) { const char* e = getenv("TFB_GEMM_TILE_MODEL"); model_c = e ? atoi(e) : -1; }
+  int pick = 0;
+  if (force_bn == 64 || force_bn == 192) pick = force_bn;
+  if (model_c >= 0 && force_bn == 0) {
+    int64_t best = -1;
+    const int cand[4] = {64, 128, 192, 256};
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (bn > 64 && bn - 64 >= N) continue;                      // wider than the problem by a whole 64-column step
+      const int64_t tiles = mt * ((N + bn - 1) / bn) * (splits > 0 ? splits : 1);
+      const int64_t cost = ((tiles + sms - 1) / sms) * (bn + model_c);
+      if (best < 0 || cost <= best) { best = cost; pick = bn; }
+    }
+  }
+  if (pick == 64) return dispatch_major<T, 64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (pick == 192 && N > 128) return dispatch_major<T, 192>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (pick == 128) return dispatch_major<T, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (pick == 256 && N >= 256) return dispatch_major<T, 256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
   bool use256 = N >= 256 && (t256 >= sms || (t128 > sms && t128 < 2 * sms && t256 <= sms));
   if (force_bn == 128) use256 = false;
   if (force_bn == 256 && N >= 256) use256 = true;
