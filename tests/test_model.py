@@ -1,6 +1,5 @@
 """Whole hot path: LidarCenterNet.forward + backward on the GPU (CUDA kernels through the C-ABI) vs the CPU oracle
 (oracle/torch_oracle.py, itself pinned to the verbatim reference) on identical weights and inputs."""
-import sys
 import os
 
 import pytest

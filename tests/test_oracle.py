@@ -20,7 +20,7 @@ def _product_container():
 
 
 def test_oracle_reproduces_reference_golden():
-    from oracle.make_golden_model import BATCH, BATCH_SEED, GRAD_KEYS, WEIGHT_SEED
+    from oracle.make_golden_model import BATCH, BATCH_SEED, WEIGHT_SEED
     g = np.load(GOLD)
     net = _product_container()  # parameter names / shapes only (the product's forward needs the GPU)
     names = [(n, tuple(p.shape)) for n, p in list(net.named_parameters()) + list(net.named_buffers()) if not n.startswith('_bev')]

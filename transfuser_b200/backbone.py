@@ -8,8 +8,6 @@ their forward is never called — every op runs through transfuser_b200.ops (han
 
 The RegNetY-3.2GF definition (timm 0.5.4 `regnety_032`: stem 32, widths 72/216/576/1512, depths 2/5/13/1, group width 24,
 SE ratio 0.25) is restated from timm's published config; timm itself is not a dependency."""
-import os
-
 import torch
 from torch import nn
 

@@ -5,7 +5,8 @@ import torch
 
 from . import _lib
 
-# 'tf32' (tcgen05 kind::tf32, default), 'simt' (exact fp32 CUDA cores: parity mode)
+# 'simt' (exact fp32 CUDA cores: the parity mode and the import-time default), 'bf16' (tcgen05 kind::f16 tensor cores, fp32
+# accumulate: the throughput mode bench.py / Trainer select), 'tf32' (tcgen05 kind::tf32 for K-major operands only)
 MODE = os.environ.get('TFB_GEMM', 'simt')
 
 
