@@ -13,12 +13,14 @@ INPUT_KEYS = ('rgb', 'points', 'target_point_image', 'target_point', 'ego_vel', 
 
 
 class Trainer:
-    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=8):
+    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=8, backbone='transFuser'):
         self.cfg, self.device = cfg, device
+        # the geometric-fusion backbone consumes two more inputs per sample (train.py:279-288)
+        self.input_keys = INPUT_KEYS + (('bev_points', 'cam_points') if backbone == 'geometric_fusion' else ())
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         gemm.set_mode(gemm_mode)
         ops.manual_seed(1234 + seed)
-        self.net = LidarCenterNet(cfg, device, 'transFuser', 'regnety_032', 'regnety_032', use_velocity=False).train()
+        self.net = LidarCenterNet(cfg, device, backbone, 'regnety_032', 'regnety_032', use_velocity=False).train()
         self.flat = optim.flatten(self.net)
         if gemm_mode == 'bf16':
             gemm.attach_bf16_weights(self.flat)
@@ -37,7 +39,7 @@ class Trainer:
         self.opt.zero_grad()
         losses = self.net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
                           target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
-                          depth=d['depth'], semantic=d['semantic'])
+                          depth=d['depth'], semantic=d['semantic'], bev_points=d.get('bev_points'), cam_points=d.get('cam_points'))
         loss = None
         for k, v in losses.items():
             loss = v * self.weights[k] if loss is None else loss + v * self.weights[k]
@@ -50,7 +52,7 @@ class Trainer:
         The dropout base seed and the optimizer step count live in device memory and are advanced by kernels inside the graph,
         so every replay is a genuinely new step. Returns True on success (falls back to eager otherwise)."""
         try:
-            self.static = {k: torch.empty(example[k].shape, dtype=example[k].dtype, device=self.device) for k in INPUT_KEYS}
+            self.static = {k: torch.empty(example[k].shape, dtype=example[k].dtype, device=self.device) for k in self.input_keys}
             self.load(example)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -73,7 +75,7 @@ class Trainer:
 
     def load(self, batch):
         """Copies a batch (pinned host or device tensors) into the static input buffers of the captured graph."""
-        for k in INPUT_KEYS:
+        for k in self.input_keys:
             self.static[k].copy_(batch[k], non_blocking=True)
 
     def replay(self):
