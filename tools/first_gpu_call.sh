@@ -1,0 +1,17 @@
+#!/bin/bash
+# One gpurun call that confirms everything written without a GPU at the end of round 1 and collects the tile-width sweep:
+#   gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
+# Results land in gpurun_out/ (merged back by gpurun).
+mkdir -p gpurun_out
+# 1. the kernels / modules that have only been emulated or wiring-tested so far (xfail markers ignored: failures are failures)
+timeout 900 python -m pytest tests/test_widen.py tests/test_pipeline.py -m gpu -q --runxfail -p no:cacheprovider > gpurun_out/first_run_tests.log 2>&1
+tail -5 gpurun_out/first_run_tests.log
+# 2. tcgen05 GEMM: forced tile widths on the training shapes (with a result check), then the wave model inside the full step
+for bn in 64 128 192 256; do
+  TFB_GEMM_BN=$bn timeout 240 python tools/gemm_bench.py > gpurun_out/gemm_bn$bn.log 2>&1
+done
+for c in 0 32 64 128; do
+  TFB_GEMM_TILE_MODEL=$c timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tile_model$c.json 2> gpurun_out/bench_tile_model$c.err
+done
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tile_default.json 2> gpurun_out/bench_tile_default.err
+grep -h '"value"' gpurun_out/bench_tile_*.json | cut -c1-160
