@@ -51,14 +51,24 @@ class InputPipeline:
             raise TypeError('expected %s, got %s' % (dtype, t.dtype))
         return t.to(self.device, non_blocking=True).contiguous()
 
-    def prepare(self, raw, normalized_nhwc=False):
+    def _out(self, out, key, shape, dtype):
+        """Destination tensor: the caller's preallocated one (e.g. a static CUDA-graph input buffer) or a fresh allocation."""
+        t = None if out is None else out.get(key)
+        if t is None:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+            raise ValueError('out[%r] must be a contiguous CUDA %s tensor of shape %s' % (key, dtype, tuple(shape)))
+        return t
+
+    def prepare(self, raw, normalized_nhwc=False, out=None):
         """raw (host or device tensors):
              rgb [B,H,W,3] uint8 (RGB), optional depth [B,H,W,3] uint8, seg [B,H,W] uint8, crop_shift [B] int32 (host values),
              points [B,N,4] float32 (padded), optional n_valid [B] int32, transforms [B,4,4] float64 (align_transform),
              target_point [B,2] float64.
            Returns rgb [B,3,h,w] float32 0..255 (or, with normalized_nhwc, the normalised NHWC tensor the backbone consumes
            directly), lidar [B,2,256,256], target_point_image [B,1,256,256], target_point [B,2] float32, and depth [B,h,w] /
-           semantic [B,h,w] int64 when their sources are given."""
+           semantic [B,h,w] int64 when their sources are given. `out` (optional dict) supplies preallocated destinations
+           by the same keys, so the three launches can write straight into the static inputs of a captured training step."""
         if self.device.type != 'cuda':
             raise RuntimeError('InputPipeline needs a CUDA device (no CPU fallback)')
         out = {}
@@ -74,10 +84,10 @@ class InputPipeline:
         seg = self._dev(raw['seg'], torch.uint8) if raw.get('seg') is not None else None
         if seg is not None and not self.has_lut:
             raise RuntimeError('config.converter is needed to map the semantic classes (data.py:36)')
-        rgb_out = None if normalized_nhwc else torch.empty((B, 3, ch, cw), dtype=torch.float32, device=self.device)
-        rgb_norm = torch.empty((B, ch, cw, 3), dtype=torch.float32, device=self.device) if normalized_nhwc else None
-        depth_out = torch.empty((B, ch, cw), dtype=torch.float32, device=self.device) if depth is not None else None
-        seg_out = torch.empty((B, ch, cw), dtype=torch.int64, device=self.device) if seg is not None else None
+        rgb_out = None if normalized_nhwc else self._out(out, 'rgb', (B, 3, ch, cw), torch.float32)
+        rgb_norm = self._out(out, 'rgb', (B, ch, cw, 3), torch.float32) if normalized_nhwc else None
+        depth_out = self._out(out, 'depth', (B, ch, cw), torch.float32) if depth is not None else None
+        seg_out = self._out(out, 'semantic', (B, ch, cw), torch.int64) if seg is not None else None
         _lib.call('tfb_camera_prep', rgb, depth, seg, shift, self.lut, B, H, W, ch, cw, rgb_out, rgb_norm, depth_out, seg_out)
         if normalized_nhwc:
             rgb_norm._tfb_nhwc_normalized = True       # ops.image_prep passes such a tensor through untouched
@@ -94,12 +104,12 @@ class InputPipeline:
         T = self._dev(torch.as_tensor(raw['transforms']).reshape(B, 16), torch.float64)
         n_valid = self._dev(raw['n_valid'], torch.int32) if raw.get('n_valid') is not None else None
         counts = torch.empty((B, 2, 256, 256), dtype=torch.int32, device=self.device)
-        lidar = torch.empty((B, 2, 256, 256), dtype=torch.float32, device=self.device)
+        lidar = self._out(out, 'lidar', (B, 2, 256, 256), torch.float32)
         _lib.call('tfb_bev_histogram_aligned', points, 1 if points.dtype == torch.float64 else 0, T, n_valid, B, points.shape[1], counts, lidar)
         out['lidar'] = lidar
 
         tp = self._dev(raw['target_point'], torch.float64)
-        tpi = torch.empty((B, 1, 256, 256), dtype=torch.float32, device=self.device)
+        tpi = self._out(out, 'target_point_image', (B, 1, 256, 256), torch.float32)
         _lib.call('tfb_draw_target_point', tp, B, tpi)
         out['target_point_image'] = tpi
         out['target_point'] = tp.float()
