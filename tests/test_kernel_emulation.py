@@ -214,3 +214,110 @@ def test_aligned_histogram_kernel():
         n = int(n_valid[b])
         want = bev_oracle.lidar_to_histogram_features(PO.align_points(f['points'][:n], Ts[b]))
         assert np.array_equal(out[b].numpy(), want)
+
+
+def test_input_pipeline_host_code_over_emulated_kernels(monkeypatch):
+    """transfuser_b200.pipeline.InputPipeline.prepare executed end to end in this container: its three C-ABI calls are routed
+    to the emulated kernels (same argument order as the entry points), everything else is the product's own host code."""
+    from transfuser_b200 import pipeline
+    from transfuser_b200.config import TrainConfig
+    inp, bev = _emulated('input_prep.cu'), _emulated('bev_hist.cu')
+    conv = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
+    calls = []
+
+    def call(name, *a):
+        calls.append(name)
+        if name == 'tfb_camera_prep':
+            inp.run_camera(*[_p(x) if (x is None or isinstance(x, torch.Tensor)) else x for x in a])
+        elif name == 'tfb_draw_target_point':
+            inp.run_draw(_p(a[0]), a[1], _p(a[2]))
+        elif name == 'tfb_bev_histogram_aligned':
+            points, is_f64, T, n_valid, B, n_max, counts, out = a
+            assert is_f64 == 0
+            counts.zero_()
+            bev.run_aligned(_p(points), _p(T), _p(n_valid), B, n_max, _p(counts), _p(out))
+        else:
+            raise AssertionError(name)
+
+    monkeypatch.setattr(pipeline._lib, 'call', call)
+    monkeypatch.setattr(pipeline.InputPipeline, '_require_cuda', lambda self: None)
+    H, W, crop = 40, 240, (32, 176)
+    fs = [PO.synthetic_frame(s, H=H, W=W, n_points=800) for s in (3, 4)]
+    for f, deg in zip(fs, (6.0, -3.0)):
+        f['degree'] = deg
+    raw = dict(rgb=torch.from_numpy(np.stack([f['rgb'] for f in fs])), depth=torch.from_numpy(np.stack([f['depth'] for f in fs])),
+               seg=torch.from_numpy(np.stack([f['seg'] for f in fs])),
+               crop_shift=torch.tensor([pipeline.crop_shift_pixels(f['degree'], W // 3, 1) for f in fs], dtype=torch.int32),
+               points=torch.from_numpy(np.stack([f['points'] for f in fs])),
+               transforms=torch.from_numpy(np.stack([pipeline.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree']) for f in fs])),
+               target_point=torch.from_numpy(np.stack([f['target_point'] for f in fs])))
+    pipe = pipeline.InputPipeline(TrainConfig(converter=conv), 'cpu', crop=crop)
+    out = pipe.prepare(raw)
+    assert calls == ['tfb_camera_prep', 'tfb_bev_histogram_aligned', 'tfb_draw_target_point']
+    for b, f in enumerate(fs):
+        shift = int(f['degree'] / 60 * (W // 3))
+        T = PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree'])
+        assert np.array_equal(out['rgb'][b].numpy(), PO.crop_rgb(f['rgb'], crop, shift).astype(np.float32))
+        assert np.array_equal(out['depth'][b].numpy(), PO.depth_from_rgb(PO.crop_rgb(f['depth'], crop, shift)).astype(np.float32))
+        assert np.array_equal(out['semantic'][b].numpy(), PO.seg_classes(f['seg'], conv, crop, shift).astype(np.int64))
+        assert np.array_equal(out['lidar'][b].numpy(), bev_oracle.lidar_to_histogram_features(PO.align_points(f['points'], T)))
+        assert np.array_equal(out['target_point_image'][b].numpy(), PO.draw_target_point(f['target_point']).astype(np.float32))
+        assert np.array_equal(out['target_point'][b].numpy(), f['target_point'].astype(np.float32))
+    norm = pipe.prepare(raw, normalized_nhwc=True)['rgb']
+    assert getattr(norm, '_tfb_nhwc_normalized', False) and norm.shape == (2, crop[0], crop[1], 3)
+    assert np.array_equal(norm[0].numpy(), PO.normalize_nhwc(PO.crop_rgb(fs[0]['rgb'], crop, int(fs[0]['degree'] / 60 * (W // 3)))))
+    # host-side rejection of a crop that leaves the frame
+    bad = dict(raw, crop_shift=torch.tensor([40, 0], dtype=torch.int32))
+    with pytest.raises(ValueError):
+        pipe.prepare(bad)
+
+
+def test_autograd_wrappers_over_emulated_kernels(monkeypatch):
+    """ops.AvgPoolGridFn / ops.GatherSumFn / ops.centernet_decode (the product's host wrappers: shapes, saved tensors, backward
+    plumbing) executed on CPU tensors with their C-ABI calls routed to the emulated kernels."""
+    from transfuser_b200 import ops
+    geo, dec = _emulated('geometric.cu'), _emulated('decode.cu')
+
+    def call(name, *a):
+        ptr = [_p(x) if (x is None or isinstance(x, torch.Tensor)) else x for x in a]
+        if name == 'tfb_avgpool_grid_fwd':
+            geo.run_avgpool_fwd(*ptr, 4 if a[5] % 4 == 0 else 1)
+        elif name == 'tfb_avgpool_grid_bwd':
+            geo.run_avgpool_bwd(*ptr, 4 if a[5] % 4 == 0 else 1)
+        elif name == 'tfb_gather_sum_fwd':
+            geo.run_gather_fwd(*ptr)
+        elif name == 'tfb_gather_sum_bwd':
+            a[2].zero_()
+            geo.run_gather_bwd(*ptr)
+        elif name == 'tfb_centernet_decode':
+            preds, B, H, W, nb, k, ratio, boxes, labels = a
+            npad = 2
+            while npad < H * W:
+                npad <<= 1
+            dec.run_decode(_p(preds), B, H, W, nb, k, npad, ctypes.c_float(ratio), ctypes.c_float(np.float32(2.0 * np.pi / nb)), _p(boxes), _p(labels))
+        else:
+            raise AssertionError(name)
+
+    monkeypatch.setattr(ops, 'call', call)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 8, 16, 24, generator=g, requires_grad=True)
+    xm = _nhwc(x.detach()).requires_grad_()
+    pts = torch.stack((torch.randint(0, 3, (2, 5, 6, 5), generator=g), torch.randint(0, 4, (2, 5, 6, 5), generator=g)), -1)
+    # product composition: pool to a 4x3 grid, gather 5 correspondences per cell of a 5x6 grid
+    mine = ops.gather_sum(ops.avgpool_grid(xm, 4, 3), pts)
+    pooled = F.adaptive_avg_pool2d(x, (4, 3))
+    want = torch.stack([pooled[b].permute(1, 2, 0)[pts[b, ..., 1], pts[b, ..., 0]].sum(2) for b in range(2)])
+    assert mine.shape == want.shape == (2, 5, 6, 8) and torch.allclose(mine, want, atol=1e-6)
+    go = torch.randn(*want.shape, generator=g)
+    gm, = torch.autograd.grad(mine, xm, go)
+    gw, = torch.autograd.grad(want, x, go)
+    assert torch.allclose(gm.permute(0, 3, 1, 2), gw, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        ops.gather_sum(xm, pts.int())
+    heat = torch.randn(2, 1, 64, 64, generator=g)
+    rest = [torch.randn(2, c, 64, 64, generator=g) for c in (2, 2, 12, 1, 1, 2)]
+    boxes, labels = ops.centernet_decode(_nhwc(torch.cat([heat] + rest, 1)), 12, 100, 4.0)
+    want_boxes, want_labels = O.decode_heatmap([heat.sigmoid()] + rest, 12, stable=True)
+    assert labels.dtype == torch.int64 and torch.equal(labels, want_labels) and torch.allclose(boxes, want_boxes, rtol=1e-6, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        ops.centernet_decode(torch.zeros(1, 64, 64, 20), 12)

@@ -45,6 +45,10 @@ class InputPipeline:
         self.has_lut = conv is not None
         self.lut = torch.from_numpy(lut).to(self.device)
 
+    def _require_cuda(self):
+        if self.device.type != 'cuda':
+            raise RuntimeError('InputPipeline needs a CUDA device (no CPU fallback)')
+
     def _dev(self, t, dtype):
         t = torch.as_tensor(t)
         if t.dtype != dtype:
@@ -69,9 +73,8 @@ class InputPipeline:
            directly), lidar [B,2,256,256], target_point_image [B,1,256,256], target_point [B,2] float32, and depth [B,h,w] /
            semantic [B,h,w] int64 when their sources are given. `out` (optional dict) supplies preallocated destinations
            by the same keys, so the three launches can write straight into the static inputs of a captured training step."""
-        if self.device.type != 'cuda':
-            raise RuntimeError('InputPipeline needs a CUDA device (no CPU fallback)')
-        out = {}
+        self._require_cuda()
+        res = {}
         rgb = self._dev(raw['rgb'], torch.uint8)
         B, H, W, _ = rgb.shape
         ch, cw = self.crop
@@ -91,11 +94,11 @@ class InputPipeline:
         _lib.call('tfb_camera_prep', rgb, depth, seg, shift, self.lut, B, H, W, ch, cw, rgb_out, rgb_norm, depth_out, seg_out)
         if normalized_nhwc:
             rgb_norm._tfb_nhwc_normalized = True       # ops.image_prep passes such a tensor through untouched
-        out['rgb'] = rgb_norm if normalized_nhwc else rgb_out
+        res['rgb'] = rgb_norm if normalized_nhwc else rgb_out
         if depth_out is not None:
-            out['depth'] = depth_out
+            res['depth'] = depth_out
         if seg_out is not None:
-            out['semantic'] = seg_out
+            res['semantic'] = seg_out
 
         points = torch.as_tensor(raw['points'])
         if points.dim() != 3 or points.shape[2] != 4 or points.dtype not in (torch.float32, torch.float64):
@@ -106,11 +109,13 @@ class InputPipeline:
         counts = torch.empty((B, 2, 256, 256), dtype=torch.int32, device=self.device)
         lidar = self._out(out, 'lidar', (B, 2, 256, 256), torch.float32)
         _lib.call('tfb_bev_histogram_aligned', points, 1 if points.dtype == torch.float64 else 0, T, n_valid, B, points.shape[1], counts, lidar)
-        out['lidar'] = lidar
+        res['lidar'] = lidar
 
         tp = self._dev(raw['target_point'], torch.float64)
         tpi = self._out(out, 'target_point_image', (B, 1, 256, 256), torch.float32)
         _lib.call('tfb_draw_target_point', tp, B, tpi)
-        out['target_point_image'] = tpi
-        out['target_point'] = tp.float()
-        return out
+        res['target_point_image'] = tpi
+        tpf = self._out(out, 'target_point', (B, 2), torch.float32)
+        tpf.copy_(tp)
+        res['target_point'] = tpf
+        return res
