@@ -56,6 +56,44 @@ using std::fma;
 using std::fmax;
 using std::fmin;
 
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline double atomicAdd(double* p, double v) {
+  uint64_t* ip = reinterpret_cast<uint64_t*>(p);
+  uint64_t old = __atomic_load_n(ip, __ATOMIC_RELAXED), want;
+  double f;
+  do {
+    memcpy(&f, &old, 8);
+    f += v;
+    memcpy(&want, &f, 8);
+  } while (!__atomic_compare_exchange_n(ip, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  memcpy(&f, &old, 8);
+  return f;
+}
+// common.cuh's block-wide reductions (warp shuffles on the device): here through a static scratch and barriers. The
+// summation order differs from the device's tree, so only use them where rounding of the reduction is not under test.
+static float emul_red[1024];
+static inline unsigned emul_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+static inline float block_sum(float v, float*) {
+  const unsigned n = blockDim.x * blockDim.y * blockDim.z;
+  __syncthreads();
+  emul_red[emul_tid()] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (unsigned i = 0; i < n; ++i) s += emul_red[i];
+  __syncthreads();
+  return s;
+}
+static inline float block_max(float v, float*) {
+  const unsigned n = blockDim.x * blockDim.y * blockDim.z;
+  __syncthreads();
+  emul_red[emul_tid()] = v;
+  __syncthreads();
+  float s = -__builtin_inff();
+  for (unsigned i = 0; i < n; ++i) s = emul_red[i] > s ? emul_red[i] : s;
+  __syncthreads();
+  return s;
+}
+
 template <typename F>
 static void emul_launch(dim3 grid, dim3 block, F kernel) {
   const unsigned nthreads = block.x * block.y * block.z;

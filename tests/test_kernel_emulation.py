@@ -50,6 +50,11 @@ extern "C" void run_camera(const uint8_t* rgb, const uint8_t* depth, const uint8
   emul_launch(dim3(3), dim3(64), [=] { camera_prep_kernel(rgb, depth, seg, shift, lut, B, H, W, ch, cw, rgb_nchw, rgb_norm, depth_out, seg_out); });
 }
 ''',
+    'losses.cu': r'''
+extern "C" void run_targets(const float* label, int B, int K, float* tgt, int H, int W, float rw, float rh, int nb, int* count) {
+  emul_launch(dim3(B), dim3(64), [=] { centernet_targets_kernel(label, K, tgt, H, W, rw, rh, nb, count); });
+}
+''',
     'bev_hist.cu': r'''
 extern "C" void run_aligned(const float* pts, const double* T, const int* n_valid, int batch, int n_max, unsigned* counts, float* out) {
   emul_launch(dim3(2, batch), dim3(64), [=] { bev_scatter_aligned_kernel<float>(pts, T, n_valid, n_max, counts); });
@@ -321,3 +326,37 @@ def test_autograd_wrappers_over_emulated_kernels(monkeypatch):
     assert labels.dtype == torch.int64 and torch.equal(labels, want_labels) and torch.allclose(boxes, want_boxes, rtol=1e-6, atol=1e-5)
     with pytest.raises(RuntimeError):
         ops.centernet_decode(torch.zeros(1, 64, 64, 20), 12)
+
+
+def test_centernet_targets_kernel_edge_cases():
+    """LidarCenterNetHead.get_targets (model.py:285-374) as rasterised by csrc/losses.cu, against the oracle (itself pinned to
+    the reference): empty label sets, the maximum of 20 boxes, boxes on the map border, coincident centres (the later box
+    wins the regression targets, the heatmap keeps the maximum), yaw angles on bin boundaries and outside [-pi, pi]."""
+    lib = _emulated('losses.cu')
+    g = torch.Generator().manual_seed(9)
+    label = torch.zeros(5, 20, 7)
+    r = lambda *s: torch.rand(*s, generator=g)
+    label[1, :, 0:2] = r(20, 2) * 253 + 1                      # sample 1: 20 random boxes
+    label[1, :, 2:4] = r(20, 2) * 32 + 8
+    label[1, :, 4] = r(20) * 2 * np.pi - np.pi
+    label[1, :, 5] = r(20) * 8
+    label[1, :, 6] = (r(20) < 0.5).float()
+    border = torch.tensor([[0.2, 0.3], [255.9, 0.1], [0.4, 255.8], [255.7, 255.9], [128.0, 0.0], [3.99, 251.9]])
+    label[2, :6, 0:2] = border                                 # sample 2: centres in the first / last cells
+    label[2, :6, 2:4] = torch.tensor([[60., 30.], [8., 8.], [100., 4.], [2., 2.], [16., 90.], [33., 12.]])
+    label[2, :6, 4] = torch.tensor([0.0, np.pi, -np.pi, 2 * np.pi / 12, -2 * np.pi / 12 / 2, 7.5])
+    label[2, :6, 5] = 1.0
+    label[3, 0] = torch.tensor([100.3, 77.7, 20., 10., 0.3, 2., 1.])       # sample 3: two boxes in the same cell + a gap row
+    label[3, 2] = torch.tensor([101.9, 78.1, 44., 30., -2.9, 5., 0.])
+    label[4, 7] = torch.tensor([200., 20., 12., 24., 3.0, 0., 0.])         # sample 4: a single box after zero rows
+    want, avg = O.centernet_targets(label, O.Cfg)
+    tgt = torch.empty(5, 10, 64, 64)
+    count = torch.zeros(1, dtype=torch.int32)                              # the entry point memsets it
+    lib.run_targets(_p(label), 5, 20, _p(tgt), 64, 64, ctypes.c_float(64 / 256), ctypes.c_float(64 / 256), 12, _p(count))
+    assert max(1, int(count)) == avg
+    assert torch.allclose(tgt[:, 0:1], want['heat'], rtol=0, atol=1e-6) and torch.equal(tgt[:, 0:1] == 1, want['heat'] == 1)
+    assert torch.equal(tgt[:, 1:3], want['wh']) and torch.equal(tgt[:, 3:5], want['offset'])
+    assert torch.allclose(tgt[:, 5:6], want['yaw_res'], rtol=0, atol=1e-6)
+    assert torch.equal(tgt[:, 6:7], want['velocity']) and torch.equal(tgt[:, 7], want['weight'][:, 0])
+    assert torch.equal(tgt[:, 8].long(), want['yaw_cls']) and torch.equal(tgt[:, 9].long(), want['brake'])
+    assert int((tgt[0] != 0).sum()) == 0
