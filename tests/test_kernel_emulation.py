@@ -55,6 +55,20 @@ extern "C" void run_targets(const float* label, int B, int K, float* tgt, int H,
   emul_launch(dim3(B), dim3(64), [=] { centernet_targets_kernel(label, K, tgt, H, W, rw, rh, nb, count); });
 }
 ''',
+    'gru_adamw.cu': r'''
+extern "C" void run_adamw(float* p, float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps, double wd, int step,
+                          const int* step_dev, float grad_scale, void* p_bf16, int zero_grad) {
+  emul_launch(dim3(3), dim3(64), [=] { adamw_kernel(p, g, m, v, n, lr, b1, b2, (float)eps, wd, step, grad_scale, (__nv_bfloat16*)p_bf16, zero_grad, step_dev); });
+}
+extern "C" void run_gru_fwd(const float* z0, const float* tp, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                            const float* w_out, const float* b_out, int B, int steps, float x_shift, float* wp, float* save) {
+  emul_launch(dim3(B), dim3(G3), [=] { gru_fwd_kernel(z0, tp, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, x_shift, wp, save); });
+}
+extern "C" void run_gru_bwd(const float* d_wp, const float* save, const float* w_ih, const float* w_hh, const float* w_out, int B, int steps,
+                            float* dz0, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* dw_out, float* db_out) {
+  emul_launch(dim3(B), dim3(G3), [=] { gru_bwd_kernel(d_wp, save, w_ih, w_hh, w_out, steps, dz0, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out); });
+}
+''',
     'bev_hist.cu': r'''
 extern "C" void run_aligned(const float* pts, const double* T, const int* n_valid, int batch, int n_max, unsigned* counts, float* out) {
   emul_launch(dim3(2, batch), dim3(64), [=] { bev_scatter_aligned_kernel<float>(pts, T, n_valid, n_max, counts); });
@@ -360,3 +374,73 @@ def test_centernet_targets_kernel_edge_cases():
     assert torch.equal(tgt[:, 6:7], want['velocity']) and torch.equal(tgt[:, 7], want['weight'][:, 0])
     assert torch.equal(tgt[:, 8].long(), want['yaw_cls']) and torch.equal(tgt[:, 9].long(), want['brake'])
     assert int((tgt[0] != 0).sum()) == 0
+
+
+def test_adamw_kernel_matches_torch_adamw():
+    """csrc/gru_adamw.cu's fused AdamW vs torch.optim.AdamW over 4 steps (n not a multiple of 4: vector body + scalar tail),
+    the bf16 weight mirror (round-to-nearest-even of the updated fp32 value), the device-resident step counter used under
+    CUDA-graph replay, gradient scaling (1/world) and the fused zero_grad."""
+    lib = _emulated('gru_adamw.cu')
+    n = 1003
+    g0 = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g0)
+    ref = p0.clone().requires_grad_()
+    opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    pd, md, vd = p0.clone(), torch.zeros(n), torch.zeros(n)            # second copy driven by the device step counter
+    mirror = torch.zeros(n, dtype=torch.bfloat16)
+    step_dev = torch.zeros(1, dtype=torch.int32)
+    f, d = ctypes.c_float, ctypes.c_double
+    for step in range(1, 5):
+        grad = torch.randn(n, generator=g0) * (10.0 ** (step - 3))
+        ref.grad = grad.clone()
+        opt.step()
+        g = (grad * 4).contiguous()                                    # summed over 4 ranks, grad_scale = 1/4
+        lib.run_adamw(_p(p), _p(g), _p(m), _p(v), ctypes.c_int64(n), d(1e-2), d(0.9), d(0.999), d(1e-8), d(1e-2), step, None, f(0.25), _p(mirror), 1)
+        assert int((g != 0).sum()) == 0                                # zero_grad fused
+        step_dev += 1                                                  # tfb_step_tick
+        g2 = (grad * 4).contiguous()
+        lib.run_adamw(_p(pd), _p(g2), _p(md), _p(vd), ctypes.c_int64(n), d(1e-2), d(0.9), d(0.999), d(1e-8), d(1e-2), 0, _p(step_dev), f(0.25), None, 0)
+        assert torch.equal(g2, grad * 4)
+        assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=2e-7), (step, (p - ref.detach()).abs().max())
+        assert torch.equal(p, pd) and torch.equal(m, md) and torch.equal(v, vd)
+        assert torch.equal(mirror, p.bfloat16())
+    st = opt.state[ref]
+    # torch >= 2.0 updates exp_avg with lerp (m + (g - m)(1 - b1)); the kernel keeps the reference-era b1*m + (1-b1)*g: same value up
+    # to fp32 rounding (cancellation when g ~ m). exp_avg_sq uses the same formula on both sides.
+    assert torch.allclose(m, st['exp_avg'], rtol=1e-5, atol=1e-7), (m - st['exp_avg']).abs().max()
+    assert torch.allclose(v, st['exp_avg_sq'], rtol=2e-6, atol=1e-14), ((v - st['exp_avg_sq']).abs() / st['exp_avg_sq']).max()
+
+
+def test_gru_kernels_match_torch_gru_rollout():
+    """forward_gru (model.py:611-646): 4 autoregressive GRUCell steps + Linear + cumulative sum; forward and full BPTT."""
+    lib = _emulated('gru_adamw.cu')
+    torch.manual_seed(5)
+    B, steps = 3, 4
+    cell, outl = torch.nn.GRUCell(4, 64), torch.nn.Linear(64, 3)
+    z0 = torch.randn(B, 64, requires_grad=True)
+    tp = torch.randn(B, 2) * 5
+    z, x = z0, torch.zeros(B, 2)
+    tpn = tp.clone()
+    tpn[:, 1] *= -1
+    wps = []
+    for _ in range(steps):
+        z = cell(torch.cat([x, tpn], dim=1), z)
+        x = outl(z)[:, :2] + x
+        wps.append(x)
+    want = torch.stack(wps, dim=1)
+    want = torch.cat((want[:, :, :1] - 1.3, want[:, :, 1:]), dim=2)
+    ps = [t.detach().contiguous() for t in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias)]
+    wp, save = torch.empty(B, steps, 2), torch.empty(B, steps, 5 * 64 + 4)
+    z0c = z0.detach().contiguous()
+    lib.run_gru_fwd(_p(z0c), _p(tp), *[_p(t) for t in ps], B, steps, ctypes.c_float(1.3), _p(wp), _p(save))
+    assert torch.allclose(wp, want.detach(), rtol=1e-5, atol=1e-5)
+    d = torch.randn(B, steps, 2)
+    grads = torch.autograd.grad(want, [z0, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias], d)
+    dz0 = torch.empty(B, 64)
+    outs = [torch.zeros_like(t) for t in ps]                           # the entry point memsets the parameter gradients
+    lib.run_gru_bwd(_p(d), _p(save), _p(ps[0]), _p(ps[1]), _p(ps[4]), B, steps, _p(dz0), *[_p(t) for t in outs])
+    for a, b, name in zip([dz0] + outs, grads, ('z0', 'w_ih', 'w_hh', 'b_ih', 'b_hh', 'w_out', 'b_out')):
+        if name in ('w_out', 'b_out'):
+            a, b = a[:2], b[:2]                                         # the third output row never reaches the waypoints
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (name, (a - b).abs().max())

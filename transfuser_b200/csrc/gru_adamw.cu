@@ -122,17 +122,20 @@ gru_bwd_kernel(const float* __restrict__ d_wp, const float* __restrict__ save, c
   if (k < HID) dz0[(int64_t)b * HID + k] = dh[k];
 }
 
+// torch.optim.AdamW semantics, scalar preparation included: torch derives 1-beta, 1-lr*wd, lr/bias_correction1 and
+// sqrt(bias_correction2) in float64 from the Python floats and rounds each to fp32 once; the hyper-parameters therefore arrive
+// here as doubles (1.f - 0.999f would be 4.7e-5 off the 0.001 torch uses).
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ p_bf16, int zero_grad,
-             const int* __restrict__ step_dev) {
-  if (step_dev) {  // step count in device memory (CUDA-graph replay): bias corrections computed here
-    const double t = (double)(*step_dev);
-    bc1 = (float)(1.0 - pow((double)beta1, t));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
-  }
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, double lr,
+             double beta1, double beta2, float eps, double wd, int step_host, float grad_scale, __nv_bfloat16* __restrict__ p_bf16,
+             int zero_grad, const int* __restrict__ step_dev) {
+  // step count in device memory when given (valid under CUDA-graph replay), else the host's
+  const double t = step_dev ? (double)(*step_dev) : (double)step_host;
+  const float step = (float)(lr / (1.0 - pow(beta1, t)));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, t));
+  const float decay = (float)(1.0 - lr * wd);
+  const float b1 = (float)beta1, b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const int64_t n4 = n / 4;
-  const float step = lr / bc1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
     float4 Mv = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
@@ -140,10 +143,10 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float gr = gg[q] * grad_scale;
-      pp[q] *= (1.f - lr * wd);
-      mm[q] = beta1 * mm[q] + (1.f - beta1) * gr;
-      vv[q] = beta2 * vv[q] + (1.f - beta2) * gr * gr;
-      pp[q] -= step * mm[q] / (sqrtf(vv[q]) / bc2_sqrt + eps);
+      pp[q] *= decay;
+      mm[q] = b1 * mm[q] + omb1 * gr;
+      vv[q] = b2 * vv[q] + omb2 * gr * gr;
+      pp[q] -= step * (mm[q] / (sqrtf(vv[q]) / bc2_sqrt + eps));
     }
     reinterpret_cast<float4*>(p)[i] = P;
     reinterpret_cast<float4*>(m)[i] = Mv;
@@ -159,10 +162,10 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
   }
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gr = g[i] * grad_scale;
-    float P = p[i] * (1.f - lr * wd);
-    const float Mv = beta1 * m[i] + (1.f - beta1) * gr;
-    const float V = beta2 * v[i] + (1.f - beta2) * gr * gr;
-    P -= step * Mv / (sqrtf(V) / bc2_sqrt + eps);
+    float P = p[i] * decay;
+    const float Mv = b1 * m[i] + omb1 * gr;
+    const float V = b2 * v[i] + omb2 * gr * gr;
+    P -= step * (Mv / (sqrtf(V) / bc2_sqrt + eps));
     p[i] = P; m[i] = Mv; v[i] = V;
     if (zero_grad) g[i] = 0.f;
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(P);
@@ -197,14 +200,12 @@ TFB_API int tfb_gru_bwd(const float* d_wp, const float* save, const float* w_ih,
 
 // zero_grad != 0: the gradient buffer is cleared in the same pass. step_dev (optional): optimizer step count in device memory
 // (incremented by tfb_step_tick) — used instead of `step`, so a captured CUDA graph stays valid across replays.
-TFB_API int tfb_adamw_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                           float weight_decay, int step, const int* step_dev, float grad_scale, void* p_bf16, int zero_grad,
+TFB_API int tfb_adamw_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                           double weight_decay, int step, const int* step_dev, float grad_scale, void* p_bf16, int zero_grad,
                            cudaStream_t stream) {
   TFB_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev));
   if (n == 0) return TFB_OK;
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  adamw_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale,
+  adamw_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, (float)eps, weight_decay, step, grad_scale,
                                                               (__nv_bfloat16*)p_bf16, zero_grad, step_dev);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
