@@ -1,103 +1,24 @@
-"""The simple CUDA kernels added for SURVEY.md §8f (decode, geometric-fusion gather / pool, input preparation), executed
-UNCHANGED on the CPU through tests/cuda_emul/cuda_emul.h (OS threads + barriers standing in for a thread block) and compared
-with the oracle / plain torch ops. This is how their indexing and arithmetic were checked in a container without a GPU; the
-`-m gpu` tests remain the parity tests proper. Test infrastructure only."""
+"""Kernels added for SURVEY.md §8f (decode, geometric-fusion gather / pool, input preparation) and the optimizer / GRU / target
+rasterisation kernels of the training step, executed UNCHANGED on the CPU through the emulation in tests/cuda_emul/ (OS threads +
+barriers standing in for a thread block; see cuda_emul.h / build_emul.py) by calling their real C-ABI entry points, and
+compared with the oracle / plain torch ops. tests/test_ops_emulated.py does the same for every op-level parity test. This is how
+indexing and arithmetic were checked in a container without a GPU; the `-m gpu` tests remain the parity tests proper.
+Test infrastructure only."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
+from cuda_emul import loader
 from oracle import bev_oracle
 from oracle import pipeline_oracle as PO
 from oracle import torch_oracle as O
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(os.path.dirname(HERE), 'transfuser_b200', 'csrc')
-OUT = os.path.join(HERE, 'cuda_emul', '_build')
 
-DRIVERS = {
-    'geometric.cu': r'''
-extern "C" void run_avgpool_fwd(const float* x, float* out, int N, int H, int W, int C, int gh, int gw, int vec) {
-  if (vec == 4) emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_fwd_kernel<4>(x, out, N, H, W, C, gh, gw); });
-  else emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_fwd_kernel<1>(x, out, N, H, W, C, gh, gw); });
-}
-extern "C" void run_avgpool_bwd(const float* dout, float* dx, int N, int H, int W, int C, int gh, int gw, int acc, int vec) {
-  if (vec == 4) emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_bwd_kernel<4>(dout, dx, N, H, W, C, gh, gw, acc); });
-  else emul_launch(dim3(3), dim3(64), [=] { avgpool_grid_bwd_kernel<1>(dout, dx, N, H, W, C, gh, gw, acc); });
-}
-extern "C" void run_gather_fwd(const float* emb, const int64_t* pts, float* out, int B, int h, int w, int C, int M, int P) {
-  emul_launch(dim3(2), dim3(64), [=] { gather_sum_fwd_kernel(emb, pts, out, B, h, w, C, M, P); });
-}
-extern "C" void run_gather_bwd(const float* dout, const int64_t* pts, float* demb, int B, int h, int w, int C, int M, int P) {
-  emul_launch(dim3(2), dim3(64), [=] { gather_sum_bwd_kernel(dout, pts, demb, B, h, w, C, M, P); });
-}
-''',
-    'decode.cu': r'''
-extern "C" void run_decode(const float* preds, int B, int H, int W, int nb, int k, int npad, float ratio, float apc, float* boxes, int* labels) {
-  emul_launch(dim3(B), dim3(kDecodeThreads), [=] { centernet_decode_kernel(preds, H, W, nb, k, npad, ratio, apc, boxes, labels); });
-}
-''',
-    'input_prep.cu': r'''
-extern "C" void run_draw(const double* tp, int B, float* out) {
-  emul_launch(dim3(4, B), dim3(64), [=] { draw_target_point_kernel(tp, out); });
-}
-extern "C" void run_camera(const uint8_t* rgb, const uint8_t* depth, const uint8_t* seg, const int* shift, const uint8_t* lut, int B, int H, int W,
-                           int ch, int cw, float* rgb_nchw, float* rgb_norm, float* depth_out, int64_t* seg_out) {
-  emul_launch(dim3(3), dim3(64), [=] { camera_prep_kernel(rgb, depth, seg, shift, lut, B, H, W, ch, cw, rgb_nchw, rgb_norm, depth_out, seg_out); });
-}
-''',
-    'losses.cu': r'''
-extern "C" void run_targets(const float* label, int B, int K, float* tgt, int H, int W, float rw, float rh, int nb, int* count) {
-  emul_launch(dim3(B), dim3(64), [=] { centernet_targets_kernel(label, K, tgt, H, W, rw, rh, nb, count); });
-}
-''',
-    'gru_adamw.cu': r'''
-extern "C" void run_adamw(float* p, float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps, double wd, int step,
-                          const int* step_dev, float grad_scale, void* p_bf16, int zero_grad) {
-  emul_launch(dim3(3), dim3(64), [=] { adamw_kernel(p, g, m, v, n, lr, b1, b2, (float)eps, wd, step, grad_scale, (__nv_bfloat16*)p_bf16, zero_grad, step_dev); });
-}
-extern "C" void run_gru_fwd(const float* z0, const float* tp, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                            const float* w_out, const float* b_out, int B, int steps, float x_shift, float* wp, float* save) {
-  emul_launch(dim3(B), dim3(G3), [=] { gru_fwd_kernel(z0, tp, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, x_shift, wp, save); });
-}
-extern "C" void run_gru_bwd(const float* d_wp, const float* save, const float* w_ih, const float* w_hh, const float* w_out, int B, int steps,
-                            float* dz0, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* dw_out, float* db_out) {
-  emul_launch(dim3(B), dim3(G3), [=] { gru_bwd_kernel(d_wp, save, w_ih, w_hh, w_out, steps, dz0, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out); });
-}
-''',
-    'bev_hist.cu': r'''
-extern "C" void run_aligned(const float* pts, const double* T, const int* n_valid, int batch, int n_max, unsigned* counts, float* out) {
-  emul_launch(dim3(2, batch), dim3(64), [=] { bev_scatter_aligned_kernel<float>(pts, T, n_valid, n_max, counts); });
-  emul_launch(dim3(kGrid / 32, kGrid / 32, batch * 2), dim3(32, 8), [=] { bev_finalize_kernel(counts, out, batch); });
-}
-''',
-}
-
-
-def _emulated(cu):
-    """Kernel part of csrc/<cu> (above its C-ABI entry points) + the emulation header + a driver, built with g++."""
-    os.makedirs(OUT, exist_ok=True)
-    text = open(os.path.join(CSRC, cu)).read()
-    body = text[:text.index('}  // namespace') + len('}  // namespace')]
-    body = body.replace('#include "common.cuh"', '#include "../cuda_emul.h"')
-    assert '<<<' not in body
-    src = os.path.join(OUT, cu.replace('.cu', '_emul.cpp'))
-    lib = os.path.join(OUT, cu.replace('.cu', '_emul.so'))
-    full = body + '\nusing namespace std;\n' + DRIVERS[cu]
-    if not (os.path.exists(src) and open(src).read() == full and os.path.exists(lib)):
-        open(src, 'w').write(full)
-        r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes',
-                            src, '-o', lib], capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr[-3000:]
-    return ctypes.CDLL(lib)
-
-
-def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+def _call(name, *args):
+    return loader.emul().call(name, *args)
 
 
 def _nhwc(x):
@@ -106,30 +27,27 @@ def _nhwc(x):
 
 @pytest.mark.parametrize('shape,grid', [((2, 8, 16, 24), (4, 3)), ((1, 6, 10, 44), (5, 22)), ((2, 4, 8, 8), (8, 8))])
 def test_avgpool_grid_kernels(shape, grid):
-    lib = _emulated('geometric.cu')
     N, C, H, W = shape
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(1), requires_grad=True)
     want = F.adaptive_avg_pool2d(x, grid)
     xm = _nhwc(x.detach())
     out = torch.empty(N, grid[0], grid[1], C)
-    vec = 4 if C % 4 == 0 else 1
-    lib.run_avgpool_fwd(_p(xm), _p(out), N, H, W, C, grid[0], grid[1], vec)
+    _call('tfb_avgpool_grid_fwd', xm, out, N, H, W, C, grid[0], grid[1])
     assert torch.equal(out.permute(0, 3, 1, 2), want.detach())          # same accumulation order as ATen's CPU kernel
     go = torch.randn(*want.shape, generator=torch.Generator().manual_seed(2))
     gw, = torch.autograd.grad(want, x, go)
     dx = torch.empty(N, H, W, C)
     gon = _nhwc(go)                                    # keep the operand alive across the ctypes call
-    lib.run_avgpool_bwd(_p(gon), _p(dx), N, H, W, C, grid[0], grid[1], 0, vec)
+    _call('tfb_avgpool_grid_bwd', gon, dx, N, H, W, C, grid[0], grid[1], 0)
     assert torch.allclose(dx.permute(0, 3, 1, 2), gw, rtol=0, atol=1e-7)
     base = torch.randn(N, H, W, C, generator=torch.Generator().manual_seed(3))
     acc = base.clone()
-    lib.run_avgpool_bwd(_p(gon), _p(acc), N, H, W, C, grid[0], grid[1], 1, vec)
+    _call('tfb_avgpool_grid_bwd', gon, acc, N, H, W, C, grid[0], grid[1], 1)
     assert torch.allclose(acc, base + dx, rtol=0, atol=1e-6)
 
 
 @pytest.mark.parametrize('B,hw,HW,C', [(2, (5, 22), (8, 8), 16), (3, (8, 8), (5, 22), 8), (1, (4, 4), (2, 3), 4)])
 def test_gather_sum_kernels(B, hw, HW, C):
-    lib = _emulated('geometric.cu')
     g = torch.Generator().manual_seed(B * 7 + C)
     emb = torch.randn(B, C, *hw, generator=g, requires_grad=True)
     pts = torch.stack((torch.randint(0, hw[1], (B, *HW, 5), generator=g), torch.randint(0, hw[0], (B, *HW, 5), generator=g)), -1)
@@ -140,25 +58,24 @@ def test_gather_sum_kernels(B, hw, HW, C):
     want = torch.diagonal(t, 0).permute(4, 3, 0, 1, 2).contiguous().sum(-1)
     em = _nhwc(emb.detach())
     out = torch.empty(B, HW[0], HW[1], C)
-    lib.run_gather_fwd(_p(em), _p(pts), _p(out), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    _call('tfb_gather_sum_fwd', em, pts, out, B, hw[0], hw[1], C, HW[0] * HW[1], 5)
     assert torch.allclose(out.permute(0, 3, 1, 2), want.detach(), rtol=0, atol=1e-6)
     go = torch.randn(*want.shape, generator=g)
     gw, = torch.autograd.grad(want, emb, go)
-    demb = torch.zeros(B, hw[0], hw[1], C)               # the entry point memsets before the launch
+    demb = torch.full((B, hw[0], hw[1], C), float('nan'))  # the entry point clears it before the scatter
     gon = _nhwc(go)
-    lib.run_gather_bwd(_p(gon), _p(pts), _p(demb), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    _call('tfb_gather_sum_bwd', gon, pts, demb, B, hw[0], hw[1], C, HW[0] * HW[1], 5)
     assert torch.allclose(demb.permute(0, 3, 1, 2), gw, rtol=1e-5, atol=1e-5)
     # out-of-range correspondences are skipped
     bad = pts.clone()
     bad[0, 0, 0, 0] = torch.tensor([hw[1], 0])
     out2 = torch.empty_like(out)
-    lib.run_gather_fwd(_p(em), _p(bad), _p(out2), B, hw[0], hw[1], C, HW[0] * HW[1], 5)
+    _call('tfb_gather_sum_fwd', em, bad, out2, B, hw[0], hw[1], C, HW[0] * HW[1], 5)
     assert torch.allclose(out2[0, 0, 0], out[0, 0, 0] - em[0, pts[0, 0, 0, 0, 1], pts[0, 0, 0, 0, 0]], atol=1e-5)
 
 
 @pytest.mark.parametrize('case,H,W', [(0, 64, 64), (1, 64, 64), (2, 64, 64), (3, 64, 64), (0, 24, 40)])
 def test_centernet_decode_kernel(case, H, W):
-    lib = _emulated('decode.cu')
     g = torch.Generator().manual_seed(40 + case)
     B = 2
     heat_logit = torch.randn(B, 1, H, W, generator=g) * 2
@@ -173,27 +90,22 @@ def test_centernet_decode_kernel(case, H, W):
     raw = _nhwc(torch.cat([heat_logit] + rest, dim=1))
     boxes = torch.empty(B, 100, 8)
     labels = torch.empty(B, 100, dtype=torch.int32)
-    npad = 2
-    while npad < H * W:
-        npad <<= 1
-    lib.run_decode(_p(raw), B, H, W, 12, 100, npad, ctypes.c_float(4.0), ctypes.c_float(np.float32(2.0 * np.pi / 12)), _p(boxes), _p(labels))
+    _call('tfb_centernet_decode', raw, B, H, W, 12, 100, 4.0, boxes, labels)
     assert torch.equal(labels.long(), want_labels)
     assert torch.equal(boxes[..., 6], want[..., 6])
     assert torch.allclose(boxes, want, rtol=1e-6, atol=1e-5), (boxes - want).abs().amax(dim=(0, 1))
 
 
 def test_target_point_kernel():
-    lib = _emulated('input_prep.cu')
     pts = [(x, y) for x in (-16.2, -16.0, 15.9, 16.0, 16.1, 0.3) for y in (-1.4, -1.3, 30.6, 30.7, 30.8, 7.77)] + [(1e12, -1e12), (float('nan'), 0.0)]
     tp = torch.tensor(pts, dtype=torch.float64)
     out = torch.empty(len(pts), 1, 256, 256)
-    lib.run_draw(_p(tp), len(pts), _p(out))
+    _call('tfb_draw_target_point', tp, len(pts), out)
     for i, p in enumerate(pts):
         assert np.array_equal(out[i].numpy(), PO.draw_target_point(np.array(p)).astype(np.float32)), p
 
 
 def test_camera_prep_kernel():
-    lib = _emulated('input_prep.cu')
     conv = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
     H, W, crop = 40, 240, (32, 176)
     fs = [PO.synthetic_frame(s, H=H, W=W) for s in (0, 1, 2)]
@@ -208,8 +120,7 @@ def test_camera_prep_kernel():
     o_rgb, o_norm = torch.empty(B, 3, *crop), torch.empty(B, *crop, 3)
     o_depth, o_seg = torch.empty(B, *crop), torch.empty(B, *crop, dtype=torch.int64)
     shift_t = torch.tensor(shifts, dtype=torch.int32)
-    lib.run_camera(_p(rgb), _p(depth), _p(seg), _p(shift_t), _p(lut), B, H, W, crop[0], crop[1],
-                   _p(o_rgb), _p(o_norm), _p(o_depth), _p(o_seg))
+    _call('tfb_camera_prep', rgb, depth, seg, shift_t, lut, B, H, W, crop[0], crop[1], o_rgb, o_norm, o_depth, o_seg)
     for b, f in enumerate(fs):
         c = PO.crop_rgb(f['rgb'], crop, shifts[b])
         assert np.array_equal(o_rgb[b].numpy(), c.astype(np.float32))
@@ -219,16 +130,15 @@ def test_camera_prep_kernel():
 
 
 def test_aligned_histogram_kernel():
-    lib = _emulated('bev_hist.cu')
     fs = [PO.synthetic_frame(s, n_points=1500) for s in (0, 1)]
     fs[1]['degree'] = 0.0
     pts = torch.from_numpy(np.stack([f['points'] for f in fs]))
     Ts = [PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree']) for f in fs]
     T = torch.from_numpy(np.stack(Ts)).reshape(2, 16).contiguous()
     n_valid = torch.tensor([1500, 1200], dtype=torch.int32)
-    counts = torch.zeros(2, 2, 256, 256, dtype=torch.int32)       # the entry point memsets before the launch
+    counts = torch.full((2, 2, 256, 256), 7, dtype=torch.int32)    # the entry point clears it before the scatter
     out = torch.empty(2, 2, 256, 256)
-    lib.run_aligned(_p(pts), _p(T), _p(n_valid), 2, 1500, _p(counts), _p(out))
+    _call('tfb_bev_histogram_aligned', pts, 0, T, n_valid, 2, 1500, counts, out)
     for b, f in enumerate(fs):
         n = int(n_valid[b])
         want = bev_oracle.lidar_to_histogram_features(PO.align_points(f['points'][:n], Ts[b]))
@@ -236,30 +146,13 @@ def test_aligned_histogram_kernel():
 
 
 def test_input_pipeline_host_code_over_emulated_kernels(monkeypatch):
-    """transfuser_b200.pipeline.InputPipeline.prepare executed end to end in this container: its three C-ABI calls are routed
-    to the emulated kernels (same argument order as the entry points), everything else is the product's own host code."""
+    """transfuser_b200.pipeline.InputPipeline.prepare executed end to end in this container: its three C-ABI calls reach the
+    emulated entry points, everything else is the product's own host code."""
     from transfuser_b200 import pipeline
     from transfuser_b200.config import TrainConfig
-    inp, bev = _emulated('input_prep.cu'), _emulated('bev_hist.cu')
-    conv = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
-    calls = []
-
-    def call(name, *a):
-        calls.append(name)
-        if name == 'tfb_camera_prep':
-            inp.run_camera(*[_p(x) if (x is None or isinstance(x, torch.Tensor)) else x for x in a])
-        elif name == 'tfb_draw_target_point':
-            inp.run_draw(_p(a[0]), a[1], _p(a[2]))
-        elif name == 'tfb_bev_histogram_aligned':
-            points, is_f64, T, n_valid, B, n_max, counts, out = a
-            assert is_f64 == 0
-            counts.zero_()
-            bev.run_aligned(_p(points), _p(T), _p(n_valid), B, n_max, _p(counts), _p(out))
-        else:
-            raise AssertionError(name)
-
-    monkeypatch.setattr(pipeline._lib, 'call', call)
+    lib = loader.patch_product(monkeypatch)
     monkeypatch.setattr(pipeline.InputPipeline, '_require_cuda', lambda self: None)
+    conv = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
     H, W, crop = 40, 240, (32, 176)
     fs = [PO.synthetic_frame(s, H=H, W=W, n_points=800) for s in (3, 4)]
     for f, deg in zip(fs, (6.0, -3.0)):
@@ -272,7 +165,7 @@ def test_input_pipeline_host_code_over_emulated_kernels(monkeypatch):
                target_point=torch.from_numpy(np.stack([f['target_point'] for f in fs])))
     pipe = pipeline.InputPipeline(TrainConfig(converter=conv), 'cpu', crop=crop)
     out = pipe.prepare(raw)
-    assert calls == ['tfb_camera_prep', 'tfb_bev_histogram_aligned', 'tfb_draw_target_point']
+    assert lib.log == ['tfb_camera_prep', 'tfb_bev_histogram_aligned', 'tfb_draw_target_point']
     for b, f in enumerate(fs):
         shift = int(f['degree'] / 60 * (W // 3))
         T = PO.align_transform(f['ego_matrix_0'], f['ego_matrix_1'], f['degree'])
@@ -293,31 +186,9 @@ def test_input_pipeline_host_code_over_emulated_kernels(monkeypatch):
 
 def test_autograd_wrappers_over_emulated_kernels(monkeypatch):
     """ops.AvgPoolGridFn / ops.GatherSumFn / ops.centernet_decode (the product's host wrappers: shapes, saved tensors, backward
-    plumbing) executed on CPU tensors with their C-ABI calls routed to the emulated kernels."""
+    plumbing) executed on CPU tensors over the emulated entry points."""
     from transfuser_b200 import ops
-    geo, dec = _emulated('geometric.cu'), _emulated('decode.cu')
-
-    def call(name, *a):
-        ptr = [_p(x) if (x is None or isinstance(x, torch.Tensor)) else x for x in a]
-        if name == 'tfb_avgpool_grid_fwd':
-            geo.run_avgpool_fwd(*ptr, 4 if a[5] % 4 == 0 else 1)
-        elif name == 'tfb_avgpool_grid_bwd':
-            geo.run_avgpool_bwd(*ptr, 4 if a[5] % 4 == 0 else 1)
-        elif name == 'tfb_gather_sum_fwd':
-            geo.run_gather_fwd(*ptr)
-        elif name == 'tfb_gather_sum_bwd':
-            a[2].zero_()
-            geo.run_gather_bwd(*ptr)
-        elif name == 'tfb_centernet_decode':
-            preds, B, H, W, nb, k, ratio, boxes, labels = a
-            npad = 2
-            while npad < H * W:
-                npad <<= 1
-            dec.run_decode(_p(preds), B, H, W, nb, k, npad, ctypes.c_float(ratio), ctypes.c_float(np.float32(2.0 * np.pi / nb)), _p(boxes), _p(labels))
-        else:
-            raise AssertionError(name)
-
-    monkeypatch.setattr(ops, 'call', call)
+    loader.patch_product(monkeypatch)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(2, 8, 16, 24, generator=g, requires_grad=True)
     xm = _nhwc(x.detach()).requires_grad_()
@@ -346,7 +217,6 @@ def test_centernet_targets_kernel_edge_cases():
     """LidarCenterNetHead.get_targets (model.py:285-374) as rasterised by csrc/losses.cu, against the oracle (itself pinned to
     the reference): empty label sets, the maximum of 20 boxes, boxes on the map border, coincident centres (the later box
     wins the regression targets, the heatmap keeps the maximum), yaw angles on bin boundaries and outside [-pi, pi]."""
-    lib = _emulated('losses.cu')
     g = torch.Generator().manual_seed(9)
     label = torch.zeros(5, 20, 7)
     r = lambda *s: torch.rand(*s, generator=g)
@@ -365,8 +235,8 @@ def test_centernet_targets_kernel_edge_cases():
     label[4, 7] = torch.tensor([200., 20., 12., 24., 3.0, 0., 0.])         # sample 4: a single box after zero rows
     want, avg = O.centernet_targets(label, O.Cfg)
     tgt = torch.empty(5, 10, 64, 64)
-    count = torch.zeros(1, dtype=torch.int32)                              # the entry point memsets it
-    lib.run_targets(_p(label), 5, 20, _p(tgt), 64, 64, ctypes.c_float(64 / 256), ctypes.c_float(64 / 256), 12, _p(count))
+    count = torch.full((1,), 99, dtype=torch.int32)                        # the entry point clears it
+    _call('tfb_centernet_targets', label, 5, 20, tgt, 64, 64, 64 / 256, 64 / 256, 12, count)
     assert max(1, int(count)) == avg
     assert torch.allclose(tgt[:, 0:1], want['heat'], rtol=0, atol=1e-6) and torch.equal(tgt[:, 0:1] == 1, want['heat'] == 1)
     assert torch.equal(tgt[:, 1:3], want['wh']) and torch.equal(tgt[:, 3:5], want['offset'])
@@ -380,7 +250,6 @@ def test_adamw_kernel_matches_torch_adamw():
     """csrc/gru_adamw.cu's fused AdamW vs torch.optim.AdamW over 4 steps (n not a multiple of 4: vector body + scalar tail),
     the bf16 weight mirror (round-to-nearest-even of the updated fp32 value), the device-resident step counter used under
     CUDA-graph replay, gradient scaling (1/world) and the fused zero_grad."""
-    lib = _emulated('gru_adamw.cu')
     n = 1003
     g0 = torch.Generator().manual_seed(0)
     p0 = torch.randn(n, generator=g0)
@@ -390,17 +259,16 @@ def test_adamw_kernel_matches_torch_adamw():
     pd, md, vd = p0.clone(), torch.zeros(n), torch.zeros(n)            # second copy driven by the device step counter
     mirror = torch.zeros(n, dtype=torch.bfloat16)
     step_dev = torch.zeros(1, dtype=torch.int32)
-    f, d = ctypes.c_float, ctypes.c_double
     for step in range(1, 5):
         grad = torch.randn(n, generator=g0) * (10.0 ** (step - 3))
         ref.grad = grad.clone()
         opt.step()
         g = (grad * 4).contiguous()                                    # summed over 4 ranks, grad_scale = 1/4
-        lib.run_adamw(_p(p), _p(g), _p(m), _p(v), ctypes.c_int64(n), d(1e-2), d(0.9), d(0.999), d(1e-8), d(1e-2), step, None, f(0.25), _p(mirror), 1)
+        _call('tfb_adamw_step', p, g, m, v, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, step, None, 0.25, mirror, 1)
         assert int((g != 0).sum()) == 0                                # zero_grad fused
-        step_dev += 1                                                  # tfb_step_tick
+        _call('tfb_step_tick', None, step_dev)
         g2 = (grad * 4).contiguous()
-        lib.run_adamw(_p(pd), _p(g2), _p(md), _p(vd), ctypes.c_int64(n), d(1e-2), d(0.9), d(0.999), d(1e-8), d(1e-2), 0, _p(step_dev), f(0.25), None, 0)
+        _call('tfb_adamw_step', pd, g2, md, vd, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, 0, step_dev, 0.25, None, 0)
         assert torch.equal(g2, grad * 4)
         assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=2e-7), (step, (p - ref.detach()).abs().max())
         assert torch.equal(p, pd) and torch.equal(m, md) and torch.equal(v, vd)
@@ -414,7 +282,6 @@ def test_adamw_kernel_matches_torch_adamw():
 
 def test_gru_kernels_match_torch_gru_rollout():
     """forward_gru (model.py:611-646): 4 autoregressive GRUCell steps + Linear + cumulative sum; forward and full BPTT."""
-    lib = _emulated('gru_adamw.cu')
     torch.manual_seed(5)
     B, steps = 3, 4
     cell, outl = torch.nn.GRUCell(4, 64), torch.nn.Linear(64, 3)
@@ -433,14 +300,58 @@ def test_gru_kernels_match_torch_gru_rollout():
     ps = [t.detach().contiguous() for t in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias)]
     wp, save = torch.empty(B, steps, 2), torch.empty(B, steps, 5 * 64 + 4)
     z0c = z0.detach().contiguous()
-    lib.run_gru_fwd(_p(z0c), _p(tp), *[_p(t) for t in ps], B, steps, ctypes.c_float(1.3), _p(wp), _p(save))
+    _call('tfb_gru_fwd', z0c, tp, *ps, B, steps, 1.3, wp, save)
     assert torch.allclose(wp, want.detach(), rtol=1e-5, atol=1e-5)
     d = torch.randn(B, steps, 2)
     grads = torch.autograd.grad(want, [z0, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, outl.weight, outl.bias], d)
     dz0 = torch.empty(B, 64)
-    outs = [torch.zeros_like(t) for t in ps]                           # the entry point memsets the parameter gradients
-    lib.run_gru_bwd(_p(d), _p(save), _p(ps[0]), _p(ps[1]), _p(ps[4]), B, steps, _p(dz0), *[_p(t) for t in outs])
+    outs = [torch.full_like(t, float('nan')) for t in ps]             # the entry point clears the parameter gradients
+    _call('tfb_gru_bwd', d, save, ps[0], ps[1], ps[4], B, steps, dz0, *outs)
     for a, b, name in zip([dz0] + outs, grads, ('z0', 'w_ih', 'w_hh', 'b_ih', 'b_hh', 'w_out', 'b_out')):
         if name in ('w_out', 'b_out'):
             a, b = a[:2], b[:2]                                         # the third output row never reaches the waypoints
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (name, (a - b).abs().max())
+
+
+def test_flat_parameter_training_loop_matches_torch(monkeypatch):
+    """optim.flatten + ops autograd functions writing gradients straight into the flat buffer + FusedAdamW (with the bf16 weight
+    mirror) for three steps, against the same network in plain torch with torch.optim.AdamW — all on CPU over the emulation."""
+    from torch import nn
+    from transfuser_b200 import gemm, ops, optim
+    loader.patch_product(monkeypatch)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.ln, self.b = nn.Linear(24, 40), nn.LayerNorm(40), nn.Linear(40, 8, bias=False)
+            self.unused = nn.Parameter(torch.ones(5))          # never receives a gradient: must stay untouched, like in torch
+
+        def forward(self, x, mine):
+            if mine:
+                return ops.linear(ops.layer_norm(ops.linear(x, self.a.weight, self.a.bias, relu=True), self.ln), self.b.weight)
+            return self.b(self.ln(F.relu(self.a(x))))
+
+    torch.manual_seed(0)
+    net, ref = Net(), Net()
+    ref.load_state_dict(net.state_dict())
+    fp = optim.flatten(net)
+    gemm.attach_bf16_weights(fp)
+    fused = optim.FusedAdamW(net.parameters(), lr=5e-3, weight_decay=0.05)
+    opt = torch.optim.AdamW(ref.parameters(), lr=5e-3, weight_decay=0.05)
+    for step in range(3):
+        x = torch.randn(12, 24)
+        fused.zero_grad()
+        opt.zero_grad()
+        l1, l2 = net(x, True).square().mean(), ref(x, False).square().mean()
+        assert abs(float(l1) - float(l2)) < 1e-5 * abs(float(l2))
+        l1.backward()
+        l2.backward()
+        # gradients were written in place into the flat buffer (no copies): each .grad is the parameter's flat view
+        for p, o in zip(fp.params, fp.offsets):
+            assert p.grad is None or p.grad.data_ptr() == fp.grad.data_ptr() + 4 * o
+        fused.step()
+        opt.step()
+        for (n, a), b in zip(net.named_parameters(), ref.parameters()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (step, n, (a - b).abs().max())
+    assert torch.equal(net.unused, torch.ones(5)) and torch.equal(ref.unused, torch.ones(5))
+    assert torch.equal(fp.bf16, fp.flat.bfloat16())

@@ -8,6 +8,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+DEV = 'cuda'   # tests/test_ops_emulated.py re-runs these functions with DEV = 'cpu' over the CPU emulation of the kernels
+DROPOUT_N, LN_ROWS, ATT_T = 1 << 20, 348, 174   # (and smaller populations there: emulated thread barriers are slow)
 
 
 def rel(a, b):
@@ -24,8 +26,8 @@ def nchw(x):
 
 
 def rnd(*shape, seed=0, scale=1.0):
-    g = torch.Generator(device='cuda').manual_seed(seed)
-    return torch.randn(*shape, device='cuda', generator=g) * scale
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, device=DEV, generator=g) * scale
 
 
 def check_grads(mine_inputs, ref_inputs, mine_out, ref_out, tol=TOL, gseed=7):
@@ -74,10 +76,10 @@ def test_batchnorm_train(shape, relu):
     from transfuser_b200 import ops
     N, H, W, C = shape
     x = (rnd(N, C, H, W, seed=4) * 2 + 0.5).requires_grad_()
-    bn = torch.nn.BatchNorm2d(C).cuda()
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
     bn.weight.data = rnd(C, seed=5) * 0.3 + 1
     bn.bias.data = rnd(C, seed=6) * 0.2
-    bn2 = torch.nn.BatchNorm2d(C).cuda()
+    bn2 = torch.nn.BatchNorm2d(C).to(DEV)
     bn2.load_state_dict(bn.state_dict())
     ref = bn(x)
     ref = F.relu(ref) if relu else ref
@@ -90,20 +92,20 @@ def test_batchnorm_train(shape, relu):
 
 def test_layernorm_linear_dropout():
     from transfuser_b200 import ops
-    x = rnd(348, 216, seed=1).requires_grad_()
-    ln = torch.nn.LayerNorm(216).cuda()
+    x = rnd(LN_ROWS, 216, seed=1).requires_grad_()
+    ln = torch.nn.LayerNorm(216).to(DEV)
     ln.weight.data = rnd(216, seed=2) * 0.2 + 1
     ln.bias.data = rnd(216, seed=3) * 0.1
-    lin = torch.nn.Linear(216, 864).cuda()
+    lin = torch.nn.Linear(216, 864).to(DEV)
     ref = F.relu(lin(ln(x)))
     xm = x.detach().clone().requires_grad_()
-    ln2, lin2 = torch.nn.LayerNorm(216).cuda(), torch.nn.Linear(216, 864).cuda()
+    ln2, lin2 = torch.nn.LayerNorm(216).to(DEV), torch.nn.Linear(216, 864).to(DEV)
     ln2.load_state_dict(ln.state_dict()); lin2.load_state_dict(lin.state_dict())
     out = ops.linear(ops.layer_norm(xm, ln2), lin2.weight, lin2.bias, relu=True)
     assert rel(out, ref) < TOL
     check_grads([xm, ln2.weight, ln2.bias, lin2.weight, lin2.bias], [x, ln.weight, ln.bias, lin.weight, lin.bias], out, ref)
     # dropout: keep-probability and scaling, same mask regenerated in backward
-    y = rnd(1 << 20, seed=9).abs().requires_grad_()
+    y = rnd(DROPOUT_N, seed=9).abs().requires_grad_()
     d = ops.DropoutFn.apply(y, 0.1, 1234)
     kept = (d != 0).float().mean().item()
     assert abs(kept - 0.9) < 5e-3
@@ -115,7 +117,7 @@ def test_layernorm_linear_dropout():
 @pytest.mark.parametrize('C,nh', [(72, 4), (216, 4)])
 def test_attention(C, nh):
     from transfuser_b200 import ops
-    B, T = 2, 174
+    B, T = 2, ATT_T
     h = rnd(B * T, C, seed=1).requires_grad_()
     ws = [rnd(C, C, seed=10 + i, scale=1 / math.sqrt(C)).requires_grad_() for i in range(3)]
     bs = [rnd(C, seed=20 + i, scale=0.1).requires_grad_() for i in range(3)]
@@ -207,9 +209,9 @@ def test_upsample(cfg):
 
 def test_image_prep_and_layout():
     from transfuser_b200 import ops
-    img = torch.randint(0, 256, (2, 3, 16, 24), device='cuda').float()
-    mean = torch.tensor([0.485, 0.456, 0.406], device='cuda').view(1, 3, 1, 1)
-    std = torch.tensor([0.229, 0.224, 0.225], device='cuda').view(1, 3, 1, 1)
+    img = torch.randint(0, 256, (2, 3, 16, 24), device=DEV).float()
+    mean = torch.tensor([0.485, 0.456, 0.406], device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=DEV).view(1, 3, 1, 1)
     assert rel(nchw(ops.image_prep(img)), ((img / 255.0) - mean) / std) < 1e-6
     x = rnd(2, 5, 7, 9, seed=1)
     assert torch.equal(ops.nchw_to_nhwc(x), nhwc(x)) and torch.equal(ops.nhwc_to_nchw(nhwc(x)), x)
@@ -219,22 +221,22 @@ def test_losses():
     from transfuser_b200 import ops
     # weighted CE (pred_bev) and plain CE (semantic)
     logits = rnd(2, 3, 20, 24, seed=1).requires_grad_()
-    tgt = torch.randint(0, 3, (2, 20, 24), device='cuda')
-    w = torch.tensor([1., 1., 3.], device='cuda')
+    tgt = torch.randint(0, 3, (2, 20, 24), device=DEV)
+    w = torch.tensor([1., 1., 3.], device=DEV)
     lm = nhwc(logits.detach()).requires_grad_()
     ref, out = F.cross_entropy(logits, tgt, weight=w), ops.CrossEntropyFn.apply(lm, tgt, w, 'wsum', 1.0)
     assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
     (g1,), (g2,) = torch.autograd.grad(out * 0.7, lm), torch.autograd.grad(ref * 0.7, logits)
     assert rel(nchw(g1), g2) < 1e-5
     logits = rnd(2, 7, 12, 16, seed=2).requires_grad_()
-    tgt = torch.randint(0, 7, (2, 12, 16), device='cuda')
+    tgt = torch.randint(0, 7, (2, 12, 16), device=DEV)
     lm = nhwc(logits.detach()).requires_grad_()
     ref, out = 1.0 * F.cross_entropy(logits, tgt), ops.CrossEntropyFn.apply(lm, tgt, None, 'count', 1.0)
     assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
     (g1,), (g2,) = torch.autograd.grad(out, lm), torch.autograd.grad(ref, logits)
     assert rel(nchw(g1), g2) < 1e-5
     # depth: 10 * l1(sigmoid(x), t)
-    x, t = rnd(2, 12, 16, seed=3).requires_grad_(), torch.rand(2, 12, 16, device='cuda')
+    x, t = rnd(2, 12, 16, seed=3).requires_grad_(), torch.rand(2, 12, 16, device=DEV)
     xm = x.detach().clone().requires_grad_()
     ref, out = 10.0 * F.l1_loss(torch.sigmoid(x), t), ops.L1Fn.apply(xm, t, True, 10.0)
     assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
@@ -244,9 +246,9 @@ def test_losses():
 def test_gru_waypoints():
     from transfuser_b200 import ops
     B = 5
-    cell, outl = torch.nn.GRUCell(4, 64).cuda(), torch.nn.Linear(64, 3).cuda()
+    cell, outl = torch.nn.GRUCell(4, 64).to(DEV), torch.nn.Linear(64, 3).to(DEV)
     z0, tp = rnd(B, 64, seed=1).requires_grad_(), rnd(B, 2, seed=2) * 5
-    z, x = z0, torch.zeros(B, 2, device='cuda')
+    z, x = z0, torch.zeros(B, 2, device=DEV)
     tpn = tp.clone(); tpn[:, 1] *= -1
     wps = []
     for _ in range(4):
