@@ -355,3 +355,61 @@ def test_flat_parameter_training_loop_matches_torch(monkeypatch):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (step, n, (a - b).abs().max())
     assert torch.equal(net.unused, torch.ones(5)) and torch.equal(ref.unused, torch.ones(5))
     assert torch.equal(fp.bf16, fp.flat.bfloat16())
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+def test_bev_histogram_kernel_bit_exact(dt):
+    """csrc/bev_hist.cu vs the numpy oracle (bit-identical to data.py:446-470) and the committed reference fixture, including the
+    adversarial points on bin edges / the last edge / outside the grid / NaN, empty and single-point clouds, ragged batches."""
+    import os
+    for seed, n in ((0, 40000), (1, 1000), (3, 64), (4, 1)):
+        pts = torch.from_numpy(bev_oracle.synthetic_points(n, seed, dt)[None].copy())
+        counts = torch.full((1, 2, 256, 256), 5, dtype=torch.int32)
+        out = torch.empty(1, 2, 256, 256)
+        _call('tfb_bev_histogram', pts, int(dt is np.float64), None, 1, n, counts, out)
+        assert np.array_equal(out[0].numpy(), bev_oracle.lidar_to_histogram_features(pts[0].numpy())), (seed, n)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'bev_hist.npz'))
+    for key in [k for k in g.files if k.startswith('out_%s_' % np.dtype(dt).name)]:
+        _, _, seed, n = key.split('_')
+        pts = torch.from_numpy(bev_oracle.synthetic_points(int(n), int(seed), dt)[None].copy())
+        counts, out = torch.empty(1, 2, 256, 256, dtype=torch.int32), torch.empty(1, 2, 256, 256)
+        _call('tfb_bev_histogram', pts, int(dt is np.float64), None, 1, int(n), counts, out)
+        assert np.array_equal(out[0].numpy(), g[key]), key
+    ns = [3000, 0, 17, 2500]
+    batch = np.full((len(ns), 3000, 4), 3.0, dtype=dt)          # padding that WOULD land inside the grid if it were counted
+    want = []
+    for i, n in enumerate(ns):
+        p = bev_oracle.synthetic_points(n, 10 + i, dt) if n else np.zeros((0, 4), dt)
+        batch[i, :n] = p
+        want.append(bev_oracle.lidar_to_histogram_features(p))
+    counts, out = torch.empty(4, 2, 256, 256, dtype=torch.int32), torch.empty(4, 2, 256, 256)
+    _call('tfb_bev_histogram', torch.from_numpy(batch), int(dt is np.float64), torch.tensor(ns, dtype=torch.int32), 4, 3000, counts, out)
+    assert np.array_equal(out.numpy(), np.stack(want)) and float(out[1].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 32), (70, 72, 72), (33, 200, 100), (1, 64, 50), (20, 3, 64), (129, 65, 17)])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_simt_gemm_kernel(shape, ta, tb):
+    """csrc/gemm_simt.cu: all four operand layouts with bias, ReLU, alpha and beta, edge tiles, vs an fp64 product."""
+    from transfuser_b200 import gemm
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias, c0 = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    out = c0.clone()
+    lib = loader.emul()
+    import transfuser_b200._lib as L
+    old, L._LIB = L._LIB, lib
+    try:
+        gemm.gemm(a, b, out, ta, tb, bias=bias, relu=True, alpha=0.5, beta=1.0, mode='simt')
+        A, B = (a.double().t() if ta else a.double()), (b.double().t() if tb else b.double())
+        want = (0.5 * (A @ B) + bias.double() + c0.double()).clamp_min(0)
+        assert ((out.double() - want).norm() / want.norm()).item() < 1e-6
+        # strided views: a column window of x as A, a column window of the output as C (the packed q|k|v layout)
+        x, w = torch.randn(40, 3 * 24, generator=g), torch.randn(24, 24, generator=g)
+        dst = torch.zeros(40, 3 * 24)
+        gemm.gemm(x[:, 24:48], w, dst[:, 48:], False, True, mode='simt')
+        assert torch.allclose(dst[:, 48:].double(), x[:, 24:48].double() @ w.double().t(), atol=1e-5) and float(dst[:, :48].abs().sum()) == 0
+    finally:
+        L._LIB = old
