@@ -11,6 +11,14 @@ from oracle import pipeline_oracle as PO
 from oracle import bev_oracle, ref_import
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'pipeline_golden.npz')
+DEV = 'cuda'   # the emulated re-runs (tests/test_widen_emulated.py, tools/emulated_module_checks.py) switch this to 'cpu'
+
+
+def _sync():
+    if DEV == 'cuda':
+        torch.cuda.synchronize()
+
+
 FIRST_RUN = pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget was spent; not yet run on hardware')
 CONVERTER = [0, 1, 2, 3, 4, 5, 6, 4, 3, 0, 2, 1, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]    # any 23-entry map to 7 classes
 
@@ -96,10 +104,10 @@ def test_input_pipeline_matches_oracle():
     from transfuser_b200 import pipeline
     from transfuser_b200.config import TrainConfig
     fs, raw = _raw_batch([0, 1, 2])
-    pipe = pipeline.InputPipeline(TrainConfig(converter=CONVERTER), 'cuda')
+    pipe = pipeline.InputPipeline(TrainConfig(converter=CONVERTER), DEV)
     out = pipe.prepare(raw)
     outn = pipe.prepare(raw, normalized_nhwc=True)
-    torch.cuda.synchronize()
+    _sync()
     for b, f in enumerate(fs):
         o = _oracle_sample(f)
         assert np.array_equal(out['rgb'][b].cpu().numpy(), o['rgb'])
@@ -118,8 +126,8 @@ def test_input_pipeline_matches_oracle():
 def test_target_point_map_borders_and_overflow():
     from transfuser_b200 import _lib
     pts = [(x, y) for x in (-16.2, -16.0, 15.9, 16.0, 16.1, 0.3) for y in (-1.4, -1.3, 30.6, 30.7, 30.8, 7.77)] + [(1e12, -1e12), (float('nan'), 0.0)]
-    tp = torch.tensor(pts, dtype=torch.float64, device='cuda')
-    out = torch.empty((len(pts), 1, 256, 256), dtype=torch.float32, device='cuda')
+    tp = torch.tensor(pts, dtype=torch.float64, device=DEV)
+    out = torch.empty((len(pts), 1, 256, 256), dtype=torch.float32, device=DEV)
     _lib.call('tfb_draw_target_point', tp, len(pts), out)
     for i, p in enumerate(pts):
         assert np.array_equal(out[i].cpu().numpy(), PO.draw_target_point(np.array(p)).astype(np.float32)), p
@@ -130,10 +138,10 @@ def test_target_point_map_borders_and_overflow():
 def test_aligned_histogram_identity_transform_equals_plain_histogram():
     """Property at full size (40k points): with the identity transform the fused kernel is the plain histogram kernel."""
     from transfuser_b200 import _lib, bev
-    pts = torch.from_numpy(np.stack([bev_oracle.synthetic_points(40000, s, np.float32) for s in (3, 4)])).cuda()
+    pts = torch.from_numpy(np.stack([bev_oracle.synthetic_points(40000, s, np.float32) for s in (3, 4)])).to(DEV)
     want = bev.lidar_to_histogram_features_batched(pts)
-    T = torch.eye(4, dtype=torch.float64, device='cuda').reshape(1, 16).repeat(2, 1).contiguous()
-    counts = torch.empty((2, 2, 256, 256), dtype=torch.int32, device='cuda')
-    got = torch.empty((2, 2, 256, 256), dtype=torch.float32, device='cuda')
+    T = torch.eye(4, dtype=torch.float64, device=DEV).reshape(1, 16).repeat(2, 1).contiguous()
+    counts = torch.empty((2, 2, 256, 256), dtype=torch.int32, device=DEV)
+    got = torch.empty((2, 2, 256, 256), dtype=torch.float32, device=DEV)
     _lib.call('tfb_bev_histogram_aligned', pts, 0, T, None, 2, 40000, counts, got)
     assert torch.equal(got, want)

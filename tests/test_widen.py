@@ -13,6 +13,14 @@ import torch.nn.functional as F
 from oracle import ref_import
 from oracle import torch_oracle as O
 
+DEV = 'cuda'   # the emulated re-runs (tests/test_widen_emulated.py, tools/emulated_module_checks.py) switch this to 'cpu'
+
+
+def _sync():
+    if DEV == 'cuda':
+        torch.cuda.synchronize()
+
+
 FIRST_RUN = pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget was spent; not yet run on hardware')
 
 
@@ -98,13 +106,13 @@ def _nhwc(x):
 @pytest.mark.parametrize('shape,grid', [((2, 72, 40, 176), (5, 22)), ((2, 216, 32, 32), (8, 8)), ((1, 1512, 5, 22), (5, 22)), ((2, 6, 16, 24), (4, 3))])
 def test_avgpool_grid_matches_torch(shape, grid):
     from transfuser_b200 import ops
-    g = torch.Generator(device='cuda').manual_seed(1)
-    x = torch.randn(*shape, device='cuda', generator=g, requires_grad=True)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(*shape, device=DEV, generator=g, requires_grad=True)
     xm = _nhwc(x.detach()).requires_grad_()
     want = F.adaptive_avg_pool2d(x, grid)
     got = ops.avgpool_grid(xm, *grid)
     assert rel(got.permute(0, 3, 1, 2), want) < 1e-6
-    go = torch.randn(*want.shape, device='cuda', generator=g)
+    go = torch.randn(*want.shape, device=DEV, generator=g)
     gw, = torch.autograd.grad(want, x, go)
     gm, = torch.autograd.grad(got, xm, _nhwc(go))
     assert rel(gm.permute(0, 3, 1, 2), gw) < 1e-6
@@ -118,17 +126,17 @@ def test_gather_sum_matches_torch_index(B, hw, HW, C):
     correspondences (data.py:636-637 pads with index 0)."""
     from transfuser_b200 import ops
     g = torch.Generator().manual_seed(B * 7 + C)
-    emb = torch.randn(B, C, *hw, generator=g).cuda().requires_grad_()
+    emb = torch.randn(B, C, *hw, generator=g).to(DEV).requires_grad_()
     pts = torch.stack((torch.randint(0, hw[1], (B, *HW, 5), generator=g), torch.randint(0, hw[0], (B, *HW, 5), generator=g)), -1)
     pts[:, 0, 0] = 0
-    pts = pts.cuda()
+    pts = pts.to(DEV)
     flat = pts.view(-1, 2)
     t = emb.permute(0, 2, 3, 1).contiguous()[:, flat[:, 1], flat[:, 0]].view(B, B, *HW, 5, -1)
     want = torch.diagonal(t, 0).permute(4, 3, 0, 1, 2).contiguous().sum(-1)                     # [B, C, H, W]
     em = _nhwc(emb.detach()).requires_grad_()
     got = ops.gather_sum(em, pts)
     assert rel(got.permute(0, 3, 1, 2), want) < 1e-6
-    go = torch.randn(*want.shape, generator=g).cuda()
+    go = torch.randn(*want.shape, generator=g).to(DEV)
     gw, = torch.autograd.grad(want, emb, go)
     gm, = torch.autograd.grad(got, em, _nhwc(go))
     assert rel(gm.permute(0, 3, 1, 2), gw) < 1e-5
@@ -158,8 +166,8 @@ def test_centernet_decode_matches_oracle(case):
     heat_logit, rest = _decode_case(case, g)
     want, want_labels = O.decode_heatmap([heat_logit.sigmoid()] + rest, 12, stable=True)
     raw = torch.cat([heat_logit] + rest, dim=1)
-    got, got_labels = ops.centernet_decode(_nhwc(raw.cuda()), 12, 100, 4.0)
-    torch.cuda.synchronize()
+    got, got_labels = ops.centernet_decode(_nhwc(raw.to(DEV)), 12, 100, 4.0)
+    _sync()
     got, got_labels = got.cpu(), got_labels.cpu()
     assert got.shape == want.shape and torch.equal(got_labels, want_labels)
     assert torch.equal(got[..., 6], want[..., 6])                       # brake class
@@ -190,8 +198,8 @@ def test_geometric_fusion_forward_backward_matches_oracle():
     ref = O.forward(P, batch, O.Cfg, train=True, backbone_name='geometric_fusion')
     w = dict(zip(C.detailed_losses, C.detailed_losses_weights))
     sum(w[k] * ref[k] for k in ref).backward()
-    net = net.cuda().train()
-    cb = {k: v.cuda() for k, v in batch.items()}
+    net = net.to(DEV).train()
+    cb = {k: v.to(DEV) for k, v in batch.items()}
     out = net(cb['rgb'], cb['lidar'], ego_waypoint=cb['ego_waypoint'], target_point=cb['target_point'],
               target_point_image=cb['target_point_image'], ego_vel=cb['ego_vel'], bev=cb['bev'], label=cb['label'],
               depth=cb['depth'], semantic=cb['semantic'], bev_points=cb['bev_points'], cam_points=cb['cam_points'])
@@ -221,8 +229,8 @@ def test_latent_tf_forward_backward_matches_oracle():
     ref = O.forward(P, batch, OC, train=True, backbone_name='latentTF')
     w = dict(zip(C.detailed_losses, C.detailed_losses_weights))
     sum(w[k] * ref[k] for k in ref).backward()
-    net = net.cuda().train()
-    cb = {k: v.cuda() for k, v in batch.items()}
+    net = net.to(DEV).train()
+    cb = {k: v.to(DEV) for k, v in batch.items()}
     out = net(cb['rgb'], cb['lidar'], ego_waypoint=cb['ego_waypoint'], target_point=cb['target_point'],
               target_point_image=cb['target_point_image'], ego_vel=cb['ego_vel'], bev=cb['bev'], label=cb['label'],
               depth=cb['depth'], semantic=cb['semantic'])
@@ -244,8 +252,8 @@ def test_forward_ego_matches_oracle(backbone):
     P = {k: v.clone() for k, v in net.state_dict().items()}
     with torch.no_grad():
         want_wp, want_boxes, want_raw = O.forward_ego(P, batch, O.Cfg, backbone_name=backbone)
-    net = net.cuda().eval()
-    cb = {k: v.cuda() for k, v in batch.items()}
+    net = net.to(DEV).eval()
+    cb = {k: v.to(DEV) for k, v in batch.items()}
     wp, boxes = net.forward_ego(cb['rgb'], cb['lidar'], cb['target_point'], cb['target_point_image'], cb['ego_vel'])
     assert rel(wp, want_wp) < 1e-3
     assert len(boxes) == len(want_boxes)
@@ -259,15 +267,15 @@ def test_fused_adamw_matches_torch_adamw_on_device():
     """optim.FusedAdamW (one kernel over the flat buffer, bf16 mirror) vs torch.optim.AdamW on the same gradients, 3 steps."""
     from transfuser_b200 import gemm, optim
     torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.ReLU(), torch.nn.Linear(53, 11)).cuda()
-    ref = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.ReLU(), torch.nn.Linear(53, 11)).cuda()
+    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.ReLU(), torch.nn.Linear(53, 11)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.ReLU(), torch.nn.Linear(53, 11)).to(DEV)
     ref.load_state_dict(net.state_dict())
     fp = optim.flatten(net)
     gemm.attach_bf16_weights(fp)
     fused = optim.FusedAdamW(net.parameters(), lr=1e-2, weight_decay=1e-2)
     opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=1e-2)
     for step in range(3):
-        x = torch.randn(16, 37, device='cuda')
+        x = torch.randn(16, 37, device=DEV)
         fused.zero_grad()
         opt.zero_grad()
         net(x).square().mean().backward()
