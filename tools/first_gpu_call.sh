@@ -15,3 +15,7 @@ for c in 0 32 64 128; do
 done
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tile_default.json 2> gpurun_out/bench_tile_default.err
 grep -h '"value"' gpurun_out/bench_tile_*.json | cut -c1-160
+# 3. per-kernel time without host launch gaps (dedicated CUDA graph of one step's launches of that entry point)
+for k in tfb_gemm_bf16_tc tfb_conv3x3_tc tfb_bn_fwd tfb_bn_bwd tfb_im2col3x3_bf16 tfb_cast_bf16 tfb_grad_prep; do
+  timeout 240 python tools/kernel_graph_timing.py $k > gpurun_out/kgt_$k.log 2>&1; tail -3 gpurun_out/kgt_$k.log
+done
