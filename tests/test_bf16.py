@@ -127,6 +127,42 @@ def test_full_model_bf16_close_to_fp32_mode():
         assert abs(a - b) <= 3e-2 * max(abs(b), 0.1), (k, a, b)
 
 
+def test_bf16_sidecars_do_not_change_the_step():
+    """bf16 sidecars (BatchNorm / SE / add / LayerNorm write the bf16 operand of the next GEMM in their own pass) against the
+    separate cast launches they replace: the sidecar is the same rounding of the same fp32 value, so the losses agree to the
+    run-to-run noise of the fp32 atomics in the step (SE pooling; amplified by batch-2 BatchNorm: 2e-3 bound), and the step needs > 100 fewer launches."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_model import build
+    from oracle import torch_oracle as O
+    from transfuser_b200 import _lib, gemm, ops
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, seed=4).items()}
+    gemm.set_mode('bf16')
+    outs, launches = {}, {}
+    old = ops.SIDECARS
+    try:
+        for on in (False, True):
+            ops.SIDECARS = on
+            net = build().cuda().train()
+            n0 = _lib.lib().launches
+            out = net(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                      target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                      depth=batch['depth'], semantic=batch['semantic'])
+            sum(out.values()).backward()
+            torch.cuda.synchronize()
+            launches[on] = _lib.lib().launches - n0
+            outs[on] = {k: v.item() for k, v in out.items()}
+            assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+    finally:
+        ops.SIDECARS = old
+    for k in outs[True]:
+        a, b = outs[True][k], outs[False][k]
+        assert abs(a - b) <= 2e-3 * max(abs(b), 0.1), (k, a, b)
+    print('C-ABI calls per fwd+bwd: %d without sidecars, %d with' % (launches[False], launches[True]))
+    assert launches[False] - launches[True] > 100
+
+
 @pytest.mark.parametrize('cfg', [(2, 40, 48, 72, 72, 3), (2, 20, 24, 216, 216, 9), (2, 32, 44, 3, 32, 1)])
 def test_conv3x3_stride2_bf16_mode(cfg):
     """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward on the exact fp32 direct kernel; dgrad as the

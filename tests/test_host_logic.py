@@ -27,7 +27,7 @@ def torch_ops(monkeypatch):
         y = F.conv2d(_nchw(x), w, bias, stride=stride, padding=w.shape[2] // 2, groups=groups)
         return _nhwc(F.relu(y) if relu else y)
 
-    def batch_norm(x, bn, relu, training):
+    def batch_norm(x, bn, relu, training, emit16=False):      # emit16: bf16-sidecar hint of the product (no effect on values)
         y = F.batch_norm(_nchw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
         return _nhwc(F.relu(y) if relu else y)
 
@@ -40,7 +40,7 @@ def torch_ops(monkeypatch):
         rows = [emb[b][pts[b, ..., 1], pts[b, ..., 0]].sum(2) for b in range(B)]      # [H,W,5,C] -> [H,W,C]
         return torch.stack(rows)
 
-    def se(x, w1, b1, w2, b2):
+    def se(x, w1, b1, w2, b2, emit16=False):
         s = x.mean((1, 2))
         s = torch.sigmoid(F.linear(F.relu(F.linear(s, w1.view(w1.shape[0], -1), b1)), w2.view(w2.shape[0], -1), b2))
         return x * s[:, None, None, :]
@@ -97,7 +97,7 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'gather_sum', gather_sum)
     monkeypatch.setattr(ops, 'avgpool_grid', lambda x, gh, gw: _nhwc(F.adaptive_avg_pool2d(_nchw(x), (gh, gw))))
     monkeypatch.setattr(ops, 'upsample', lambda x, Ho, Wo, ac=False: _nhwc(F.interpolate(_nchw(x), (Ho, Wo), mode='bilinear', align_corners=ac)))
-    monkeypatch.setattr(ops, 'add', lambda a, b, relu=False: F.relu(a + b) if relu else a + b)
+    monkeypatch.setattr(ops, 'add', lambda a, b, relu=False, emit16=False: F.relu(a + b) if relu else a + b)
     monkeypatch.setattr(ops, 'image_prep', image_prep)
     monkeypatch.setattr(ops, 'nchw_to_nhwc', _nhwc)
     monkeypatch.setattr(ops, 'nhwc_to_nchw', lambda t: _nchw(t).contiguous())
@@ -110,7 +110,7 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'TokensFn', _Apply(tokens))
     monkeypatch.setattr(ops, 'AttentionFn', _Apply(attention))
     monkeypatch.setattr(ops, 'GptUpAddFn', _Apply(gpt_up_add))
-    monkeypatch.setattr(ops, 'layer_norm', lambda x, ln: F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps))
+    monkeypatch.setattr(ops, 'layer_norm', lambda x, ln, emit16=False: F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps))
     monkeypatch.setattr(ops, 'dropout', lambda x, p, training: x)       # the tests run with all dropout probabilities at 0
     monkeypatch.setattr(ops, 'next_seed', lambda: 0)
     return ops

@@ -1,0 +1,181 @@
+"""bf16 sidecars (ops._emit16 / _as16): in the bf16 tensor-core mode the producers of a GEMM / conv operand — BatchNorm apply, SE
+gating, residual add(+ReLU), LayerNorm — write the bf16 copy of their output in the same pass, and the consumer takes it instead of
+launching tfb_cast_bf16. Run here on the CPU emulation of the unchanged kernel sources (tests/cuda_emul/): the sidecar must be
+BIT-identical to the cast of the fp32 output (so the step's numerics do not change), the fp32 output must not change, and the
+consumers must pick it up. The tensor-core GEMM itself cannot be emulated: its host wrapper is replaced by a torch stand-in that
+checks the operand it was handed. Test infrastructure only."""
+import pytest
+import torch
+import torch.nn as nn
+
+from cuda_emul import loader
+
+
+@pytest.fixture()
+def lib(monkeypatch):
+    from transfuser_b200 import gemm
+    lib = loader.patch_product(monkeypatch)
+    gemm.set_mode('bf16')          # sidecars exist in the tensor-core mode only (conftest resets the mode after the test)
+    yield lib
+
+
+def _rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _cast(lib, x):
+    y = torch.empty(x.shape, dtype=torch.bfloat16)
+    lib.call('tfb_cast_bf16', x.contiguous(), y, x.numel())
+    return y
+
+
+def _same_bits(a, b):
+    return torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+@pytest.mark.parametrize('relu', [False, True])
+@pytest.mark.parametrize('shape', [(2, 5, 7, 24), (1, 3, 3, 72)])
+def test_batchnorm_sidecar(lib, shape, relu):
+    from transfuser_b200 import ops
+    bn = nn.BatchNorm2d(shape[-1])
+    with torch.no_grad():
+        bn.weight.copy_(_rnd(shape[-1], seed=1).abs() + 0.5)
+        bn.bias.copy_(_rnd(shape[-1], seed=2))
+    x = _rnd(*shape, seed=3).requires_grad_(True)
+    y = ops.batch_norm(x, bn, relu, True, emit16=True)
+    s = y._tfb16
+    assert s.dtype == torch.bfloat16 and s.shape == y.shape and not s.requires_grad
+    assert _same_bits(s, _cast(lib, y.detach()))
+    assert torch.equal(s.float(), y.detach().bfloat16().float())     # the emulated cast itself = torch's round-to-nearest-even
+    y0 = ops.batch_norm(x, _clone_bn(bn), relu, True)
+    assert not hasattr(y0, '_tfb16')
+    assert torch.equal(y0.detach(), y.detach())                      # the fp32 output does not depend on the sidecar
+    g = _rnd(*shape, seed=4)
+    gx, = torch.autograd.grad(y, x, g)                               # backward takes the extra (None) gradient slot
+    assert torch.isfinite(gx).all()
+    # eval mode (running statistics) emits a sidecar too
+    bn.eval()
+    with torch.no_grad():
+        ye = ops.batch_norm(x.detach(), bn, relu, False, emit16=True)
+    assert _same_bits(ye._tfb16, _cast(lib, ye))
+
+
+def _clone_bn(bn):
+    c = nn.BatchNorm2d(bn.num_features)
+    c.load_state_dict(bn.state_dict())
+    return c
+
+
+@pytest.mark.parametrize('n', [64, 67, 3])
+@pytest.mark.parametrize('relu', [False, True])
+def test_add_sidecar(lib, n, relu):
+    from transfuser_b200 import ops
+    a, b = _rnd(2, n, seed=5).requires_grad_(True), _rnd(2, n, seed=6).requires_grad_(True)
+    y = ops.add(a, b, relu=relu, emit16=True)
+    want = (a + b).detach()
+    want = want.clamp_min(0) if relu else want
+    assert torch.equal(y.detach(), want)
+    assert _same_bits(y._tfb16, _cast(lib, y.detach()))              # incl. the scalar tail when n % 4 != 0
+    ga, gb = torch.autograd.grad(y, (a, b), torch.ones_like(y))
+    assert torch.equal(ga, gb)
+    assert not hasattr(ops.add(a, b, relu=relu), '_tfb16')
+
+
+@pytest.mark.parametrize('C', [24, 6])
+def test_se_sidecar(lib, C):
+    from transfuser_b200 import ops
+    N, H, W, Cr = 2, 4, 5, 8
+    x = _rnd(N, H, W, C, seed=7).requires_grad_(True)
+    w1, b1 = _rnd(Cr, C, 1, 1, seed=8).requires_grad_(True), _rnd(Cr, seed=9).requires_grad_(True)
+    w2, b2 = _rnd(C, Cr, 1, 1, seed=10).requires_grad_(True), _rnd(C, seed=11).requires_grad_(True)
+    if C % 4:
+        pytest.skip('SE pooling requires C % 4 == 0 (every RegNetY width)')
+    y = ops.SEFn.apply(x, w1, b1, w2, b2, True)
+    y0 = ops.SEFn.apply(x, w1, b1, w2, b2)
+    assert torch.equal(y.detach(), y0.detach()) and not hasattr(y0, '_tfb16')
+    assert _same_bits(y._tfb16, _cast(lib, y.detach()))
+    grads = torch.autograd.grad(y, (x, w1, b1, w2, b2), _rnd(N, H, W, C, seed=12))
+    grads0 = torch.autograd.grad(y0, (x, w1, b1, w2, b2), _rnd(N, H, W, C, seed=12))
+    for a, b in zip(grads, grads0):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('R,C', [(5, 72), (3, 1512), (2, 7)])
+def test_layernorm_sidecar(lib, R, C):
+    from transfuser_b200 import ops
+    ln = nn.LayerNorm(C)
+    with torch.no_grad():
+        ln.weight.copy_(_rnd(C, seed=13))
+        ln.bias.copy_(_rnd(C, seed=14))
+    x = _rnd(R, C, seed=15).requires_grad_(True)
+    y = ops.layer_norm(x, ln, emit16=True)
+    y0 = ops.layer_norm(x, ln)
+    assert torch.equal(y.detach(), y0.detach()) and not hasattr(y0, '_tfb16')
+    assert _same_bits(y._tfb16, _cast(lib, y.detach()))
+    gx, = torch.autograd.grad(y, x, _rnd(R, C, seed=16))
+    gx0, = torch.autograd.grad(y0, x, _rnd(R, C, seed=16))
+    assert torch.equal(gx, gx0)
+
+
+def test_no_sidecar_outside_bf16_mode(lib):
+    from transfuser_b200 import gemm, ops
+    gemm.set_mode('simt')
+    a, b = _rnd(4, 8, seed=1), _rnd(4, 8, seed=2)
+    assert not hasattr(ops.add(a, b, emit16=True), '_tfb16')
+    gemm.set_mode('bf16')
+    ops_sidecars = ops.SIDECARS
+    try:
+        ops.SIDECARS = False
+        assert not hasattr(ops.add(a, b, emit16=True), '_tfb16')
+    finally:
+        ops.SIDECARS = ops_sidecars
+
+
+def test_consumers_take_the_sidecar(lib, monkeypatch):
+    """linear() / conv2d() 1x1 / the attention projections hand the producer's sidecar (same storage, reshaped) to the tensor-core
+    GEMM and launch no cast for the activation; a tensor without a sidecar still gets its cast."""
+    from transfuser_b200 import gemm as G, ops
+    seen, operands = [], []
+
+    def fake_gemm_bf16(a, b, out, trans_a=False, trans_b=False, bias=None, relu=False, alpha=1.0, beta=0.0, splits=1):
+        seen.append(a)
+        operands.append(b)
+        A = a.float().t() if trans_a else a.float()
+        Bm = b.float().t() if trans_b else b.float()
+        r = alpha * (A @ Bm)
+        if bias is not None:
+            r = r + bias
+        if relu:
+            r = r.clamp_min(0)
+        out.copy_(r if beta == 0.0 else r + beta * out)
+        return out
+    monkeypatch.setattr(G, 'gemm_bf16', fake_gemm_bf16)
+    monkeypatch.setattr(G, 'weight_bf16', lambda w: w.detach().bfloat16())
+    ln = nn.LayerNorm(64)
+    x = _rnd(2, 20, 64, seed=20)
+    w, b = _rnd(32, 64, seed=21).requires_grad_(True), _rnd(32, seed=22).requires_grad_(True)
+    h = ops.layer_norm(x, ln, emit16=True)
+    lib.log.clear()
+    y = ops.linear(h, w, b)
+    assert 'tfb_cast_bf16' not in lib.log
+    assert seen[-1].data_ptr() == h._tfb16.data_ptr() and seen[-1].shape == (40, 64)
+    want = h.detach().bfloat16().float().view(40, 64) @ w.detach().bfloat16().float().t() + b.detach()
+    assert torch.allclose(y.detach().view(40, 32), want, rtol=1e-5, atol=1e-5)
+    # NHWC 1x1 conv after BatchNorm
+    bn = nn.BatchNorm2d(64)
+    f = ops.batch_norm(_rnd(2, 4, 5, 64, seed=23), bn, True, True, emit16=True)
+    lib.log.clear()
+    ops.conv2d(f, _rnd(32, 64, 1, 1, seed=24).requires_grad_(True))
+    assert 'tfb_cast_bf16' not in lib.log and seen[-1].data_ptr() == f._tfb16.data_ptr()
+    # no sidecar -> one cast, as before
+    lib.log.clear()
+    ops.linear(_rnd(40, 64, seed=25), w, b)
+    assert lib.log.count('tfb_cast_bf16') == 1
+    # backward of the sidecar-fed linear: wgrad reads the saved sidecar
+    seen.clear()
+    hx = _rnd(2, 20, 64, seed=26).requires_grad_(True)
+    h = ops.layer_norm(hx, ln, emit16=True)
+    y = ops.linear(h, w, b, relu=True)
+    gw, gh = torch.autograd.grad(y, (w, hx), _rnd(2, 20, 32, seed=27))
+    assert any(t.data_ptr() == h._tfb16.data_ptr() for t in operands)      # wgrad: dW = g^T xs with xs = the sidecar
+    assert torch.isfinite(gw).all() and torch.isfinite(gh).all()

@@ -25,9 +25,10 @@ class _ConvBn(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
         self.stride, self.groups, self.act = stride, groups, act
 
-    def run(self, x):
+    def run(self, x, emit16=False):
+        """emit16: the output is the operand of a tensor-core GEMM / conv next (bf16 mode: BatchNorm writes its bf16 copy too)."""
         y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups)
-        return ops.batch_norm(y, self.bn, self.act, self.bn.training)
+        return ops.batch_norm(y, self.bn, self.act, self.bn.training, emit16)
 
 
 class _SE(nn.Module):
@@ -37,7 +38,8 @@ class _SE(nn.Module):
         self.fc2 = nn.Conv2d(rd_channels, channels, 1, bias=True)
 
     def run(self, x):
-        return ops.SEFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+        # the gated output always feeds the 1x1 conv3 GEMM: emit its bf16 copy in the gating pass
+        return ops.SEFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, True)
 
 
 class _Bottleneck(nn.Module):
@@ -50,10 +52,11 @@ class _Bottleneck(nn.Module):
         self.downsample = _ConvBn(cin, cout, 1, stride=stride, act=False) if (cin != cout or stride != 1) else None
         nn.init.zeros_(self.conv3.bn.weight)  # timm zero_init_last_bn
 
-    def run(self, x):
-        y = self.conv3.run(self.se.run(self.conv2.run(self.conv1.run(x))))
+    def run(self, x, emit16=True):
+        """emit16: the block output feeds a 1x1 conv next (the following block's conv1, or the channel-change conv)."""
+        y = self.conv3.run(self.se.run(self.conv2.run(self.conv1.run(x, emit16=self.conv2.stride == 1))))
         sc = self.downsample.run(x) if self.downsample is not None else x
-        return ops.add(y, sc, relu=True)
+        return ops.add(y, sc, relu=True, emit16=emit16)
 
 
 class _Stage(nn.Module):
@@ -62,9 +65,11 @@ class _Stage(nn.Module):
         for i in range(depth):
             self.add_module('b%d' % (i + 1), _Bottleneck(cin if i == 0 else cout, cout, 2 if i == 0 else 1, group_w, se_ratio))
 
-    def run(self, x):
-        for blk in self.children():
-            x = blk.run(x)
+    def run(self, x, last16=True):
+        """last16 = False when the stage output goes to a GPT fusion (token pooling / upsample-add), not straight into a conv."""
+        blocks = list(self.children())
+        for i, blk in enumerate(blocks):
+            x = blk.run(x, emit16=last16 or i + 1 < len(blocks))
         return x
 
 
@@ -141,13 +146,13 @@ class Block(nn.Module):
 
     def run(self, x, B, T):
         a, training = self.attn, self.training
-        h = ops.layer_norm(x, self.ln1)
+        h = ops.layer_norm(x, self.ln1, emit16=True)
         p_att = a.attn_pdrop if training else 0.0
         y = ops.AttentionFn.apply(h, a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
                                   B, T, a.n_head, p_att, ops.next_seed())
         y = ops.dropout(ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training)
         x = ops.add(x, y)
-        h = ops.layer_norm(x, self.ln2)
+        h = ops.layer_norm(x, self.ln2, emit16=True)
         h = ops.linear(h, self.mlp[0].weight, self.mlp[0].bias, relu=True)
         h = ops.dropout(ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), a.resid_pdrop, training)
         return ops.add(x, h)
@@ -241,11 +246,11 @@ class TransfuserBackbone(nn.Module):
         x = ops.image_prep(image) if self.image_encoder.normalize else ops.nchw_to_nhwc(image)
         l = ops.nchw_to_nhwc(lidar)
         if not self.two_streams:
-            x = ie.stem.run(x)
-            l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
+            x = ie.stem.run(x, emit16=True)
+            l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training, emit16=True)
             for i in range(1, 5):
-                x = getattr(ie, 's%d' % i).run(x)
-                l = getattr(le, 's%d' % i).run(l)
+                x = getattr(ie, 's%d' % i).run(x, last16=False)
+                l = getattr(le, 's%d' % i).run(l, last16=False)
                 x, l = getattr(self, 'transformer%d' % i).run(x, l)
                 if taps is not None:
                     taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
@@ -257,20 +262,20 @@ class TransfuserBackbone(nn.Module):
             side = ops.side_stream(image.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
-            x = ie.stem.run(x)
+                l = ops.batch_norm(ops.conv2d(l, le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training, emit16=True)
+            x = ie.stem.run(x, emit16=True)
             for i in range(1, 5):
                 with torch.cuda.stream(side):
-                    l = getattr(le, 's%d' % i).run(l)
-                x = getattr(ie, 's%d' % i).run(x)
+                    l = getattr(le, 's%d' % i).run(l, last16=False)
+                x = getattr(ie, 's%d' % i).run(x, last16=False)
                 main.wait_stream(side)
-                l.record_stream(main)
+                ops.record_stream(l, main)
                 x, l = getattr(self, 'transformer%d' % i).run(x, l)
                 if taps is not None:
                     taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
                 if i < 4:
                     side.wait_stream(main)
-                    l.record_stream(side)
+                    ops.record_stream(l, side)
         x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
@@ -302,7 +307,7 @@ class _PlainEncoder(nn.Module):
 
     def run(self, x):
         net = self._net
-        x = net.stem.run(x)
+        x = net.stem.run(x, emit16=True)
         for i in range(1, 5):
             x = getattr(net, 's%d' % i).run(x)
         return x
@@ -350,7 +355,7 @@ class LateFusionBackbone(nn.Module):
                 l = self.lidar_encoder.run(l)
             x = self.image_encoder.run(ops.image_prep(image))
             main.wait_stream(side)
-            l.record_stream(main)
+            ops.record_stream(l, main)
         else:
             x = self.image_encoder.run(ops.image_prep(image))
             l = self.lidar_encoder.run(ops.nchw_to_nhwc(lidar))
@@ -450,13 +455,13 @@ class GeometricFusionBackbone(nn.Module):
             torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
             ops.tick(image.device)
         ie, le = self.image_encoder.features, self.lidar_encoder._model
-        x = ie.stem.run(ops.image_prep(image))
-        l = ops.batch_norm(ops.conv2d(ops.nchw_to_nhwc(lidar), le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training)
+        x = ie.stem.run(ops.image_prep(image), emit16=True)
+        l = ops.batch_norm(ops.conv2d(ops.nchw_to_nhwc(lidar), le.conv1.weight, None, 2, 1), le.bn1, True, le.bn1.training, emit16=True)
         ih, iw, lh, lw = cfg.img_vert_anchors, cfg.img_horz_anchors, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors
         prev_lidar_embd = None
         for i in range(1, 5):
-            x = getattr(ie, 's%d' % i).run(x)
-            l = getattr(le, 's%d' % i).run(l)
+            x = getattr(ie, 's%d' % i).run(x, last16=False)
+            l = getattr(le, 's%d' % i).run(l, last16=False)
             ic, lc = getattr(self, 'image_conv%d' % i), getattr(self, 'lidar_conv%d' % i)
             img_embd = ops.linear(ops.avgpool_grid(x, ih, iw), ic.weight, ic.bias)          # [B,5,22,512]
             # scale 4's LiDAR embedding is never read (the image branch gathers from scale 3's, geometric_fusion.py:277)
@@ -470,8 +475,8 @@ class GeometricFusionBackbone(nn.Module):
             if i < 4:
                 dl = ops.upsample(dl, l.shape[1], l.shape[2], False)
                 dx = ops.upsample(dx, x.shape[1], x.shape[2], False)
-            l = ops.add(l, dl)
-            x = ops.add(x, dx)
+            l = ops.add(l, dl, emit16=True)       # feeds the next stage's 1x1 conv1 / the channel-change conv
+            x = ops.add(x, dx, emit16=True)
             prev_lidar_embd = lidar_embd
         x = ops.conv2d(x, self.change_channel_conv_image.weight, self.change_channel_conv_image.bias)
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)

@@ -76,6 +76,16 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return red[0];
 }
 
+// Stores four fp32 values as four bf16 (round-to-nearest-even) with one 8-byte access: the "bf16 sidecar" that producers of a
+// tensor-core operand write next to their fp32 output, so the consumer needs no separate cast pass. `dst + i4*4` must be 8-byte aligned.
+__device__ __forceinline__ void tfb_store_bf16x4(__nv_bfloat16* dst, int64_t i4, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  reinterpret_cast<uint2*>(dst)[i4] = o;
+}
+
 // Counter-based RNG for dropout: one 32-bit hash per (seed, element index); regenerated in backward, no mask storage.
 __device__ __forceinline__ uint32_t tfb_hash32(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;

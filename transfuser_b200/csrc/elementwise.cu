@@ -8,17 +8,20 @@
 namespace {
 
 __global__ void __launch_bounds__(256) add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
-                                                       int64_t n, int relu) {
+                                                       int64_t n, int relu, __nv_bfloat16* __restrict__ y16) {
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
     float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     reinterpret_cast<float4*>(y)[i] = o;
+    if (y16) tfb_store_bf16x4(y16, i, o.x, o.y, o.z, o.w);
   }
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float o = a[i] + b[i];
-    y[i] = relu ? fmaxf(o, 0.f) : o;
+    o = relu ? fmaxf(o, 0.f) : o;
+    y[i] = o;
+    if (y16) y16[i] = __float2bfloat16_rn(o);
   }
 }
 
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(256) pool_hw_kernel(const float* __restrict__ 
 template <int VEC>
 __global__ void __launch_bounds__(256) scale_nc_kernel(const float* __restrict__ x, const float* __restrict__ gate,
                                                        const float* __restrict__ add, float add_scale, float* __restrict__ y,
-                                                       int64_t total, int HW, int C) {
+                                                       int64_t total, int HW, int C, __nv_bfloat16* __restrict__ y16) {
   const int Cv = C / VEC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / VEC; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cv) * VEC;
@@ -83,10 +86,12 @@ __global__ void __launch_bounds__(256) scale_nc_kernel(const float* __restrict__
         v.x = fmaf(a.x, add_scale, v.x); v.y = fmaf(a.y, add_scale, v.y); v.z = fmaf(a.z, add_scale, v.z); v.w = fmaf(a.w, add_scale, v.w);
       }
       reinterpret_cast<float4*>(y)[i] = v;
+      if (y16) tfb_store_bf16x4(y16, i, v.x, v.y, v.z, v.w);
     } else {
       float v = x[i] * gate[n * C + c];
       if (add) v = fmaf(add[n * C + c], add_scale, v);
       y[i] = v;
+      if (y16) y16[i] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -365,10 +370,11 @@ __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict_
 
 }  // namespace
 
-TFB_API int tfb_add_relu(const float* a, const float* b, float* y, int64_t n, int relu, cudaStream_t stream) {
+// y16_bf16 (optional, here and in tfb_se_scale_fwd): bf16 copy of y written in the same pass.
+TFB_API int tfb_add_relu(const float* a, const float* b, float* y, int64_t n, int relu, void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(a && b && y && n >= 0);
   if (n == 0) return TFB_OK;
-  add_relu_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(a, b, y, n, relu);
+  add_relu_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(a, b, y, n, relu, (__nv_bfloat16*)y16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -411,11 +417,12 @@ TFB_API int tfb_pool_hw_bwd(const float* dout, float* dx, int N, int HW, int C, 
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
-TFB_API int tfb_se_scale_fwd(const float* x, const float* gate, float* y, int N, int HW, int C, cudaStream_t stream) {
+TFB_API int tfb_se_scale_fwd(const float* x, const float* gate, float* y, int N, int HW, int C, void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && gate && y && N > 0 && HW > 0 && C > 0);
   const int64_t total = (int64_t)N * HW * C;
-  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
-  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C);
+  __nv_bfloat16* y16 = (__nv_bfloat16*)y16_bf16;
+  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C, y16);
+  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(x, gate, nullptr, 0.f, y, total, HW, C, y16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -434,8 +441,8 @@ TFB_API int tfb_se_bwd_apply(const float* dy, const float* gate, const float* dp
                              cudaStream_t stream) {
   TFB_REQUIRE(dy && gate && dpool && dx && N > 0 && HW > 0 && C > 0);
   const int64_t total = (int64_t)N * HW * C;
-  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
-  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C);
+  if (C % 4 == 0) scale_nc_kernel<4><<<tfb_grid(total / 4, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C, nullptr);
+  else            scale_nc_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dy, gate, dpool, 1.f / (float)HW, dx, total, HW, C, nullptr);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -182,7 +182,8 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
 // y = (x - mean) * invstd * gamma + beta (ReLU); 4 channels per thread (C % 4 == 0).
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total4, int C4, const float* __restrict__ mean,
-                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                __nv_bfloat16* __restrict__ y16) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -197,6 +198,7 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t tota
     o.w = fmaf((v.w - mu.w) * is.w, ga.w, be.w);
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     reinterpret_cast<float4*>(y)[i] = o;
+    if (y16) tfb_store_bf16x4(y16, i, o.x, o.y, o.z, o.w);
   }
 }
 
@@ -237,7 +239,8 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
 // ---------------- LayerNorm over the last dim of [R, C] ----------------
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const float* __restrict__ gamma,
-              const float* __restrict__ beta, float eps, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+              const float* __restrict__ beta, float eps, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+              __nv_bfloat16* __restrict__ y16) {
   __shared__ float red[32];
   const int64_t r = blockIdx.x;
   const float* xr = x + r * C;
@@ -249,7 +252,12 @@ ln_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const f
   const float var = block_sum(v, red) / (float)C;
   const float rstd = rsqrtf(var + eps);
   float* yr = y + r * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = fmaf((xr[c] - mean) * rstd, gamma[c], beta[c]);
+  __nv_bfloat16* hr = y16 ? y16 + r * C : nullptr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float o = fmaf((xr[c] - mean) * rstd, gamma[c], beta[c]);
+    yr[c] = o;
+    if (hr) hr[c] = __float2bfloat16_rn(o);
+  }
   if (threadIdx.x == 0) { save_mean[r] = mean; save_rstd[r] = rstd; }
 }
 
@@ -369,25 +377,28 @@ int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, in
 }  // namespace
 
 // sums_ws: (2*C + 1) doubles, ZERO on entry, left zero on exit (shared by all layers of a stream; no memset launches).
+// y16_bf16 (optional): bf16 copy of y written in the same pass (operand of the next layer's tensor-core GEMM / conv).
 TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps,
                        float momentum, int relu, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                       double* sums_ws, cudaStream_t stream) {
+                       double* sums_ws, void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && sums_ws && M > 0 && C > 0 && C % 4 == 0);
   Finalize fin = {1, 2 * C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var};
   launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, fin, stream);
   TFB_CHECK_LAUNCH();
   const int64_t total4 = M * C / 4;
-  bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu);
+  bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu,
+                                                             (__nv_bfloat16*)y16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
 // eval-mode BN: normalise with the running statistics (mean, 1/sqrt(var+eps) computed by the caller into save_*).
 TFB_API int tfb_bn_apply(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, const float* mean,
-                         const float* invstd, int relu, cudaStream_t stream) {
+                         const float* invstd, int relu, void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && mean && invstd && M > 0 && C > 0 && C % 4 == 0);
   const int64_t total4 = M * C / 4;
-  bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, mean, invstd, gamma, beta, relu);
+  bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, mean, invstd, gamma, beta, relu,
+                                                             (__nv_bfloat16*)y16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -429,9 +440,9 @@ TFB_API int tfb_grad_prep(const float* dy, const float* y, float* g32, void* g16
 }
 
 TFB_API int tfb_layernorm_fwd(const float* x, float* y, int64_t R, int C, const float* gamma, const float* beta, float eps,
-                              float* save_mean, float* save_rstd, cudaStream_t stream) {
+                              float* save_mean, float* save_rstd, void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_rstd && R > 0 && C > 0);
-  ln_fwd_kernel<<<(unsigned)R, 256, 0, stream>>>(x, y, C, gamma, beta, eps, save_mean, save_rstd);
+  ln_fwd_kernel<<<(unsigned)R, 256, 0, stream>>>(x, y, C, gamma, beta, eps, save_mean, save_rstd, (__nv_bfloat16*)y16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -48,6 +48,49 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# bf16 sidecars: in bf16 mode the producer of a tensor-core operand (BatchNorm, SE gating, residual add, LayerNorm) writes the bf16
+# copy in the same pass as its fp32 output; it travels as the `_tfb16` attribute of the fp32 tensor and the consuming GEMM / conv
+# takes it instead of running a cast pass of its own. SIDECARS = False restores the separate cast launches.
+SIDECARS = os.environ.get('TFB_SIDECARS', '1') == '1'
+
+
+def _emit16(x, want):
+    """bf16 buffer for the sidecar of a tensor shaped like x, or None when not wanted."""
+    if want and SIDECARS and G.MODE == 'bf16':
+        return torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    return None
+
+
+def _attach16(y, y16):
+    if y16 is not None:
+        y._tfb16 = y16
+    return y
+
+
+def _as16(x):
+    """bf16 copy of the contiguous fp32 tensor x: its sidecar when the producer wrote one, else a cast pass."""
+    s = getattr(x, '_tfb16', None)
+    if s is not None and s.shape == x.shape:
+        return s
+    return G.to_bf16(x)
+
+
+def record_stream(t, stream):
+    """Tensor.record_stream for a tensor that crosses streams, sidecar included."""
+    t.record_stream(stream)
+    s = getattr(t, '_tfb16', None)
+    if s is not None:
+        s.record_stream(stream)
+
+
+def _view16(x, v):
+    """v = a view (reshape) of x: carries x's sidecar over to v under the same reshape."""
+    s = getattr(x, '_tfb16', None)
+    if s is not None and v.is_contiguous() and x.is_contiguous():
+        v._tfb16 = s.view(v.shape)
+    return v
+
+
 _WS = {}
 _SIDE = {}
 TWO_STREAMS = os.environ.get('TFB_TWO_STREAMS', '1') == '1'
@@ -149,7 +192,7 @@ class LinearFn(Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         ctx.tc = G.tc_ok(M, N, K, K, N)
         if ctx.tc:
-            xs = G.to_bf16(x)
+            xs = _as16(x)
             G.gemm_bf16(xs, G.weight_bf16(w2), y, trans_b=True, bias=bias, relu=relu)
         else:
             xs = x
@@ -193,7 +236,7 @@ class LinearFn(Function):
 
 def linear(x, w, bias=None, relu=False):
     lead = x.shape[:-1]
-    y = LinearFn.apply(x.reshape(-1, x.shape[-1]), w, bias, relu)
+    y = LinearFn.apply(_view16(x, x.reshape(-1, x.shape[-1])), w, bias, relu)
     return y.view(*lead, y.shape[-1])
 
 
@@ -308,7 +351,7 @@ class Conv3x3TCFn(Function):
     def forward(ctx, x, w, bias, groups, relu):
         x = _c(x)
         Cout, Cin = w.shape[0], w.shape[1] * groups
-        y = _conv_tc_run(G.to_bf16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu)
+        y = _conv_tc_run(_as16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu)
         ctx.save_for_backward(x, w, y if relu else None, bias)
         ctx.cfg = (groups, relu, bias is not None)
         return y
@@ -380,7 +423,7 @@ def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
         x, stride = Subsample2Fn.apply(x), 1
     if w.shape[2] == 1 and stride == 1 and groups == 1:
         N, H, W, C = x.shape
-        return LinearFn.apply(x.reshape(-1, C), w, bias, relu).view(N, H, W, w.shape[0])
+        return LinearFn.apply(_view16(x, x.reshape(-1, C)), w, bias, relu).view(N, H, W, w.shape[0])
     if G.MODE == 'bf16' and w.shape[2] == 3 and stride == 1 and _conv_tc_plan(w.shape[1] * groups, w.shape[0], groups) is not None:
         return Conv3x3TCFn.apply(x, w, bias, groups, relu)
     return Conv2dFn.apply(x, w, bias, stride, groups, relu)
@@ -391,18 +434,20 @@ class BatchNormTrainFn(Function):
     """BatchNorm2d in training mode (+ fused ReLU): batch statistics, running-stat update (momentum, unbiased var)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False):
         x = _c(x)
         C = x.shape[-1]
         M = x.numel() // C
         y = torch.empty_like(x)
+        y16 = _emit16(y, emit16)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = _ws(x.device)
-        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws)
+        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws,
+             y16)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.relu = relu
-        return y
+        return _attach16(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
@@ -415,34 +460,37 @@ class BatchNormTrainFn(Function):
         db = _gbuf(bias)
         ws = _ws(x.device)
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws)
-        return dx, dg, db, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None
 
 
-def batch_norm(x, bn, relu, training):
-    """bn: an nn.BatchNorm2d used as a parameter/buffer container."""
+def batch_norm(x, bn, relu, training, emit16=False):
+    """bn: an nn.BatchNorm2d used as a parameter/buffer container. emit16: the output feeds a tensor-core GEMM / conv next, so
+    (bf16 mode) its bf16 copy is written in the same pass."""
     if training:
-        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16)
     if torch.is_grad_enabled() and x.requires_grad:
         raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
     C = x.shape[-1]
     y = torch.empty_like(x)
+    y16 = _emit16(y, emit16)
     invstd = torch.rsqrt(bn.running_var + bn.eps)
-    call('tfb_bn_apply', _c(x), y, x.numel() // C, C, bn.weight, bn.bias, bn.running_mean, invstd, int(relu))
-    return y
+    call('tfb_bn_apply', _c(x), y, x.numel() // C, C, bn.weight, bn.bias, bn.running_mean, invstd, int(relu), y16)
+    return _attach16(y, y16)
 
 
 class LayerNormFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, emit16=False):
         x = _c(x)
         C = x.shape[-1]
         R = x.numel() // C
         y = torch.empty_like(x)
+        y16 = _emit16(y, emit16)
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
-        call('tfb_layernorm_fwd', x, y, R, C, weight, bias, float(eps), mean, rstd)
+        call('tfb_layernorm_fwd', x, y, R, C, weight, bias, float(eps), mean, rstd, y16)
         ctx.save_for_backward(x, weight, mean, rstd, bias)
-        return y
+        return _attach16(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
@@ -454,11 +502,11 @@ class LayerNormFn(Function):
         dg = _gbuf(weight)
         db = _gbuf(bias)
         call('tfb_layernorm_bwd', x, dy, dx, R, C, weight, mean, rstd, dg, db, 0)
-        return dx, dg, db, None
+        return dx, dg, db, None, None
 
 
-def layer_norm(x, ln):
-    return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
+def layer_norm(x, ln, emit16=False):
+    return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, emit16)
 
 
 # ------------------------------------------------------------------ squeeze-excite, residual
@@ -466,7 +514,7 @@ class SEFn(Function):
     """timm SEModule: x * sigmoid(fc2(relu(fc1(mean_hw(x))))) — pooling, two tiny GEMMs and the gating, fwd + bwd."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, emit16=False):
         x = _c(x)
         N, H, W, C = x.shape
         Cr = w1.shape[0]
@@ -484,9 +532,10 @@ class SEFn(Function):
             gemm(h, w2.view(C, Cr), s, trans_b=True, bias=b2, mode='simt')
             call('tfb_sigmoid_fwd', s, gate, s.numel())
         y = torch.empty_like(x)
-        call('tfb_se_scale_fwd', x, gate, y, N, H * W, C)
+        y16 = _emit16(y, emit16)
+        call('tfb_se_scale_fwd', x, gate, y, N, H * W, C, y16)
         ctx.save_for_backward(x, w1, w2, pooled, h, gate, b1, b2)
-        return y
+        return _attach16(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
@@ -518,21 +567,22 @@ class SEFn(Function):
             gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
         dx = torch.empty_like(x)
         call('tfb_se_bwd_apply', dy, gate, dpool, dx, N, H * W, C)
-        return dx, dw1, db1, dw2, db2
+        return dx, dw1, db1, dw2, db2, None
 
 
 class AddFn(Function):
     """y = a + b (ReLU optional): the Bottleneck shortcut (timm) and the GPT residuals (transfuser.py:546-547)."""
 
     @staticmethod
-    def forward(ctx, a, b, relu):
+    def forward(ctx, a, b, relu, emit16=False):
         a, b = _c(a), _c(b)
         y = torch.empty_like(a)
-        call('tfb_add_relu', a, b, y, a.numel(), int(relu))
+        y16 = _emit16(y, emit16)
+        call('tfb_add_relu', a, b, y, a.numel(), int(relu), y16)
         ctx.relu = relu
         if relu:
             ctx.save_for_backward(y)
-        return y
+        return _attach16(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
@@ -540,11 +590,11 @@ class AddFn(Function):
         if ctx.relu:
             (y,) = ctx.saved_tensors
             dy = _relu_bwd(y, dy)
-        return dy, dy, None
+        return dy, dy, None, None
 
 
-def add(a, b, relu=False):
-    return AddFn.apply(a, b, relu)
+def add(a, b, relu=False, emit16=False):
+    return AddFn.apply(a, b, relu, emit16)
 
 
 class DropoutFn(Function):
@@ -583,7 +633,7 @@ class AttentionFn(Function):
         dev = h.device
         qkv = torch.empty((B * T, 3 * C), dtype=torch.float32, device=dev)
         tc = G.tc_ok(B * T, C, C, C)
-        hs_ = G.to_bf16(h) if tc else h
+        hs_ = _as16(h) if tc else h
         for i, (w_, b_) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
             if tc:
                 G.gemm_bf16(hs_, G.weight_bf16(w_), qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_)
