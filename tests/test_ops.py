@@ -162,6 +162,36 @@ def test_se_add_pool():
     check_grads([am], [a], out3, ref3)
 
 
+@pytest.mark.parametrize('N,C,Cr', [(10, 1512, 144), (10, 576, 54), (16, 216, 18), (2, 72, 8), (1, 80, 3)])
+def test_se_fused_mlp_backward(N, C, Cr):
+    """tfb_se_mlp_bwd (two launches) against the eight-launch path it replaces and against torch autograd, at the RegNetY-3.2GF
+    SE sizes (C up to 1512, reduction width = round(block input width / 4))."""
+    from transfuser_b200 import ops
+    H, W = 3, 4
+    x = rnd(N, C, H, W, seed=1).requires_grad_()
+    w1, b1 = rnd(Cr, C, 1, 1, seed=2, scale=0.1).requires_grad_(), rnd(Cr, seed=3, scale=0.1).requires_grad_()
+    w2, b2 = rnd(C, Cr, 1, 1, seed=4, scale=0.3).requires_grad_(), rnd(C, seed=5, scale=0.1).requires_grad_()
+    ref = x * torch.sigmoid(F.conv2d(F.relu(F.conv2d(x.mean((2, 3), keepdim=True), w1, b1)), w2, b2))
+    g = rnd(N, C, H, W, seed=6)
+    want = torch.autograd.grad(ref, [x, w1, b1, w2, b2], g)
+    got = {}
+    old = ops.SE_FUSED_BWD
+    try:
+        for fused in (True, False):
+            ops.SE_FUSED_BWD = fused
+            xm = nhwc(x.detach()).requires_grad_()
+            ps = [t.detach().clone().requires_grad_() for t in (w1, b1, w2, b2)]
+            out = ops.SEFn.apply(xm, *ps)
+            got[fused] = torch.autograd.grad(out, [xm] + ps, nhwc(g))
+    finally:
+        ops.SE_FUSED_BWD = old
+    for i, (a, u, b_) in enumerate(zip(got[True], got[False], want)):
+        if i == 0:
+            a, u = nchw(a), nchw(u)
+        assert rel(a.reshape(b_.shape), b_) < TOL, ('fused vs torch', i, rel(a.reshape(b_.shape), b_))
+        assert rel(a, u) < 1e-5, ('fused vs unfused', i, rel(a, u))
+
+
 @pytest.mark.parametrize('C,hw', [(72, ((40, 176), (64, 64))), (576, ((10, 44), (16, 16))), (1512, ((5, 22), (8, 8)))])
 def test_gpt_tokens_and_view_quirk(C, hw):
     """Token build (adaptive avg pool + permute + pos_emb) and the reference's non-inverse `.view` on the way back

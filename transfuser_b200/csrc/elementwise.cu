@@ -368,6 +368,98 @@ __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict_
     y[i] = accumulate ? fmaf(x[i], f, y[i]) : x[i] * f;
 }
 
+// ---------------- squeeze-excite MLP backward, fused (batch N <= 16) ----------------
+// gate = sigmoid(fc2(h)), h = relu(fc1(pooled)). Given dgate[N,C] (from se_bwd_reduce) the chain
+//   ds = dgate*gate*(1-gate);  dw2 = ds^T h;  db2 = colsum ds;  dh = (ds w2) * (h > 0);  dw1 = dh^T pooled;  db1 = colsum dh;
+//   dpool = dh w1
+// used to be eight launches of [N,C]-sized kernels (sigmoid', 2 weight-gradient GEMMs, 2 column sums, 2 skinny GEMMs, relu'). It is
+// two: both run one CTA per 64-channel chunk of C; the only cross-chunk quantity, dh (a sum over all of C), leaves kernel 1 as
+// per-chunk partials dh_part[chunk][N][Cr] that every CTA of kernel 2 sums in chunk order (deterministic, no atomics, no memset).
+constexpr int SE_CHUNK = 64;
+constexpr int SE_MAX_N = 16;
+constexpr int SE_MAX_CR = 512;   // static shared memory: (64 + 512) * 16 floats = 36 KiB
+
+__global__ void __launch_bounds__(256) se_mlp_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                          const float* __restrict__ h, const float* __restrict__ w2,
+                                                          float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dh_part,
+                                                          int N, int C, int Cr) {
+  __shared__ float ds[SE_MAX_N * SE_CHUNK];  // [N][SE_CHUNK]
+  __shared__ float hs[SE_MAX_N * SE_MAX_CR]; // [N][Cr]
+  const int c0 = blockIdx.x * SE_CHUNK;
+  const int cw = min(SE_CHUNK, C - c0);
+  for (int i = threadIdx.x; i < N * SE_CHUNK; i += blockDim.x) {
+    const int n = i / SE_CHUNK, j = i % SE_CHUNK;
+    float v = 0.f;
+    if (j < cw) {
+      const float g = gate[(int64_t)n * C + c0 + j];
+      v = dgate[(int64_t)n * C + c0 + j] * g * (1.f - g);
+    }
+    ds[i] = v;
+  }
+  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) hs[i] = h[i];
+  __syncthreads();
+  if (threadIdx.x < cw) {
+    float t = 0.f;
+    for (int n = 0; n < N; ++n) t += ds[n * SE_CHUNK + threadIdx.x];
+    db2[c0 + threadIdx.x] = t;
+  }
+  for (int i = threadIdx.x; i < cw * Cr; i += blockDim.x) {          // dw2[c][r] = sum_n ds[n][c] h[n][r]
+    const int j = i / Cr, r = i % Cr;
+    float t = 0.f;
+    for (int n = 0; n < N; ++n) t = fmaf(ds[n * SE_CHUNK + j], hs[n * Cr + r], t);
+    dw2[(int64_t)(c0 + j) * Cr + r] = t;
+  }
+  float* part = dh_part + (int64_t)blockIdx.x * N * Cr;
+  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) {           // partial dh[n][r] = sum_{c in chunk} ds[n][c] w2[c][r]
+    const int n = i / Cr, r = i % Cr;
+    float t = 0.f;
+    for (int j = 0; j < cw; ++j) t = fmaf(ds[n * SE_CHUNK + j], w2[(int64_t)(c0 + j) * Cr + r], t);
+    part[i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restrict__ dh_part, int nchunks, const float* __restrict__ h,
+                                                          const float* __restrict__ pooled, const float* __restrict__ w1,
+                                                          float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpool,
+                                                          int N, int C, int Cr) {
+  __shared__ float ps[SE_MAX_N * SE_CHUNK];  // [N][SE_CHUNK] pooled chunk
+  __shared__ float dh[SE_MAX_N * SE_MAX_CR]; // [N][Cr]
+  const int c0 = blockIdx.x * SE_CHUNK;
+  const int cw = min(SE_CHUNK, C - c0);
+  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < nchunks; ++k) t += dh_part[(int64_t)k * N * Cr + i];
+    dh[i] = h[i] > 0.f ? t : 0.f;
+  }
+  for (int i = threadIdx.x; i < N * SE_CHUNK; i += blockDim.x) {
+    const int n = i / SE_CHUNK, j = i % SE_CHUNK;
+    ps[i] = j < cw ? pooled[(int64_t)n * C + c0 + j] : 0.f;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
+      float t = 0.f;
+      for (int n = 0; n < N; ++n) t += dh[n * Cr + r];
+      db1[r] = t;
+    }
+  }
+  for (int i = threadIdx.x; i < Cr * SE_CHUNK; i += blockDim.x) {    // dw1[r][c] = sum_n dh[n][r] pooled[n][c]
+    const int r = i / SE_CHUNK, j = i % SE_CHUNK;
+    if (j >= cw) continue;
+    float t = 0.f;
+    for (int n = 0; n < N; ++n) t = fmaf(dh[n * Cr + r], ps[n * SE_CHUNK + j], t);
+    dw1[(int64_t)r * C + c0 + j] = t;
+  }
+  for (int i = threadIdx.x; i < N * SE_CHUNK; i += blockDim.x) {     // dpool[n][c] = sum_r dh[n][r] w1[r][c]
+    const int n = i / SE_CHUNK, j = i % SE_CHUNK;
+    if (j >= cw) continue;
+    float t = 0.f;
+    for (int r = 0; r < Cr; ++r) t = fmaf(dh[n * Cr + r], w1[(int64_t)r * C + c0 + j], t);
+    dpool[(int64_t)n * C + c0 + j] = t;
+  }
+}
+
+
 }  // namespace
 
 // y16_bf16 (optional, here and in tfb_se_scale_fwd): bf16 copy of y written in the same pass.
@@ -434,6 +526,21 @@ TFB_API int tfb_se_bwd_reduce(const float* x, const float* dy, float* dgate, int
   if (splits > 32) splits = 32;
   dim3 grid((C / 4 + 31) / 32, N, splits), block(32, 8);
   pool_hw_kernel<1><<<grid, block, 0, stream>>>(x, dy, dgate, HW, C, 1.f);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+// Fused backward of the squeeze-excite MLP (see se_mlp_bwd1_kernel): dgate, gate, pooled [N,C]; h [N,Cr]; w1 [Cr,C]; w2 [C,Cr] ->
+// dw1 [Cr,C], db1 [Cr], dw2 [C,Cr], db2 [C], dpool [N,C] (all overwritten). N <= 16, Cr <= 512.
+// dh_part: workspace of ceil(C / 64) * N * Cr floats (fully written before it is read; no initialisation needed).
+TFB_API int tfb_se_mlp_bwd(const float* dgate, const float* gate, const float* h, const float* pooled, const float* w1, const float* w2,
+                           float* dw1, float* db1, float* dw2, float* db2, float* dpool, float* dh_part, int N, int C, int Cr,
+                           cudaStream_t stream) {
+  TFB_REQUIRE(dgate && gate && h && pooled && w1 && w2 && dw1 && db1 && dw2 && db2 && dpool && dh_part);
+  TFB_REQUIRE(N > 0 && N <= SE_MAX_N && C > 0 && Cr > 0 && Cr <= SE_MAX_CR);
+  const int nchunks = (C + SE_CHUNK - 1) / SE_CHUNK;
+  se_mlp_bwd1_kernel<<<nchunks, 256, 0, stream>>>(dgate, gate, h, w2, dw2, db2, dh_part, N, C, Cr);
+  TFB_CHECK_LAUNCH();
+  se_mlp_bwd2_kernel<<<nchunks, 256, 0, stream>>>(dh_part, nchunks, h, pooled, w1, dw1, db1, dpool, N, C, Cr);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

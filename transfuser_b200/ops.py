@@ -52,6 +52,7 @@ def _c(t):
 # copy in the same pass as its fp32 output; it travels as the `_tfb16` attribute of the fp32 tensor and the consuming GEMM / conv
 # takes it instead of running a cast pass of its own. SIDECARS = False restores the separate cast launches.
 SIDECARS = os.environ.get('TFB_SIDECARS', '1') == '1'
+SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
 
 
 def _emit16(x, want):
@@ -546,25 +547,29 @@ class SEFn(Function):
         dev = x.device
         dgate = torch.empty((N, C), dtype=torch.float32, device=dev)
         call('tfb_se_bwd_reduce', x, dy, dgate, N, H * W, C)
-        ds = torch.empty_like(dgate)
-        call('tfb_sigmoid_bwd', gate, dgate, ds, ds.numel())
-        dw2 = _gbuf(w2)
-        gemm(ds, h, dw2.view(C, Cr), trans_a=True, mode='simt')
-        db2 = _colsum(ds, _gbuf(b2))
-        dh = torch.empty((N, Cr), dtype=torch.float32, device=dev)
-        if N <= 16:
-            call('tfb_gemm_small_m', 0, N, Cr, C, ds, C, w2, Cr, dh, Cr, None, 0)
-        else:
-            gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
-        dh = _relu_bwd(h, dh)
-        dw1 = _gbuf(w1)
-        gemm(dh, pooled, dw1.view(Cr, C), trans_a=True, mode='simt')
-        db1 = _colsum(dh, _gbuf(b1))
+        dw2, db2, dw1, db1 = _gbuf(w2), _gbuf(b2), _gbuf(w1), _gbuf(b1)
         dpool = torch.empty((N, C), dtype=torch.float32, device=dev)
-        if N <= 16:
-            call('tfb_gemm_small_m', 0, N, C, Cr, dh, Cr, w1, C, dpool, C, None, 0)
+        if N <= 16 and Cr <= 512 and SE_FUSED_BWD:
+            # the whole MLP backward (sigmoid', both weight / bias gradients, both skinny GEMMs, relu') in two launches
+            part = torch.empty(((C + 63) // 64, N, Cr), dtype=torch.float32, device=dev)
+            call('tfb_se_mlp_bwd', dgate, gate, h, pooled, w1, w2, dw1, db1, dw2, db2, dpool, part, N, C, Cr)
         else:
-            gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
+            ds = torch.empty_like(dgate)
+            call('tfb_sigmoid_bwd', gate, dgate, ds, ds.numel())
+            gemm(ds, h, dw2.view(C, Cr), trans_a=True, mode='simt')
+            _colsum(ds, db2)
+            dh = torch.empty((N, Cr), dtype=torch.float32, device=dev)
+            if N <= 16:
+                call('tfb_gemm_small_m', 0, N, Cr, C, ds, C, w2, Cr, dh, Cr, None, 0)
+            else:
+                gemm(ds, w2.view(C, Cr), dh, trans_b=False, mode='simt')
+            dh = _relu_bwd(h, dh)
+            gemm(dh, pooled, dw1.view(Cr, C), trans_a=True, mode='simt')
+            _colsum(dh, db1)
+            if N <= 16:
+                call('tfb_gemm_small_m', 0, N, C, Cr, dh, Cr, w1, C, dpool, C, None, 0)
+            else:
+                gemm(dh, w1.view(Cr, C), dpool, trans_b=False, mode='simt')
         dx = torch.empty_like(x)
         call('tfb_se_bwd_apply', dy, gate, dpool, dx, N, H * W, C)
         return dx, dw1, db1, dw2, db2, None
