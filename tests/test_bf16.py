@@ -127,6 +127,41 @@ def test_full_model_bf16_close_to_fp32_mode():
         assert abs(a - b) <= 3e-2 * max(abs(b), 0.1), (k, a, b)
 
 
+@pytest.mark.parametrize('C', [72, 576, 1512])
+def test_qkv_pack_fused_projection_bf16(C):
+    """A GPT Block on flat parameters (optim.flatten packs query | key | value back to back): the fused [3C, C] projection (one
+    tensor-core GEMM each for forward, dgrad, wgrad; one bias reduction) against the three-GEMM path on the same bf16 operands.
+    Same products, different accumulation grouping: outputs and gradients agree to 1e-4 relative L2 (fp32 accumulation)."""
+    from transfuser_b200 import gemm, ops, optim
+    from transfuser_b200.backbone import Block
+    B, T, nh = 10, 174, 4
+    res = {}
+    old = ops.QKV_FUSED
+    try:
+        for fused in (True, False):
+            ops.QKV_FUSED = fused
+            torch.manual_seed(3)
+            blk = Block(C, nh, 4, 0.0, 0.0).cuda().train()
+            fp = optim.flatten(blk)
+            gemm.attach_bf16_weights(fp)
+            a = blk.attn
+            assert (ops._pack3(a.query.weight, a.key.weight, a.value.weight) is not None)
+            x = torch.randn(B * T, C, device='cuda', generator=torch.Generator(device='cuda').manual_seed(4)).requires_grad_()
+            y = blk.run(x, B, T)
+            y.backward(torch.randn(B * T, C, device='cuda', generator=torch.Generator(device='cuda').manual_seed(5)))
+            torch.cuda.synchronize()
+            for p, o in zip(fp.params, fp.offsets):                  # gradients landed in the flat buffer, no copies
+                assert p.grad is not None and p.grad.data_ptr() == fp.grad.data_ptr() + 4 * o
+            res[fused] = [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for _, p in sorted(blk.named_parameters())]
+            names = ['y', 'dx'] + [n for n, _ in sorted(blk.named_parameters())]
+    finally:
+        ops.QKV_FUSED = old
+    for n, u, v in zip(names, res[True], res[False]):
+        if n == 'attn.key.bias':
+            continue                                                 # true gradient 0 (softmax shift invariance): pure rounding noise
+        assert rel(u, v) < 1e-4, (n, rel(u, v))
+
+
 def test_bf16_sidecars_do_not_change_the_step():
     """bf16 sidecars (BatchNorm / SE / add / LayerNorm write the bf16 operand of the next GEMM in their own pass) against the
     separate cast launches they replace: the sidecar is the same rounding of the same fp32 value, so the losses agree to the

@@ -357,6 +357,68 @@ def test_flat_parameter_training_loop_matches_torch(monkeypatch):
     assert torch.equal(fp.bf16, fp.flat.bfloat16())
 
 
+def test_flat_qkv_pack_gpt_block_training_loop(monkeypatch):
+    """optim.FlatParams lays query / key / value weights (and biases) back to back, so ops.AttentionFn runs the three projections,
+    their dgrad / wgrad and the bias gradients as one GEMM / reduction each on the [3C, C] pack, writing the gradients straight into
+    the pack's span of the flat gradient buffer. Two optimizer steps of the product's GPT Block (transfuser.py:530-549) over the
+    emulated kernels against the same block in plain torch + torch.optim.AdamW; then the same with the fusion switched off."""
+    from torch import nn
+    from transfuser_b200 import ops, optim
+    from transfuser_b200.backbone import Block
+    lib = loader.patch_product(monkeypatch)
+    C, nh, B, T = 24, 4, 2, 9
+
+    def torch_block(blk, x):
+        a = blk.attn
+        h = F.layer_norm(x, (C,), blk.ln1.weight, blk.ln1.bias, blk.ln1.eps)
+        q, k, v = (lin(h).view(B, T, nh, C // nh).transpose(1, 2) for lin in (a.query, a.key, a.value))
+        att = F.softmax(q @ k.transpose(-2, -1) / (C // nh) ** 0.5, dim=-1)
+        x = x + a.proj((att @ v).transpose(1, 2).reshape(B * T, C))
+        h = F.layer_norm(x, (C,), blk.ln2.weight, blk.ln2.bias, blk.ln2.eps)
+        return x + blk.mlp[2](F.relu(blk.mlp[0](h)))
+
+    for fused_qkv in (True, False):
+        monkeypatch.setattr(ops, 'QKV_FUSED', fused_qkv)
+        torch.manual_seed(1)
+        net, ref = Block(C, nh, 4, 0.0, 0.0), Block(C, nh, 4, 0.0, 0.0)
+        ref.load_state_dict(net.state_dict())
+        fp = optim.flatten(net)
+        a = net.attn
+        off = {id(p): o for p, o in zip(fp.params, fp.offsets)}
+        assert off[id(a.key.weight)] == off[id(a.query.weight)] + C * C and off[id(a.value.weight)] == off[id(a.key.weight)] + C * C
+        assert off[id(a.key.bias)] == off[id(a.query.bias)] + C and off[id(a.value.bias)] == off[id(a.key.bias)] + C
+        assert all(torch.equal(v, ref.state_dict()[k]) for k, v in net.state_dict().items())      # re-homing kept the values
+        fused = optim.FusedAdamW(net.parameters(), lr=3e-3, weight_decay=0.05)
+        opt = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=0.05)
+        net.train(), ref.train()
+        for step in range(2):
+            x = torch.randn(B * T, C)
+            fused.zero_grad()
+            opt.zero_grad()
+            lib.log.clear()
+            l1, l2 = net.run(x, B, T).square().mean(), torch_block(ref, x).square().mean()
+            assert abs(float(l1) - float(l2)) < 1e-5 * abs(float(l2))
+            n_fwd = lib.log.count('tfb_gemm_f32_simt')
+            l1.backward()
+            l2.backward()
+            n_all = lib.log.count('tfb_gemm_f32_simt')
+            # forward: q|k|v (1 or 3) + scores + AV + proj + 2 MLP; backward: 4 attention products + dgrad/wgrad of q|k|v (2 or 6)
+            # + 2 each for proj and the two MLP layers
+            assert (n_fwd, n_all - n_fwd) == ((6, 12) if fused_qkv else (8, 16)), (n_fwd, n_all - n_fwd)
+            assert lib.log.count('tfb_colsum') == (1 if fused_qkv else 3)       # (Linear bias gradients come out of tfb_grad_prep)
+            for p, o in zip(fp.params, fp.offsets):
+                assert p.grad is not None and p.grad.data_ptr() == fp.grad.data_ptr() + 4 * o
+            for (n, p), q in zip(net.named_parameters(), ref.parameters()):
+                tol = 1e-6 + 1e-4 * float(q.grad.abs().max())
+                assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=tol), (step, n, (p.grad - q.grad).abs().max())
+            fused.step()
+            opt.step()
+            for (n, p), q in zip(net.named_parameters(), ref.parameters()):
+                if n == 'attn.key.bias':
+                    continue        # its true gradient is 0 (softmax shift invariance): Adam normalises the rounding noise to +-lr
+                assert torch.allclose(p, q, rtol=1e-4, atol=2e-5), (step, n, (p - q).abs().max())
+
+
 @pytest.mark.parametrize('dt', [np.float32, np.float64])
 def test_bev_histogram_kernel_bit_exact(dt):
     """csrc/bev_hist.cu vs the numpy oracle (bit-identical to data.py:446-470) and the committed reference fixture, including the

@@ -12,6 +12,15 @@ DEV = 'cuda'   # tests/test_ops_emulated.py re-runs these functions with DEV = '
 DROPOUT_N, LN_ROWS, ATT_T = 1 << 20, 348, 174   # (and smaller populations there: emulated thread barriers are slow)
 
 
+_NOLOG = []
+
+
+def _calls():
+    """The emulated library's call log when the test runs over the CPU emulation (tests/test_ops_emulated.py), else _NOLOG."""
+    from transfuser_b200 import _lib
+    return getattr(_lib._LIB, 'log', _NOLOG)
+
+
 def rel(a, b):
     a, b = a.double(), b.double()
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
@@ -114,8 +123,11 @@ def test_layernorm_linear_dropout():
     assert torch.equal(gy != 0, d != 0)
 
 
+@pytest.mark.parametrize('packed', [False, True])
 @pytest.mark.parametrize('C,nh', [(72, 4), (216, 4)])
-def test_attention(C, nh):
+def test_attention(C, nh, packed):
+    """packed: query / key / value parameters back to back in one buffer, as optim.FlatParams lays them out -> the projections,
+    their dgrad, wgrad and bias gradients each run as ONE GEMM / reduction on the [3C, C] pack (ops._pack3)."""
     from transfuser_b200 import ops
     B, T = 2, ATT_T
     h = rnd(B * T, C, seed=1).requires_grad_()
@@ -127,9 +139,19 @@ def test_attention(C, nh):
     att = F.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // nh)), dim=-1)
     ref = (att @ v).transpose(1, 2).reshape(B * T, C)
     hm = h.detach().clone().requires_grad_()
-    wm = [w.detach().clone().requires_grad_() for w in ws]
-    bm = [b.detach().clone().requires_grad_() for b in bs]
+    if packed:
+        flat = torch.cat([w.detach().reshape(-1) for w in ws] + [b.detach() for b in bs]).contiguous()
+        wm = [flat[i * C * C:(i + 1) * C * C].view(C, C).requires_grad_() for i in range(3)]
+        bm = [flat[3 * C * C + i * C:3 * C * C + (i + 1) * C].requires_grad_() for i in range(3)]
+        assert ops._pack3(*wm).shape == (3 * C, C) and ops._pack3(*bm).shape == (3 * C,)
+    else:
+        wm = [w.detach().clone().requires_grad_() for w in ws]
+        bm = [b.detach().clone().requires_grad_() for b in bs]
+        assert ops._pack3(*wm) is None
+    n0 = len(_calls())
     out = ops.AttentionFn.apply(hm, wm[0], bm[0], wm[1], bm[1], wm[2], bm[2], B, T, nh, 0.0, 1)
+    if _calls() is not _NOLOG:
+        assert len(_calls()) - n0 == (4 if packed else 6)      # q|k|v GEMM(s) + scores + softmax + AV
     assert rel(out, ref) < TOL
     g = rnd(B * T, C, seed=5)
     rg = torch.autograd.grad(ref, [h] + ws + [bs[0], bs[2]], g)

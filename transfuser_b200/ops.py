@@ -52,6 +52,7 @@ def _c(t):
 # copy in the same pass as its fp32 output; it travels as the `_tfb16` attribute of the fp32 tensor and the consuming GEMM / conv
 # takes it instead of running a cast pass of its own. SIDECARS = False restores the separate cast launches.
 SIDECARS = os.environ.get('TFB_SIDECARS', '1') == '1'
+QKV_FUSED = os.environ.get('TFB_QKV_FUSED', '1') == '1'           # one q|k|v GEMM when the flat buffer packs the three weights
 SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
 
 
@@ -138,6 +139,32 @@ def _gbuf(p):
         fp, off = info
         return fp.grad[off:off + p.numel()].view(p.shape)
     return torch.empty(p.shape, dtype=torch.float32, device=p.device)
+
+
+def _pack3(a, b, c):
+    """The tensor that three equally-shaped contiguous tensors form when they lie back to back in ONE storage (the q|k|v packs
+    of optim.FlatParams): shape [3 * a.shape[0], ...]. None when they do not."""
+    if a is None or b is None or c is None or not (a.shape == b.shape == c.shape):
+        return None
+    if not (a.is_contiguous() and b.is_contiguous() and c.is_contiguous()):
+        return None
+    n = a.numel() * a.element_size()
+    base = a.untyped_storage().data_ptr()
+    if b.data_ptr() != a.data_ptr() + n or c.data_ptr() != b.data_ptr() + n or c.untyped_storage().data_ptr() != base:
+        return None
+    return a.detach().as_strided((3 * a.shape[0],) + tuple(a.shape[1:]), a.stride())
+
+
+def _gbuf3(pq, pk, pv):
+    """Gradient buffer of a q|k|v pack as ONE [3n, ...] tensor: the pack's span of the flat gradient buffer when all three
+    parameters are flat and have no .grad yet (their gradients are then views of it, adopted by autograd without a copy)."""
+    infos = [getattr(p, '_tfb_flat', None) for p in (pq, pk, pv)]
+    n = pq.numel()
+    if all(i is not None for i in infos) and all(p.grad is None for p in (pq, pk, pv)) \
+            and infos[1][1] == infos[0][1] + n and infos[2][1] == infos[1][1] + n:
+        fp, off = infos[0]
+        return fp.grad[off:off + 3 * n].view((3 * pq.shape[0],) + tuple(pq.shape[1:]))
+    return torch.empty((3 * pq.shape[0],) + tuple(pq.shape[1:]), dtype=torch.float32, device=pq.device)
 
 
 def _colsum(x2d, out=None):
@@ -639,11 +666,20 @@ class AttentionFn(Function):
         qkv = torch.empty((B * T, 3 * C), dtype=torch.float32, device=dev)
         tc = G.tc_ok(B * T, C, C, C)
         hs_ = _as16(h) if tc else h
-        for i, (w_, b_) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+        w3, b3 = (_pack3(wq, wk, wv), _pack3(bq, bk, bv)) if QKV_FUSED else (None, None)
+        packed = w3 is not None and b3 is not None
+        if packed:
+            # the three projections as ONE GEMM on the [3C, C] weight the flat parameter buffer holds contiguously
             if tc:
-                G.gemm_bf16(hs_, G.weight_bf16(w_), qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_)
+                G.gemm_bf16(hs_, G.weight_bf16(w3), qkv, trans_b=True, bias=b3)
             else:
-                gemm(h, w_, qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_, mode='simt')
+                gemm(h, w3, qkv, trans_b=True, bias=b3, mode='simt')
+        else:
+            for i, (w_, b_) in enumerate(((wq, bq), (wk, bk), (wv, bv))):
+                if tc:
+                    G.gemm_bf16(hs_, G.weight_bf16(w_), qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_)
+                else:
+                    gemm(h, w_, qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_, mode='simt')
         S = torch.empty((B, nh, T, T), dtype=torch.float32, device=dev)
         q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         bgemm(q, k, S, T, T, hs, 3 * C, 3 * C, T, False, True, B, nh, (T * 3 * C, hs), (T * 3 * C, hs), (nh * T * T, T * T))
@@ -653,13 +689,13 @@ class AttentionFn(Function):
         y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         bgemm(Pd, v, y, T, hs, T, T, 3 * C, C, False, False, B, nh, (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs))
         ctx.save_for_backward(hs_, wq, wk, wv, qkv, S, Pd, bq, bk, bv)
-        ctx.cfg = (B, T, nh, p_drop, seed, scale, tc)
+        ctx.cfg = (B, T, nh, p_drop, seed, scale, tc, packed)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         h, wq, wk, wv, qkv, P, Pd, bq, bk, bv = ctx.saved_tensors
-        B, T, nh, p_drop, seed, scale, tc = ctx.cfg
+        B, T, nh, p_drop, seed, scale, tc, packed = ctx.cfg
         dy = _c(dy)
         C = h.shape[1]
         hs = C // nh
@@ -676,7 +712,21 @@ class AttentionFn(Function):
         bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
         dh = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         grads = []
-        if tc:
+        w3 = _pack3(wq, wk, wv) if packed else None
+        if w3 is not None:
+            # fused q|k|v: dh = dqkv W3 (one GEMM, K = 3C), dW3 = dqkv^T h (one GEMM), db3 = column sums of dqkv (one reduction)
+            dw3, db3 = _gbuf3(wq, wk, wv), _gbuf3(bq, bk, bv)
+            if tc:
+                d16 = G.to_bf16(dqkv)
+                G.gemm_bf16(d16, G.weight_bf16(w3), dh, trans_b=False)
+                G.gemm_bf16(d16, h, dw3, trans_a=True, splits=_wgrad_splits(B * T, 3 * C, C))
+            else:
+                gemm(dqkv, w3, dh, trans_b=False, mode='simt')
+                gemm(dqkv, h, dw3, trans_a=True, mode='simt')
+            _colsum(dqkv, db3)
+            for i in range(3):
+                grads += [dw3[i * C:(i + 1) * C], db3[i * C:(i + 1) * C]]
+        elif tc:
             d16 = G.to_bf16(dqkv)
             for i, w_ in enumerate((wq, wk, wv)):
                 G.gemm_bf16(d16[:, i * C:(i + 1) * C], G.weight_bf16(w_), dh, trans_b=False, beta=0.0 if i == 0 else 1.0)

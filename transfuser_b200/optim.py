@@ -13,6 +13,23 @@ from . import ops as ops_mod
 ALIGN = 64  # elements: keeps every parameter 256-byte aligned (TMA / float4 friendly)
 
 
+def _qkv_packs(model):
+    """[(query.p, key.p, value.p)] parameter triples (weights, then biases) of every attention module: laid out back to back in
+    the flat buffer (no padding between the members) they ARE the [3C, C] weight / [3C] bias of one fused q|k|v projection
+    (ops.AttentionFn: one GEMM instead of three in forward, dgrad and wgrad, one bias-gradient reduction instead of three)."""
+    packs = []
+    for m in model.modules():
+        q, k, v = (getattr(m, n, None) for n in ('query', 'key', 'value'))
+        if not all(isinstance(t, torch.nn.Linear) for t in (q, k, v)):
+            continue
+        for name in ('weight', 'bias'):
+            trio = tuple(getattr(t, name) for t in (q, k, v))
+            if all(isinstance(t, torch.nn.Parameter) for t in trio) and len({t.shape for t in trio}) == 1 \
+                    and trio[0].numel() % 8 == 0 and len({id(t) for t in trio}) == 3:
+                packs.append(trio)
+    return packs
+
+
 class FlatParams:
     def __init__(self, model):
         params, seen = [], set()
@@ -20,12 +37,32 @@ class FlatParams:
             if id(p) not in seen:
                 seen.add(id(p))
                 params.append(p)
-        dev = params[0].device
-        offs, total = [], 0
+        # q|k|v packs: the three members take the place of the first one in parameter order, contiguous and unpadded
+        pack_of = {}
+        for trio in _qkv_packs(model) if isinstance(model, torch.nn.Module) else []:
+            if all(id(t) in seen for t in trio) and not any(id(t) in pack_of for t in trio):
+                for t in trio:
+                    pack_of[id(t)] = trio
+        ordered, placed = [], set()
         for p in params:
-            offs.append(total)
-            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
-        self.params, self.offsets, self.total = params, offs, total
+            if id(p) in placed:
+                continue
+            group = pack_of.get(id(p), (p,))
+            for t in group:
+                placed.add(id(t))
+            ordered.append(group)
+        dev = params[0].device
+        params, offs, lens, total = [], [], [], 0
+        for group in ordered:
+            start = total
+            for t in group:
+                params.append(t)
+                offs.append(total)
+                lens.append(t.numel())
+                total += t.numel()
+            total = start + (total - start + ALIGN - 1) // ALIGN * ALIGN
+            lens[-1] = total - offs[-1]                  # the padding belongs to the last member's span
+        self.params, self.offsets, self.lengths, self.total = params, offs, lens, total
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, o in zip(params, offs):
@@ -49,11 +86,11 @@ class FlatParams:
         no moment update), so the fused optimizer skips them too."""
         base = self.grad.data_ptr()
         no_grad = []
-        for p, o in zip(self.params, self.offsets):
+        for p, o, ln in zip(self.params, self.offsets, self.lengths):
             g = p.grad
             if g is None:
                 self.grad[o:o + p.numel()].zero_()
-                no_grad.append((o, (p.numel() + ALIGN - 1) // ALIGN * ALIGN))
+                no_grad.append((o, ln))
             elif g.data_ptr() != base + 4 * o:
                 self.grad[o:o + p.numel()].copy_(g.reshape(-1))
         return no_grad
