@@ -121,6 +121,14 @@ def test_layernorm_linear_dropout():
     assert torch.allclose(d[d != 0], (y / 0.9)[d != 0], rtol=1e-6)
     (gy,) = torch.autograd.grad(d.sum(), y)
     assert torch.equal(gy != 0, d != 0)
+    # residual + dropout in one launch: the same mask as DropoutFn with the same seed (incl. the scalar tail of an odd length)
+    for n in (DROPOUT_N, 1027):
+        yb, res = y.detach()[:n].clone().requires_grad_(), rnd(n, seed=10).requires_grad_()
+        fused = ops.AddDropoutFn.apply(res, yb, 0.1, 1234)
+        assert torch.equal(fused.detach(), res.detach() + ops.DropoutFn.apply(yb.detach(), 0.1, 1234))
+        gr, gb = torch.autograd.grad(fused, (res, yb), torch.ones_like(fused))
+        assert torch.equal(gr, torch.ones_like(gr)) and torch.equal(gb != 0, d.detach()[:n] != 0)
+    assert ops.add_dropout(res, yb, 0.1, False).equal(res + yb) and ops.add_dropout(res, yb, 0.0, True).equal(res + yb)
 
 
 @pytest.mark.parametrize('packed', [False, True])

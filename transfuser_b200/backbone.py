@@ -150,12 +150,10 @@ class Block(nn.Module):
         p_att = a.attn_pdrop if training else 0.0
         y = ops.AttentionFn.apply(h, a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
                                   B, T, a.n_head, p_att, ops.next_seed())
-        y = ops.dropout(ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training)
-        x = ops.add(x, y)
+        x = ops.add_dropout(x, ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training)
         h = ops.layer_norm(x, self.ln2, emit16=True)
         h = ops.linear(h, self.mlp[0].weight, self.mlp[0].bias, relu=True)
-        h = ops.dropout(ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), a.resid_pdrop, training)
-        return ops.add(x, h)
+        return ops.add_dropout(x, ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), a.resid_pdrop, training)
 
 
 class GPT(nn.Module):

@@ -273,11 +273,30 @@ __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, fl
   }
 }
 
+// y = (res ? res : 0) + x * keep_scale(seed, element index): dropout, optionally fused with the residual add that follows it in
+// the GPT block (x + drop(branch), transfuser.py:546-547). 4 elements per thread (16-byte accesses), scalar tail.
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
-                                                      const uint64_t* __restrict__ seed_dev, uint64_t seed_off) {
+                                                      const uint64_t* __restrict__ seed_dev, uint64_t seed_off,
+                                                      const float* __restrict__ res) {
   const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = x[i] * tfb_dropout_scale(seed, (uint64_t)i, p);
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 o;
+    o.x = v.x * tfb_dropout_scale(seed, (uint64_t)(4 * i + 0), p);
+    o.y = v.y * tfb_dropout_scale(seed, (uint64_t)(4 * i + 1), p);
+    o.z = v.z * tfb_dropout_scale(seed, (uint64_t)(4 * i + 2), p);
+    o.w = v.w * tfb_dropout_scale(seed, (uint64_t)(4 * i + 3), p);
+    if (res) {
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float o = x[i] * tfb_dropout_scale(seed, (uint64_t)i, p);
+    y[i] = res ? res[i] + o : o;
+  }
 }
 
 // one warp per row of length L: P = softmax(scale * S); Pd = dropout(P). P and Pd may alias S when p == 0.
@@ -627,10 +646,12 @@ TFB_API int tfb_upsample_bilinear_bwd(const float* dy, float* dx, int N, int Hi,
 }
 // Dropout mask = f(*seed_dev + seed_off, element index): the base seed lives in device memory (advanced by tfb_step_tick once
 // per step, also inside a captured CUDA graph), seed_off identifies the call site; the backward regenerates the same mask.
-TFB_API int tfb_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* seed_dev, uint64_t seed_off, cudaStream_t stream) {
+// y = dropout(x) (+ residual when given): the mask is a hash of (*seed_dev + seed_off, element index), regenerated in backward.
+TFB_API int tfb_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* seed_dev, uint64_t seed_off, const float* residual,
+                        cudaStream_t stream) {
   TFB_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f);
   if (n == 0) return TFB_OK;
-  dropout_kernel<<<tfb_grid(n, 256), 256, 0, stream>>>(x, y, n, p, seed_dev, seed_off);
+  dropout_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(x, y, n, p, seed_dev, seed_off, residual);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

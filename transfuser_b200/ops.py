@@ -634,7 +634,7 @@ class DropoutFn(Function):
     def forward(ctx, x, p, seed):
         x = _c(x)
         y = torch.empty_like(x)
-        call('tfb_dropout', x, y, x.numel(), float(p), seed_state(x.device), seed)
+        call('tfb_dropout', x, y, x.numel(), float(p), seed_state(x.device), seed, None)
         ctx.p, ctx.seed = p, seed
         return y
 
@@ -642,7 +642,7 @@ class DropoutFn(Function):
     def backward(ctx, dy):
         dy = _c(dy)
         dx = torch.empty_like(dy)
-        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), seed_state(dy.device), ctx.seed)
+        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), seed_state(dy.device), ctx.seed, None)
         return dx, None, None
 
 
@@ -650,6 +650,32 @@ def dropout(x, p, training):
     if not training or p <= 0.0:
         return x
     return DropoutFn.apply(x, p, next_seed())
+
+
+class AddDropoutFn(Function):
+    """res + dropout(x) in one pass (the GPT block's residual connections, transfuser.py:546-547); backward regenerates the mask."""
+
+    @staticmethod
+    def forward(ctx, res, x, p, seed):
+        res, x = _c(res), _c(x)
+        y = torch.empty_like(x)
+        call('tfb_dropout', x, y, x.numel(), float(p), seed_state(x.device), seed, res)
+        ctx.p, ctx.seed = p, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        call('tfb_dropout', dy, dx, dy.numel(), float(ctx.p), seed_state(dy.device), ctx.seed, None)
+        return dy, dx, None, None
+
+
+def add_dropout(res, x, p, training):
+    """res + dropout(x, p): one launch in training mode, a plain add otherwise."""
+    if not training or p <= 0.0:
+        return add(res, x)
+    return AddDropoutFn.apply(res, x, p, next_seed())
 
 
 # ------------------------------------------------------------------ attention (SelfAttention.forward, transfuser.py:510-527)
