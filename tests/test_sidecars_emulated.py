@@ -179,3 +179,55 @@ def test_consumers_take_the_sidecar(lib, monkeypatch):
     gw, gh = torch.autograd.grad(y, (w, hx), _rnd(2, 20, 32, seed=27))
     assert any(t.data_ptr() == h._tfb16.data_ptr() for t in operands)      # wgrad: dW = g^T xs with xs = the sidecar
     assert torch.isfinite(gw).all() and torch.isfinite(gh).all()
+
+
+def test_backward_sidecar_batchnorm_to_conv(lib, monkeypatch):
+    """BatchNorm backward (bwd16) writes the bf16 copy of dx in its dx pass and offers it under (address, size); the 1x1 conv in
+    front of the BatchNorm (no bias, no ReLU) takes it in its backward instead of launching tfb_grad_prep over dy. The copy is
+    bit-identical to the cast of dx; a gradient nobody offered, or one that was modified in place afterwards, is not matched."""
+    from transfuser_b200 import gemm as G, ops
+    operands = []
+
+    def fake_gemm_bf16(a, b, out, trans_a=False, trans_b=False, bias=None, relu=False, alpha=1.0, beta=0.0, splits=1):
+        operands.append((a, b))
+        A = a.float().t() if trans_a else a.float()
+        Bm = b.float().t() if trans_b else b.float()
+        r = alpha * (A @ Bm)
+        if bias is not None:
+            r = r + bias
+        out.copy_(r.clamp_min(0) if relu else r)
+        return out
+    monkeypatch.setattr(G, 'gemm_bf16', fake_gemm_bf16)
+    monkeypatch.setattr(G, 'weight_bf16', lambda w: w.detach().bfloat16())
+    ops._BWD16.clear()
+    N, H, W, Cin, Cout = 2, 4, 5, 64, 32
+    x = _rnd(N, H, W, Cin, seed=30).requires_grad_(True)
+    w = (_rnd(Cout, Cin, 1, 1, seed=31) / 8).requires_grad_(True)
+    bn = nn.BatchNorm2d(Cout)
+    y = ops.batch_norm(ops.conv2d(x, w), bn, True, True, bwd16=True)
+    g = _rnd(N, H, W, Cout, seed=32)
+    lib.log.clear()
+    operands.clear()
+    gx, gw = torch.autograd.grad(y, (x, w), g)
+    assert 'tfb_grad_prep' not in lib.log and 'tfb_cast_bf16' not in lib.log
+    assert not ops._BWD16                                            # the entry was consumed
+    # reference: the same chain without the sidecar (grad_prep casts dy)
+    x2, w2 = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    y2 = ops.batch_norm(ops.conv2d(x2, w2), _clone_bn(nn.BatchNorm2d(Cout)), True, True)
+    lib.log.clear()
+    gx2, gw2 = torch.autograd.grad(y2, (x2, w2), g)
+    assert lib.log.count('tfb_grad_prep') == 1
+    assert torch.equal(gx, gx2) and torch.equal(gw, gw2)             # same bf16 operand bits -> identical stand-in GEMM results
+    # direct check of the kernel output + the registry rules
+    xb = _rnd(6, 8, seed=33).view(1, 2, 3, 8).requires_grad_(True)
+    yb = ops.batch_norm(xb, nn.BatchNorm2d(8), False, True, bwd16=True)
+    dx, = torch.autograd.grad(yb, xb, _rnd(1, 2, 3, 8, seed=34))
+    (t, t16, ver), = ops._BWD16.values()
+    assert t.data_ptr() == dx.data_ptr() and _same_bits(t16, _cast(lib, dx))
+    assert ops._take16(_rnd(1, 2, 3, 8, seed=35)) is None            # never offered
+    dx.add_(1.0)                                                     # modified after the offer: stale, must not be matched
+    assert ops._take16(dx) is None and not ops._BWD16
+    # tick() drops whatever was not consumed
+    ops._offer16(dx, torch.empty(dx.shape, dtype=torch.bfloat16))
+    ops.tick('cpu')
+    assert not ops._BWD16

@@ -28,7 +28,8 @@ class _ConvBn(nn.Module):
     def run(self, x, emit16=False):
         """emit16: the output is the operand of a tensor-core GEMM / conv next (bf16 mode: BatchNorm writes its bf16 copy too)."""
         y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups)
-        return ops.batch_norm(y, self.bn, self.act, self.bn.training, emit16)
+        # bwd16: this conv has no bias / ReLU of its own, so BatchNorm's dx is exactly the dy its tensor-core dgrad / wgrad read
+        return ops.batch_norm(y, self.bn, self.act, self.bn.training, emit16, bwd16=self.conv.in_channels % 8 == 0)
 
 
 class _SE(nn.Module):

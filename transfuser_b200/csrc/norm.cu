@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t M, int C,
                     const double* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, const float* __restrict__ dgamma,
-                    const float* __restrict__ dbeta) {
+                    const float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx16) {
   const int C4 = C / 4;
   const int64_t total4 = M * C4;
   const double invM = 1.0 / (double)M;
@@ -233,6 +233,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
       o[q] = gas[q] * iss[q] * (g - mg - xh * mgx);
     }
     reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dx16) tfb_store_bf16x4(dx16, i, o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -403,16 +404,17 @@ TFB_API int tfb_bn_apply(const float* x, float* y, int64_t M, int C, const float
   return TFB_OK;
 }
 
-// sums_ws: as for tfb_bn_fwd.
+// sums_ws: as for tfb_bn_fwd. dx16_bf16 (optional): bf16 copy of dx written in the same pass (operand of the tensor-core dgrad /
+// wgrad of the convolution in front of this BatchNorm).
 TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
                        const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
-                       cudaStream_t stream) {
+                       void* dx16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0 && C % 4 == 0);
   Finalize fin = {2, 2 * C, M, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
   launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, fin, stream);
   TFB_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<tfb_grid(M * C / 4, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
-                                                                dgamma, dbeta);
+                                                                dgamma, dbeta, (__nv_bfloat16*)dx16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -37,6 +37,7 @@ def tick(device):
     """Advance the device-side dropout seed (call once per training step)."""
     call('tfb_step_tick', seed_state(device), None)
     _SEED['off'] = 0
+    _BWD16.clear()
 
 
 def next_seed():
@@ -75,6 +76,27 @@ def _as16(x):
     if s is not None and s.shape == x.shape:
         return s
     return G.to_bf16(x)
+
+
+# Backward sidecars: BatchNorm backward writes the bf16 copy of dx next to dx when the convolution in front of it runs its dgrad /
+# wgrad on the tensor cores; that convolution's backward finds it here by (address, size) instead of running a cast pass over dy.
+# An entry keeps a reference to the fp32 gradient, so its memory cannot be recycled (and the key cannot alias another live tensor)
+# while the entry exists; entries are popped by the consumer and dropped wholesale at the start of the next step (tick()).
+_BWD16 = {}
+
+
+def _offer16(t, t16):
+    if len(_BWD16) > 512:
+        _BWD16.clear()
+    _BWD16[(t.data_ptr(), t.numel())] = (t, t16, t._version)
+
+
+def _take16(t):
+    """bf16 sidecar of the contiguous fp32 gradient t (same memory as the tensor it was offered for), or None."""
+    e = _BWD16.pop((t.data_ptr(), t.numel()), None)
+    if e is None or e[0]._version != e[2] or t.dtype != torch.float32 or not t.is_contiguous():
+        return None
+    return e[1].view(t.shape)
 
 
 def record_stream(t, stream):
@@ -240,7 +262,11 @@ class LinearFn(Function):
         M, K = xs.shape
         N = w2.shape[0]
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        g, gb, db = _grad_prep(dy, y if ctx.relu else None, not ctx.tc, ctx.tc, bias_p if want_db else None)
+        gb = _take16(dy) if (ctx.tc and not ctx.relu and not want_db) else None
+        if gb is not None:
+            g, db = None, None              # dy's producer (BatchNorm backward) already wrote its bf16 copy: no pass over dy here
+        else:
+            g, gb, db = _grad_prep(dy, y if ctx.relu else None, not ctx.tc, ctx.tc, bias_p if want_db else None)
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
@@ -302,8 +328,9 @@ class Conv2dFn(Function):
                 dx = torch.empty_like(x)
                 call('tfb_conv2d_dgrad', g, w, dx, N, H, W, Cin, Cout, ks, stride, groups)
         if ctx.needs_input_grad[1]:
-            if G.MODE == 'bf16' and ks == 3 and Cout % 8 == 0:
-                dw = _conv_wgrad_tc(x, G.to_bf16(g), w, groups, stride)
+            if G.MODE == 'bf16' and ks == 3 and Cout % 8 == 0 and _conv_wgrad_tc_ok(x.shape, Cout, groups, stride):
+                g16 = _take16(dy) if not relu else None       # (the 3-channel stems stay on the direct kernel: no cast for them)
+                dw = _conv_wgrad_tc(x, g16 if g16 is not None else G.to_bf16(g), w, groups, stride)
                 if dw is not None and has_bias:
                     db = _colsum(g.view(-1, Cout), _gbuf(bias_p))
             if dw is None:
@@ -345,6 +372,15 @@ def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
     return y
 
 
+def _conv_wgrad_tc_ok(x_shape, Cout, groups, stride):
+    """Shapes _conv_wgrad_tc takes: 16-byte aligned channel windows and enough output pixels for a split-K GEMM."""
+    N, H, W, Cin = x_shape
+    Cig, Cog = Cin // groups, Cout // groups
+    if Cig % 8 or (groups > 1 and Cog % 8):
+        return False
+    return N * ((H - 1) // stride + 1) * ((W - 1) // stride + 1) >= 512
+
+
 def _conv_wgrad_tc(x, g16, w, groups, stride):
     """dW of a 3x3 conv on the tensor cores: im2col(x) in bf16, then one split-K GEMM per channel group
     (dW_g[Cog, 9*Cig] = dy_g^T col_g, batched over groups in a single launch), then the [co][tap][ci] -> [co][ci][tap] permute.
@@ -352,12 +388,10 @@ def _conv_wgrad_tc(x, g16, w, groups, stride):
     N, H, W, Cin = x.shape
     Cout = w.shape[0]
     Cig, Cog = Cin // groups, Cout // groups
-    if Cig % 8 or (groups > 1 and Cog % 8):
+    if not _conv_wgrad_tc_ok(x.shape, Cout, groups, stride):
         return None
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     M = N * Ho * Wo
-    if M < 512:
-        return None
     col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
     call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
     ldg = g16.shape[-1]                      # >= Cout when dy was zero-padded to 8 channels
@@ -394,7 +428,11 @@ class Conv3x3TCFn(Function):
         dx = dw = db = None
         if Cout % 8 == 0:
             # everything downstream runs on the tensor cores: only the bf16 copy of g (and the bias gradient) is produced
-            g, g16, db = _grad_prep(dy.view(-1, Cout), y.view(-1, Cout) if relu else None, False, True, bias_p if has_bias else None)
+            g16 = _take16(dy) if not (relu or has_bias) else None
+            if g16 is not None:
+                g = None
+            else:
+                g, g16, db = _grad_prep(dy.view(-1, Cout), y.view(-1, Cout) if relu else None, False, True, bias_p if has_bias else None)
             g16 = g16.view(N, H, W, Cout)
         else:
             g = _relu_bwd(y, dy) if relu else dy
@@ -462,7 +500,7 @@ class BatchNormTrainFn(Function):
     """BatchNorm2d in training mode (+ fused ReLU): batch statistics, running-stat update (momentum, unbiased var)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False, bwd16=False):
         x = _c(x)
         C = x.shape[-1]
         M = x.numel() // C
@@ -474,7 +512,7 @@ class BatchNormTrainFn(Function):
         call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws,
              y16)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
-        ctx.relu = relu
+        ctx.relu, ctx.bwd16 = relu, bwd16
         return _attach16(y, y16)
 
     @staticmethod
@@ -487,15 +525,19 @@ class BatchNormTrainFn(Function):
         dg = _gbuf(weight)
         db = _gbuf(bias)
         ws = _ws(x.device)
-        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws)
-        return dx, dg, db, None, None, None, None, None, None
+        dx16 = _emit16(dx, ctx.bwd16)
+        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws, dx16)
+        if dx16 is not None:
+            _offer16(dx, dx16)
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
-def batch_norm(x, bn, relu, training, emit16=False):
+def batch_norm(x, bn, relu, training, emit16=False, bwd16=False):
     """bn: an nn.BatchNorm2d used as a parameter/buffer container. emit16: the output feeds a tensor-core GEMM / conv next, so
-    (bf16 mode) its bf16 copy is written in the same pass."""
+    (bf16 mode) its bf16 copy is written in the same pass. bwd16: the same for dx in backward (the convolution in front of this
+    BatchNorm has no bias / ReLU of its own and runs dgrad + wgrad on the tensor cores)."""
     if training:
-        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16)
+        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16, bwd16)
     if torch.is_grad_enabled() and x.requires_grad:
         raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
     C = x.shape[-1]
