@@ -99,6 +99,48 @@ def test_batchnorm_train(shape, relu):
     check_grads([xm, bn2.weight, bn2.bias], [x, bn.weight, bn.bias], out, ref)
 
 
+@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 6, 7, 216), (1, 5, 22, 1512)])
+def test_batchnorm_add_relu_fused(shape):
+    """relu(bn(x) + shortcut) — the Bottleneck tail — as ONE BatchNorm call (add + ReLU inside the normalise pass; ReLU mask and the
+    shortcut's gradient inside the backward passes) against torch and against the unfused product path (eval mode too)."""
+    from transfuser_b200 import ops
+    N, H, W, C = shape
+    x = (rnd(N, C, H, W, seed=4) * 2 + 0.5).requires_grad_()
+    sc = rnd(N, C, H, W, seed=8).requires_grad_()
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    bn.weight.data = rnd(C, seed=5) * 0.3 + 1
+    bn.bias.data = rnd(C, seed=6) * 0.2
+    state = {k: v.clone() for k, v in bn.state_dict().items()}
+    ref = F.relu(bn(x) + sc)
+    outs = {}
+    old = ops.BN_ADD_FUSED
+    try:
+        for fused in (True, False):
+            ops.BN_ADD_FUSED = fused
+            bn2 = torch.nn.BatchNorm2d(C).to(DEV)
+            bn2.load_state_dict(state)
+            xm, sm = nhwc(x.detach()).requires_grad_(), nhwc(sc.detach()).requires_grad_()
+            n0 = len(_calls())
+            out = ops.batch_norm(xm, bn2, True, True, residual=sm)
+            if _calls() is not _NOLOG:
+                assert len(_calls()) - n0 == (1 if fused else 2)
+            bn.load_state_dict(state)
+            ref = F.relu(bn(x) + sc)
+            assert rel(nchw(out), ref) < TOL
+            assert rel(bn2.running_mean, bn.running_mean) < TOL and rel(bn2.running_var, bn.running_var) < TOL
+            check_grads([xm, sm, bn2.weight, bn2.bias], [x, sc, bn.weight, bn.bias], out, ref)
+            outs[fused] = out.detach()
+            bn2.eval()
+            with torch.no_grad():
+                ev = ops.batch_norm(xm.detach(), bn2, True, False, residual=sm.detach())
+                bn.eval()
+                assert rel(nchw(ev), F.relu(bn(x) + sc)) < TOL
+                bn.train()
+    finally:
+        ops.BN_ADD_FUSED = old
+    assert torch.equal(outs[True], outs[False])          # same arithmetic, one pass instead of two
+
+
 def test_layernorm_linear_dropout():
     from transfuser_b200 import ops
     x = rnd(LN_ROWS, 216, seed=1).requires_grad_()

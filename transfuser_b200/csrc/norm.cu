@@ -72,7 +72,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int relu, Finalize fin) {
+                 const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
   double d0 = 0.0, d1 = 0.0;
@@ -87,7 +87,8 @@ colreduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
       } else {
         const float xh = (v - mu) * is;
         float g = dy[r * C + c];
-        if (relu && !(fmaf(xh, ga, be) > 0.f)) g = 0.f;
+        if (ymask) { if (!(ymask[r * C + c] > 0.f)) g = 0.f; }
+        else if (relu && !(fmaf(xh, ga, be) > 0.f)) g = 0.f;
         a0 += g; a1 = fmaf(g, xh, a1);
       }
       if (++cnt == 64) { d0 += a0; d1 += a1; a0 = a1 = 0.f; cnt = 0; }  // bound fp32 partial length
@@ -115,7 +116,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int relu, Finalize fin) {
+                  const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
   double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
@@ -132,12 +133,18 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
       const float4 v0 = *reinterpret_cast<const float4*>(x + r * ldx + c);
       const float4 v1 = two ? *reinterpret_cast<const float4*>(x + (r + step) * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      float4 m0 = make_float4(1.f, 1.f, 1.f, 1.f), m1 = m0;       // mask source (output of the fused add + ReLU), when given
       if (MODE == 1) {
         g0 = *reinterpret_cast<const float4*>(dy + r * C + c);
         if (two) g1 = *reinterpret_cast<const float4*>(dy + (r + step) * C + c);
+        if (ymask) {
+          m0 = *reinterpret_cast<const float4*>(ymask + r * C + c);
+          if (two) m1 = *reinterpret_cast<const float4*>(ymask + (r + step) * C + c);
+        }
       }
       const float xv[2][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}};
       const float gv[2][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}};
+      const float mv[2][4] = {{m0.x, m0.y, m0.z, m0.w}, {m1.x, m1.y, m1.z, m1.w}};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h == 1 && !two) break;
@@ -148,7 +155,8 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
           } else {
             const float xh = (xv[h][q] - mu[q]) * is[q];
             float g = gv[h][q];
-            if (relu && !(fmaf(xh, ga[q], be[q]) > 0.f)) g = 0.f;
+            if (ymask) { if (!(mv[h][q] > 0.f)) g = 0.f; }
+            else if (relu && !(fmaf(xh, ga[q], be[q]) > 0.f)) g = 0.f;
             a0[q] += g; a1[q] = fmaf(g, xh, a1[q]);
           }
         }
@@ -183,7 +191,7 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total4, int C4, const float* __restrict__ mean,
                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                __nv_bfloat16* __restrict__ y16) {
+                __nv_bfloat16* __restrict__ y16, const float* __restrict__ res) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -196,6 +204,10 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t tota
     o.y = fmaf((v.y - mu.y) * is.y, ga.y, be.y);
     o.z = fmaf((v.z - mu.z) * is.z, ga.z, be.z);
     o.w = fmaf((v.w - mu.w) * is.w, ga.w, be.w);
+    if (res) {                                    // Bottleneck shortcut: act(bn(x) + residual) in one pass
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     reinterpret_cast<float4*>(y)[i] = o;
     if (y16) tfb_store_bf16x4(y16, i, o.x, o.y, o.z, o.w);
@@ -208,7 +220,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t M, int C,
                     const double* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, const float* __restrict__ dgamma,
-                    const float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx16) {
+                    const float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx16, const float* __restrict__ ymask,
+                    float* __restrict__ gout) {
   const int C4 = C / 4;
   const int64_t total4 = M * C4;
   const double invM = 1.0 / (double)M;
@@ -223,17 +236,23 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
     const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, iss[4] = {is.x, is.y, is.z, is.w};
     const float gas[4] = {ga.x, ga.y, ga.z, ga.w}, bes[4] = {be.x, be.y, be.z, be.w};
-    float o[4];
+    float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (ymask) mk = reinterpret_cast<const float4*>(ymask)[i];
+    const float ms[4] = {mk.x, mk.y, mk.z, mk.w};
+    float o[4], gm[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float xh = (xs[q] - mus[q]) * iss[q];
       float g = gs[q];
-      if (relu && !(fmaf(xh, gas[q], bes[q]) > 0.f)) g = 0.f;
+      if (ymask) { if (!(ms[q] > 0.f)) g = 0.f; }
+      else if (relu && !(fmaf(xh, gas[q], bes[q]) > 0.f)) g = 0.f;
+      gm[q] = g;
       const float mg = (float)((double)dbeta[c + q] * invM), mgx = (float)((double)dgamma[c + q] * invM);
       o[q] = gas[q] * iss[q] * (g - mg - xh * mgx);
     }
     reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
     if (dx16) tfb_store_bf16x4(dx16, i, o[0], o[1], o[2], o[3]);
+    if (gout) reinterpret_cast<float4*>(gout)[i] = make_float4(gm[0], gm[1], gm[2], gm[3]);
   }
 }
 
@@ -347,7 +366,7 @@ grad_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, floa
 
 template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
-                     const float* gamma, const float* beta, int relu, Finalize fin, cudaStream_t stream);
+                     const float* gamma, const float* beta, int relu, const float* ymask, Finalize fin, cudaStream_t stream);
 
 int colreduce_splits(int64_t M, int slabs) {
   int64_t want = (4LL * tfb_num_sms() + slabs - 1) / slabs;
@@ -360,17 +379,18 @@ int colreduce_splits(int64_t M, int slabs) {
 
 template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
-                     const float* gamma, const float* beta, int relu, Finalize fin, cudaStream_t stream) {
-  const bool vec = C % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!dy || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+                     const float* gamma, const float* beta, int relu, const float* ymask, Finalize fin, cudaStream_t stream) {
+  const bool vec = C % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!dy || (reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                   (!ymask || (reinterpret_cast<uintptr_t>(ymask) & 15) == 0);
   dim3 block(32, 8);
   if (vec) {
     const int slabs = (C / 4 + 31) / 32;
     dim3 grid(slabs, colreduce_splits(M, slabs));
-    colreduce4_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, fin);
+    colreduce4_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, ymask, fin);
   } else {
     const int slabs = (C + 31) / 32;
     dim3 grid(slabs, colreduce_splits(M, slabs));
-    colreduce_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, fin);
+    colreduce_kernel<MODE><<<grid, block, 0, stream>>>(x, ldx, dy, M, C, out, mean, invstd, gamma, beta, relu, ymask, fin);
   }
   return 0;
 }
@@ -379,42 +399,47 @@ int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, in
 
 // sums_ws: (2*C + 1) doubles, ZERO on entry, left zero on exit (shared by all layers of a stream; no memset launches).
 // y16_bf16 (optional): bf16 copy of y written in the same pass (operand of the next layer's tensor-core GEMM / conv).
+// residual (optional, [M, C]): y = act(bn(x) + residual) — the Bottleneck's last BatchNorm + shortcut add + ReLU in one pass.
 TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps,
                        float momentum, int relu, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                       double* sums_ws, void* y16_bf16, cudaStream_t stream) {
+                       double* sums_ws, void* y16_bf16, const float* residual, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && sums_ws && M > 0 && C > 0 && C % 4 == 0);
   Finalize fin = {1, 2 * C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var};
-  launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, fin, stream);
+  launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, nullptr, fin, stream);
   TFB_CHECK_LAUNCH();
   const int64_t total4 = M * C / 4;
   bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu,
-                                                             (__nv_bfloat16*)y16_bf16);
+                                                             (__nv_bfloat16*)y16_bf16, residual);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
 // eval-mode BN: normalise with the running statistics (mean, 1/sqrt(var+eps) computed by the caller into save_*).
 TFB_API int tfb_bn_apply(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, const float* mean,
-                         const float* invstd, int relu, void* y16_bf16, cudaStream_t stream) {
+                         const float* invstd, int relu, void* y16_bf16, const float* residual, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && mean && invstd && M > 0 && C > 0 && C % 4 == 0);
   const int64_t total4 = M * C / 4;
   bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, mean, invstd, gamma, beta, relu,
-                                                             (__nv_bfloat16*)y16_bf16);
+                                                             (__nv_bfloat16*)y16_bf16, residual);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
 // sums_ws: as for tfb_bn_fwd. dx16_bf16 (optional): bf16 copy of dx written in the same pass (operand of the tensor-core dgrad /
 // wgrad of the convolution in front of this BatchNorm).
+// ymask / gmasked (optional, [M, C]): backward of y = relu(bn(x) + residual) (tfb_bn_fwd with a residual): the ReLU mask is
+// (ymask > 0) with ymask = that y, the masked gradient g = dy * mask drives the BatchNorm backward (pass relu = 0) and is also
+// written to gmasked — it is the gradient of the residual branch.
 TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
                        const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
-                       void* dx16_bf16, cudaStream_t stream) {
+                       void* dx16_bf16, const float* ymask, float* gmasked, cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0 && C % 4 == 0);
   Finalize fin = {2, 2 * C, M, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
-  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, fin, stream);
+  TFB_REQUIRE(!gmasked || ymask);
+  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, ymask, fin, stream);
   TFB_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<tfb_grid(M * C / 4, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
-                                                                dgamma, dbeta, (__nv_bfloat16*)dx16_bf16);
+                                                                dgamma, dbeta, (__nv_bfloat16*)dx16_bf16, ymask, gmasked);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -424,7 +449,7 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
 TFB_API int tfb_colsum(const float* x, int64_t ldx, int64_t M, int C, float* out, double* sums_ws, cudaStream_t stream) {
   TFB_REQUIRE(x && out && sums_ws && M > 0 && C > 0 && ldx >= C);
   Finalize fin = {3, C, M, 0.f, 0.f, out, nullptr, nullptr, nullptr};
-  launch_colreduce<0>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, fin, stream);
+  launch_colreduce<0>(x, ldx, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, nullptr, fin, stream);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -54,6 +54,7 @@ def _c(t):
 # takes it instead of running a cast pass of its own. SIDECARS = False restores the separate cast launches.
 SIDECARS = os.environ.get('TFB_SIDECARS', '1') == '1'
 QKV_FUSED = os.environ.get('TFB_QKV_FUSED', '1') == '1'           # one q|k|v GEMM when the flat buffer packs the three weights
+BN_ADD_FUSED = os.environ.get('TFB_BN_ADD_FUSED', '1') == '1'     # conv3.bn + shortcut add + ReLU as one BatchNorm call
 SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
 
 
@@ -510,7 +511,7 @@ class BatchNormTrainFn(Function):
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = _ws(x.device)
         call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws,
-             y16)
+             y16, None)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.relu, ctx.bwd16 = relu, bwd16
         return _attach16(y, y16)
@@ -526,17 +527,57 @@ class BatchNormTrainFn(Function):
         db = _gbuf(bias)
         ws = _ws(x.device)
         dx16 = _emit16(dx, ctx.bwd16)
-        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws, dx16)
+        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws, dx16, None, None)
         if dx16 is not None:
             _offer16(dx, dx16)
         return dx, dg, db, None, None, None, None, None, None, None
 
 
-def batch_norm(x, bn, relu, training, emit16=False, bwd16=False):
-    """bn: an nn.BatchNorm2d used as a parameter/buffer container. emit16: the output feeds a tensor-core GEMM / conv next, so
+class BatchNormAddReluFn(Function):
+    """relu(BatchNorm2d(x) + residual), training mode: the tail of timm's Bottleneck (conv3.bn -> + shortcut -> ReLU) with the add
+    and the ReLU inside BatchNorm's normalise pass (forward) and the ReLU mask + the shortcut's gradient inside BatchNorm's backward
+    passes — two launches and four passes over the block-sized activation fewer than BatchNorm, add+ReLU, ReLU', BatchNorm'."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, running_mean, running_var, momentum, eps, emit16=False, bwd16=False):
+        x, res = _c(x), _c(res)
+        C = x.shape[-1]
+        M = x.numel() // C
+        y = torch.empty_like(x)
+        y16 = _emit16(y, emit16)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
+             _ws(x.device), y16, res)
+        ctx.save_for_backward(x, weight, bias, mean, invstd, y)
+        ctx.bwd16 = bwd16
+        return _attach16(y, y16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, invstd, y = ctx.saved_tensors
+        dy = _c(dy)
+        C = x.shape[-1]
+        M = x.numel() // C
+        dx, g = torch.empty_like(x), torch.empty_like(x)
+        dg, db = _gbuf(weight), _gbuf(bias)
+        dx16 = _emit16(dx, ctx.bwd16)
+        call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, 0, dg, db, _ws(x.device), dx16, y, g)
+        if dx16 is not None:
+            _offer16(dx, dx16)
+        return dx, g, dg, db, None, None, None, None, None, None
+
+
+def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None):
+    """bn: an nn.BatchNorm2d used as a parameter/buffer container. residual: act(bn(x) + residual) in the same pass (relu required). emit16: the output feeds a tensor-core GEMM / conv next, so
     (bf16 mode) its bf16 copy is written in the same pass. bwd16: the same for dx in backward (the convolution in front of this
     BatchNorm has no bias / ReLU of its own and runs dgrad + wgrad on the tensor cores)."""
+    if residual is not None and not (relu and BN_ADD_FUSED):
+        return add(batch_norm(x, bn, False, training, False, bwd16), residual, relu=relu, emit16=emit16)
     if training:
+        if residual is not None:
+            return BatchNormAddReluFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, emit16,
+                                            bwd16)
         return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16, bwd16)
     if torch.is_grad_enabled() and x.requires_grad:
         raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
@@ -544,7 +585,8 @@ def batch_norm(x, bn, relu, training, emit16=False, bwd16=False):
     y = torch.empty_like(x)
     y16 = _emit16(y, emit16)
     invstd = torch.rsqrt(bn.running_var + bn.eps)
-    call('tfb_bn_apply', _c(x), y, x.numel() // C, C, bn.weight, bn.bias, bn.running_mean, invstd, int(relu), y16)
+    call('tfb_bn_apply', _c(x), y, x.numel() // C, C, bn.weight, bn.bias, bn.running_mean, invstd, int(relu), y16,
+         _c(residual) if residual is not None else None)
     return _attach16(y, y16)
 
 
