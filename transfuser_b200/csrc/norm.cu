@@ -307,10 +307,11 @@ ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
   }
 }
 
-// dgamma[c] = sum_r dy*xhat, dbeta[c] = sum_r dy  (column reduction; rows are few thousand)
+// dgamma[c] = sum_r dy*xhat, dbeta[c] = sum_r dy  (column reduction; rows are few thousand). Partial sums meet in the self-cleaning
+// fp64 workspace (sums = [sum dy | sum dy*xhat]) and the last block writes dbeta / dgamma: no memsets of the outputs.
 __global__ void __launch_bounds__(256)
 ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t R, int C, const float* __restrict__ save_mean,
-                    const float* __restrict__ save_rstd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    const float* __restrict__ save_rstd, double* __restrict__ sums, Finalize fin) {
   __shared__ float sg[8][33], sb[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
@@ -328,9 +329,10 @@ ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
     float ta = 0.f, tb = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ta += sg[j][threadIdx.x]; tb += sb[j][threadIdx.x]; }
-    atomicAdd(&dgamma[c], ta);
-    atomicAdd(&dbeta[c], tb);
+    atomicAdd(&sums[c], (double)tb);
+    atomicAdd(&sums[C + c], (double)ta);
   }
+  finalize_last_block(sums, C, fin);
 }
 
 // Backward prologue of a dense layer, one pass over dy [M, C]:  g = relu ? dy * (y > 0) : dy;  optional outputs: g in fp32, g in
@@ -474,21 +476,20 @@ TFB_API int tfb_layernorm_fwd(const float* x, float* y, int64_t R, int C, const 
   return TFB_OK;
 }
 
-// dx (+)= LN backward; dgamma/dbeta are overwritten.
+// dx (+)= LN backward; dgamma/dbeta are overwritten. sums_ws: (2*C + 1) doubles, zero on entry, left zero on exit (as for tfb_bn_fwd).
 TFB_API int tfb_layernorm_bwd(const float* x, const float* dy, float* dx, int64_t R, int C, const float* gamma,
                               const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, int accumulate_dx,
-                              cudaStream_t stream) {
-  TFB_REQUIRE(x && dy && dx && gamma && save_mean && save_rstd && dgamma && dbeta && R > 0 && C > 0);
+                              double* sums_ws, cudaStream_t stream) {
+  TFB_REQUIRE(x && dy && dx && gamma && save_mean && save_rstd && dgamma && dbeta && sums_ws && R > 0 && C > 0);
   ln_bwd_dx_kernel<<<(unsigned)R, 256, 0, stream>>>(x, dy, dx, C, gamma, save_mean, save_rstd, accumulate_dx);
   TFB_CHECK_LAUNCH();
-  if (cudaMemsetAsync(dgamma, 0, (size_t)C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  if (cudaMemsetAsync(dbeta, 0, (size_t)C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   const int slabs = (C + 31) / 32;
   int splits = (int)ceil_div64(R, 8 * 8);
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
   dim3 grid(slabs, splits), block(32, 8);
-  ln_bwd_param_kernel<<<grid, block, 0, stream>>>(x, dy, R, C, save_mean, save_rstd, dgamma, dbeta);
+  Finalize fin = {2, 2 * C, R, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
+  ln_bwd_param_kernel<<<grid, block, 0, stream>>>(x, dy, R, C, save_mean, save_rstd, sums_ws, fin);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -613,7 +613,7 @@ class LayerNormFn(Function):
         dx = torch.empty_like(x)
         dg = _gbuf(weight)
         db = _gbuf(bias)
-        call('tfb_layernorm_bwd', x, dy, dx, R, C, weight, mean, rstd, dg, db, 0)
+        call('tfb_layernorm_bwd', x, dy, dx, R, C, weight, mean, rstd, dg, db, 0, _ws(x.device))
         return dx, dg, db, None, None
 
 
