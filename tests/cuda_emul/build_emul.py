@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'transfuser_b200', 'csrc')
 OUT = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT, 'libtfb200_emul.so')
-FILES = ('api.cu', 'bev_hist.cu', 'conv_simt.cu', 'decode.cu', 'elementwise.cu', 'gemm_simt.cu', 'geometric.cu', 'gru_adamw.cu',
+FILES = ('api.cu', 'bev_hist.cu', 'conv_pack.cu', 'conv_simt.cu', 'decode.cu', 'elementwise.cu', 'gemm_simt.cu', 'geometric.cu', 'gru_adamw.cu',
          'input_prep.cu', 'losses.cu', 'norm.cu')
 def _split_top(s):
     parts, depth, cur = [], 0, ''

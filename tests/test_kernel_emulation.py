@@ -475,3 +475,47 @@ def test_simt_gemm_kernel(shape, ta, tb):
         assert torch.allclose(dst[:, 48:].double(), x[:, 24:48].double() @ w.double().t(), atol=1e-5) and float(dst[:, :48].abs().sum()) == 0
     finally:
         L._LIB = old
+
+
+def test_conv3x3_weight_pack_batched_matches_single_pack():
+    """tfb_conv3x3_pack_weights_batched (every registered conv of the model in one launch, device-resident descriptor table) writes
+    exactly what per-conv tfb_conv3x3_pack_weights calls write, for the dense / grouped, forward / dgrad plans of ops._conv_tc_plan;
+    the single pack itself is checked against the layout definition (conv_pack.cu) restated in numpy."""
+    from transfuser_b200 import ops
+    cases = [(64, 64, 1), (32, 32, 1), (512, 128, 1), (72, 72, 3), (216, 216, 9), (128, 64, 1), (32, 7 + 1, 1)]
+    rows, keep, singles = [], [], []
+    for n, (cin, cout, groups) in enumerate(cases):
+        w = torch.randn(cout, cin // groups, 3, 3, generator=torch.Generator().manual_seed(n))
+        for mode in (0, 1):
+            c_read, c_write = (cin, cout) if mode == 0 else (cout, cin)
+            plan = ops._conv_tc_plan(c_read, c_write, groups)
+            if plan is None:
+                continue
+            shape = (plan['gblocks'], plan['nchunks'], 9, plan['NB'], plan['KC'])
+            args = (cout, cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'], plan['gblocks'])
+            one = torch.full(shape, 7.0, dtype=torch.bfloat16)
+            _call('tfb_conv3x3_pack_weights', w, one, *args)
+            many = torch.full(shape, 9.0, dtype=torch.bfloat16)
+            rows.append([w.data_ptr(), many.data_ptr()] + list(args))
+            keep.append((w, many))
+            singles.append(one)
+            # layout definition, restated
+            want = np.zeros(shape, np.float32)
+            wn = w.numpy()
+            cig, cog = cin // groups, cout // groups
+            for gb in range(shape[0]):
+                for ch in range(shape[1]):
+                    for j in range(min(plan['nb_real'], shape[3])):
+                        oc = gb * plan['nb_real'] + j
+                        for kk in range(shape[4]):
+                            rc = gb * plan['c_step'] + ch * plan['KC'] + kk
+                            if mode == 0 and oc < cout and rc < cin and rc // cig == oc // cog:
+                                want[gb, ch, :, j, kk] = wn[oc, rc - (oc // cog) * cig].reshape(9)
+                            if mode == 1 and oc < cin and rc < cout and rc // cog == oc // cig:
+                                want[gb, ch, :, j, kk] = wn[rc, oc - (oc // cig) * cig].reshape(9)[::-1]
+            assert torch.equal(one.float(), torch.from_numpy(want).bfloat16().float()), (cin, cout, groups, mode)
+    table = torch.tensor(rows, dtype=torch.int64)
+    _call('tfb_conv3x3_pack_weights_batched', table, len(rows), 3)
+    assert len(rows) >= 10
+    for (w, many), one in zip(keep, singles):
+        assert torch.equal(many.view(torch.int16), one.view(torch.int16))

@@ -231,3 +231,71 @@ def test_backward_sidecar_batchnorm_to_conv(lib, monkeypatch):
     ops._offer16(dx, torch.empty(dx.shape, dtype=torch.bfloat16))
     ops.tick('cpu')
     assert not ops._BWD16
+
+
+def test_packed_conv_weight_registry(lib, monkeypatch):
+    """ops._conv_tc_run keeps one persistent packed buffer per (weight, direction); tick() re-packs all of them in one launch and the
+    convs of that step skip their own pack; a weight whose version moved, invalidate_packs() (fused AdamW / graph replay), or a
+    step without tick() (eval) fall back to the per-call pack, so a stale pack is never read. The tensor-core conv itself is
+    intercepted (not emulable): the stand-in records the packed weights it was handed."""
+    import gc
+    from transfuser_b200 import ops
+    seen = []
+    real_call = ops.call
+
+    def call(name, *args):
+        if name == 'tfb_conv3x3_tc':
+            seen.append(args[1].clone())
+            args[3].zero_()
+            return
+        return real_call(name, *args)
+    monkeypatch.setattr(ops, 'call', call)
+    monkeypatch.setattr(ops, 'PACK_BATCHED', True)
+    ops._PACKS.clear()
+    ops._PACK_STATE.update(sig=None, table=None)
+    w = nn.Parameter(_rnd(64, 64, 3, 3, seed=40))
+    w2 = nn.Parameter(_rnd(72, 24, 3, 3, seed=41))
+    x, x2 = torch.zeros(1, 8, 16, 64, dtype=torch.bfloat16), torch.zeros(1, 8, 16, 72, dtype=torch.bfloat16)
+    plan, plan2 = ops._conv_tc_plan(64, 64, 1), ops._conv_tc_plan(72, 72, 3)
+
+    def fresh_pack(wt, pl, mode, groups):
+        out = torch.empty((pl['gblocks'], pl['nchunks'], 9, pl['NB'], pl['KC']), dtype=torch.bfloat16)
+        real_call('tfb_conv3x3_pack_weights', wt.detach(), out, wt.shape[0], wt.shape[1] * groups, groups, mode, pl['NB'], pl['KC'], pl['c_step'],
+                  pl['nchunks'], pl['nb_real'], pl['gblocks'])
+        return out
+
+    def run(expect_single):
+        lib.log.clear()
+        seen.clear()
+        ops._conv_tc_run(x, w, None, plan, 0, 64, 1, False)
+        ops._conv_tc_run(x2, w2, None, plan2, 1, 72, 3, False)
+        assert lib.log.count('tfb_conv3x3_pack_weights') == expect_single
+        assert _same_bits(seen[0], fresh_pack(w, plan, 0, 1)) and _same_bits(seen[1], fresh_pack(w2, plan2, 1, 3))
+
+    run(2)                                   # first use: registered + packed per call
+    run(2)                                   # no tick() yet (eval-style use): still per call
+    ops.tick('cpu')
+    assert lib.log.count('tfb_conv3x3_pack_weights_batched') == 1
+    run(0)                                   # inside the step: the batched pack is reused
+    run(0)
+    with torch.no_grad():
+        w.mul_(2.0)                          # version bump (torch optimizer / load_state_dict): only this conv re-packs
+    run(1)
+    ops.tick('cpu')
+    run(0)
+    w2.data.mul_(0.5)                        # silent update (what the fused AdamW kernel does) + the invalidation that goes with it
+    ops.invalidate_packs()
+    run(2)
+    table = ops._PACK_STATE['table']
+    ops.tick('cpu')
+    assert ops._PACK_STATE['table'] is table          # unchanged registry: the descriptor table is not rebuilt (graph capture safe)
+    run(0)
+    monkeypatch.setattr(ops, 'PACK_BATCHED', False)
+    run(2)
+    monkeypatch.setattr(ops, 'PACK_BATCHED', True)
+    del w2
+    gc.collect()
+    w2 = nn.Parameter(_rnd(72, 24, 3, 3, seed=42))    # a new weight (possibly at the old address / id): never served the old pack
+    ops.tick('cpu')
+    run(1)
+    assert len(ops._PACKS) == 2

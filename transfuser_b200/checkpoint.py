@@ -44,7 +44,10 @@ def load_model(model, src, strict=True, map_location=None):
 
 
 def refresh_mirrors(model):
-    """After parameters changed outside the fused optimizer: re-derive the bf16 weight mirror (tensor-core mode)."""
+    """After parameters changed outside the fused optimizer: re-derive the bf16 weight mirror (tensor-core mode) and drop the
+    packed conv weights of the current step."""
+    from . import ops
+    ops.invalidate_packs()
     fp = getattr(model, '_tfb_flat_params', None)
     if fp is not None and fp.bf16 is not None:
         from . import gemm

@@ -173,40 +173,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   }
 }
 
-// out[gb][chunk][tap][j][kk] (bf16): the B operand rows for output channel j of block gb and reduction channel kk.
-// mode 0 (forward): value = w[co = gb*nb_real + j][ci - group(co)*Cig][tap],      ci = gb*c_step + chunk*KC + kk (same group only)
-// mode 1 (dgrad)  : value = w[co = gb*c_step + chunk*KC + kk][ci' - group*Cig][8 - tap], ci' = gb*nb_real + j (conv input channel)
-__global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int groups, int mode, int NB, int KC,
-                    int c_step, int nchunks, int nb_real, int gblocks) {
-  const int Cig = Cin / groups, Cog = Cout / groups;
-  const int64_t total = (int64_t)gblocks * nchunks * 9 * NB * KC;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % KC);
-    const int j = (int)((i / KC) % NB);
-    const int tap = (int)((i / ((int64_t)KC * NB)) % 9);
-    const int chunk = (int)((i / ((int64_t)KC * NB * 9)) % nchunks);
-    const int gb = (int)(i / ((int64_t)KC * NB * 9 * nchunks));
-    float v = 0.f;
-    const int oc = gb * nb_real + j;            // channel of the tensor this kernel WRITES
-    const int rc = gb * c_step + chunk * KC + kk;  // channel of the tensor this kernel READS
-    if (j < nb_real) {
-      if (mode == 0) {
-        if (oc < Cout && rc < Cin) {
-          const int g = oc / Cog;
-          if (rc / Cig == g) v = w[((int64_t)oc * Cig + (rc - g * Cig)) * 9 + tap];
-        }
-      } else {
-        if (oc < Cin && rc < Cout) {
-          const int g = oc / Cig;
-          if (rc / Cog == g) v = w[((int64_t)rc * Cig + (oc - g * Cig)) * 9 + (8 - tap)];
-        }
-      }
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
-}
-
 // col[m][g][tap][c] (bf16) = x[n, ho*stride - 1 + tap/3, wo*stride - 1 + tap%3, g*Cg + c] (0 outside), m = (n, ho, wo): the im2col
 // matrix whose column windows are the B operands of the per-group wgrad GEMMs (dW_g = dy_g^T col_g). c fastest: coalesced.
 __global__ void __launch_bounds__(256)
@@ -295,17 +261,6 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
 }
 
 }  // namespace
-
-// Packs fp32 PyTorch-layout 3x3 weights [Cout][Cin/groups][3][3] into the bf16 B-operand layout [gblocks][nchunks][9][NB][KC].
-TFB_API int tfb_conv3x3_pack_weights(const float* w, void* out_bf16, int Cout, int Cin, int groups, int mode, int NB, int KC,
-                                     int c_step, int nchunks, int nb_real, int gblocks, cudaStream_t stream) {
-  TFB_REQUIRE(w && out_bf16 && Cout > 0 && Cin > 0 && groups > 0 && (mode == 0 || mode == 1) && NB > 0 && KC > 0);
-  const int64_t total = (int64_t)gblocks * nchunks * 9 * NB * KC;
-  pack_weights_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(w, (__nv_bfloat16*)out_bf16, Cout, Cin, groups, mode, NB, KC, c_step,
-                                                               nchunks, nb_real, gblocks);
-  TFB_CHECK_LAUNCH();
-  return TFB_OK;
-}
 
 // y[N,H,W,Cy] (fp32) = conv3x3(x16[N,H,W,Cx] bf16, packed weights) (+bias) (ReLU). Block gb reads channels
 // [gb*c_step + chunk*KC, +KC) for chunk < nchunks and writes channels [gb*nb_real, +min(nb_real, Cy - gb*nb_real)).

@@ -4,6 +4,7 @@ hand-written sm_100a kernel launch; torch supplies device memory, the current st
 Activations are NHWC fp32 ([N, H, W, C], contiguous); parameters keep the reference's PyTorch layouts so that the
 reference's state_dicts load unchanged."""
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -38,6 +39,7 @@ def tick(device):
     call('tfb_step_tick', seed_state(device), None)
     _SEED['off'] = 0
     _BWD16.clear()
+    _prepack_all(device)
 
 
 def next_seed():
@@ -361,14 +363,79 @@ def _conv_tc_plan(c_read, c_write, groups):
     return dict(NB=nb, KC=kc, c_step=0, nchunks=nchunks, nb_real=nb if gblocks > 1 else c_write, gblocks=gblocks)
 
 
+# Packed bf16 weights of the tensor-core 3x3 convs. Every (weight, direction) gets a persistent packed buffer on first use. Inside a
+# training step (between tick() and the optimizer step) the weights do not change, so tick() re-packs ALL registered convs in one
+# launch (tfb_conv3x3_pack_weights_batched) and the convs of that step's forward and backward reuse the buffers; anything else
+# (eval, a weight whose tensor version moved, PACK_BATCHED off) packs per call as before. invalidate_packs() must follow every
+# weight update that does not bump tensor versions (the fused AdamW kernel, CUDA-graph replays).
+PACK_BATCHED = os.environ.get('TFB_PACK_BATCHED', '1') == '1'
+_PACKS = {}                      # (id(weight), mode) -> _Pack
+_PACK_STATE = {'epoch': 0, 'sig': None, 'table': None}
+
+
+class _Pack:
+    __slots__ = ('wref', 'ptr', 'wp', 'args', 'epoch', 'version')
+
+
+def invalidate_packs():
+    _PACK_STATE['epoch'] += 1
+
+
+def _packed_weights(w, plan, mode, groups):
+    args = (groups, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'], plan['gblocks'])
+    key = (id(w), mode)
+    e = _PACKS.get(key)
+    if e is not None and (e.wref() is not w or e.ptr != w.data_ptr() or e.args != args or e.wp.device != w.device):
+        e = None
+    if e is None:
+        e = _Pack()
+        e.wref, e.ptr, e.args, e.epoch, e.version = weakref.ref(w), w.data_ptr(), args, -1, -1
+        e.wp = torch.empty((plan['gblocks'], plan['nchunks'], 9, plan['NB'], plan['KC']), dtype=torch.bfloat16, device=w.device)
+        if len(_PACKS) > 4096:
+            _PACKS.clear()
+        _PACKS[key] = e
+        _PACK_STATE['sig'] = None
+    return e
+
+
+def _prepack_all(device):
+    """One launch re-packs every registered conv weight that lives on `device` (called by tick() at the start of a training step)."""
+    if not PACK_BATCHED:
+        return
+    device = torch.device(device)
+    live = []
+    for key, e in list(_PACKS.items()):
+        w = e.wref()
+        if w is None:
+            del _PACKS[key]
+            _PACK_STATE['sig'] = None
+        elif w.data_ptr() == e.ptr and w.is_contiguous() and w.device.type == device.type and device.index in (None, w.device.index):
+            live.append((key[1], e, w))
+    if not live:
+        return
+    rows = []
+    for mode, e, w in live:
+        groups = e.args[0]
+        rows.append([e.ptr, e.wp.data_ptr(), w.shape[0], w.shape[1] * groups, groups, mode] + list(e.args[1:]))
+    sig = tuple(map(tuple, rows))
+    if _PACK_STATE['sig'] != sig:
+        _PACK_STATE['table'] = torch.tensor(rows, dtype=torch.int64).to(device)
+        _PACK_STATE['sig'] = sig
+    call('tfb_conv3x3_pack_weights_batched', _PACK_STATE['table'], len(rows), 8)
+    _PACK_STATE['epoch'] += 1
+    for _, e, w in live:
+        e.epoch, e.version = _PACK_STATE['epoch'], w._version
+
+
 def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
     N, H, W, c_read = x16.shape
     Cout, Cin = (w.shape[0], w.shape[1] * groups)
-    wp = torch.empty((plan['gblocks'], plan['nchunks'], 9, plan['NB'], plan['KC']), dtype=torch.bfloat16, device=x16.device)
-    call('tfb_conv3x3_pack_weights', w, wp, Cout, Cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
-         plan['gblocks'])
+    e = _packed_weights(w, plan, mode, groups)
+    if not (PACK_BATCHED and e.epoch == _PACK_STATE['epoch'] and e.version == w._version):
+        call('tfb_conv3x3_pack_weights', w, e.wp, Cout, Cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'],
+             plan['nb_real'], plan['gblocks'])
     y = torch.empty((N, H, W, c_write), dtype=torch.float32, device=x16.device)
-    call('tfb_conv3x3_tc', x16, wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
+    call('tfb_conv3x3_tc', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
          plan['gblocks'], int(relu))
     return y
 

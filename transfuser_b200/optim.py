@@ -154,6 +154,7 @@ class FusedAdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         _lib.call('tfb_step_tick', None, self._step_dev)   # device-side step count: valid under CUDA-graph replay
+        ops_mod.invalidate_packs()                         # the kernel below rewrites the weights without bumping tensor versions
         b1, b2 = g['betas']
         spans = chunks or [(0, fp.total, None)]
         for lo, hi, work in spans:

@@ -80,4 +80,5 @@ class Trainer:
 
     def replay(self):
         self.graph.replay()
+        ops.invalidate_packs()        # the replayed optimizer kernel changed the weights behind Python's back
         return self.static_loss
