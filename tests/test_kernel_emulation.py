@@ -519,3 +519,30 @@ def test_conv3x3_weight_pack_batched_matches_single_pack():
     assert len(rows) >= 10
     for (w, many), one in zip(keep, singles):
         assert torch.equal(many.view(torch.int16), one.view(torch.int16))
+
+
+@pytest.mark.parametrize('N,H,W,C,groups,stride', [(2, 6, 7, 48, 2, 1), (1, 9, 8, 72, 3, 2), (2, 5, 4, 64, 1, 1), (1, 4, 6, 32, 1, 2),
+                                                    (1, 3, 3, 216, 9, 1)])
+def test_im2col_channel_tap_order(N, H, W, C, groups, stride):
+    """tfb_im2col3x3_bf16 writes col[m][c][tap] (tap fastest) = F.unfold's channel-major patch order, i.e. the order of PyTorch's
+    weight layout [co][ci][kh][kw]: dW = dy^T col then IS the weight gradient, no permute pass. Checked bit-exactly (bf16 rounding
+    of the same fp32 values), zero padding at the borders included, and through the implied fp32 GEMM against torch's conv wgrad."""
+    g = torch.Generator().manual_seed(N * 100 + C)
+    x = torch.randn(N, C, H, W, generator=g)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    col = torch.full((N * Ho * Wo, 9 * C), 3.0, dtype=torch.bfloat16)
+    xm = _nhwc(x)
+    _call('tfb_im2col3x3_bf16', xm, col, N, H, W, C, stride, groups)
+    want = F.unfold(x, 3, padding=1, stride=stride).permute(0, 2, 1).reshape(N * Ho * Wo, 9 * C).bfloat16()
+    assert torch.equal(col.view(torch.int16), want.view(torch.int16))
+    # dW_g = dy_g^T col_g in PyTorch layout
+    Cout = 2 * groups * 4
+    w = torch.randn(Cout, C // groups, 3, 3, generator=g, requires_grad=True)
+    xb = x.bfloat16().float()
+    y = F.conv2d(xb, w, None, stride=stride, padding=1, groups=groups)
+    dy = torch.randn(y.shape, generator=g)
+    gw, = torch.autograd.grad(y, w, dy)
+    dym = dy.permute(0, 2, 3, 1).reshape(-1, Cout)
+    Cig, Cog = C // groups, Cout // groups
+    got = torch.cat([dym[:, k * Cog:(k + 1) * Cog].t() @ col.float()[:, k * 9 * Cig:(k + 1) * 9 * Cig] for k in range(groups)])
+    assert torch.allclose(got.view(Cout, Cig, 3, 3), gw, rtol=1e-4, atol=1e-4)

@@ -59,6 +59,49 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const int64_t
     out[i] = __float2bfloat16_rn(pack_value(w, i, a));
 }
 
+// col[m][g][c][tap] (bf16) = x[n, ho*stride - 1 + tap/3, wo*stride - 1 + tap%3, g*Cg + c] (0 outside), m = (n, ho, wo): the im2col
+// matrix whose column windows are the B operands of the per-group wgrad GEMMs (dW_g = dy_g^T col_g). Column order (c, tap) with
+// the tap fastest = the order of PyTorch's weight layout [co][ci][kh][kw], so the GEMM writes dW in place (no permute pass).
+// One thread = 8 consecutive channels x 9 taps of one (pixel, group): 18 16-byte loads, 144 contiguous bytes stored (Cg % 8 == 0).
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo, int stride,
+                 int groups) {
+  const int Cg = C / groups, Cg8 = Cg / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups * Cg8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % Cg8);
+    const int g = (int)((i / Cg8) % groups);
+    const int64_t m = i / ((int64_t)Cg8 * groups);
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), n = (int)(m / ((int64_t)Wo * Ho));
+    float v[9][8];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const float4* p = reinterpret_cast<const float4*>(x + (((int64_t)n * H + hi) * W + wi) * C + g * Cg + c8 * 8);
+        a = p[0];
+        b = p[1];
+      }
+      v[tap][0] = a.x; v[tap][1] = a.y; v[tap][2] = a.z; v[tap][3] = a.w;
+      v[tap][4] = b.x; v[tap][5] = b.y; v[tap][6] = b.z; v[tap][7] = b.w;
+    }
+    // 72 outputs in (channel, tap) order, eight per 16-byte store
+    uint4* dst = reinterpret_cast<uint4*>(col + m * 9 * (int64_t)C + ((int64_t)g * Cg + c8 * 8) * 9);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      uint32_t q[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int e0 = s * 8 + 2 * h, e1 = e0 + 1;
+        __nv_bfloat162 pr = __floats2bfloat162_rn(v[e0 % 9][e0 / 9], v[e1 % 9][e1 / 9]);
+        q[h] = *reinterpret_cast<uint32_t*>(&pr);
+      }
+      dst[s] = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+  }
+}
+
 }  // namespace
 
 // Packs fp32 PyTorch-layout 3x3 weights [Cout][Cin/groups][3][3] into the bf16 B-operand layout [gblocks][nchunks][9][NB][KC].
@@ -77,6 +120,17 @@ TFB_API int tfb_conv3x3_pack_weights(const float* w, void* out_bf16, int Cout, i
 TFB_API int tfb_conv3x3_pack_weights_batched(const void* table_dev, int n, int blocks_x, cudaStream_t stream) {
   TFB_REQUIRE(table_dev && n > 0 && n <= 65535 && blocks_x > 0);
   pack_weights_batched_kernel<<<dim3((unsigned)blocks_x, (unsigned)n), 256, 0, stream>>>((const int64_t*)table_dev);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// im2col for the tensor-core wgrad: x fp32 NHWC -> col bf16 [N*Ho*Wo][groups][C/groups][9] (stride 1 or 2, pad 1; tap fastest).
+TFB_API int tfb_im2col3x3_bf16(const float* x, void* col_bf16, int N, int H, int W, int C, int stride, int groups, cudaStream_t stream) {
+  TFB_REQUIRE(x && col_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && groups > 0 && (stride == 1 || stride == 2) && C % groups == 0 &&
+              (C / groups) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(col_bf16) & 15) == 0);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  im2col3x3_kernel<<<tfb_grid(total, 256, 16), 256, 0, stream>>>(x, (__nv_bfloat16*)col_bf16, N, H, W, C, Ho, Wo, stride, groups);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -173,34 +173,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   }
 }
 
-// col[m][g][tap][c] (bf16) = x[n, ho*stride - 1 + tap/3, wo*stride - 1 + tap%3, g*Cg + c] (0 outside), m = (n, ho, wo): the im2col
-// matrix whose column windows are the B operands of the per-group wgrad GEMMs (dW_g = dy_g^T col_g). c fastest: coalesced.
-__global__ void __launch_bounds__(256)
-im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo, int stride,
-                 int groups) {
-  // one thread = 8 consecutive channels of one (pixel, group, tap): two 16-byte loads, one 16-byte store (Cg % 8 == 0)
-  const int Cg = C / groups, Cg8 = Cg / 8;
-  const int64_t total = (int64_t)N * Ho * Wo * groups * 9 * Cg8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % Cg8);
-    const int tap = (int)((i / Cg8) % 9);
-    const int g = (int)((i / ((int64_t)Cg8 * 9)) % groups);
-    const int64_t m = i / ((int64_t)Cg8 * 9 * groups);
-    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), n = (int)(m / ((int64_t)Wo * Ho));
-    const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
-      const float4* p = reinterpret_cast<const float4*>(x + (((int64_t)n * H + hi) * W + wi) * C + g * Cg + c8 * 8);
-      const float4 a = p[0], b = p[1];
-      __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x, a.y), q1 = __floats2bfloat162_rn(a.z, a.w);
-      __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x, b.y), q3 = __floats2bfloat162_rn(b.z, b.w);
-      o.x = *reinterpret_cast<uint32_t*>(&q0); o.y = *reinterpret_cast<uint32_t*>(&q1);
-      o.z = *reinterpret_cast<uint32_t*>(&q2); o.w = *reinterpret_cast<uint32_t*>(&q3);
-    }
-    reinterpret_cast<uint4*>(col)[i] = o;
-  }
-}
-
 // y[m][0..Cp) (bf16) = x[m][0..C) zero-padded to Cp columns (narrow dy of the last decoder layers -> 16-byte rows for TMA)
 __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t M, int C, int Cp) {
   const int64_t total = M * Cp;
@@ -208,15 +180,6 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
     const int c = (int)(i % Cp);
     const int64_t m = i / Cp;
     y[i] = __float2bfloat16_rn(c < C ? x[m * C + c] : 0.f);
-  }
-}
-
-// dw[co][ci][tap] = dwp[co][tap][ci]  (GEMM output order -> PyTorch weight layout)
-__global__ void __launch_bounds__(256) permute_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cg) {
-  const int total = Cout * Cg * 9;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i % 9, ci = (i / 9) % Cg, co = i / (9 * Cg);
-    dw[i] = dwp[(co * 9 + tap) * Cg + ci];
   }
 }
 
@@ -274,24 +237,6 @@ TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias
 #undef CASE
   tfb_set_last_error("tfb_conv3x3_tc: unsupported (KC, NB) tile");
   return TFB_ERR_UNSUPPORTED;
-}
-
-// im2col for the tensor-core wgrad: x fp32 NHWC -> col bf16 [N*Ho*Wo][groups][9][C/groups] (stride 1 or 2, pad 1).
-TFB_API int tfb_im2col3x3_bf16(const float* x, void* col_bf16, int N, int H, int W, int C, int stride, int groups, cudaStream_t stream) {
-  TFB_REQUIRE(x && col_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2) && groups > 0 && C % groups == 0);
-  TFB_REQUIRE((C / groups) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(col_bf16) & 15) == 0);
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  const int64_t total = (int64_t)N * Ho * Wo * (C / 8) * 9;
-  im2col3x3_kernel<<<tfb_grid(total, 256, 16), 256, 0, stream>>>(x, (__nv_bfloat16*)col_bf16, N, H, W, C, Ho, Wo, stride, groups);
-  TFB_CHECK_LAUNCH();
-  return TFB_OK;
-}
-
-TFB_API int tfb_conv3x3_permute_dw(const float* dwp, float* dw, int Cout, int Cg, cudaStream_t stream) {
-  TFB_REQUIRE(dwp && dw && Cout > 0 && Cg > 0);
-  permute_dw_kernel<<<tfb_grid((int64_t)Cout * Cg * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cg);
-  TFB_CHECK_LAUNCH();
-  return TFB_OK;
 }
 
 TFB_API int tfb_cast_bf16_pad(const float* x, void* y_bf16, int64_t M, int C, int Cp, cudaStream_t stream) {

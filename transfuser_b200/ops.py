@@ -450,9 +450,9 @@ def _conv_wgrad_tc_ok(x_shape, Cout, groups, stride):
 
 
 def _conv_wgrad_tc(x, g16, w, groups, stride):
-    """dW of a 3x3 conv on the tensor cores: im2col(x) in bf16, then one split-K GEMM per channel group
-    (dW_g[Cog, 9*Cig] = dy_g^T col_g, batched over groups in a single launch), then the [co][tap][ci] -> [co][ci][tap] permute.
-    Returns None when the shape does not fit (channel windows must be 16-byte aligned)."""
+    """dW of a 3x3 conv on the tensor cores: im2col(x) in bf16 with (channel, tap) column order, then one split-K GEMM per channel
+    group (dW_g[Cog, Cig*9] = dy_g^T col_g, batched over groups in a single launch) that writes PyTorch's [co][ci][kh][kw] layout
+    directly into the gradient buffer. Returns None when the shape does not fit (channel windows must be 16-byte aligned)."""
     N, H, W, Cin = x.shape
     Cout = w.shape[0]
     Cig, Cog = Cin // groups, Cout // groups
@@ -462,14 +462,16 @@ def _conv_wgrad_tc(x, g16, w, groups, stride):
     M = N * Ho * Wo
     col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
     call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
-    ldg = g16.shape[-1]                      # >= Cout when dy was zero-padded to 8 channels
-    dwp = torch.empty((max(Cout, ldg) if groups == 1 else Cout, 9 * Cig), dtype=torch.float32, device=x.device)
+    ldg = g16.shape[-1]                      # > Cout when dy was zero-padded to 8 channels (the 7- / 1-channel decoder outputs)
+    rows = max(Cout, ldg) if groups == 1 else Cout
+    dw = _gbuf(w)
+    dwp = dw.view(Cout, 9 * Cig) if rows == Cout else torch.empty((rows, 9 * Cig), dtype=torch.float32, device=x.device)
     ntiles = groups * ((9 * Cig + 127) // 128)
     splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
-    call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else dwp.shape[0], 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
+    call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else rows, 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
          9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
-    dw = _gbuf(w)
-    call('tfb_conv3x3_permute_dw', dwp, dw, Cout, Cig)
+    if rows != Cout:
+        call('tfb_scale_dev', dwp, None, 1.0, dw, Cout * 9 * Cig, 0)      # the first Cout rows are the gradient; the rest is padding
     return dw
 
 
