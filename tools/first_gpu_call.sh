@@ -15,6 +15,12 @@ for c in 0 32 64 128; do
 done
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tile_default.json 2> gpurun_out/bench_tile_default.err
 grep -h '"value"' gpurun_out/bench_tile_*.json | cut -c1-160
+# 2b. A/B of the launch / pass reductions written without a GPU: each flag off in turn, then all off
+for f in TFB_SIDECARS TFB_SE_FUSED_BWD TFB_QKV_FUSED TFB_BN_ADD_FUSED TFB_PACK_BATCHED; do
+  env $f=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_${f}_off.json 2> gpurun_out/bench_ab_${f}_off.err
+done
+TFB_SIDECARS=0 TFB_SE_FUSED_BWD=0 TFB_QKV_FUSED=0 TFB_BN_ADD_FUSED=0 TFB_PACK_BATCHED=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_all_off.json 2> gpurun_out/bench_ab_all_off.err
+grep -h '"value"' gpurun_out/bench_ab_*.json | cut -c1-160
 # 3. per-kernel time without host launch gaps (dedicated CUDA graph of one step's launches of that entry point)
 for k in tfb_gemm_bf16_tc tfb_conv3x3_tc tfb_bn_fwd tfb_bn_bwd tfb_im2col3x3_bf16 tfb_cast_bf16 tfb_grad_prep; do
   timeout 240 python tools/kernel_graph_timing.py $k > gpurun_out/kgt_$k.log 2>&1; tail -3 gpurun_out/kgt_$k.log
