@@ -382,10 +382,10 @@ def invalidate_packs():
 
 
 def _packed_weights(w, plan, mode, groups):
-    args = (groups, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'], plan['gblocks'])
-    key = (id(w), mode)
+    args = (tuple(w.shape), groups, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'], plan['gblocks'])
+    key = (w.data_ptr(), mode)               # by address: the same parameter may reach forward and backward as different wrappers
     e = _PACKS.get(key)
-    if e is not None and (e.wref() is not w or e.ptr != w.data_ptr() or e.args != args or e.wp.device != w.device):
+    if e is not None and (e.wref() is None or e.args != args or e.wp.device != w.device):
         e = None
     if e is None:
         e = _Pack()
@@ -406,19 +406,21 @@ def _prepack_all(device):
     live = []
     for key, e in list(_PACKS.items()):
         w = e.wref()
-        if w is None:
+        if w is None or w.data_ptr() != e.ptr:        # the parameter died or was re-homed (optim.flatten): forget the entry
             del _PACKS[key]
             _PACK_STATE['sig'] = None
-        elif w.data_ptr() == e.ptr and w.is_contiguous() and w.device.type == device.type and device.index in (None, w.device.index):
+        elif w.is_contiguous() and w.device.type == device.type and device.index in (None, w.device.index):
             live.append((key[1], e, w))
     if not live:
         return
     rows = []
     for mode, e, w in live:
-        groups = e.args[0]
-        rows.append([e.ptr, e.wp.data_ptr(), w.shape[0], w.shape[1] * groups, groups, mode] + list(e.args[1:]))
+        groups = e.args[1]
+        rows.append([e.ptr, e.wp.data_ptr(), w.shape[0], w.shape[1] * groups, groups, mode] + list(e.args[2:]))
     sig = tuple(map(tuple, rows))
     if _PACK_STATE['sig'] != sig:
+        if device.type == 'cuda' and torch.cuda.is_current_stream_capturing():
+            return          # no host-to-device copy inside a graph capture: this step's convs pack per call (epoch not advanced)
         _PACK_STATE['table'] = torch.tensor(rows, dtype=torch.int64).to(device)
         _PACK_STATE['sig'] = sig
     call('tfb_conv3x3_pack_weights_batched', _PACK_STATE['table'], len(rows), 8)
