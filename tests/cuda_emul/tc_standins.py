@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY. torch stand-ins for the three tensor-core entry points (tcgen05 / TMA: not emulable), written from the
+CONTRACT in include/tfb200.h — operand layouts, leading dimensions, column windows, the packed-weight format of csrc/conv_pack.cu —
+so that the product's bf16-mode host path (sidecars, packed weights, q|k|v packs, im2col + batched wgrad, flat gradients) can run
+end to end on the CPU emulation with every CUDA-core kernel real and only the MMA itself replaced. They check what the real
+kernels require (16-byte alignment, leading dimensions % 8) and compute in fp32 from the bf16 operands, like the hardware does."""
+import torch
+import torch.nn.functional as F
+
+TC_NAMES = ('tfb_gemm_bf16_tc', 'tfb_conv3x3_tc', 'tfb_gemm_bf16_tc_wgrad_batched')
+
+
+def _mat(t, rows, cols, ld):
+    assert t.data_ptr() % 16 == 0 and ld % 8 == 0, 'TMA: 16-byte aligned base and leading dimension'
+    return torch.as_strided(t, (rows, cols), (ld, 1))
+
+
+def gemm_bf16_tc(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits):
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and C.dtype == torch.float32
+    a = _mat(A, K, M, lda).t() if ta else _mat(A, M, K, lda)
+    b = _mat(B, N, K, ldb).t() if tb else _mat(B, K, N, ldb)
+    out = torch.as_strided(C, (M, N), (ldc, 1))
+    r = alpha * (a.float() @ b.float())
+    if bias is not None:
+        r = r + torch.as_strided(bias, (N,), (1,))
+    if beta != 0.0:
+        r = r + beta * out
+    assert not (relu and splits > 1)
+    out.copy_(r.clamp_min(0) if relu else r)
+
+
+def gemm_bf16_tc_wgrad_batched(M, N, K, A, lda, a_step, B, ldb, b_step, C, ldc, c_bstride, nbatch, splits):
+    assert A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and lda % 8 == 0 and ldb % 8 == 0 and a_step % 8 == 0 and b_step % 8 == 0
+    for b in range(nbatch):
+        a = torch.as_strided(A, (K, M), (lda, 1), A.storage_offset() + b * a_step)
+        bb = torch.as_strided(B, (K, N), (ldb, 1), B.storage_offset() + b * b_step)
+        torch.as_strided(C, (M, N), (ldc, 1), C.storage_offset() + b * c_bstride).copy_(a.float().t() @ bb.float())
+
+
+def conv3x3_tc(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu):
+    """y = conv3x3(x16, packed weights): block gb reads channels gb*c_step + chunk*KC + kk, writes channels gb*nb_real + j; tap t
+    multiplies the input pixel shifted by (t/3 - 1, t%3 - 1); out-of-image pixels and channels >= Cx read as zero."""
+    assert x16.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16 and Cx % 8 == 0 and x16.data_ptr() % 16 == 0 and wp.data_ptr() % 16 == 0
+    wpk = torch.as_strided(wp, (gblocks, nchunks, 9, NB, KC), (nchunks * 9 * NB * KC, 9 * NB * KC, NB * KC, KC, 1)).float()
+    dense = torch.zeros(Cy, Cx, 9)
+    for gb in range(gblocks):
+        for ch in range(nchunks):
+            for j in range(min(nb_real, NB)):
+                oc = gb * nb_real + j
+                if oc >= Cy:
+                    continue
+                rc0 = gb * c_step + ch * KC
+                n = max(0, min(KC, Cx - rc0))
+                if n:
+                    dense[oc, rc0:rc0 + n] += wpk[gb, ch, :, j, :n].t()
+    xin = torch.as_strided(x16, (N, H, W, Cx), (H * W * Cx, W * Cx, Cx, 1)).float().permute(0, 3, 1, 2)
+    out = F.conv2d(xin, dense.view(Cy, Cx, 3, 3), None if bias is None else torch.as_strided(bias, (Cy,), (1,)), padding=1)
+    out = out.clamp_min(0) if relu else out
+    torch.as_strided(y, (N, H, W, Cy), (H * W * Cy, W * Cy, Cy, 1)).copy_(out.permute(0, 2, 3, 1))
+
+
+class WithTensorCoreStandins:
+    """Wraps the emulated library: the three tensor-core entry points go to the stand-ins above, everything else to the emulation."""
+
+    def __init__(self, emul):
+        self.emul = emul
+        self.log = emul.log
+        self.launches = 0
+        self.profiler = None
+        self.fns = {'tfb_gemm_bf16_tc': gemm_bf16_tc, 'tfb_conv3x3_tc': conv3x3_tc, 'tfb_gemm_bf16_tc_wgrad_batched': gemm_bf16_tc_wgrad_batched}
+
+    def call(self, name, *args):
+        fn = self.fns.get(name)
+        if fn is None:
+            return self.emul.call(name, *args)
+        self.log.append(name)
+        self.launches += 1
+        fn(*args)

@@ -102,6 +102,16 @@ im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, i
   }
 }
 
+// y[m][0..Cp) (bf16) = x[m][0..C) zero-padded to Cp columns (narrow dy of the last decoder layers -> 16-byte rows for TMA)
+__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t M, int C, int Cp) {
+  const int64_t total = M * Cp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int64_t m = i / Cp;
+    y[i] = __float2bfloat16_rn(c < C ? x[m * C + c] : 0.f);
+  }
+}
+
 }  // namespace
 
 // Packs fp32 PyTorch-layout 3x3 weights [Cout][Cin/groups][3][3] into the bf16 B-operand layout [gblocks][nchunks][9][NB][KC].
@@ -131,6 +141,14 @@ TFB_API int tfb_im2col3x3_bf16(const float* x, void* col_bf16, int N, int H, int
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   im2col3x3_kernel<<<tfb_grid(total, 256, 16), 256, 0, stream>>>(x, (__nv_bfloat16*)col_bf16, N, H, W, C, Ho, Wo, stride, groups);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// Narrow dy of the last decoder layers (7 / 1 channels) -> zero-padded bf16 rows of Cp channels (16-byte rows for TMA).
+TFB_API int tfb_cast_bf16_pad(const float* x, void* y_bf16, int64_t M, int C, int Cp, cudaStream_t stream) {
+  TFB_REQUIRE(x && y_bf16 && M > 0 && C > 0 && Cp >= C);
+  cast_pad_kernel<<<tfb_grid(M * Cp, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y_bf16, M, C, Cp);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

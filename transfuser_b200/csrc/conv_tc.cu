@@ -173,16 +173,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   }
 }
 
-// y[m][0..Cp) (bf16) = x[m][0..C) zero-padded to Cp columns (narrow dy of the last decoder layers -> 16-byte rows for TMA)
-__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t M, int C, int Cp) {
-  const int64_t total = M * Cp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    const int64_t m = i / Cp;
-    y[i] = __float2bfloat16_rn(c < C ? x[m * C + c] : 0.f);
-  }
-}
-
 template <int KC, int NB>
 int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy, int c_step,
                 int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
@@ -239,9 +229,3 @@ TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias
   return TFB_ERR_UNSUPPORTED;
 }
 
-TFB_API int tfb_cast_bf16_pad(const float* x, void* y_bf16, int64_t M, int C, int Cp, cudaStream_t stream) {
-  TFB_REQUIRE(x && y_bf16 && M > 0 && C > 0 && Cp >= C);
-  cast_pad_kernel<<<tfb_grid(M * Cp, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y_bf16, M, C, Cp);
-  TFB_CHECK_LAUNCH();
-  return TFB_OK;
-}
