@@ -27,7 +27,7 @@ def torch_ops(monkeypatch):
         y = F.conv2d(_nchw(x), w, bias, stride=stride, padding=w.shape[2] // 2, groups=groups)
         return _nhwc(F.relu(y) if relu else y)
 
-    def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None):    # emit16 / bwd16: bf16-sidecar hints
+    def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None, pool=False):    # emit16 / bwd16: bf16-sidecar hints
         y = F.batch_norm(_nchw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
         if residual is not None:
             y = y + _nchw(residual)               # the Bottleneck tail: relu(bn(x) + shortcut)

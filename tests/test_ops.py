@@ -234,6 +234,38 @@ def test_se_add_pool():
     check_grads([am], [a], out3, ref3)
 
 
+@pytest.mark.parametrize('shape', [(3, 20, 24, 72), (2, 5, 22, 1512), (2, 40, 44, 216)])
+def test_batchnorm_with_se_pool(shape):
+    """conv2.bn -> SE: the squeeze-excite average pool comes out of BatchNorm's normalise pass (accumulator cleared by the statistics
+    kernel, no memset / pooling launch); BatchNorm's own output is unchanged and SE(bn(x)) matches torch forward and backward."""
+    from transfuser_b200 import ops
+    N, H, W, C = shape
+    Cr = 8
+    x = (rnd(N, C, H, W, seed=1) * 2 + 0.3).requires_grad_()
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    bn.weight.data = rnd(C, seed=2) * 0.3 + 1
+    bn.bias.data = rnd(C, seed=3) * 0.2
+    bn2 = torch.nn.BatchNorm2d(C).to(DEV)
+    bn2.load_state_dict(bn.state_dict())
+    bn3 = torch.nn.BatchNorm2d(C).to(DEV)
+    bn3.load_state_dict(bn.state_dict())
+    w1, b1 = rnd(Cr, C, 1, 1, seed=4, scale=0.1).requires_grad_(), rnd(Cr, seed=5, scale=0.1).requires_grad_()
+    w2, b2 = rnd(C, Cr, 1, 1, seed=6, scale=0.3).requires_grad_(), rnd(C, seed=7, scale=0.1).requires_grad_()
+    yb = F.relu(bn(x))
+    ref = yb * torch.sigmoid(F.conv2d(F.relu(F.conv2d(yb.mean((2, 3), keepdim=True), w1, b1)), w2, b2))
+    xm = nhwc(x.detach()).requires_grad_()
+    ps = [t.detach().clone().requires_grad_() for t in (w1, b1, w2, b2)]
+    y = ops.batch_norm(xm, bn2, True, True, pool=True)
+    assert torch.equal(y.detach(), ops.batch_norm(xm.detach(), bn3, True, True))          # the normalised output itself is unchanged
+    assert rel(y._tfb_pooled, y.detach().mean((1, 2))) < 1e-5
+    n0 = len(_calls())
+    out = ops.SEFn.apply(y, *ps)
+    if _calls() is not _NOLOG:
+        assert 'tfb_pool_hw_fwd' not in _calls()[n0:]
+    assert rel(nchw(out), ref) < TOL
+    check_grads([xm, bn2.weight, bn2.bias] + ps, [x, bn.weight, bn.bias, w1, b1, w2, b2], out, ref)
+
+
 @pytest.mark.parametrize('N,C,Cr', [(10, 1512, 144), (10, 576, 54), (16, 216, 18), (2, 72, 8), (1, 80, 3)])
 def test_se_fused_mlp_backward(N, C, Cr):
     """tfb_se_mlp_bwd (two launches) against the eight-launch path it replaces and against torch autograd, at the RegNetY-3.2GF

@@ -25,13 +25,13 @@ class _ConvBn(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
         self.stride, self.groups, self.act = stride, groups, act
 
-    def run(self, x, emit16=False, residual=None):
+    def run(self, x, emit16=False, residual=None, pool=False):
         """emit16: the output is the operand of a tensor-core GEMM / conv next (bf16 mode: BatchNorm writes its bf16 copy too).
         residual: relu(bn(conv(x)) + residual) — the Bottleneck tail, add and ReLU fused into the BatchNorm passes."""
         y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups)
         # bwd16: this conv has no bias / ReLU of its own, so BatchNorm's dx is exactly the dy its tensor-core dgrad / wgrad read
         return ops.batch_norm(y, self.bn, self.act or residual is not None, self.bn.training, emit16,
-                              bwd16=self.conv.in_channels % 8 == 0, residual=residual)
+                              bwd16=self.conv.in_channels % 8 == 0, residual=residual, pool=pool)
 
 
 class _SE(nn.Module):
@@ -57,7 +57,7 @@ class _Bottleneck(nn.Module):
 
     def run(self, x, emit16=True):
         """emit16: the block output feeds a 1x1 conv next (the following block's conv1, or the channel-change conv)."""
-        y = self.se.run(self.conv2.run(self.conv1.run(x, emit16=self.conv2.stride == 1)))
+        y = self.se.run(self.conv2.run(self.conv1.run(x, emit16=self.conv2.stride == 1), pool=True))   # SE pool inside conv2.bn
         sc = self.downsample.run(x) if self.downsample is not None else x
         return self.conv3.run(y, emit16=emit16, residual=sc)      # relu(conv3.bn(conv3(y)) + shortcut)
 

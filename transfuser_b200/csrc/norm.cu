@@ -23,6 +23,8 @@ struct Finalize {
   float* o1;             // save_invstd | dgamma
   float* running_mean;
   float* running_var;
+  float* zero_buf;       // optional: zero_n floats cleared by the last block (the SE pooling accumulator of the NEXT kernel on the
+  int zero_n;            // stream, tfb_bn_fwd with pooling: saves the memset node)
 };
 
 __device__ __forceinline__ void finalize_last_block(double* sums, int C, const Finalize& f) {
@@ -62,6 +64,7 @@ __device__ __forceinline__ void finalize_last_block(double* sums, int C, const F
     sums[c] = 0.0;
     if (f.nsums > C) sums[C + c] = 0.0;
   }
+  for (int i = tid; i < f.zero_n; i += nthr) f.zero_buf[i] = 0.f;
   if (tid == 0) *reinterpret_cast<unsigned int*>(sums + f.nsums) = 0u;
 }
 
@@ -211,6 +214,45 @@ bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t tota
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     reinterpret_cast<float4*>(y)[i] = o;
     if (y16) tfb_store_bf16x4(y16, i, o.x, o.y, o.z, o.w);
+  }
+}
+
+// BatchNorm apply (+ReLU) that also accumulates the squeeze-excite pooling of its own output: pooled[n][c] += mean_hw(y[n][:, c]).
+// Thread mapping of pool_hw_kernel (elementwise.cu): block (32 channel quads, 8 row phases), grid (quad slabs, n, HW splits);
+// `pooled` was zeroed by the statistics kernel that runs right before this one (Finalize::zero_buf).
+__global__ void __launch_bounds__(256)
+bn_apply_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                     float* __restrict__ pooled, float inv_hw) {
+  __shared__ float4 sm[8][33];
+  const int n = blockIdx.y, c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const int64_t base = (int64_t)n * HW * C + c;
+    for (int p = blockIdx.z * 8 + threadIdx.y; p < HW; p += gridDim.z * 8) {
+      const float4 v = *reinterpret_cast<const float4*>(x + base + (int64_t)p * C);
+      float4 o;
+      o.x = fmaf((v.x - mu.x) * is.x, ga.x, be.x);
+      o.y = fmaf((v.y - mu.y) * is.y, ga.y, be.y);
+      o.z = fmaf((v.z - mu.z) * is.z, ga.z, be.z);
+      o.w = fmaf((v.w - mu.w) * is.w, ga.w, be.w);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(y + base + (int64_t)p * C) = o;
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 v = sm[j][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    float* o = pooled + (int64_t)n * C + c;
+    atomicAdd(o + 0, t.x * inv_hw); atomicAdd(o + 1, t.y * inv_hw); atomicAdd(o + 2, t.z * inv_hw); atomicAdd(o + 3, t.w * inv_hw);
   }
 }
 
@@ -402,13 +444,26 @@ int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, in
 // sums_ws: (2*C + 1) doubles, ZERO on entry, left zero on exit (shared by all layers of a stream; no memset launches).
 // y16_bf16 (optional): bf16 copy of y written in the same pass (operand of the next layer's tensor-core GEMM / conv).
 // residual (optional, [M, C]): y = act(bn(x) + residual) — the Bottleneck's last BatchNorm + shortcut add + ReLU in one pass.
+// pooled (optional, [pool_batch, C], M = pool_batch * HW): also the squeeze-excite pooling of the output, pooled[n][c] =
+// mean over the HW pixels of sample n of y — cleared by the statistics kernel, accumulated by the apply kernel (no memset, no
+// separate pooling pass); excludes y16_bf16 / residual.
 TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps,
                        float momentum, int relu, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                       double* sums_ws, void* y16_bf16, const float* residual, cudaStream_t stream) {
+                       double* sums_ws, void* y16_bf16, const float* residual, float* pooled, int pool_batch, cudaStream_t stream) {
   TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && sums_ws && M > 0 && C > 0 && C % 4 == 0);
-  Finalize fin = {1, 2 * C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var};
+  TFB_REQUIRE(!pooled || (pool_batch > 0 && M % pool_batch == 0 && !y16_bf16 && !residual));
+  Finalize fin = {1, 2 * C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var, pooled, pooled ? pool_batch * C : 0};
   launch_colreduce<0>(x, C, nullptr, M, C, sums_ws, nullptr, nullptr, nullptr, nullptr, 0, nullptr, fin, stream);
   TFB_CHECK_LAUNCH();
+  if (pooled) {
+    const int HW = (int)(M / pool_batch);
+    int splits = (HW + 255) / 256;
+    if (splits > 32) splits = 32;
+    dim3 grid((C / 4 + 31) / 32, pool_batch, splits), block(32, 8);
+    bn_apply_pool_kernel<<<grid, block, 0, stream>>>(x, y, HW, C, save_mean, save_invstd, gamma, beta, relu, pooled, 1.f / (float)HW);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   const int64_t total4 = M * C / 4;
   bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu,
                                                              (__nv_bfloat16*)y16_bf16, residual);

@@ -57,6 +57,7 @@ def _c(t):
 SIDECARS = os.environ.get('TFB_SIDECARS', '1') == '1'
 QKV_FUSED = os.environ.get('TFB_QKV_FUSED', '1') == '1'           # one q|k|v GEMM when the flat buffer packs the three weights
 BN_ADD_FUSED = os.environ.get('TFB_BN_ADD_FUSED', '1') == '1'     # conv3.bn + shortcut add + ReLU as one BatchNorm call
+SE_POOL_FUSED = os.environ.get('TFB_SE_POOL_FUSED', '1') == '1'   # SE average pool inside the preceding BatchNorm's pass
 SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
 
 
@@ -572,19 +573,24 @@ class BatchNormTrainFn(Function):
     """BatchNorm2d in training mode (+ fused ReLU): batch statistics, running-stat update (momentum, unbiased var)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False, bwd16=False):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False, bwd16=False, pool=False):
         x = _c(x)
         C = x.shape[-1]
         M = x.numel() // C
         y = torch.empty_like(x)
-        y16 = _emit16(y, emit16)
+        pool = pool and SE_POOL_FUSED and x.dim() == 4
+        y16 = _emit16(y, emit16 and not pool)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = _ws(x.device)
+        # pool: the squeeze-excite average pool of the output comes out of the normalise pass (SEFn picks it up from y._tfb_pooled)
+        pooled = torch.empty((x.shape[0], C), dtype=torch.float32, device=x.device) if pool else None
         call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws,
-             y16, None)
+             y16, None, pooled, x.shape[0] if pool else 0)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.relu, ctx.bwd16 = relu, bwd16
+        if pool:
+            y._tfb_pooled = pooled
         return _attach16(y, y16)
 
     @staticmethod
@@ -601,7 +607,7 @@ class BatchNormTrainFn(Function):
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws, dx16, None, None)
         if dx16 is not None:
             _offer16(dx, dx16)
-        return dx, dg, db, None, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None, None
 
 
 class BatchNormAddReluFn(Function):
@@ -619,7 +625,7 @@ class BatchNormAddReluFn(Function):
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
-             _ws(x.device), y16, res)
+             _ws(x.device), y16, res, None, 0)
         ctx.save_for_backward(x, weight, bias, mean, invstd, y)
         ctx.bwd16 = bwd16
         return _attach16(y, y16)
@@ -639,8 +645,9 @@ class BatchNormAddReluFn(Function):
         return dx, g, dg, db, None, None, None, None, None, None
 
 
-def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None):
-    """bn: an nn.BatchNorm2d used as a parameter/buffer container. residual: act(bn(x) + residual) in the same pass (relu required). emit16: the output feeds a tensor-core GEMM / conv next, so
+def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None, pool=False):
+    """bn: an nn.BatchNorm2d used as a parameter/buffer container. residual: act(bn(x) + residual) in the same pass (relu required).
+    pool: the output feeds a squeeze-excite module next — its global average pool is accumulated in the normalise pass (training). emit16: the output feeds a tensor-core GEMM / conv next, so
     (bf16 mode) its bf16 copy is written in the same pass. bwd16: the same for dx in backward (the convolution in front of this
     BatchNorm has no bias / ReLU of its own and runs dgrad + wgrad on the tensor cores)."""
     if residual is not None and not (relu and BN_ADD_FUSED):
@@ -649,7 +656,8 @@ def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None):
         if residual is not None:
             return BatchNormAddReluFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, emit16,
                                             bwd16)
-        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16, bwd16)
+        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16, bwd16,
+                                      pool)
     if torch.is_grad_enabled() and x.requires_grad:
         raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
     C = x.shape[-1]
@@ -702,8 +710,10 @@ class SEFn(Function):
         N, H, W, C = x.shape
         Cr = w1.shape[0]
         dev = x.device
-        pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
-        call('tfb_pool_hw_fwd', x, pooled, N, H * W, C)
+        pooled = getattr(x, '_tfb_pooled', None)             # written by the BatchNorm in front (batch_norm(..., pool=True))
+        if pooled is None or pooled.shape != (N, C):
+            pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+            call('tfb_pool_hw_fwd', x, pooled, N, H * W, C)
         h = torch.empty((N, Cr), dtype=torch.float32, device=dev)
         gate = torch.empty((N, C), dtype=torch.float32, device=dev)
         if N <= 16:
