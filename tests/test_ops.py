@@ -52,7 +52,9 @@ def check_grads(mine_inputs, ref_inputs, mine_out, ref_out, tol=TOL, gseed=7):
 
 @pytest.mark.parametrize('cfg', [
     # N, H, W, Cin, Cout, k, stride, groups, bias, relu
-    (2, 16, 24, 3, 32, 3, 2, 1, False, False),      # stem
+    (2, 16, 24, 3, 32, 3, 2, 1, False, False),      # stem (wgrad: the warp-per-pixel kernel for Cin <= 4)
+    (1, 9, 11, 2, 40, 3, 1, 1, True, False),        # 2 input channels, 40 output channels (two 32-wide co blocks), bias
+    (2, 10, 7, 4, 8, 3, 2, 1, True, True),          # 4 input channels, stride 2, bias + relu
     (2, 12, 20, 72, 72, 3, 1, 3, False, False),     # grouped 3x3, group width 24
     (2, 12, 20, 72, 72, 3, 2, 3, False, False),     # grouped, stride 2
     (1, 10, 14, 216, 216, 3, 1, 9, False, False),

@@ -223,6 +223,66 @@ conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
   if (dbias && ib == 0 && threadIdx.x < CB && co0 + threadIdx.x < Cog) atomicAdd(&dbias[g * Cog + co0 + threadIdx.x], bsum);
 }
 
+// ---------------------------------------------------------------- wgrad, few input channels (the two stems: Cin = 3)
+// The generic kernel above tiles 32 ci x 32 co per CTA: with 3 input channels 29/32 of its lanes and of its smem staging are padding
+// (0.5 TFLOP/s measured on the 160x704 stem). Here a WARP owns one output pixel at a time and its 32 lanes own 32 output channels:
+// dy[p][co] is one coalesced 128-byte load, the <= 4 x KS*KS tap-shifted inputs are warp-uniform (broadcast) loads, and every lane keeps
+// its [ci][tap] accumulators in registers. The 8 warps of a CTA meet in shared memory; one atomicAdd per weight and CTA.
+template <int KS>
+__global__ void __launch_bounds__(256)
+conv_wgrad_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias,
+                           int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int stride, int pix_per_cta) {
+  constexpr int T = KS * KS, P = KS / 2, CI = 4, NW = 8;
+  __shared__ float red[NW][32][CI * T + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.y * 32 + lane;
+  const bool co_ok = co < Cout;
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+  const int64_t p_end = min(npix, p_begin + pix_per_cta);
+  float acc[CI][T];
+#pragma unroll
+  for (int c = 0; c < CI; ++c)
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[c][t] = 0.f;
+  float bsum = 0.f;
+  for (int64_t p = p_begin + warp; p < p_end; p += NW) {
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), n = (int)(p / ((int64_t)Wo * Ho));
+    const float d = co_ok ? dy[p * Cout + co] : 0.f;
+    bsum += d;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int hi = ho * stride - P + t / KS, wi = wo * stride - P + t % KS;
+      if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;          // warp-uniform branch
+      const float* xp = x + (((int64_t)n * H + hi) * W + wi) * Cin;
+#pragma unroll
+      for (int c = 0; c < CI; ++c)
+        if (c < Cin) acc[c][t] = fmaf(d, __ldg(xp + c), acc[c][t]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CI; ++c)
+#pragma unroll
+    for (int t = 0; t < T; ++t) red[warp][lane][c * T + t] = acc[c][t];
+  red[warp][lane][CI * T] = bsum;
+  __syncthreads();
+  const int nout = 32 * (CI * T + 1);
+  for (int e = threadIdx.x; e < nout; e += blockDim.x) {
+    const int l = e / (CI * T + 1), k = e % (CI * T + 1);
+    const int oc = blockIdx.y * 32 + l;
+    if (oc >= Cout) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < NW; ++w8) s += red[w8][l][k];
+    if (k == CI * T) {
+      if (dbias) atomicAdd(&dbias[oc], s);
+    } else {
+      const int c = k / T, t = k % T;
+      if (c < Cin) atomicAdd(&dw[((int64_t)oc * Cin + c) * T + t], s);
+    }
+  }
+}
+
 template <int KS>
 int launch_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
                int stride, int groups, int relu, cudaStream_t stream) {
@@ -271,6 +331,18 @@ int launch_wgrad(const float* x, const float* dy, float* dw, float* dbias, int N
   splits = ceil_div64(npix, ppc);
   if (cudaMemsetAsync(dw, 0, (size_t)Cout * Cig * KS * KS * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   if (dbias && cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  if (groups == 1 && Cin <= 4 && KS == 3) {
+    // stems: one warp per pixel, lanes over output channels (see conv_wgrad_smallcin_kernel); ~4 waves of CTAs, >= 256 pixels each
+    const int cob32 = (Cout + 31) / 32;
+    int64_t sp = (4LL * tfb_num_sms() + cob32 - 1) / cob32;
+    int64_t pp = ceil_div64(npix, sp);
+    if (pp < 256) pp = 256;
+    pp = ceil_div64(pp, 8) * 8;
+    dim3 grid2((unsigned)ceil_div64(npix, pp), cob32);
+    conv_wgrad_smallcin_kernel<KS><<<grid2, 256, 0, stream>>>(x, dy, dw, dbias, N, H, W, Cin, Ho, Wo, Cout, stride, (int)pp);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   dim3 grid((unsigned)splits, by);
   conv_wgrad_kernel<KS><<<grid, 256, 0, stream>>>(x, dy, dw, dbias, N, H, W, Cin, Ho, Wo, Cout, stride, groups, (int)ppc);
   TFB_CHECK_LAUNCH();
