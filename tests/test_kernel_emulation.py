@@ -546,3 +546,18 @@ def test_im2col_channel_tap_order(N, H, W, C, groups, stride):
     Cig, Cog = C // groups, Cout // groups
     got = torch.cat([dym[:, k * Cog:(k + 1) * Cog].t() @ col.float()[:, k * 9 * Cig:(k + 1) * 9 * Cig] for k in range(groups)])
     assert torch.allclose(got.view(Cout, Cig, 3, 3), gw, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('M,Cin,Cout,bias', [(4100, 64, 1, False), (4099, 64, 12, True), (700, 72, 3, True), (517, 130, 16, False), (33, 8, 2, True)])
+def test_conv1x1_wgrad_narrow_output_kernel(M, Cin, Cout, bias):
+    """tfb_conv2d_wgrad, k = 1, Cout <= 16 (the CenterNet head outputs 64 -> {1, 2, 3, 12}): threads over input channels, dy broadcast,
+    register accumulators — dW = dy^T x and dbias = column sums of dy against torch, ragged pixel counts / channel blocks included."""
+    g = torch.Generator().manual_seed(M + Cout)
+    x, dy = torch.randn(M, Cin, generator=g), torch.randn(M, Cout, generator=g)
+    dw = torch.full((Cout, Cin), float('nan'))
+    db = torch.full((Cout,), float('nan')) if bias else None
+    _call('tfb_conv2d_wgrad', x, dy, dw, db, 1, M, 1, Cin, Cout, 1, 1, 1)
+    want = dy.double().t() @ x.double()
+    assert torch.allclose(dw.double(), want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    if bias:
+        assert torch.allclose(db.double(), dy.double().sum(0), rtol=1e-4, atol=1e-4)

@@ -283,6 +283,62 @@ conv_wgrad_smallcin_kernel(const float* __restrict__ x, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- wgrad of a 1x1 conv with few OUTPUT channels (CenterNet head
+// outputs: 64 -> {1, 2, 3, 12}). dW[co][ci] = sum_p dy[p][co] x[p][ci]: the generic 32 x 32 tile wastes up to 31/32 of its lanes
+// (0.09 TFLOP/s measured for Cout = 1). Here 64 consecutive threads own 64 input channels (x[p][ci..] is one coalesced 256-byte
+// load), the <= 16 dy values of the pixel are block-uniform (broadcast) loads, each thread keeps its [co] accumulators in registers;
+// the 4 pixel phases of a CTA meet in shared memory, one atomicAdd per weight and CTA.
+__global__ void __launch_bounds__(256)
+conv1x1_wgrad_narrowout_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                               float* __restrict__ dbias, int64_t npix, int Cin, int Cout, int pix_per_cta) {
+  constexpr int CO = 16, CB = 64, NP = 4;
+  __shared__ float red[NP][CB][CO + 1];
+  const int cl = threadIdx.x % CB, ph = threadIdx.x / CB;
+  const int ci = blockIdx.y * CB + cl;
+  const bool ci_ok = ci < Cin;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+  const int64_t p_end = min(npix, p_begin + pix_per_cta);
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int64_t p = p_begin + ph; p < p_end; p += NP) {
+    const float xv = ci_ok ? x[p * Cin + ci] : 0.f;
+    const float* d = dy + p * Cout;
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+      if (c < Cout) acc[c] = fmaf(__ldg(d + c), xv, acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) red[ph][cl][c] = acc[c];
+  __syncthreads();
+  for (int e = threadIdx.x; e < CB * CO; e += blockDim.x) {
+    const int c = e / CB, l = e % CB;                    // l fastest: consecutive threads -> consecutive ci of one co row
+    const int cc = blockIdx.y * CB + l;
+    if (c >= Cout || cc >= Cin) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) s += red[j][l][c];
+    atomicAdd(&dw[(int64_t)c * Cin + cc], s);
+  }
+  if (dbias && blockIdx.y == 0) {                        // dbias[co] = sum_p dy[p][co]: the CTA's pixel range, 16 threads x strided pixels
+    __syncthreads();
+    float* bs = &red[0][0][0];
+    if (threadIdx.x < 256) {
+      const int c = threadIdx.x % CO, q = threadIdx.x / CO;   // 16 pixel phases
+      float s = 0.f;
+      if (c < Cout)
+        for (int64_t p = p_begin + q; p < p_end; p += 16) s += dy[p * Cout + c];
+      bs[q * CO + c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < Cout) {
+      float s = 0.f;
+      for (int q = 0; q < 16; ++q) s += bs[q * CO + threadIdx.x];
+      atomicAdd(&dbias[threadIdx.x], s);
+    }
+  }
+}
+
 template <int KS>
 int launch_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
                int stride, int groups, int relu, cudaStream_t stream) {
@@ -331,6 +387,18 @@ int launch_wgrad(const float* x, const float* dy, float* dw, float* dbias, int N
   splits = ceil_div64(npix, ppc);
   if (cudaMemsetAsync(dw, 0, (size_t)Cout * Cig * KS * KS * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   if (dbias && cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
+  if (groups == 1 && KS == 1 && stride == 1 && Cout <= 16) {
+    // narrow-output 1x1 conv (head outputs): threads over input channels, dy broadcast (see conv1x1_wgrad_narrowout_kernel)
+    const int cib64 = (Cin + 63) / 64;
+    int64_t sp = (4LL * tfb_num_sms() + cib64 - 1) / cib64;
+    int64_t pp = ceil_div64(npix, sp);
+    if (pp < 128) pp = 128;
+    pp = ceil_div64(pp, 16) * 16;
+    dim3 grid2((unsigned)ceil_div64(npix, pp), cib64);
+    conv1x1_wgrad_narrowout_kernel<<<grid2, 256, 0, stream>>>(x, dy, dw, dbias, npix, Cin, Cout, (int)pp);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   if (groups == 1 && Cin <= 4 && KS == 3) {
     // stems: one warp per pixel, lanes over output channels (see conv_wgrad_smallcin_kernel); ~4 waves of CTAs, >= 256 pixels each
     const int cob32 = (Cout + 31) / 32;
