@@ -561,3 +561,22 @@ def test_conv1x1_wgrad_narrow_output_kernel(M, Cin, Cout, bias):
     assert torch.allclose(dw.double(), want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
     if bias:
         assert torch.allclose(db.double(), dy.double().sum(0), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('H,W,gh,gw,C', [(40, 176, 5, 22, 8), (37, 50, 5, 22, 4), (5, 22, 5, 22, 8), (16, 16, 8, 8, 12), (3, 9, 8, 8, 4)])
+def test_gpt_up_add_backward_gather(H, W, gh, gw, C):
+    """tfb_gpt_up_add_bwd as a gather (no atomics, no zero fill): every element of its token range is written exactly once (NaN-filled
+    destination), the rest of dtok is untouched, and the values equal autograd through F.interpolate on the view-quirk slab — also
+    for non-integer scales and for a feature map smaller than the anchor grid."""
+    N, T, t_off = 2, gh * gw + 7, 3
+    g = torch.Generator().manual_seed(H * W)
+    dy = torch.randn(N, H, W, C, generator=g)
+    dtok = torch.full((N, T, C), float('nan'))
+    _call('tfb_gpt_up_add_bwd', dy, dtok, N, H, W, C, gh, gw, t_off, T)
+    slab = torch.zeros(N, C, gh, gw, requires_grad=True)          # the (C, gh, gw) view of the token slab (transfuser.py:363-364)
+    up = F.interpolate(slab, size=(H, W), mode='bilinear', align_corners=False)
+    want, = torch.autograd.grad(up, slab, dy.permute(0, 3, 1, 2))
+    got = dtok[:, t_off:t_off + gh * gw].reshape(N, C, gh, gw)     # same memory re-interpretation as the reference's .view
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    assert torch.isnan(dtok[:, :t_off]).all() and torch.isnan(dtok[:, t_off + gh * gw:]).all()

@@ -247,6 +247,46 @@ gpt_up_add_kernel(const float* __restrict__ feat, float* __restrict__ tok, float
   }
 }
 
+// Backward of the upsample + add w.r.t. the token slab as a GATHER: one thread per slab element (n, c, cell) sums the bilinear
+// weights x dy over the pixels whose interpolation touches the cell (a ~2s x 2s window for scale s) — no atomics (the scatter
+// version issued 4 strided atomicAdds per pixel and channel, up to 20 M per call, all pixels of a cell colliding), every slab
+// element is written exactly once, so dtok needs no zero fill. c is the fastest thread index: dy reads are coalesced.
+__global__ void __launch_bounds__(256)
+gpt_up_add_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ dtok, int N, int H, int W, int C, int gh, int gw, int t_off,
+                             int T) {
+  const int G = gh * gw;
+  const int64_t total = (int64_t)N * G * C;
+  const float sy = (float)H / (float)gh, sx = (float)W / (float)gw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int cell = (int)((i / C) % G);
+    const int n = (int)(i / ((int64_t)C * G));
+    const int gy = cell / gw, gx = cell % gw;
+    // pixels with source coordinate in [g - 1, g + 1): conservative window, membership re-checked with the exact lerp_coord
+    int y0 = (int)floorf(((float)gy - 0.5f) * sy - 0.5f) - 1, y1 = (int)ceilf(((float)gy + 1.5f) * sy - 0.5f) + 1;
+    int x0 = (int)floorf(((float)gx - 0.5f) * sx - 0.5f) - 1, x1 = (int)ceilf(((float)gx + 1.5f) * sx - 0.5f) + 1;
+    if (y0 < 0) y0 = 0;
+    if (x0 < 0) x0 = 0;
+    if (y1 > H - 1) y1 = H - 1;
+    if (x1 > W - 1) x1 = W - 1;
+    float acc = 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      const Lerp ly = lerp_coord(y, gh, H, 0);
+      const float wy = (ly.i0 == gy ? ly.l0 : 0.f) + (ly.i1 == gy ? ly.l1 : 0.f);
+      if (wy == 0.f && ly.i0 != gy && ly.i1 != gy) continue;
+      const float* row = dy + (((int64_t)n * H + y) * W) * C + c;
+      float racc = 0.f;
+      for (int x = x0; x <= x1; ++x) {
+        const Lerp lx = lerp_coord(x, gw, W, 0);
+        const float wx = (lx.i0 == gx ? lx.l0 : 0.f) + (lx.i1 == gx ? lx.l1 : 0.f);
+        if (lx.i0 == gx || lx.i1 == gx) racc = fmaf(wx, row[(int64_t)x * C], racc);
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+    dtok[((int64_t)n * T + t_off) * C + (int64_t)c * G + cell] = acc;
+  }
+}
+
 // generic NHWC bilinear upsample. MODE 0: y = up(x)   MODE 1: dx += up^T(dy) (atomics, dx zeroed by the launcher)
 template <int MODE>
 __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi, int Ho,
@@ -621,9 +661,9 @@ TFB_API int tfb_gpt_up_add_fwd(const float* feat, const float* tok, float* out, 
 }
 TFB_API int tfb_gpt_up_add_bwd(const float* dy, float* dtok, int N, int H, int W, int C, int gh, int gw, int t_off, int T,
                                cudaStream_t stream) {
-  TFB_REQUIRE(dy && dtok && N > 0);
-  const int64_t total = (int64_t)N * H * W * C;
-  gpt_up_add_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dy, dtok, nullptr, N, H, W, C, gh, gw, t_off, T);
+  TFB_REQUIRE(dy && dtok && N > 0 && H > 0 && W > 0 && C > 0 && gh > 0 && gw > 0);
+  // overwrites dtok[n][t_off .. t_off + gh*gw)[:] (every element exactly once): no zero fill, no atomics
+  gpt_up_add_bwd_gather_kernel<<<tfb_grid((int64_t)N * gh * gw * C, 256), 256, 0, stream>>>(dy, dtok, N, H, W, C, gh, gw, t_off, T);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

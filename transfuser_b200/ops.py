@@ -981,7 +981,7 @@ class GptUpAddFn(Function):
     def backward(ctx, di, dl):
         N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, T = ctx.cfg
         di, dl = _c(di), _c(dl)
-        dtok = torch.zeros((N, T, C), dtype=torch.float32, device=di.device)
+        dtok = torch.empty((N, T, C), dtype=torch.float32, device=di.device)     # both calls together write every element once
         call('tfb_gpt_up_add_bwd', di, dtok, N, Hi, Wi, C, ghi, gwi, 0, T)
         call('tfb_gpt_up_add_bwd', dl, dtok, N, Hl, Wl, C, ghl, gwl, ghi * gwi, T)
         return di, dl, dtok, None, None, None, None
