@@ -580,3 +580,19 @@ def test_gpt_up_add_backward_gather(H, W, gh, gw, C):
     assert torch.isfinite(got).all()
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
     assert torch.isnan(dtok[:, :t_off]).all() and torch.isnan(dtok[:, t_off + gh * gw:]).all()
+
+
+@pytest.mark.parametrize('Hi,Wi,Ho,Wo,C,ac', [(5, 22, 40, 176, 4, 0), (8, 8, 16, 16, 8, 0), (64, 64, 160, 160, 2, 1), (7, 5, 19, 23, 3, 0),
+                                              (7, 5, 19, 23, 3, 1), (6, 6, 6, 6, 4, 1), (9, 9, 4, 5, 4, 0), (4, 4, 1, 1, 4, 1)])
+def test_upsample_bilinear_backward_gather(Hi, Wi, Ho, Wo, C, ac):
+    """tfb_upsample_bilinear_bwd as a gather (no atomics, no memset): dx written exactly once (NaN-filled destination) and equal to
+    autograd through F.interpolate — integer / fractional scales, align_corners on and off, identity and down-sampling sizes."""
+    N = 2
+    g = torch.Generator().manual_seed(Hi * Wo + ac)
+    dy = torch.randn(N, Ho, Wo, C, generator=g)
+    dx = torch.full((N, Hi, Wi, C), float('nan'))
+    _call('tfb_upsample_bilinear_bwd', dy, dx, N, Hi, Wi, Ho, Wo, C, ac)
+    x = torch.zeros(N, C, Hi, Wi, requires_grad=True)
+    want, = torch.autograd.grad(F.interpolate(x, size=(Ho, Wo), mode='bilinear', align_corners=bool(ac)), x, dy.permute(0, 3, 1, 2))
+    assert torch.isfinite(dx).all()
+    assert torch.allclose(dx.permute(0, 3, 1, 2), want, rtol=1e-5, atol=1e-5)

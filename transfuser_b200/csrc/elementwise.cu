@@ -217,6 +217,25 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out, int align_c
   return r;
 }
 
+// Conservative range [lo, hi] of destination indices whose interpolation can touch source cell g (lerp_coord's i0 or i1 == g): the
+// source coordinate is monotone in the destination index, so the touching set is contiguous; callers re-check membership exactly.
+__device__ __forceinline__ void lerp_window(int g, int in, int out, int align_corners, int* lo, int* hi) {
+  float a, b;
+  if (align_corners) {
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    if (scale <= 0.f) { *lo = 0; *hi = out - 1; return; }
+    a = ((float)g - 1.f) / scale;
+    b = ((float)g + 1.f) / scale;
+  } else {
+    const float inv = (float)out / (float)in;
+    a = ((float)g - 0.5f) * inv - 0.5f;
+    b = ((float)g + 1.5f) * inv - 0.5f;
+  }
+  int l = (int)floorf(a) - 1, h = (int)ceilf(b) + 1;
+  *lo = l < 0 ? 0 : l;
+  *hi = h > out - 1 ? out - 1 : h;
+}
+
 // GPT output slab [gh*gw][C] of sample n, *viewed* as (C, gh, gw) without permuting (transfuser.py:363-364), bilinearly
 // upsampled (align_corners=False) to (H, W) and added to the NHWC feature map.
 // MODE 0: out = feat + up(view(tok))      MODE 1 (backward): dtok += up^T(dy)  (atomics; dtok zeroed by the caller)
@@ -256,24 +275,20 @@ gpt_up_add_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ d
                              int T) {
   const int G = gh * gw;
   const int64_t total = (int64_t)N * G * C;
-  const float sy = (float)H / (float)gh, sx = (float)W / (float)gw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int cell = (int)((i / C) % G);
     const int n = (int)(i / ((int64_t)C * G));
     const int gy = cell / gw, gx = cell % gw;
     // pixels with source coordinate in [g - 1, g + 1): conservative window, membership re-checked with the exact lerp_coord
-    int y0 = (int)floorf(((float)gy - 0.5f) * sy - 0.5f) - 1, y1 = (int)ceilf(((float)gy + 1.5f) * sy - 0.5f) + 1;
-    int x0 = (int)floorf(((float)gx - 0.5f) * sx - 0.5f) - 1, x1 = (int)ceilf(((float)gx + 1.5f) * sx - 0.5f) + 1;
-    if (y0 < 0) y0 = 0;
-    if (x0 < 0) x0 = 0;
-    if (y1 > H - 1) y1 = H - 1;
-    if (x1 > W - 1) x1 = W - 1;
+    int y0, y1, x0, x1;
+    lerp_window(gy, gh, H, 0, &y0, &y1);
+    lerp_window(gx, gw, W, 0, &x0, &x1);
     float acc = 0.f;
     for (int y = y0; y <= y1; ++y) {
       const Lerp ly = lerp_coord(y, gh, H, 0);
       const float wy = (ly.i0 == gy ? ly.l0 : 0.f) + (ly.i1 == gy ? ly.l1 : 0.f);
-      if (wy == 0.f && ly.i0 != gy && ly.i1 != gy) continue;
+      if (ly.i0 != gy && ly.i1 != gy) continue;
       const float* row = dy + (((int64_t)n * H + y) * W) * C + c;
       float racc = 0.f;
       for (int x = x0; x <= x1; ++x) {
@@ -310,6 +325,40 @@ __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, fl
       atomicAdd(xp + o10, ly.l1 * lx.l0 * g);
       atomicAdd(xp + o11, ly.l1 * lx.l1 * g);
     }
+  }
+}
+
+// Backward of the bilinear upsample as a gather (see gpt_up_add_bwd_gather_kernel): one thread per INPUT element (n, yi, xi, c) sums
+// weight x dy over the output pixels that interpolate from it; no atomics, no zero fill, dx written exactly once.
+__global__ void __launch_bounds__(256)
+upsample_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                           int align_corners) {
+  const int64_t total = (int64_t)N * Hi * Wi * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int xi = (int)((i / C) % Wi);
+    const int yi = (int)((i / ((int64_t)C * Wi)) % Hi);
+    const int n = (int)(i / ((int64_t)C * Wi * Hi));
+    int y0, y1, x0, x1;
+    lerp_window(yi, Hi, Ho, align_corners, &y0, &y1);
+    lerp_window(xi, Wi, Wo, align_corners, &x0, &x1);
+    float acc = 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      const Lerp ly = lerp_coord(y, Hi, Ho, align_corners);
+      if (ly.i0 != yi && ly.i1 != yi) continue;
+      const float wy = (ly.i0 == yi ? ly.l0 : 0.f) + (ly.i1 == yi ? ly.l1 : 0.f);
+      const float* row = dy + (((int64_t)n * Ho + y) * Wo) * C + c;
+      float racc = 0.f;
+      for (int x = x0; x <= x1; ++x) {
+        const Lerp lx = lerp_coord(x, Wi, Wo, align_corners);
+        if (lx.i0 == xi || lx.i1 == xi) {
+          const float wx = (lx.i0 == xi ? lx.l0 : 0.f) + (lx.i1 == xi ? lx.l1 : 0.f);
+          racc = fmaf(wx, row[(int64_t)x * C], racc);
+        }
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+    dx[i] = acc;
   }
 }
 
@@ -678,9 +727,7 @@ TFB_API int tfb_upsample_bilinear_fwd(const float* x, float* y, int N, int Hi, i
 TFB_API int tfb_upsample_bilinear_bwd(const float* dy, float* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
                                       cudaStream_t stream) {
   TFB_REQUIRE(dy && dx && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
-  if (cudaMemsetAsync(dx, 0, (size_t)N * Hi * Wi * C * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
-  const int64_t total = (int64_t)N * Ho * Wo * C;
-  upsample_kernel<1><<<tfb_grid(total, 256), 256, 0, stream>>>(dx, const_cast<float*>(dy), N, Hi, Wi, Ho, Wo, C, align_corners);
+  upsample_bwd_gather_kernel<<<tfb_grid((int64_t)N * Hi * Wi * C, 256), 256, 0, stream>>>(dy, dx, N, Hi, Wi, Ho, Wo, C, align_corners);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
