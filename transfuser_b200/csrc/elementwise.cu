@@ -236,6 +236,57 @@ __device__ __forceinline__ void lerp_window(int g, int in, int out, int align_co
   *hi = h > out - 1 ? out - 1 : h;
 }
 
+// sum over destination pixels (y, x) of w_y(y -> gy) * w_x(x -> gx) * d[y * row_stride + x * col_stride]: the adjoint of bilinear
+// interpolation for ONE source cell (gy, gx) of a [gh, gw] grid interpolated to [H, W]. The x weights of the (conservative) window
+// are computed once into registers (windows up to GATHER_W pixels: scale factors up to ~10), zero-weight pixels are skipped.
+constexpr int GATHER_W = 24;
+__device__ __forceinline__ float bilinear_adjoint_gather(const float* __restrict__ d, int64_t row_stride, int64_t col_stride, int gy, int gh,
+                                                         int H, int gx, int gw, int W, int align_corners) {
+  int y0, y1, x0, x1;
+  lerp_window(gy, gh, H, align_corners, &y0, &y1);
+  lerp_window(gx, gw, W, align_corners, &x0, &x1);
+  const int nx = x1 - x0 + 1;
+  float acc = 0.f;
+  if (nx <= GATHER_W) {
+    float wxs[GATHER_W];
+#pragma unroll
+    for (int j = 0; j < GATHER_W; ++j) {
+      float w = 0.f;
+      if (j < nx) {
+        const Lerp lx = lerp_coord(x0 + j, gw, W, align_corners);
+        w = (lx.i0 == gx ? lx.l0 : 0.f) + (lx.i1 == gx ? lx.l1 : 0.f);
+      }
+      wxs[j] = w;
+    }
+    for (int y = y0; y <= y1; ++y) {
+      const Lerp ly = lerp_coord(y, gh, H, align_corners);
+      const float wy = (ly.i0 == gy ? ly.l0 : 0.f) + (ly.i1 == gy ? ly.l1 : 0.f);
+      if (wy == 0.f) continue;
+      const float* row = d + (int64_t)y * row_stride + (int64_t)x0 * col_stride;
+      float racc = 0.f;
+#pragma unroll
+      for (int j = 0; j < GATHER_W; ++j)
+        if (wxs[j] != 0.f) racc = fmaf(wxs[j], row[(int64_t)j * col_stride], racc);
+      acc = fmaf(wy, racc, acc);
+    }
+  } else {
+    for (int y = y0; y <= y1; ++y) {
+      const Lerp ly = lerp_coord(y, gh, H, align_corners);
+      const float wy = (ly.i0 == gy ? ly.l0 : 0.f) + (ly.i1 == gy ? ly.l1 : 0.f);
+      if (wy == 0.f) continue;
+      const float* row = d + (int64_t)y * row_stride;
+      float racc = 0.f;
+      for (int x = x0; x <= x1; ++x) {
+        const Lerp lx = lerp_coord(x, gw, W, align_corners);
+        const float wx = (lx.i0 == gx ? lx.l0 : 0.f) + (lx.i1 == gx ? lx.l1 : 0.f);
+        if (wx != 0.f) racc = fmaf(wx, row[(int64_t)x * col_stride], racc);
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+  }
+  return acc;
+}
+
 // GPT output slab [gh*gw][C] of sample n, *viewed* as (C, gh, gw) without permuting (transfuser.py:363-364), bilinearly
 // upsampled (align_corners=False) to (H, W) and added to the NHWC feature map.
 // MODE 0: out = feat + up(view(tok))      MODE 1 (backward): dtok += up^T(dy)  (atomics; dtok zeroed by the caller)
@@ -280,24 +331,7 @@ gpt_up_add_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ d
     const int cell = (int)((i / C) % G);
     const int n = (int)(i / ((int64_t)C * G));
     const int gy = cell / gw, gx = cell % gw;
-    // pixels with source coordinate in [g - 1, g + 1): conservative window, membership re-checked with the exact lerp_coord
-    int y0, y1, x0, x1;
-    lerp_window(gy, gh, H, 0, &y0, &y1);
-    lerp_window(gx, gw, W, 0, &x0, &x1);
-    float acc = 0.f;
-    for (int y = y0; y <= y1; ++y) {
-      const Lerp ly = lerp_coord(y, gh, H, 0);
-      const float wy = (ly.i0 == gy ? ly.l0 : 0.f) + (ly.i1 == gy ? ly.l1 : 0.f);
-      if (ly.i0 != gy && ly.i1 != gy) continue;
-      const float* row = dy + (((int64_t)n * H + y) * W) * C + c;
-      float racc = 0.f;
-      for (int x = x0; x <= x1; ++x) {
-        const Lerp lx = lerp_coord(x, gw, W, 0);
-        const float wx = (lx.i0 == gx ? lx.l0 : 0.f) + (lx.i1 == gx ? lx.l1 : 0.f);
-        if (lx.i0 == gx || lx.i1 == gx) racc = fmaf(wx, row[(int64_t)x * C], racc);
-      }
-      acc = fmaf(wy, racc, acc);
-    }
+    const float acc = bilinear_adjoint_gather(dy + (int64_t)n * H * W * C + c, (int64_t)W * C, C, gy, gh, H, gx, gw, W, 0);
     dtok[((int64_t)n * T + t_off) * C + (int64_t)c * G + cell] = acc;
   }
 }
@@ -339,25 +373,7 @@ upsample_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ dx,
     const int xi = (int)((i / C) % Wi);
     const int yi = (int)((i / ((int64_t)C * Wi)) % Hi);
     const int n = (int)(i / ((int64_t)C * Wi * Hi));
-    int y0, y1, x0, x1;
-    lerp_window(yi, Hi, Ho, align_corners, &y0, &y1);
-    lerp_window(xi, Wi, Wo, align_corners, &x0, &x1);
-    float acc = 0.f;
-    for (int y = y0; y <= y1; ++y) {
-      const Lerp ly = lerp_coord(y, Hi, Ho, align_corners);
-      if (ly.i0 != yi && ly.i1 != yi) continue;
-      const float wy = (ly.i0 == yi ? ly.l0 : 0.f) + (ly.i1 == yi ? ly.l1 : 0.f);
-      const float* row = dy + (((int64_t)n * Ho + y) * Wo) * C + c;
-      float racc = 0.f;
-      for (int x = x0; x <= x1; ++x) {
-        const Lerp lx = lerp_coord(x, Wi, Wo, align_corners);
-        if (lx.i0 == xi || lx.i1 == xi) {
-          const float wx = (lx.i0 == xi ? lx.l0 : 0.f) + (lx.i1 == xi ? lx.l1 : 0.f);
-          racc = fmaf(wx, row[(int64_t)x * C], racc);
-        }
-      }
-      acc = fmaf(wy, racc, acc);
-    }
+    const float acc = bilinear_adjoint_gather(dy + (int64_t)n * Ho * Wo * C + c, (int64_t)Wo * C, C, yi, Hi, Ho, xi, Wi, Wo, align_corners);
     dx[i] = acc;
   }
 }
