@@ -138,7 +138,7 @@ def test_conv_trunk_bf16_mode_matches_fp32_mode(lib):
 def test_gpt_block_bf16_mode_matches_fp32_mode(lib):
     from transfuser_b200 import gemm, optim
     from transfuser_b200.backbone import Block
-    C, nh, B, T = 64, 4, 2, 24
+    C, nh, B, T = 32, 4, 2, 16
     torch.manual_seed(2)
     ref = Block(C, nh, 4, 0.0, 0.0).train()
     state = {k: v.clone() for k, v in ref.state_dict().items()}

@@ -27,7 +27,9 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
-def main(backbone):
+def main(backbone, second=False):
+    """second = True: the reference run keeps the options ON too — measures the run-to-run noise of the step itself (fp32 atomics land
+    in thread-scheduling order on the emulation, as they do in warp-scheduling order on the GPU) that the on/off comparison sits in."""
     mp = pytest.MonkeyPatch()
     emul = loader.patch_product(mp)
     lib = tc_standins.WithTensorCoreStandins(emul)
@@ -43,7 +45,7 @@ def main(backbone):
     res = {}
     for on in (True, False):
         for f in FLAGS:
-            setattr(ops, f, on)
+            setattr(ops, f, on or second)
         gemm.set_mode('bf16')
         ops._PACKS.clear()
         ops._PACK_STATE.update(sig=None, table=None)
@@ -84,4 +86,4 @@ def main(backbone):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1] if len(sys.argv) > 1 else 'transFuser')
+    main(sys.argv[1] if len(sys.argv) > 1 else 'transFuser', second=len(sys.argv) > 2 and sys.argv[2] == 'noise')

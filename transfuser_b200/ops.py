@@ -392,9 +392,8 @@ def _packed_weights(w, plan, mode, groups):
         e = _Pack()
         e.wref, e.ptr, e.args, e.epoch, e.version = weakref.ref(w), w.data_ptr(), args, -1, -1
         e.wp = torch.empty((plan['gblocks'], plan['nchunks'], 9, plan['NB'], plan['KC']), dtype=torch.bfloat16, device=w.device)
-        if len(_PACKS) > 4096:
-            _PACKS.clear()
-        _PACKS[key] = e
+        _PACKS[key] = e                        # (entries of dead weights are pruned by _prepack_all; nothing else is ever dropped:
+        #                                        a captured CUDA graph may hold the addresses of the packed buffers)
         _PACK_STATE['sig'] = None
     return e
 
@@ -423,6 +422,7 @@ def _prepack_all(device):
         if device.type == 'cuda' and torch.cuda.is_current_stream_capturing():
             return          # no host-to-device copy inside a graph capture: this step's convs pack per call (epoch not advanced)
         _PACK_STATE['table'] = torch.tensor(rows, dtype=torch.int64).to(device)
+        _PACK_STATE.setdefault('keep', []).append(_PACK_STATE['table'])   # never freed: a captured graph may still read an old table
         _PACK_STATE['sig'] = sig
     call('tfb_conv3x3_pack_weights_batched', _PACK_STATE['table'], len(rows), 8)
     _PACK_STATE['epoch'] += 1
