@@ -98,7 +98,7 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'linear', linear)
     monkeypatch.setattr(ops, 'gather_sum', gather_sum)
     monkeypatch.setattr(ops, 'avgpool_grid', lambda x, gh, gw: _nhwc(F.adaptive_avg_pool2d(_nchw(x), (gh, gw))))
-    monkeypatch.setattr(ops, 'upsample', lambda x, Ho, Wo, ac=False: _nhwc(F.interpolate(_nchw(x), (Ho, Wo), mode='bilinear', align_corners=ac)))
+    monkeypatch.setattr(ops, 'upsample', lambda x, Ho, Wo, ac=False, emit16=False: _nhwc(F.interpolate(_nchw(x), (Ho, Wo), mode='bilinear', align_corners=ac)))
     monkeypatch.setattr(ops, 'add', lambda a, b, relu=False, emit16=False: F.relu(a + b) if relu else a + b)
     monkeypatch.setattr(ops, 'image_prep', image_prep)
     monkeypatch.setattr(ops, 'nchw_to_nhwc', _nhwc)

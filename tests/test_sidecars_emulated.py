@@ -299,3 +299,15 @@ def test_packed_conv_weight_registry(lib, monkeypatch):
     ops.tick('cpu')
     run(1)
     assert len(ops._PACKS) == 2
+
+
+@pytest.mark.parametrize('ac', [False, True])
+def test_upsample_sidecar(lib, ac):
+    from transfuser_b200 import ops
+    x = _rnd(2, 5, 7, 12, seed=50).requires_grad_(True)
+    y = ops.upsample(x, 20, 21, ac, emit16=True)
+    y0 = ops.upsample(x, 20, 21, ac)
+    assert torch.equal(y.detach(), y0.detach()) and not hasattr(y0, '_tfb16')
+    assert _same_bits(y._tfb16, _cast(lib, y.detach()))
+    g = _rnd(2, 20, 21, 12, seed=51)
+    assert torch.equal(torch.autograd.grad(y, x, g)[0], torch.autograd.grad(y0, x, g)[0])

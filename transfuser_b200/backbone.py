@@ -281,7 +281,7 @@ class TransfuserBackbone(nn.Module):
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
         f = self.config.bev_upsample_factor
-        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False, emit16=True)
         p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
         p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
         p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)
@@ -364,7 +364,7 @@ class LateFusionBackbone(nn.Module):
         l = ops.conv2d(l, self.reduce_channels_conv_lidar.weight, self.reduce_channels_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
         f = self.config.bev_upsample_factor
-        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False, emit16=True)
         p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
         p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
         p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)
@@ -483,7 +483,7 @@ class GeometricFusionBackbone(nn.Module):
         l = ops.conv2d(l, self.change_channel_conv_lidar.weight, self.change_channel_conv_lidar.bias)
         fused = ops.add(ops.PoolHWFn.apply(x), ops.PoolHWFn.apply(l))
         f = cfg.bev_upsample_factor
-        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False)
+        up = lambda t: ops.upsample(t, t.shape[1] * f, t.shape[2] * f, False, emit16=True)
         p5 = ops.conv2d(l, self.c5_conv.weight, self.c5_conv.bias, relu=True)
         p4 = ops.conv2d(up(p5), self.up_conv5.weight, self.up_conv5.bias, relu=True)
         p3 = ops.conv2d(up(p4), self.up_conv4.weight, self.up_conv4.bias, relu=True)

@@ -339,7 +339,7 @@ gpt_up_add_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ d
 // generic NHWC bilinear upsample. MODE 0: y = up(x)   MODE 1: dx += up^T(dy) (atomics, dx zeroed by the launcher)
 template <int MODE>
 __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi, int Ho,
-                                                       int Wo, int C, int align_corners) {
+                                                       int Wo, int C, int align_corners, __nv_bfloat16* __restrict__ y16) {
   const int64_t total = (int64_t)N * Ho * Wo * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(256) upsample_kernel(float* __restrict__ x, fl
     const int64_t o00 = ((int64_t)ly.i0 * Wi + lx.i0) * C, o01 = ((int64_t)ly.i0 * Wi + lx.i1) * C;
     const int64_t o10 = ((int64_t)ly.i1 * Wi + lx.i0) * C, o11 = ((int64_t)ly.i1 * Wi + lx.i1) * C;
     if (MODE == 0) {
-      y[i] = ly.l0 * (lx.l0 * xp[o00] + lx.l1 * xp[o01]) + ly.l1 * (lx.l0 * xp[o10] + lx.l1 * xp[o11]);
+      const float v = ly.l0 * (lx.l0 * xp[o00] + lx.l1 * xp[o01]) + ly.l1 * (lx.l0 * xp[o10] + lx.l1 * xp[o11]);
+      y[i] = v;
+      if (y16) y16[i] = __float2bfloat16_rn(v);      // bf16 sidecar: the operand of the 3x3 conv that follows every upsample
     } else {
       const float g = y[i];
       atomicAdd(xp + o00, ly.l0 * lx.l0 * g);
@@ -732,11 +734,13 @@ TFB_API int tfb_gpt_up_add_bwd(const float* dy, float* dtok, int N, int H, int W
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
+// y16_bf16 (optional): bf16 copy of y written in the same pass.
 TFB_API int tfb_upsample_bilinear_fwd(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
-                                      cudaStream_t stream) {
+                                      void* y16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
   const int64_t total = (int64_t)N * Ho * Wo * C;
-  upsample_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(const_cast<float*>(x), y, N, Hi, Wi, Ho, Wo, C, align_corners);
+  upsample_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(const_cast<float*>(x), y, N, Hi, Wi, Ho, Wo, C, align_corners,
+                                                               (__nv_bfloat16*)y16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -73,9 +73,9 @@ class _Decoder(nn.Module):
         cfg = self.config
         c = lambda seq, t, last_relu: ops.conv2d(ops.conv2d(t, seq[0].weight, seq[0].bias, relu=True), seq[2].weight, seq[2].bias, relu=last_relu)
         x = c(self.deconv1, x, True)
-        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_1, x.shape[2] * cfg.deconv_scale_factor_1, False)
+        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_1, x.shape[2] * cfg.deconv_scale_factor_1, False, emit16=True)
         x = c(self.deconv2, x, True)
-        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_2, x.shape[2] * cfg.deconv_scale_factor_2, False)
+        x = ops.upsample(x, x.shape[1] * cfg.deconv_scale_factor_2, x.shape[2] * cfg.deconv_scale_factor_2, False, emit16=True)
         return c(self.deconv3, x, False)
 
 

@@ -989,13 +989,14 @@ class GptUpAddFn(Function):
 
 class UpsampleFn(Function):
     @staticmethod
-    def forward(ctx, x, Ho, Wo, align_corners):
+    def forward(ctx, x, Ho, Wo, align_corners, emit16=False):
         x = _c(x)
         N, Hi, Wi, C = x.shape
         y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
-        call('tfb_upsample_bilinear_fwd', x, y, N, Hi, Wi, Ho, Wo, C, int(align_corners))
+        y16 = _emit16(y, emit16)
+        call('tfb_upsample_bilinear_fwd', x, y, N, Hi, Wi, Ho, Wo, C, int(align_corners), y16)
         ctx.cfg = (N, Hi, Wi, Ho, Wo, C, int(align_corners))
-        return y
+        return _attach16(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
@@ -1003,11 +1004,12 @@ class UpsampleFn(Function):
         dy = _c(dy)
         dx = torch.empty((N, Hi, Wi, C), dtype=torch.float32, device=dy.device)
         call('tfb_upsample_bilinear_bwd', dy, dx, N, Hi, Wi, Ho, Wo, C, ac)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def upsample(x, Ho, Wo, align_corners=False):
-    return UpsampleFn.apply(x, Ho, Wo, align_corners)
+def upsample(x, Ho, Wo, align_corners=False, emit16=False):
+    """emit16: the result feeds a tensor-core conv next (decoders, FPN top-down): its bf16 copy is written in the same pass."""
+    return UpsampleFn.apply(x, Ho, Wo, align_corners, emit16)
 
 
 class AvgPoolGridFn(Function):
