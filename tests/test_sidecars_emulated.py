@@ -311,3 +311,17 @@ def test_upsample_sidecar(lib, ac):
     assert _same_bits(y._tfb16, _cast(lib, y.detach()))
     g = _rnd(2, 20, 21, 12, seed=51)
     assert torch.equal(torch.autograd.grad(y, x, g)[0], torch.autograd.grad(y0, x, g)[0])
+
+
+def test_gpt_up_add_sidecar(lib):
+    from transfuser_b200 import ops
+    img, lid, tok = _rnd(2, 10, 44, 8, seed=60), _rnd(2, 16, 16, 8, seed=61), _rnd(2, 174, 8, seed=62)
+    oi, ol = ops.GptUpAddFn.apply(img, lid, tok, 5, 22, 8, 8)
+    assert _same_bits(oi._tfb16, _cast(lib, oi)) and _same_bits(ol._tfb16, _cast(lib, ol))
+    old = ops.SIDECARS
+    try:
+        ops.SIDECARS = False
+        pi, pl = ops.GptUpAddFn.apply(img, lid, tok, 5, 22, 8, 8)
+    finally:
+        ops.SIDECARS = old
+    assert torch.equal(pi, oi) and torch.equal(pl, ol) and not hasattr(pi, '_tfb16')

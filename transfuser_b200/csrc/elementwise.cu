@@ -293,7 +293,7 @@ __device__ __forceinline__ float bilinear_adjoint_gather(const float* __restrict
 template <int MODE>
 __global__ void __launch_bounds__(256)
 gpt_up_add_kernel(const float* __restrict__ feat, float* __restrict__ tok, float* __restrict__ out, int N, int H, int W, int C, int gh,
-                  int gw, int t_off, int T) {
+                  int gw, int t_off, int T, __nv_bfloat16* __restrict__ out16) {
   const int64_t total = (int64_t)N * H * W * C;
   const int G = gh * gw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -306,7 +306,9 @@ gpt_up_add_kernel(const float* __restrict__ feat, float* __restrict__ tok, float
     const int i00 = ly.i0 * gw + lx.i0, i01 = ly.i0 * gw + lx.i1, i10 = ly.i1 * gw + lx.i0, i11 = ly.i1 * gw + lx.i1;
     if (MODE == 0) {
       const float v = ly.l0 * (lx.l0 * slab[i00] + lx.l1 * slab[i01]) + ly.l1 * (lx.l0 * slab[i10] + lx.l1 * slab[i11]);
-      out[i] = feat[i] + v;
+      const float o = feat[i] + v;
+      out[i] = o;
+      if (out16) out16[i] = __float2bfloat16_rn(o);      // bf16 sidecar for the next stage's 1x1 conv
     } else {
       const float g = feat[i];  // dy
       atomicAdd(slab + i00, ly.l0 * lx.l0 * g);
@@ -718,11 +720,13 @@ TFB_API int tfb_tokens_bwd(const float* g, float* dimg, int Hi, int Wi, int ghi,
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
+// out16_bf16 (optional): bf16 copy of out written in the same pass.
 TFB_API int tfb_gpt_up_add_fwd(const float* feat, const float* tok, float* out, int N, int H, int W, int C, int gh, int gw, int t_off,
-                               int T, cudaStream_t stream) {
+                               int T, void* out16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(feat && tok && out && N > 0);
   const int64_t total = (int64_t)N * H * W * C;
-  gpt_up_add_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(feat, const_cast<float*>(tok), out, N, H, W, C, gh, gw, t_off, T);
+  gpt_up_add_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(feat, const_cast<float*>(tok), out, N, H, W, C, gh, gw, t_off, T,
+                                                                 (__nv_bfloat16*)out16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -972,10 +972,11 @@ class GptUpAddFn(Function):
         _, Hl, Wl, _ = lid.shape
         T = tok.shape[1]
         oi, ol = torch.empty_like(img), torch.empty_like(lid)
-        call('tfb_gpt_up_add_fwd', img, tok, oi, N, Hi, Wi, C, ghi, gwi, 0, T)
-        call('tfb_gpt_up_add_fwd', lid, tok, ol, N, Hl, Wl, C, ghl, gwl, ghi * gwi, T)
+        oi16, ol16 = _emit16(oi, True), _emit16(ol, True)       # both feed the 1x1 convs of the next stage / the channel-change conv
+        call('tfb_gpt_up_add_fwd', img, tok, oi, N, Hi, Wi, C, ghi, gwi, 0, T, oi16)
+        call('tfb_gpt_up_add_fwd', lid, tok, ol, N, Hl, Wl, C, ghl, gwl, ghi * gwi, T, ol16)
         ctx.cfg = (N, Hi, Wi, Hl, Wl, C, ghi, gwi, ghl, gwl, T)
-        return oi, ol
+        return _attach16(oi, oi16), _attach16(ol, ol16)
 
     @staticmethod
     def backward(ctx, di, dl):
