@@ -165,7 +165,8 @@ def test_gpt_block_bf16_mode_matches_fp32_mode(lib):
         assert rel(a, b) < (TOL if i == 0 else GRAD_TOL_VS_FP32), (n, rel(a, b))
     # q|k|v as one GEMM in forward, dgrad and wgrad (3) + proj (3) + two MLP layers (6); LayerNorm outputs reach them as sidecars
     assert lib.log.count('tfb_gemm_bf16_tc') == 12
-    assert lib.log.count('tfb_cast_bf16') == 3             # attention output -> proj, MLP hidden -> mlp.2, dqkv: no LayerNorm-output casts
+    assert lib.log.count('tfb_cast_bf16') == 2             # attention output -> proj, MLP hidden -> mlp.2: no LayerNorm-output casts,
+    assert lib.log.count('tfb_colsum') == 0                # and dqkv gets its bf16 copy and its bias gradients in ONE tfb_grad_prep pass
     from transfuser_b200 import ops
     old = {f: getattr(ops, f) for f in FLAGS}
     try:

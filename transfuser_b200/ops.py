@@ -908,13 +908,15 @@ class AttentionFn(Function):
             # fused q|k|v: dh = dqkv W3 (one GEMM, K = 3C), dW3 = dqkv^T h (one GEMM), db3 = column sums of dqkv (one reduction)
             dw3, db3 = _gbuf3(wq, wk, wv), _gbuf3(bq, bk, bv)
             if tc:
-                d16 = G.to_bf16(dqkv)
+                # one pass over dqkv: its bf16 copy (operand of both GEMMs) and the three bias gradients (column sums)
+                d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dev)
+                call('tfb_grad_prep', dqkv, None, None, d16, db3, _ws(dev), B * T, 3 * C)
                 G.gemm_bf16(d16, G.weight_bf16(w3), dh, trans_b=False)
                 G.gemm_bf16(d16, h, dw3, trans_a=True, splits=_wgrad_splits(B * T, 3 * C, C))
             else:
                 gemm(dqkv, w3, dh, trans_b=False, mode='simt')
                 gemm(dqkv, h, dw3, trans_a=True, mode='simt')
-            _colsum(dqkv, db3)
+                _colsum(dqkv, db3)
             for i in range(3):
                 grads += [dw3[i * C:(i + 1) * C], db3[i * C:(i + 1) * C]]
         elif tc:
