@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restric
 //         stride-1 equivalent input of a stride-2 conv's dgrad); TO = float or bf16.
 template <int MODE, typename TO>
 __global__ void __launch_bounds__(256) stride2_kernel(const float* __restrict__ src, TO* __restrict__ dst, int N, int H, int W, int Ho,
-                                                      int Wo, int C) {
+                                                      int Wo, int C, __nv_bfloat16* __restrict__ dst16) {
   const int64_t total = MODE == 0 ? (int64_t)N * Ho * Wo * C : (int64_t)N * H * W * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(256) stride2_kernel(const float* __restrict__ 
     }
     if (sizeof(TO) == 4) reinterpret_cast<float*>(dst)[i] = v;
     else reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+    if (dst16) dst16[i] = __float2bfloat16_rn(v);          // optional bf16 sidecar of an fp32 result
   }
 }
 
@@ -796,10 +797,11 @@ TFB_API int tfb_scale_dev(const float* x, const float* s_dev, float k, float* y,
 }
 
 // xs[N,Ho,Wo,C] = x[N, ::2, ::2, C] with Ho = (H+1)/2, Wo = (W+1)/2.
-TFB_API int tfb_subsample2(const float* x, float* xs, int N, int H, int W, int C, cudaStream_t stream) {
+// xs16_bf16 (optional): bf16 copy of xs written in the same pass.
+TFB_API int tfb_subsample2(const float* x, float* xs, int N, int H, int W, int C, void* xs16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(x && xs && N > 0 && H > 0 && W > 0 && C > 0);
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  stride2_kernel<0, float><<<tfb_grid((int64_t)N * Ho * Wo * C, 256), 256, 0, stream>>>(x, xs, N, H, W, Ho, Wo, C);
+  stride2_kernel<0, float><<<tfb_grid((int64_t)N * Ho * Wo * C, 256), 256, 0, stream>>>(x, xs, N, H, W, Ho, Wo, C, (__nv_bfloat16*)xs16_bf16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -808,8 +810,8 @@ TFB_API int tfb_dilate2(const float* src, void* dst, int N, int H, int W, int C,
   TFB_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0);
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int grid = tfb_grid((int64_t)N * H * W * C, 256);
-  if (out_bf16) stride2_kernel<1, __nv_bfloat16><<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, N, H, W, Ho, Wo, C);
-  else          stride2_kernel<1, float><<<grid, 256, 0, stream>>>(src, (float*)dst, N, H, W, Ho, Wo, C);
+  if (out_bf16) stride2_kernel<1, __nv_bfloat16><<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, N, H, W, Ho, Wo, C, nullptr);
+  else          stride2_kernel<1, float><<<grid, 256, 0, stream>>>(src, (float*)dst, N, H, W, Ho, Wo, C, nullptr);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

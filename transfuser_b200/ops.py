@@ -545,9 +545,10 @@ class Subsample2Fn(Function):
         x = _c(x)
         N, H, W, C = x.shape
         xs = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), dtype=torch.float32, device=x.device)
-        call('tfb_subsample2', x, xs, N, H, W, C)
+        xs16 = _emit16(xs, True)                   # the only consumer is the shortcut's 1x1 GEMM
+        call('tfb_subsample2', x, xs, N, H, W, C, xs16)
         ctx.shape = (N, H, W, C)
-        return xs
+        return _attach16(xs, xs16)
 
     @staticmethod
     def backward(ctx, d):
