@@ -19,7 +19,7 @@ TOL = 3e-2     # forward, bf16 operands (8 mantissa bits) through a few layers w
 # with every host-side option of DESIGN.md 4b switched off (the configuration that passed `-m gpu` on the B200 earlier in the round).
 GRAD_TOL_VS_FP32 = 0.25
 TOL_VS_PLAIN_BF16 = 1e-3
-FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')
+FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'SE_POOL_FUSED', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')
 
 
 def rel(a, b):

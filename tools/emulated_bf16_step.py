@@ -19,7 +19,7 @@ from oracle import torch_oracle as O  # noqa: E402
 from transfuser_b200 import LidarCenterNet, _lib, gemm, ops, optim  # noqa: E402
 from transfuser_b200.config import TrainConfig  # noqa: E402
 
-FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')
+FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'SE_POOL_FUSED', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')
 
 
 def rel(a, b):

@@ -3,6 +3,9 @@
 #   gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
 # Results land in gpurun_out/ (merged back by gpurun).
 mkdir -p gpurun_out
+# 0. everything: the parity tests proper (the second session of round 1 changed many CUDA-core kernels without a GPU)
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/first_run_all_gpu_tests.log 2>&1
+tail -5 gpurun_out/first_run_all_gpu_tests.log
 # 1. the kernels / modules that have only been emulated or wiring-tested so far (xfail markers ignored: failures are failures)
 timeout 900 python -m pytest tests/test_widen.py tests/test_pipeline.py -m gpu -q --runxfail -p no:cacheprovider > gpurun_out/first_run_tests.log 2>&1
 tail -5 gpurun_out/first_run_tests.log
@@ -16,12 +19,12 @@ done
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tile_default.json 2> gpurun_out/bench_tile_default.err
 grep -h '"value"' gpurun_out/bench_tile_*.json | cut -c1-160
 # 2b. A/B of the launch / pass reductions written without a GPU: each flag off in turn, then all off
-for f in TFB_SIDECARS TFB_SE_FUSED_BWD TFB_QKV_FUSED TFB_BN_ADD_FUSED TFB_PACK_BATCHED; do
+for f in TFB_SIDECARS TFB_SE_FUSED_BWD TFB_SE_POOL_FUSED TFB_QKV_FUSED TFB_BN_ADD_FUSED TFB_PACK_BATCHED; do
   env $f=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_${f}_off.json 2> gpurun_out/bench_ab_${f}_off.err
 done
-TFB_SIDECARS=0 TFB_SE_FUSED_BWD=0 TFB_QKV_FUSED=0 TFB_BN_ADD_FUSED=0 TFB_PACK_BATCHED=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_all_off.json 2> gpurun_out/bench_ab_all_off.err
+TFB_SIDECARS=0 TFB_SE_FUSED_BWD=0 TFB_SE_POOL_FUSED=0 TFB_QKV_FUSED=0 TFB_BN_ADD_FUSED=0 TFB_PACK_BATCHED=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_all_off.json 2> gpurun_out/bench_ab_all_off.err
 grep -h '"value"' gpurun_out/bench_ab_*.json | cut -c1-160
 # 3. per-kernel time without host launch gaps (dedicated CUDA graph of one step's launches of that entry point)
-for k in tfb_gemm_bf16_tc tfb_conv3x3_tc tfb_bn_fwd tfb_bn_bwd tfb_im2col3x3_bf16 tfb_cast_bf16 tfb_grad_prep; do
+for k in tfb_gemm_bf16_tc tfb_conv3x3_tc tfb_bn_fwd tfb_bn_bwd tfb_im2col3x3_bf16 tfb_cast_bf16 tfb_grad_prep tfb_conv2d_wgrad tfb_upsample_bilinear_bwd tfb_gpt_up_add_bwd tfb_se_mlp_bwd; do
   timeout 240 python tools/kernel_graph_timing.py $k > gpurun_out/kgt_$k.log 2>&1; tail -3 gpurun_out/kgt_$k.log
 done
