@@ -181,3 +181,36 @@ def test_gpt_block_bf16_mode_matches_fp32_mode(lib):
     for n, a, b in zip(names, got, plain):
         if n != 'attn.key.bias':
             assert rel(a, b) < TOL_VS_PLAIN_BF16, (n, rel(a, b))
+
+
+def test_shared_input_im2col_is_built_once(lib):
+    """The CenterNet heads / BEV head convolve the same p2 map: in backward the bf16 im2col matrix of a shared input is built by the
+    first wgrad and reused by the others (same weight gradients as separate im2cols)."""
+    from transfuser_b200 import gemm, ops
+    gemm.set_mode('bf16')
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 16, 16, 64, generator=g).requires_grad_(True)
+    ws = [(torch.randn(64, 64, 3, 3, generator=g) / 24).requires_grad_(True) for _ in range(3)]
+    bs = [torch.randn(64, generator=g).requires_grad_(True) for _ in range(3)]
+    rs = [torch.randn(2, 16, 16, 64, generator=g) for _ in range(3)]
+
+    def run():
+        ops.tick('cpu')
+        lib.log.clear()
+        loss = sum((ops.conv2d(x, w, b, relu=True) * r).sum() for w, b, r in zip(ws, bs, rs))
+        grads = torch.autograd.grad(loss, [x] + ws + bs)
+        return [t.clone() for t in grads], lib.log.count('tfb_im2col3x3_bf16')
+    got, n_shared = run()
+    assert n_shared == 1
+    orig = ops._COL_CACHE
+    try:
+        class _Never(dict):
+            def get(self, k, d=None):
+                return None
+        ops._COL_CACHE = _Never()
+        want, n_sep = run()
+    finally:
+        ops._COL_CACHE = orig
+    assert n_sep == 3
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

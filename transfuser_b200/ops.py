@@ -39,6 +39,7 @@ def tick(device):
     call('tfb_step_tick', seed_state(device), None)
     _SEED['off'] = 0
     _BWD16.clear()
+    _COL_CACHE.clear()
     _prepack_all(device)
 
 
@@ -443,6 +444,9 @@ def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
     return y
 
 
+_COL_CACHE = {}     # (input address, shape, stride, groups) -> (input tensor, its bf16 im2col matrix, input version); dropped at tick()
+
+
 def _conv_wgrad_tc_ok(x_shape, Cout, groups, stride):
     """Shapes _conv_wgrad_tc takes: 16-byte aligned channel windows and enough output pixels for a split-K GEMM."""
     N, H, W, Cin = x_shape
@@ -463,8 +467,18 @@ def _conv_wgrad_tc(x, g16, w, groups, stride):
         return None
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     M = N * Ho * Wo
-    col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
-    call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
+    # the seven CenterNet heads and the BEV head all convolve the same p2 map: its im2col matrix is built once per backward
+    key = (x.data_ptr(), tuple(x.shape), stride, groups)
+    hit = _COL_CACHE.get(key)
+    if hit is not None and hit[2] == x._version:          # (the entry pins the input it was built from: the address cannot be reused)
+        col = hit[1]
+    else:
+        col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
+        call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
+        if col.numel() * 2 <= (128 << 20):                # small maps only (p2: 47 MB); the 160x704 decoder maps are not shared anyway
+            if len(_COL_CACHE) >= 2:
+                _COL_CACHE.pop(next(iter(_COL_CACHE)))
+            _COL_CACHE[key] = (x, col, x._version)
     ldg = g16.shape[-1]                      # > Cout when dy was zero-padded to 8 channels (the 7- / 1-channel decoder outputs)
     rows = max(Cout, ldg) if groups == 1 else Cout
     dw = _gbuf(w)
