@@ -198,7 +198,9 @@ def test_shared_input_im2col_is_built_once(lib):
         ops.tick('cpu')
         lib.log.clear()
         loss = sum((ops.conv2d(x, w, b, relu=True) * r).sum() for w, b, r in zip(ws, bs, rs))
+        n_cast_fwd = lib.log.count('tfb_cast_bf16')
         grads = torch.autograd.grad(loss, [x] + ws + bs)
+        assert n_cast_fwd <= 1                      # the shared input is cast to bf16 once (ops._as16 keeps the copy on the tensor)
         return [t.clone() for t in grads], lib.log.count('tfb_im2col3x3_bf16')
     got, n_shared = run()
     assert n_shared == 1

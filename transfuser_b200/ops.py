@@ -78,9 +78,12 @@ def _attach16(y, y16):
 def _as16(x):
     """bf16 copy of the contiguous fp32 tensor x: its sidecar when the producer wrote one, else a cast pass."""
     s = getattr(x, '_tfb16', None)
-    if s is not None and s.shape == x.shape:
+    if s is not None and s.shape == x.shape and getattr(x, '_tfb16v', x._version) == x._version:
         return s
-    return G.to_bf16(x)
+    s = G.to_bf16(x)
+    if SIDECARS:
+        x._tfb16, x._tfb16v = s, x._version      # a tensor with several tensor-core consumers (p2 -> 8 head convs) is cast once
+    return s
 
 
 # Backward sidecars: BatchNorm backward writes the bf16 copy of dx next to dx when the convolution in front of it runs its dgrad /
