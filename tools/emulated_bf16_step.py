@@ -73,6 +73,20 @@ def main(backbone, second=False):
     print('gradients, options on vs off: median %.2e  p95 %.2e  max %.2e (%s)' %
           (errs[len(errs) // 2][0], errs[int(len(errs) * 0.95)][0], errs[-1][0], errs[-1][1]))
     print('C-ABI calls per forward+backward: %d -> %d' % (n0, n1))
+    # where the gap appears: parameters grouped by depth (backward runs from the heads at the top of this list towards the stems)
+    import re
+    order = ['head|pred_bev|join|decoder|output', 'change_channel|up_conv|c5_conv', 'transformer4', r'\.s4\.|layer4', 'transformer3', r'\.s3\.|layer3',
+             'transformer2', r'\.s2\.|layer2', 'transformer1', r'\.s1\.|layer1', 'stem|conv1|bn1']
+    left = dict(errs and [(n, e) for e, n in errs])
+    for pat in order:
+        sel = sorted(e for n, e in left.items() if re.search(pat, n))
+        for n in [n for n in left if re.search(pat, n)]:
+            del left[n]
+        if sel:
+            print('  %-44s %4d tensors  median %.2e  max %.2e' % (pat, len(sel), sel[len(sel) // 2], sel[-1]))
+    if left:
+        sel = sorted(left.values())
+        print('  %-44s %4d tensors  median %.2e  max %.2e' % ('(other)', len(sel), sel[len(sel) // 2], sel[-1]))
 
     class C(O.Cfg):
         embd_pdrop = attn_pdrop = resid_pdrop = 0.0
