@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY. torch stand-ins for the three tensor-core entry points (tcgen05 / TMA: not emulable), written from the
+"""TEST INFRASTRUCTURE ONLY. torch stand-ins for the tensor-core entry points (tcgen05 / TMA: not emulable), written from the
 CONTRACT in include/tfb200.h — operand layouts, leading dimensions, column windows, the packed-weight format of csrc/conv_pack.cu —
 so that the product's bf16-mode host path (sidecars, packed weights, q|k|v packs, im2col + batched wgrad, flat gradients) can run
 end to end on the CPU emulation with every CUDA-core kernel real and only the MMA itself replaced. They check what the real
@@ -6,7 +6,7 @@ kernels require (16-byte alignment, leading dimensions % 8) and compute in fp32 
 import torch
 import torch.nn.functional as F
 
-TC_NAMES = ('tfb_gemm_bf16_tc', 'tfb_conv3x3_tc', 'tfb_gemm_bf16_tc_wgrad_batched')
+TC_NAMES = ('tfb_gemm_bf16_tc', 'tfb_conv3x3_tc', 'tfb_conv3x3_tc_strided', 'tfb_gemm_bf16_tc_wgrad_batched', 'tfb_attn_fwd_tc', 'tfb_attn_bwd_tc')
 
 
 def _mat(t, rows, cols, ld):
@@ -37,7 +37,11 @@ def gemm_bf16_tc_wgrad_batched(M, N, K, A, lda, a_step, B, ldb, b_step, C, ldc, 
 
 
 def conv3x3_tc(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu):
-    """y = conv3x3(x16, packed weights): block gb reads channels gb*c_step + chunk*KC + kk, writes channels gb*nb_real + j; tap t
+    conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1)
+
+
+def conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, stride):
+    """y = conv3x3(x16, packed weights; pad 1, stride 1 or 2): block gb reads channels gb*c_step + chunk*KC + kk, writes channels gb*nb_real + j; tap t
     multiplies the input pixel shifted by (t/3 - 1, t%3 - 1); out-of-image pixels and channels >= Cx read as zero."""
     assert x16.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16 and Cx % 8 == 0 and x16.data_ptr() % 16 == 0 and wp.data_ptr() % 16 == 0
     wpk = torch.as_strided(wp, (gblocks, nchunks, 9, NB, KC), (nchunks * 9 * NB * KC, 9 * NB * KC, NB * KC, KC, 1)).float()
@@ -53,9 +57,61 @@ def conv3x3_tc(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_re
                 if n:
                     dense[oc, rc0:rc0 + n] += wpk[gb, ch, :, j, :n].t()
     xin = torch.as_strided(x16, (N, H, W, Cx), (H * W * Cx, W * Cx, Cx, 1)).float().permute(0, 3, 1, 2)
-    out = F.conv2d(xin, dense.view(Cy, Cx, 3, 3), None if bias is None else torch.as_strided(bias, (Cy,), (1,)), padding=1)
+    out = F.conv2d(xin, dense.view(Cy, Cx, 3, 3), None if bias is None else torch.as_strided(bias, (Cy,), (1,)), padding=1, stride=stride)
     out = out.clamp_min(0) if relu else out
-    torch.as_strided(y, (N, H, W, Cy), (H * W * Cy, W * Cy, Cy, 1)).copy_(out.permute(0, 2, 3, 1))
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    torch.as_strided(y, (N, Ho, Wo, Cy), (Ho * Wo * Cy, Wo * Cy, Cy, 1)).copy_(out.permute(0, 2, 3, 1))
+
+
+def _attn_keep(seed_dev, seed_off, B, nh, T, p_drop):
+    """The dropout keep-scale of csrc/attn_tc.cu (drop_scale): [B, nh, T, T], 0 or 1/(1-p)."""
+    if p_drop <= 0.0:
+        return torch.ones(B, nh, T, T)
+    seed = (int(seed_dev.view(-1)[0].item()) if seed_dev is not None else 0) + int(seed_off)
+    lo, hi, M = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, 0xFFFFFFFF
+    x = (torch.arange(B * nh * T * T, dtype=torch.int64) * 0x9E3779B1 + lo) & M
+    x = ((x ^ (x >> 16)) * 0x85EBCA6B) & M
+    x = x ^ hi
+    x = ((x ^ (x >> 13)) * 0xC2B2AE35) & M
+    x = x ^ (x >> 16)
+    u = (x >> 8).float() * (1.0 / 16777216.0)
+    return torch.where(u < p_drop, torch.zeros(()), torch.full((), 1.0 / (1.0 - p_drop))).view(B, nh, T, T)
+
+
+def _heads(t2d, B, T, nh, hs):
+    return t2d.reshape(B, T, nh, hs).permute(0, 2, 1, 3)
+
+
+def attn_fwd_tc(qkv, qkv_bf16, B, T, nh, hs, y32, y16, lse, scale, p_drop, seed_dev, seed_off):
+    C = nh * hs
+    x = torch.as_strided(qkv, (B * T, 3 * C), (3 * C, 1)).bfloat16().float()     # the tensor cores see bf16 operands
+    q, k, v = (_heads(x[:, i * C:(i + 1) * C], B, T, nh, hs) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    torch.as_strided(lse, (B, nh, T), (nh * T, T, 1)).copy_(torch.logsumexp(s, -1))
+    pd = (torch.softmax(s, -1) * _attn_keep(seed_dev, seed_off, B, nh, T, p_drop)).bfloat16().float()
+    y = (pd @ v).permute(0, 2, 1, 3).reshape(B * T, C)
+    if y32 is not None:
+        torch.as_strided(y32, (B * T, C), (C, 1)).copy_(y)
+    if y16 is not None:
+        torch.as_strided(y16, (B * T, C), (C, 1)).copy_(y)
+
+
+def attn_bwd_tc(qkv, qkv_bf16, dy, dy_bf16, dy32, y32, lse, dsum, B, T, nh, hs, dqkv32, dqkv16, scale, p_drop, seed_dev, seed_off):
+    C = nh * hs
+    x = torch.as_strided(qkv, (B * T, 3 * C), (3 * C, 1)).bfloat16().float()
+    q, k, v = (_heads(x[:, i * C:(i + 1) * C], B, T, nh, hs) for i in range(3))
+    do = _heads(torch.as_strided(dy, (B * T, C), (C, 1)).bfloat16().float(), B, T, nh, hs)
+    keep = _attn_keep(seed_dev, seed_off, B, nh, T, p_drop)
+    p = torch.exp((q @ k.transpose(-1, -2)) * scale - torch.as_strided(lse, (B, nh, T), (nh * T, T, 1)).unsqueeze(-1))
+    D = (_heads(torch.as_strided(dy32, (B * T, C), (C, 1)), B, T, nh, hs) * _heads(torch.as_strided(y32, (B * T, C), (C, 1)), B, T, nh, hs)).sum(-1, keepdim=True)
+    dv = (p * keep).bfloat16().float().transpose(-1, -2) @ do
+    ds = (scale * p * ((do @ v.transpose(-1, -2)) * keep - D)).bfloat16().float()
+    dq, dk = ds @ k, ds.transpose(-1, -2) @ q
+    out = torch.cat([t.permute(0, 2, 1, 3).reshape(B * T, C) for t in (dq, dk, dv)], dim=1)
+    if dqkv32 is not None:
+        torch.as_strided(dqkv32, (B * T, 3 * C), (3 * C, 1)).copy_(out)
+    if dqkv16 is not None:
+        torch.as_strided(dqkv16, (B * T, 3 * C), (3 * C, 1)).copy_(out)
 
 
 class WithTensorCoreStandins:
@@ -66,7 +122,8 @@ class WithTensorCoreStandins:
         self.log = emul.log
         self.launches = 0
         self.profiler = None
-        self.fns = {'tfb_gemm_bf16_tc': gemm_bf16_tc, 'tfb_conv3x3_tc': conv3x3_tc, 'tfb_gemm_bf16_tc_wgrad_batched': gemm_bf16_tc_wgrad_batched}
+        self.fns = {'tfb_gemm_bf16_tc': gemm_bf16_tc, 'tfb_conv3x3_tc': conv3x3_tc, 'tfb_conv3x3_tc_strided': conv3x3_tc_strided, 'tfb_gemm_bf16_tc_wgrad_batched': gemm_bf16_tc_wgrad_batched,
+                    'tfb_attn_fwd_tc': attn_fwd_tc, 'tfb_attn_bwd_tc': attn_bwd_tc}
 
     def call(self, name, *args):
         fn = self.fns.get(name)

@@ -164,8 +164,12 @@ def test_qkv_pack_fused_projection_bf16(C):
 
 def test_bf16_sidecars_do_not_change_the_step():
     """bf16 sidecars (BatchNorm / SE / add / LayerNorm write the bf16 operand of the next GEMM in their own pass) against the
-    separate cast launches they replace: the sidecar is the same rounding of the same fp32 value, so the losses agree to the
-    run-to-run noise of the fp32 atomics in the step (SE pooling; amplified by batch-2 BatchNorm: 2e-3 bound), and the step needs > 100 fewer launches."""
+    separate cast launches they replace. The sidecar is the same rounding of the same fp32 value, but the bf16 step is not
+    run-to-run reproducible: fp32 atomics (split-K wgrad, SE pooling) change the summation order, one flipped bf16 rounding is
+    amplified by the batch-2 BatchNorms, and two runs of the SAME configuration differ by 0.4-1.5 % in the worst loss
+    (measured on a B200, profiles/r2_sidecar_noise.txt; round 1's guessed 2e-3 bound was below that noise floor). So: the
+    on/off difference must stay inside 4x the off/off noise measured in this very test (floor 1 %), and the step needs > 100
+    fewer launches."""
     import sys
     import os
     sys.path.insert(0, os.path.dirname(__file__))
@@ -174,28 +178,37 @@ def test_bf16_sidecars_do_not_change_the_step():
     from transfuser_b200 import _lib, gemm, ops
     batch = {k: v.cuda() for k, v in O.synthetic_batch(2, seed=4).items()}
     gemm.set_mode('bf16')
-    outs, launches = {}, {}
     old = ops.SIDECARS
+
+    def run(on):
+        ops.SIDECARS = on
+        net = build().cuda().train()
+        n0 = _lib.lib().launches
+        out = net(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
+                  target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
+                  depth=batch['depth'], semantic=batch['semantic'])
+        sum(out.values()).backward()
+        torch.cuda.synchronize()
+        assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+        return {k: v.item() for k, v in out.items()}, _lib.lib().launches - n0
+
+    def dist(a, b):
+        return max(abs(a[k] - b[k]) / max(abs(b[k]), 0.1) for k in a)
+
     try:
-        for on in (False, True):
-            ops.SIDECARS = on
-            net = build().cuda().train()
-            n0 = _lib.lib().launches
-            out = net(batch['rgb'], batch['lidar'], ego_waypoint=batch['ego_waypoint'], target_point=batch['target_point'],
-                      target_point_image=batch['target_point_image'], ego_vel=batch['ego_vel'], bev=batch['bev'], label=batch['label'],
-                      depth=batch['depth'], semantic=batch['semantic'])
-            sum(out.values()).backward()
-            torch.cuda.synchronize()
-            launches[on] = _lib.lib().launches - n0
-            outs[on] = {k: v.item() for k, v in out.items()}
-            assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+        off0, l_off = run(False)
+        off1, _ = run(False)
+        off2, _ = run(False)
+        on0, l_on = run(True)
+        on1, _ = run(True)
     finally:
         ops.SIDECARS = old
-    for k in outs[True]:
-        a, b = outs[True][k], outs[False][k]
-        assert abs(a - b) <= 2e-3 * max(abs(b), 0.1), (k, a, b)
-    print('C-ABI calls per fwd+bwd: %d without sidecars, %d with' % (launches[False], launches[True]))
-    assert launches[False] - launches[True] > 100
+    noise = max(dist(off0, off1), dist(off0, off2), dist(off1, off2), dist(on0, on1))
+    worst = max(dist(on0, off0), dist(on1, off1), dist(on0, off2))
+    print('bf16 step: run-to-run noise %.3e, sidecars on vs off %.3e; C-ABI calls %d -> %d' % (noise, worst, l_off, l_on))
+    assert noise < 5e-2, noise                      # the noise itself stays a few percent
+    assert worst <= max(4 * noise, 1e-2), (worst, noise)
+    assert l_off - l_on > 100
 
 
 @pytest.mark.parametrize('cfg', [(2, 40, 48, 72, 72, 3), (2, 20, 24, 216, 216, 9), (2, 32, 44, 3, 32, 1)])

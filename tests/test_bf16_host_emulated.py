@@ -165,8 +165,10 @@ def test_gpt_block_bf16_mode_matches_fp32_mode(lib):
         assert rel(a, b) < (TOL if i == 0 else GRAD_TOL_VS_FP32), (n, rel(a, b))
     # q|k|v as one GEMM in forward, dgrad and wgrad (3) + proj (3) + two MLP layers (6); LayerNorm outputs reach them as sidecars
     assert lib.log.count('tfb_gemm_bf16_tc') == 12
-    assert lib.log.count('tfb_cast_bf16') == 2             # attention output -> proj, MLP hidden -> mlp.2: no LayerNorm-output casts,
-    assert lib.log.count('tfb_colsum') == 0                # and dqkv gets its bf16 copy and its bias gradients in ONE tfb_grad_prep pass
+    assert lib.log.count('tfb_cast_bf16') == 1             # MLP hidden -> mlp.2 only: no LayerNorm-output casts, and the fused attention
+    assert lib.log.count('tfb_attn_fwd_tc') == 1 and lib.log.count('tfb_attn_bwd_tc') == 1   # writes the bf16 copies of y and dqkv itself
+    assert lib.log.count('tfb_colsum') == 1                # (the three bias gradients: one column reduction over dqkv)
+    assert lib.log.count('tfb_gemm_f32_simt') == 0 and lib.log.count('tfb_softmax_fwd') == 0   # no T x T tensor in HBM
     from transfuser_b200 import ops
     old = {f: getattr(ops, f) for f in FLAGS}
     try:

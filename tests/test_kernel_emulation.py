@@ -264,11 +264,11 @@ def test_adamw_kernel_matches_torch_adamw():
         ref.grad = grad.clone()
         opt.step()
         g = (grad * 4).contiguous()                                    # summed over 4 ranks, grad_scale = 1/4
-        _call('tfb_adamw_step', p, g, m, v, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, step, None, 0.25, mirror, 1)
+        _call('tfb_adamw_step', p, g, m, v, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, step, None, 0.25, mirror, 1, None)
         assert int((g != 0).sum()) == 0                                # zero_grad fused
         _call('tfb_step_tick', None, step_dev)
         g2 = (grad * 4).contiguous()
-        _call('tfb_adamw_step', pd, g2, md, vd, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, 0, step_dev, 0.25, None, 0)
+        _call('tfb_adamw_step', pd, g2, md, vd, n, 1e-2, 0.9, 0.999, 1e-8, 1e-2, 0, step_dev, 0.25, None, 0, None)
         assert torch.equal(g2, grad * 4)
         assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=2e-7), (step, (p - ref.detach()).abs().max())
         assert torch.equal(p, pd) and torch.equal(m, md) and torch.equal(v, vd)

@@ -2,9 +2,8 @@
 model.py:685-731, 376-497) and the GeometricFusionBackbone variant (geometric_fusion.py, BASELINE config 4).
 
 CPU part: drop-in key sets and the host-side box geometry against the verbatim reference (build container only).
-GPU part: the new kernels against plain fp32 PyTorch ops / the CPU oracle. These kernels were written after round 1's
-GPU budget was spent: they compile for sm_100a and their host logic is CPU-tested, but they have not yet been executed on
-hardware, so the GPU tests are marked xfail(strict=False) until a run confirms them (an XPASS is the confirmation)."""
+GPU part: the new kernels against plain fp32 PyTorch ops / the CPU oracle (first run on a B200 in round 2: all green,
+profiles/r2_gpu_tests_first_run.log)."""
 import numpy as np
 import pytest
 import torch
@@ -19,9 +18,6 @@ DEV = 'cuda'   # the emulated re-runs (tests/test_widen_emulated.py, tools/emula
 def _sync():
     if DEV == 'cuda':
         torch.cuda.synchronize()
-
-
-FIRST_RUN = pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget was spent; not yet run on hardware')
 
 
 def rel(a, b):
@@ -102,7 +98,6 @@ def _nhwc(x):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize('shape,grid', [((2, 72, 40, 176), (5, 22)), ((2, 216, 32, 32), (8, 8)), ((1, 1512, 5, 22), (5, 22)), ((2, 6, 16, 24), (4, 3))])
 def test_avgpool_grid_matches_torch(shape, grid):
     from transfuser_b200 import ops
@@ -119,7 +114,6 @@ def test_avgpool_grid_matches_torch(shape, grid):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize('B,hw,HW,C', [(2, (5, 22), (8, 8), 512), (3, (8, 8), (5, 22), 512), (1, (4, 4), (2, 3), 8)])
 def test_gather_sum_matches_torch_index(B, hw, HW, C):
     """The reference's B x B advanced index + diagonal + sum (geometric_fusion.py:145-148), including repeated and all-zero
@@ -156,7 +150,6 @@ def _decode_case(case, g):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize('case', [0, 1, 2, 3])
 def test_centernet_decode_matches_oracle(case):
     """One-launch decode vs oracle.decode_heatmap (pinned to model.py:376-497 in tests/test_oracle.py; stable=True fixes the
@@ -187,7 +180,6 @@ def _build(backbone, seed):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_geometric_fusion_forward_backward_matches_oracle():
     """BASELINE config 4: the 11 losses vs the fp32 CPU oracle (1e-3 relative, north_star), gradients finite and in the oracle's
     noise band. The product pools before the 1x1 embed and up-samples after the 1x1 deconv (exact reassociations)."""
@@ -217,7 +209,6 @@ def test_geometric_fusion_forward_backward_matches_oracle():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_latent_tf_forward_backward_matches_oracle():
     """latentTF.py: same kernels as the TransFuser path, positional grid instead of the LiDAR histogram."""
     net, C = _build('latentTF', 12)
@@ -243,7 +234,6 @@ def test_latent_tf_forward_backward_matches_oracle():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 @pytest.mark.parametrize('backbone', ['transFuser', 'late_fusion'])
 def test_forward_ego_matches_oracle(backbone):
     """Eval-mode inference (running-stat BatchNorm, no dropout) + decode + host box geometry vs the CPU oracle's forward_ego."""
@@ -262,7 +252,6 @@ def test_forward_ego_matches_oracle(backbone):
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_fused_adamw_matches_torch_adamw_on_device():
     """optim.FusedAdamW (one kernel over the flat buffer, bf16 mirror) vs torch.optim.AdamW on the same gradients, 3 steps."""
     from transfuser_b200 import gemm, optim

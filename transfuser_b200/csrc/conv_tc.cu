@@ -32,7 +32,9 @@ template <int KC, int NB, int STAGES>
 __global__ void __launch_bounds__(192)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, float* __restrict__ y,
                   const float* __restrict__ bias, int H, int W, int Cout, int tiles_w, int tiles_h, int c_step, int nchunks,
-                  int nb_real, int relu, int gblocks, int total_tiles) {
+                  int nb_real, int relu, int gblocks, int total_tiles, int stride) {
+  // H, W: OUTPUT height / width. stride 2: the activation map steps two pixels per box element, so tile pixel (h, w) reads the
+  // input pixel (2h + dy, 2w + dx) of tap (dy, dx).
   // PERSISTENT: tile t = (spatial tile, channel block), channel block fastest (CTAs running together re-use the same activation
   // patch out of L2); double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
   constexpr int ROWB = KC * 2;                 // bytes per smem row
@@ -84,7 +86,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE;
           tc::mbar_expect_tx(&full_bar[s], STAGE);
-          tc::tma_load_4d(&tma_x, &full_bar[s], sa, gb * c_step + chunk * KC, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n);
+          tc::tma_load_4d(&tma_x, &full_bar[s], sa, gb * c_step + chunk * KC, w0 * stride + tap % 3 - 1, h0 * stride + tap / 3 - 1, n);
           tc::tma_load_2d(&tma_w, &full_bar[s], sa + A_BYTES, 0, ((gb * nchunks + chunk) * 9 + tap) * NB);
         }
       }
@@ -174,17 +176,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
 }
 
 template <int KC, int NB>
-int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy, int c_step,
-                int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
+int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int Hin, int Win, int Cx, int Cy, int c_step,
+                int nchunks, int nb_real, int gblocks, int relu, int stride, cudaStream_t stream) {
+  const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output size (kernel 3, pad 1)
   constexpr int STAGES = NB <= 64 ? 6 : 4;
   constexpr int STAGE = BM * KC * 2 + NB * KC * 2;
   constexpr int SMEM = STAGES * STAGE + 256 + 4 * 32 * 36 * 4 + 1024;   // ring + barriers/TMEM slot + epilogue staging + alignment slack
   CUtensorMap mx, mw;
-  const uint64_t xd[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-  const uint64_t xs[3] = {(uint64_t)Cx * 2, (uint64_t)W * Cx * 2, (uint64_t)H * W * Cx * 2};
-  const uint32_t xb[4] = {(uint32_t)KC, TW, TH, 1};
+  const uint64_t xd[4] = {(uint64_t)Cx, (uint64_t)Win, (uint64_t)Hin, (uint64_t)N};
+  const uint64_t xs[3] = {(uint64_t)Cx * 2, (uint64_t)Win * Cx * 2, (uint64_t)Hin * Win * Cx * 2};
+  const uint32_t xb[4] = {(uint32_t)KC, (uint32_t)(TW * stride), (uint32_t)(TH * stride), 1};
+  const uint32_t xe[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!tc::make_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x16, xd, xs, xb, swz)) {
+  if (!tc::make_map(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x16, xd, xs, xb, swz, xe)) {
     tfb_set_last_error("cuTensorMapEncodeTiled(activation, 4-D) failed");
     return TFB_ERR_DRIVER;
   }
@@ -208,20 +212,21 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
   const int per_sm = (SMEM <= 110 * 1024) ? 2 : 1;
   const int64_t cap = (int64_t)tfb_num_sms() * per_sm;
   const int grid = (int)(total < cap ? total : cap);
-  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu, gblocks, (int)total);
+  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu, gblocks, (int)total, stride);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
 }  // namespace
 
-// y[N,H,W,Cy] (fp32) = conv3x3(x16[N,H,W,Cx] bf16, packed weights) (+bias) (ReLU). Block gb reads channels
-// [gb*c_step + chunk*KC, +KC) for chunk < nchunks and writes channels [gb*nb_real, +min(nb_real, Cy - gb*nb_real)).
-TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
-                           int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
-  TFB_REQUIRE(x16 && wpack && y && N > 0 && H > 0 && W > 0 && Cx > 0 && Cy > 0 && Cx % 8 == 0);
+// y[N,Ho,Wo,Cy] (fp32) = conv3x3(x16[N,H,W,Cx] bf16, packed weights; pad 1, stride 1 or 2) (+bias) (ReLU), Ho = (H-1)/stride + 1.
+// Block gb reads channels [gb*c_step + chunk*KC, +KC) for chunk < nchunks and writes channels [gb*nb_real, +min(nb_real, Cy - gb*nb_real)).
+// stride 2 (first block of every RegNetY stage): the TMA map traverses the activation with element strides {1, 2, 2, 1}.
+TFB_API int tfb_conv3x3_tc_strided(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
+                                   int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, int stride, cudaStream_t stream) {
+  TFB_REQUIRE(x16 && wpack && y && N > 0 && H > 0 && W > 0 && Cx > 0 && Cy > 0 && Cx % 8 == 0 && (stride == 1 || stride == 2));
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0);
-#define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stream)
+#define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stride, stream)
   CASE(64, 16); CASE(64, 32); CASE(64, 48); CASE(64, 64); CASE(64, 128);
   CASE(32, 16); CASE(32, 32); CASE(32, 64);
 #undef CASE
@@ -229,3 +234,8 @@ TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias
   return TFB_ERR_UNSUPPORTED;
 }
 
+// Stride-1 form of tfb_conv3x3_tc_strided.
+TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
+                           int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
+  return tfb_conv3x3_tc_strided(x16, wpack, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1, stream);
+}

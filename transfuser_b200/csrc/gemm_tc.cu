@@ -32,40 +32,38 @@ template <> struct Elem<__nv_bfloat16> {
   static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 };
 
-template <int BN, int STAGES>
-struct SmemLayout {
-  static constexpr int kABytes = BM * 128;
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kStageOut = kBarOffset + 256;                              // 4 warps x 32 rows x 36 floats epilogue staging
-  static constexpr int kTotal = kStageOut + 4 * 32 * 36 * 4 + 1024;               // + alignment slack
-};
+// Shared memory: STAGES x (A tile 128 x 128 B | B tile BN x 128 B), barriers, 4 x (32 x 36 floats) epilogue staging. BN (the tile
+// width, any multiple of 16 up to 256; a multiple of 64 for an MN-major B) and STAGES are RUNTIME values: the host picks the width
+// that fills whole waves of the persistent grid (M = 1740 token GEMMs: N = 1512 -> 160, N = 4536 -> 224) and the deepest ring that fits.
+constexpr int kABytes = BM * 128;
+constexpr int kSmemMax = 232448;                              // 227 KB opt-in limit
+constexpr int kSmemFixed = 256 + 4 * 32 * 36 * 4 + 1024;      // barriers + epilogue staging + alignment slack
+constexpr uint32_t kAccCols = 256;                            // TMEM columns per accumulator buffer (2 buffers = all 512)
 
-template <typename T, int BN, bool A_MN, bool B_MN, int STAGES>
+template <typename T, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ Cbase,
                int64_t ldc, int M, int N, int num_kb, int kb_per_split, const float* __restrict__ bias, float alpha, float beta,
                int relu, int atomic_out, int splits, int a_step, int b_step, int64_t c_bstride, int tiles_m, int tiles_n,
-               int total_tiles) {
+               int total_tiles, int BN, int STAGES) {
   // PERSISTENT: gridDim.x CTAs (<= one per SM) walk the tile list t = blockIdx.x, += gridDim.x. A tile is (m-tile, n-tile, z),
   // z = batch * splits + split; m fastest so that concurrently running CTAs share the same B (weight) tile in L2.
   // The TMEM accumulator is double buffered (2 x BN columns): the epilogue warps drain tile i while the MMA warp already
   // accumulates tile i+1, and the TMA producer runs ahead across tile boundaries through the shared-memory ring.
   using E = Elem<T>;
-  using L = SmemLayout<BN, STAGES>;
   constexpr int BK = E::kPerRow;  // K elements per stage
+  const int stage_bytes = kABytes + BN * 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
+  float* stage_out = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 256);
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_a);
@@ -94,17 +92,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;
+      int s = 0, ph = 0;
+      const int nb_chunks = (BN + E::kPerRow - 1) / E::kPerRow;
+      const uint32_t tx_bytes = (uint32_t)(kABytes + (B_MN ? nb_chunks * BK * 128 : BN * 128));
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int m0, n0, bz, sz, kb_begin, nkb;
         decode(t, m0, n0, bz, sz, kb_begin, nkb);
         const int am0 = m0 + bz * a_step, bn0 = n0 + bz * b_step;
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
+        for (int i = 0; i < nkb; ++i) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          tc::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          tc::mbar_expect_tx(&full_bar[s], tx_bytes);
           const int k0 = (kb_begin + i) * BK;
           if (!A_MN) {
             tc::tma_load_2d(&tma_a, &full_bar[s], sa, k0, am0);
@@ -116,18 +115,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (!B_MN) {
             tc::tma_load_2d(&tma_b, &full_bar[s], sb, k0, bn0);
           } else {
-#pragma unroll
-            for (int j = 0; j < BN / E::kPerRow; ++j)
+            for (int j = 0; j < nb_chunks; ++j)
               tc::tma_load_2d(&tma_b, &full_bar[s], sb + j * BK * 128, bn0 + j * E::kPerRow, k0);
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(E::kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BM, BN);
-      int it = 0, lt = 0;
+      const uint32_t idesc = tc::make_idesc(E::kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BM, (uint32_t)BN);
+      int s = 0, ph = 0, lt = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
         int m0, n0, bz, sz, kb_begin, nkb;
         decode(t, m0, n0, bz, sz, kb_begin, nkb);
@@ -135,12 +134,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc::mbar_wait(&tmem_empty_bar[as], aph ^ 1);   // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
         const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols;
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
+        for (int i = 0; i < nkb; ++i) {
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + s * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < BK / E::kUmmaK; ++k) {
             // K-major: advance 32 B inside the 128 B swizzle row; MN-major: advance kUmmaK rows of 128 B.
@@ -153,6 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             else                tc::umma_f16(acc_addr, adesc, bdesc, idesc, acc);
           }
           tc::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         tc::umma_commit(&tmem_full_bar[as]);  // accumulator complete
       }
@@ -175,11 +174,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool fast = !atomic_out && beta == 0.f && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(cwarp + n0) & 15) == 0);
       if (fast) {
         // coalesced path: 32-column chunks through this warp's padded smem staging buffer
-        float* stage = reinterpret_cast<float*>(smem + L::kStageOut) + q * (32 * 36);
+        float* stage = stage_out + q * (32 * 36);
         const int rows_valid = M - (m0 + q * 32);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-          const int cols_valid = N - (n0 + c0);
+          const int cols_valid = min(N - (n0 + c0), BN - c0);
           if (cols_valid <= 0) break;   // warp-uniform
           float* dst = cwarp + n0 + c0;
           tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
@@ -254,14 +253,17 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
-template <typename T, int BN, bool A_MN, bool B_MN>
-int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+template <typename T, bool A_MN, bool B_MN>
+int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
               int relu, float alpha, float beta, int splits, cudaStream_t stream, int nbatch = 1, int a_step = 0, int b_step = 0,
               int64_t c_bstride = 0) {
   using E = Elem<T>;
-  constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
-  using L = SmemLayout<BN, STAGES>;
   constexpr int BK = E::kPerRow;
+  TFB_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && (!B_MN || BN % E::kPerRow == 0));
+  const int stage_bytes = kABytes + BN * 128;
+  int stages = (kSmemMax - kSmemFixed) / stage_bytes;
+  if (stages > 8) stages = 8;
+  const int smem_total = stages * stage_bytes + kSmemFixed;
   CUtensorMap ma, mb;
   bool ok;
   const int64_t Mext = (int64_t)(nbatch - 1) * a_step + M, Next = (int64_t)(nbatch - 1) * b_step + N;   // extents of the shared maps
@@ -289,10 +291,10 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
       }
     } else if (beta != 1.f) { tfb_set_last_error("split-K needs beta in {0,1}"); return TFB_ERR_ARG; }
   }
-  auto kern = gemm_tc_kernel<T, BN, A_MN, B_MN, STAGES>;
+  auto kern = gemm_tc_kernel<T, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) {
       tfb_set_last_error("cudaFuncSetAttribute(smem) failed");
       return TFB_ERR_DRIVER;
     }
@@ -302,21 +304,45 @@ int launch_tc(int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t 
   const int64_t total = (int64_t)tiles_m * tiles_n * splits * nbatch;
   if (total > 0x7fffffff) { tfb_set_last_error("too many tiles"); return TFB_ERR_ARG; }
   const int grid = (int)(total < tfb_num_sms() ? total : tfb_num_sms());
-  kern<<<grid, 192, L::kTotal, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
-                                         b_step, c_bstride, tiles_m, tiles_n, (int)total);
+  kern<<<grid, 192, smem_total, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
+                                          b_step, c_bstride, tiles_m, tiles_n, (int)total, BN, stages);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
-template <typename T, int BN>
-int dispatch_major(int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
+template <typename T>
+int dispatch_major(int BN, int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
                    int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream) {
   // BLAS-style flags: op(A)[m][k] = transA ? A[k*lda+m] : A[m*lda+k];  op(B)[k][n] = transB ? B[n*ldb+k] : B[k*ldb+n]
   const bool a_mn = transA != 0, b_mn = transB == 0;
-  if (!a_mn && !b_mn) return launch_tc<T, BN, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  if (!a_mn && b_mn)  return launch_tc<T, BN, false, true>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  if (a_mn && b_mn)   return launch_tc<T, BN, true, true>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  return launch_tc<T, BN, true, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (!a_mn && !b_mn) return launch_tc<T, false, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (!a_mn && b_mn)  return launch_tc<T, false, true>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (a_mn && b_mn)   return launch_tc<T, true, true>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return launch_tc<T, true, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+}
+
+// Tile width for a [M, N] output with `zs` independent K-splits / batches. The kernel is bound by the bytes each CTA pulls from L2
+// per k-block ((128 + BN) * 128 B against ~42 B/clk per SM), so the cost of a tile is ~ (128 + BN) plus a fixed prologue / epilogue
+// share; the persistent grid runs ceil(tiles / SMs) waves. step = 16 (K-major B) or 64 (MN-major B: whole 128-byte swizzle rows).
+int pick_bn(int M, int N, int zs, int step) {
+  static int force_bn = -1, model_c = -2;
+  if (force_bn < 0) { const char* e = getenv("TFB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+  if (model_c == -2) { const char* e = getenv("TFB_GEMM_TILE_MODEL"); model_c = e ? atoi(e) : 64; }
+  const int nmax = ((N + step - 1) / step) * step;                 // one tile covers all of N
+  if (force_bn > 0) { int bn = ((force_bn + step - 1) / step) * step; if (bn > 256) bn = 256; return bn < nmax ? bn : (nmax > 256 ? 256 : nmax); }
+  const int64_t mt = (M + BM - 1) / BM;
+  const int sms = tfb_num_sms();
+  int best_bn = 0;
+  int64_t best = -1;
+  for (int bn = step < 32 ? 32 : step; bn <= 256; bn += step) {
+    const int use = bn < nmax ? bn : nmax;                         // never wider than the problem
+    if (use > 256) continue;
+    const int64_t tiles = mt * ((N + use - 1) / use) * zs;
+    const int64_t cost = ((tiles + sms - 1) / sms) * (128 + use + model_c);
+    if (best < 0 || cost < best || (cost == best && use > best_bn)) { best = cost; best_bn = use; }
+    if (use == nmax) break;
+  }
+  return best_bn;
 }
 
 template <typename T>
@@ -326,40 +352,10 @@ int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t
   // TMA: 16-byte aligned bases and leading dimensions.
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
   TFB_REQUIRE((lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0);
-  if (N <= 64) return dispatch_major<T, 64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  // 128x256 tiles when they still fill the chip (or when 128x128 would need a nearly empty second wave)
-  static int force_bn = -1;
-  if (force_bn < 0) { const char* e = getenv("TFB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
-  const int64_t mt = (M + BM - 1) / BM;
-  const int64_t t128 = mt * ((N + 127) / 128) * (splits > 0 ? splits : 1), t256 = mt * ((N + 255) / 256) * (splits > 0 ? splits : 1);
-  const int sms = tfb_num_sms();
-  // Experiment switches (not the default path): TFB_GEMM_BN=64|192 forces those tile widths; TFB_GEMM_TILE_MODEL=<c> picks the
-  // width in {64,128,192,256} that minimises waves(BN) * (BN + c): full waves of the persistent grid times a per-tile cost of
-  // BN columns plus a fixed overhead of c column-equivalents (M = 1740 token GEMMs lose up to half a wave to quantisation).
-  static int model_c = -2;
-  if (model_c == -2) { const char* e = getenv("TFB_GEMM_TILE_MODEL"); model_c = e ? atoi(e) : -1; }
-  int pick = 0;
-  if (force_bn == 64 || force_bn == 192) pick = force_bn;
-  if (model_c >= 0 && force_bn == 0) {
-    int64_t best = -1;
-    const int cand[4] = {64, 128, 192, 256};
-    for (int i = 0; i < 4; ++i) {
-      const int bn = cand[i];
-      if (bn > 64 && bn - 64 >= N) continue;                      // wider than the problem by a whole 64-column step
-      const int64_t tiles = mt * ((N + bn - 1) / bn) * (splits > 0 ? splits : 1);
-      const int64_t cost = ((tiles + sms - 1) / sms) * (bn + model_c);
-      if (best < 0 || cost <= best) { best = cost; pick = bn; }
-    }
-  }
-  if (pick == 64) return dispatch_major<T, 64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  if (pick == 192 && N > 128) return dispatch_major<T, 192>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  if (pick == 128) return dispatch_major<T, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  if (pick == 256 && N >= 256) return dispatch_major<T, 256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  bool use256 = N >= 256 && (t256 >= sms || (t128 > sms && t128 < 2 * sms && t256 <= sms));
-  if (force_bn == 128) use256 = false;
-  if (force_bn == 256 && N >= 256) use256 = true;
-  if (use256) return dispatch_major<T, 256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  return dispatch_major<T, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  const int step = transB == 0 ? Elem<T>::kPerRow : 16;
+  const int num_kb = (K + Elem<T>::kPerRow - 1) / Elem<T>::kPerRow;
+  const int zs = splits < 1 ? 1 : (splits > num_kb ? num_kb : splits);
+  return dispatch_major<T>(pick_bn(M, N, zs, step), transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
 }
 
 }  // namespace
@@ -374,8 +370,9 @@ TFB_API int tfb_gemm_bf16_tc_wgrad_batched(int M, int N, int K, const void* A, i
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
   TFB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_step % 8 == 0 && b_step % 8 == 0);
   using T = __nv_bfloat16;
-  if (N <= 64) return launch_tc<T, 64, true, true>(M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
-  return launch_tc<T, 128, true, true>(M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
+  const int num_kb = (K + 63) / 64;
+  const int zs = (splits < 1 ? 1 : (splits > num_kb ? num_kb : splits)) * nbatch;
+  return launch_tc<T, true, true>(pick_bn(M, N, zs, 64), M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
 }
 
 // TF32 operands straight from fp32 storage (kind::tf32). Only the K-major x K-major case (y = x W^T) is wired up: MN-major
@@ -386,8 +383,7 @@ TFB_API int tfb_gemm_tf32_tc(int transA, int transB, int M, int N, int K, const 
   TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
   if (transA || !transB) { tfb_set_last_error("tfb_gemm_tf32_tc: only transA=0, transB=1 is supported"); return TFB_ERR_UNSUPPORTED; }
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && lda % 4 == 0 && ldb % 4 == 0);
-  if (N <= 64) return launch_tc<float, 64, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
-  return launch_tc<float, 128, false, false>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return launch_tc<float, false, false>(pick_bn(M, N, 1, 16), M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
 }
 
 TFB_API int tfb_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,

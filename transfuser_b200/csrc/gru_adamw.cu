@@ -128,9 +128,12 @@ gru_bwd_kernel(const float* __restrict__ d_wp, const float* __restrict__ save, c
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, double lr,
              double beta1, double beta2, float eps, double wd, int step_host, float grad_scale, __nv_bfloat16* __restrict__ p_bf16,
-             int zero_grad, const int* __restrict__ step_dev) {
+             int zero_grad, const int* __restrict__ step_dev, const double* __restrict__ hp_dev) {
   // step count in device memory when given (valid under CUDA-graph replay), else the host's
   const double t = step_dev ? (double)(*step_dev) : (double)step_host;
+  // hyper-parameters in device memory when given ([lr, beta1, beta2, eps, weight_decay]): a learning-rate schedule (train.py:194-199)
+  // then takes effect inside a replayed CUDA graph, where the host scalars are frozen at capture time
+  if (hp_dev) { lr = hp_dev[0]; beta1 = hp_dev[1]; beta2 = hp_dev[2]; eps = (float)hp_dev[3]; wd = hp_dev[4]; }
   const float step = (float)(lr / (1.0 - pow(beta1, t)));
   const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, t));
   const float decay = (float)(1.0 - lr * wd);
@@ -200,13 +203,14 @@ TFB_API int tfb_gru_bwd(const float* d_wp, const float* save, const float* w_ih,
 
 // zero_grad != 0: the gradient buffer is cleared in the same pass. step_dev (optional): optimizer step count in device memory
 // (incremented by tfb_step_tick) — used instead of `step`, so a captured CUDA graph stays valid across replays.
+// hp_dev (optional): [lr, beta1, beta2, eps, weight_decay] as doubles in device memory, used instead of the scalar arguments.
 TFB_API int tfb_adamw_step(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
                            double weight_decay, int step, const int* step_dev, float grad_scale, void* p_bf16, int zero_grad,
-                           cudaStream_t stream) {
+                           const double* hp_dev, cudaStream_t stream) {
   TFB_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev));
   if (n == 0) return TFB_OK;
   adamw_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, (float)eps, weight_decay, step, grad_scale,
-                                                              (__nv_bfloat16*)p_bf16, zero_grad, step_dev);
+                                                              (__nv_bfloat16*)p_bf16, zero_grad, step_dev, hp_dev);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

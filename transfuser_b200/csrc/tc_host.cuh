@@ -23,13 +23,15 @@ inline EncodeTiledFn get_encode() {
 }
 
 // rank-R map; dims / box innermost first; strides_bytes has R-1 entries (dim 0 is contiguous). OOB elements read as zero.
+// elem_strides (optional): traversal step per dimension; the box extents are in traversal units, so a box of extent b with step s
+// delivers ceil(b / s) elements of that dimension to shared memory (a stride-2 convolution reads every other pixel this way).
 inline bool make_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t d[5], s[4];
   cuuint32_t b[5], e[5];
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   return enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

@@ -104,6 +104,13 @@ class LidarCenterNet(nn.Module):
             raise RuntimeError('PointPillars is out of scope (config.py:42 default False)')
         if not self.gru_concat_target_point:
             raise RuntimeError('gru_concat_target_point=False is not implemented (config.py:31 default True)')
+        # sizes the kernels hard-code (csrc/losses.cu: 12 yaw bins / 21 head channels; csrc/gru_adamw.cu: hidden size 64, 4 + 64 inputs)
+        if config.num_dir_bins != 12:
+            raise RuntimeError('num_dir_bins=%r is not implemented (the CenterNet loss kernels assume config.py default 12)' % (config.num_dir_bins,))
+        if config.gru_hidden_size != 64:
+            raise RuntimeError('gru_hidden_size=%r is not implemented (the GRU kernels assume config.py default 64)' % (config.gru_hidden_size,))
+        if getattr(config, 'n_scale', 4) != 4:
+            raise RuntimeError('n_scale=%r is not implemented (config.py default 4)' % (config.n_scale,))
         self.backbone = backbone
         if backbone == 'transFuser':
             self._model = TransfuserBackbone(config, image_architecture, lidar_architecture, use_velocity=use_velocity).to(self.device)

@@ -60,6 +60,9 @@ QKV_FUSED = os.environ.get('TFB_QKV_FUSED', '1') == '1'           # one q|k|v GE
 BN_ADD_FUSED = os.environ.get('TFB_BN_ADD_FUSED', '1') == '1'     # conv3.bn + shortcut add + ReLU as one BatchNorm call
 SE_POOL_FUSED = os.environ.get('TFB_SE_POOL_FUSED', '1') == '1'   # SE average pool inside the preceding BatchNorm's pass
 SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
+CONV_S2_TC = os.environ.get('TFB_CONV_S2_TC', '1') == '1'       # bf16 mode: stride-2 3x3 convs forward on the tcgen05 kernel (TMA element strides)
+WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: weight-gradient GEMMs on a third stream (they only feed AdamW)
+ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
 def _emit16(x, want):
@@ -71,7 +74,7 @@ def _emit16(x, want):
 
 def _attach16(y, y16):
     if y16 is not None:
-        y._tfb16 = y16
+        y._tfb16, y._tfb16v = y16, y._version       # version stamp: an in-place edit of y afterwards invalidates the sidecar (_as16)
     return y
 
 
@@ -149,6 +152,49 @@ def join_side_streams():
 
 
 
+_JOIN_QUEUED = [False]
+
+
+def _join_after_backward():
+    _JOIN_QUEUED[0] = False
+    join_side_streams()
+
+
+class _OnWgradStream:
+    """`with _OnWgradStream(dev, t1, t2, ...):` — runs the enclosed launches on the weight-gradient stream. Weight gradients feed
+    nothing but the optimizer, so their GEMMs (split-K, a few dozen CTAs each) need not sit on the critical dx chain: they run next
+    to it and are joined (join_side_streams) before the gradient all-reduce / AdamW. The listed tensors are the ones the launches
+    read or write; record_stream keeps the caching allocator from recycling them while the side stream still uses them."""
+
+    def __init__(self, device, *tensors):
+        self.on = WGRAD_STREAM and G.MODE == 'bf16' and torch.device(device).type == 'cuda'
+        self.device, self.tensors = device, tensors
+
+    def __enter__(self):
+        if self.on:
+            device = torch.device(self.device)
+            if not _JOIN_QUEUED[0] and torch._C._current_graph_task_id() != -1:
+                # inside a backward pass: make the caller's stream wait for the side streams when this backward() returns
+                _JOIN_QUEUED[0] = True
+                torch.autograd.Variable._execution_engine.queue_callback(_join_after_backward)
+            key = ('wgrad', device)
+            s = _SIDE.get(key)
+            if s is None:
+                s = _SIDE[key] = torch.cuda.Stream(device=device)
+            s.wait_stream(torch.cuda.current_stream(device))
+            for t in self.tensors:
+                if t is not None:
+                    t.record_stream(s)
+            self.ctx = torch.cuda.stream(s)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _ws(device):
     """The per-device reduction workspace (fp64 sums + arrival counter) shared by every BatchNorm / bias-gradient reduction:
     the kernels require it to be zero on entry and leave it zero on exit (last-block finalisation), so it is zeroed only once."""
@@ -167,7 +213,9 @@ def _gbuf(p):
     info = getattr(p, '_tfb_flat', None)
     if info is not None and p.grad is None:
         fp, off = info
-        return fp.grad[off:off + p.numel()].view(p.shape)
+        if off not in fp.taken:                      # a second producer in the same backward (shared parameter) must not overwrite
+            fp.taken.add(off)                        # the first one's result: it gets a fresh buffer and autograd adds the two
+            return fp.grad[off:off + p.numel()].view(p.shape)
     return torch.empty(p.shape, dtype=torch.float32, device=p.device)
 
 
@@ -191,8 +239,10 @@ def _gbuf3(pq, pk, pv):
     infos = [getattr(p, '_tfb_flat', None) for p in (pq, pk, pv)]
     n = pq.numel()
     if all(i is not None for i in infos) and all(p.grad is None for p in (pq, pk, pv)) \
-            and infos[1][1] == infos[0][1] + n and infos[2][1] == infos[1][1] + n:
+            and infos[1][1] == infos[0][1] + n and infos[2][1] == infos[1][1] + n \
+            and not any(i[1] in infos[0][0].taken for i in infos):
         fp, off = infos[0]
+        fp.taken.update(i[1] for i in infos)
         return fp.grad[off:off + 3 * n].view((3 * pq.shape[0],) + tuple(pq.shape[1:]))
     return torch.empty((3 * pq.shape[0],) + tuple(pq.shape[1:]), dtype=torch.float32, device=pq.device)
 
@@ -287,7 +337,8 @@ class LinearFn(Function):
         if ctx.needs_input_grad[1]:
             dw = _gbuf(w)
             if ctx.tc:
-                G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
+                with _OnWgradStream(dy.device, gb, xs, dw):
+                    G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
             elif M >= 4096:
                 # long contraction, narrow output (head 1x1 convs): the pixel-split direct-conv wgrad kernel (k = 1)
                 call('tfb_conv2d_wgrad', xs, g, dw, None, 1, M, 1, K, N, 1, 1, 1)
@@ -311,8 +362,13 @@ class Conv2dFn(Function):
         N, H, W, Cin = x.shape
         Cout, ks = w.shape[0], w.shape[2]
         Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
-        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
-        call('tfb_conv2d_fwd', x, w, bias, y, N, H, W, Cin, Cout, ks, stride, groups, int(relu))
+        plan = _conv_tc_plan(Cin, Cout, groups) if (G.MODE == 'bf16' and CONV_S2_TC and ks == 3 and stride == 2) else None
+        if plan is not None:
+            # stride 2 on the tensor cores: same implicit-GEMM kernel, the TMA map steps two pixels per box element
+            y = _conv_tc_run(_as16(x), w, bias, plan, 0, Cout, groups, relu, stride=2)
+        else:
+            y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+            call('tfb_conv2d_fwd', x, w, bias, y, N, H, W, Cin, Cout, ks, stride, groups, int(relu))
         ctx.save_for_backward(x, w, y if relu else None, bias)
         ctx.cfg = (N, H, W, Cin, Cout, ks, stride, groups, relu, bias is not None)
         return y
@@ -434,16 +490,20 @@ def _prepack_all(device):
         e.epoch, e.version = _PACK_STATE['epoch'], w._version
 
 
-def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu):
+def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu, stride=1):
     N, H, W, c_read = x16.shape
     Cout, Cin = (w.shape[0], w.shape[1] * groups)
     e = _packed_weights(w, plan, mode, groups)
     if not (PACK_BATCHED and e.epoch == _PACK_STATE['epoch'] and e.version == w._version):
         call('tfb_conv3x3_pack_weights', w, e.wp, Cout, Cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'],
              plan['nb_real'], plan['gblocks'])
-    y = torch.empty((N, H, W, c_write), dtype=torch.float32, device=x16.device)
-    call('tfb_conv3x3_tc', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
-         plan['gblocks'], int(relu))
+    y = torch.empty((N, (H - 1) // stride + 1, (W - 1) // stride + 1, c_write), dtype=torch.float32, device=x16.device)
+    if stride == 1:
+        call('tfb_conv3x3_tc', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
+             plan['gblocks'], int(relu))
+    else:
+        call('tfb_conv3x3_tc_strided', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'],
+             plan['nb_real'], plan['gblocks'], int(relu), stride)
     return y
 
 
@@ -472,26 +532,27 @@ def _conv_wgrad_tc(x, g16, w, groups, stride):
     M = N * Ho * Wo
     # the seven CenterNet heads and the BEV head all convolve the same p2 map: its im2col matrix is built once per backward
     key = (x.data_ptr(), tuple(x.shape), stride, groups)
-    hit = _COL_CACHE.get(key)
-    if hit is not None and hit[2] == x._version:          # (the entry pins the input it was built from: the address cannot be reused)
-        col = hit[1]
-    else:
-        col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
-        call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
-        if col.numel() * 2 <= (128 << 20):                # small maps only (p2: 47 MB); the 160x704 decoder maps are not shared anyway
-            if len(_COL_CACHE) >= 2:
-                _COL_CACHE.pop(next(iter(_COL_CACHE)))
-            _COL_CACHE[key] = (x, col, x._version)
     ldg = g16.shape[-1]                      # > Cout when dy was zero-padded to 8 channels (the 7- / 1-channel decoder outputs)
     rows = max(Cout, ldg) if groups == 1 else Cout
     dw = _gbuf(w)
-    dwp = dw.view(Cout, 9 * Cig) if rows == Cout else torch.empty((rows, 9 * Cig), dtype=torch.float32, device=x.device)
-    ntiles = groups * ((9 * Cig + 127) // 128)
-    splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
-    call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else rows, 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
-         9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
-    if rows != Cout:
-        call('tfb_scale_dev', dwp, None, 1.0, dw, Cout * 9 * Cig, 0)      # the first Cout rows are the gradient; the rest is padding
+    with _OnWgradStream(x.device, x, g16, dw):
+        hit = _COL_CACHE.get(key)
+        if hit is not None and hit[2] == x._version:          # (the entry pins the input it was built from: the address cannot be reused)
+            col = hit[1]
+        else:
+            col = torch.empty((M, 9 * Cin), dtype=torch.bfloat16, device=x.device)
+            call('tfb_im2col3x3_bf16', x, col, N, H, W, Cin, stride, groups)
+            if col.numel() * 2 <= (128 << 20):                # small maps only (p2: 47 MB); the 160x704 decoder maps are not shared anyway
+                if len(_COL_CACHE) >= 2:
+                    _COL_CACHE.pop(next(iter(_COL_CACHE)))
+                _COL_CACHE[key] = (x, col, x._version)
+        dwp = dw.view(Cout, 9 * Cig) if rows == Cout else torch.empty((rows, 9 * Cig), dtype=torch.float32, device=x.device)
+        ntiles = groups * ((9 * Cig + 127) // 128)
+        splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
+        call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else rows, 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
+             9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
+        if rows != Cout:
+            call('tfb_scale_dev', dwp, None, 1.0, dw, Cout * 9 * Cig, 0)      # the first Cout rows are the gradient; the rest is padding
     return dw
 
 
@@ -889,36 +950,53 @@ class AttentionFn(Function):
                     G.gemm_bf16(hs_, G.weight_bf16(w_), qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_)
                 else:
                     gemm(h, w_, qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_, mode='simt')
+        scale = 1.0 / (hs ** 0.5)
+        fused = tc and ATTN_FUSED and T <= 192 and hs % 2 == 0
+        if fused:
+            # one launch: scores in TMEM, softmax on the TMEM lanes, probabilities through shared memory (csrc/attn_tc.cu)
+            y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
+            y16 = _emit16(y, True)                           # the output feeds the proj GEMM
+            lse = torch.empty((B, nh, T), dtype=torch.float32, device=dev)
+            call('tfb_attn_fwd_tc', qkv, 0, B, T, nh, hs, y, y16, lse, scale, float(p_drop), seed_state(dev), seed)
+            ctx.save_for_backward(hs_, wq, wk, wv, qkv, y, lse, bq, bk, bv)
+            ctx.cfg = (B, T, nh, p_drop, seed, scale, tc, packed, True)
+            return _attach16(y, y16)
         S = torch.empty((B, nh, T, T), dtype=torch.float32, device=dev)
         q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         bgemm(q, k, S, T, T, hs, 3 * C, 3 * C, T, False, True, B, nh, (T * 3 * C, hs), (T * 3 * C, hs), (nh * T * T, T * T))
-        scale = 1.0 / (hs ** 0.5)
         Pd = torch.empty_like(S) if p_drop > 0 else S
         call('tfb_softmax_fwd', S, S, Pd, B * nh * T, T, scale, float(p_drop), seed_state(dev), seed)
         y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         bgemm(Pd, v, y, T, hs, T, T, 3 * C, C, False, False, B, nh, (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs))
         ctx.save_for_backward(hs_, wq, wk, wv, qkv, S, Pd, bq, bk, bv)
-        ctx.cfg = (B, T, nh, p_drop, seed, scale, tc, packed)
+        ctx.cfg = (B, T, nh, p_drop, seed, scale, tc, packed, False)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         h, wq, wk, wv, qkv, P, Pd, bq, bk, bv = ctx.saved_tensors
-        B, T, nh, p_drop, seed, scale, tc, packed = ctx.cfg
+        B, T, nh, p_drop, seed, scale, tc, packed, fused = ctx.cfg
         dy = _c(dy)
         C = h.shape[1]
         hs = C // nh
         dev = h.device
-        q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         dqkv = torch.empty_like(qkv)
         dq, dk, dv = dqkv[:, 0:C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
-        sP, sQ, sY = (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs)
-        dP = torch.empty_like(P)
-        bgemm(dy, v, dP, T, T, hs, C, 3 * C, T, False, True, B, nh, sY, sQ, sP)          # dPd = dy v^T
-        bgemm(Pd, dy, dv, T, hs, T, T, C, 3 * C, True, False, B, nh, sP, sY, sQ)         # dv  = Pd^T dy
-        call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed_state(dev), seed)    # dS (in place)
-        bgemm(dP, k, dq, T, hs, T, T, 3 * C, 3 * C, False, False, B, nh, sP, sQ, sQ)     # dq  = dS k
-        bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
+        d16 = None
+        if fused:
+            y, lse = P, Pd                                   # (saved in their place by the fused forward)
+            d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dev)
+            dsum = torch.empty((B, nh, T), dtype=torch.float32, device=dev)
+            call('tfb_attn_bwd_tc', qkv, 0, dy, 0, dy, y, lse, dsum, B, T, nh, hs, dqkv, d16, scale, float(p_drop), seed_state(dev), seed)
+        else:
+            q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+            sP, sQ, sY = (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs)
+            dP = torch.empty_like(P)
+            bgemm(dy, v, dP, T, T, hs, C, 3 * C, T, False, True, B, nh, sY, sQ, sP)          # dPd = dy v^T
+            bgemm(Pd, dy, dv, T, hs, T, T, C, 3 * C, True, False, B, nh, sP, sY, sQ)         # dv  = Pd^T dy
+            call('tfb_softmax_bwd', P, dP, dP, B * nh * T, T, scale, float(p_drop), seed_state(dev), seed)    # dS (in place)
+            bgemm(dP, k, dq, T, hs, T, T, 3 * C, 3 * C, False, False, B, nh, sP, sQ, sQ)     # dq  = dS k
+            bgemm(dP, q, dk, T, hs, T, T, 3 * C, 3 * C, True, False, B, nh, sP, sQ, sQ)      # dk  = dS^T q
         dh = torch.empty((B * T, C), dtype=torch.float32, device=dev)
         grads = []
         w3 = _pack3(wq, wk, wv) if packed else None
@@ -926,11 +1004,15 @@ class AttentionFn(Function):
             # fused q|k|v: dh = dqkv W3 (one GEMM, K = 3C), dW3 = dqkv^T h (one GEMM), db3 = column sums of dqkv (one reduction)
             dw3, db3 = _gbuf3(wq, wk, wv), _gbuf3(bq, bk, bv)
             if tc:
-                # one pass over dqkv: its bf16 copy (operand of both GEMMs) and the three bias gradients (column sums)
-                d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dev)
-                call('tfb_grad_prep', dqkv, None, None, d16, db3, _ws(dev), B * T, 3 * C)
+                if d16 is not None:
+                    _colsum(dqkv, db3)                       # the fused attention backward wrote the bf16 copy itself
+                else:
+                    # one pass over dqkv: its bf16 copy (operand of both GEMMs) and the three bias gradients (column sums)
+                    d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dev)
+                    call('tfb_grad_prep', dqkv, None, None, d16, db3, _ws(dev), B * T, 3 * C)
                 G.gemm_bf16(d16, G.weight_bf16(w3), dh, trans_b=False)
-                G.gemm_bf16(d16, h, dw3, trans_a=True, splits=_wgrad_splits(B * T, 3 * C, C))
+                with _OnWgradStream(dev, d16, h, dw3):
+                    G.gemm_bf16(d16, h, dw3, trans_a=True, splits=_wgrad_splits(B * T, 3 * C, C))
             else:
                 gemm(dqkv, w3, dh, trans_b=False, mode='simt')
                 gemm(dqkv, h, dw3, trans_a=True, mode='simt')
@@ -938,7 +1020,8 @@ class AttentionFn(Function):
             for i in range(3):
                 grads += [dw3[i * C:(i + 1) * C], db3[i * C:(i + 1) * C]]
         elif tc:
-            d16 = G.to_bf16(dqkv)
+            if d16 is None:
+                d16 = G.to_bf16(dqkv)
             for i, w_ in enumerate((wq, wk, wv)):
                 G.gemm_bf16(d16[:, i * C:(i + 1) * C], G.weight_bf16(w_), dh, trans_b=False, beta=0.0 if i == 0 else 1.0)
             for i, (d, w_, b_) in enumerate(((dq, wq, bq), (dk, wk, bk), (dv, wv, bv))):

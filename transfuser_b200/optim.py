@@ -72,14 +72,16 @@ class FlatParams:
             p.grad = None
             p._tfb_flat = (self, o)
         self.bf16 = None
+        self.taken = set()        # offsets whose gradient span was handed to a backward kernel in the current step (ops._gbuf)
 
     def set_grads_to_none(self):
         """zero_grad(set_to_none=True): with .grad None the backward kernels write each gradient straight into its span of
         the flat buffer (ops._gbuf) and autograd adopts that view as p.grad — no accumulate / copy kernels."""
         for p in self.params:
             p.grad = None
+        self.taken.clear()
 
-    def gather_stragglers(self):
+    def gather_stragglers(self, reduced=False):
         """Before the optimizer reads the flat gradient buffer: a parameter whose .grad is not its flat view (accumulated by
         autograd into a fresh tensor) is copied in; a parameter that received no gradient is zeroed. Returns the (offset,
         padded length) spans of the parameters without a gradient: torch.optim.AdamW leaves those untouched (no weight decay,
@@ -92,6 +94,11 @@ class FlatParams:
                 self.grad[o:o + p.numel()].zero_()
                 no_grad.append((o, ln))
             elif g.data_ptr() != base + 4 * o:
+                if reduced:
+                    # the data-parallel all-reduce of this span was launched from the backward hooks and has already read (or is
+                    # reading) the flat buffer: copying now would update this parameter with the local, unreduced gradient
+                    raise RuntimeError('gradient of a %s parameter was not written into the flat buffer (ops._gbuf) before the '
+                                       'gradient all-reduce' % (tuple(p.shape),))
                 self.grad[o:o + p.numel()].copy_(g.reshape(-1))
         return no_grad
 
@@ -128,6 +135,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._flat = None
         self._m = self._v = None
         self._step_dev = None
+        self._hp_dev = None       # [lr, beta1, beta2, eps, weight_decay] in device memory: read by the kernel, so a schedule that edits
+        self._hp_host = None      # param_groups keeps working under CUDA-graph replay (sync_hparams() before every launch / replay)
         self.check_grads = True   # set False once the producer set is known to be complete (saves a Python sweep per step)
         self._no_grad_spans = []  # parameters that never receive a gradient (as found by the last checked step)
 
@@ -141,7 +150,24 @@ class FusedAdamW(torch.optim.Optimizer):
             self._m = torch.zeros_like(self._flat.flat)
             self._v = torch.zeros_like(self._flat.flat)
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=self._flat.flat.device)
+            self._hp_dev = torch.zeros(5, dtype=torch.float64, device=self._flat.flat.device)
         return self._flat
+
+    def sync_hparams(self):
+        """Uploads lr / betas / eps / weight_decay of param_groups[0] to the device scalars the kernel reads, when they changed.
+        (A plain copy_ from a host tensor: legal outside graph capture only — Trainer.replay() calls this before each replay.)"""
+        self._flat_of()
+        g = self.param_groups[0]
+        hp = (float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']), float(g['weight_decay']))
+        if hp != self._hp_host:
+            if self._hp_dev.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('optimizer hyper-parameters changed during CUDA-graph capture')
+            self._hp_dev.copy_(torch.tensor(hp, dtype=torch.float64))
+            self._hp_host = hp
+
+    def step_count(self):
+        """Optimizer steps taken so far: the device-side counter (the only one that advances under CUDA-graph replay)."""
+        return int(self._step_dev.item()) if self._step_dev is not None else self._step
 
     def zero_grad(self, set_to_none=True):
         self._flat_of().set_grads_to_none()
@@ -149,9 +175,11 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, chunks=None):
         fp = self._flat_of()
+        ops_mod.join_side_streams()       # weight gradients are produced on side streams (ops._OnWgradStream, the LiDAR branch)
         if self.check_grads:
-            self._no_grad_spans = fp.gather_stragglers()
+            self._no_grad_spans = fp.gather_stragglers(reduced=chunks is not None and any(w is not None for _, _, w in chunks))
         g = self.param_groups[0]
+        self.sync_hparams()
         self._step += 1
         _lib.call('tfb_step_tick', None, self._step_dev)   # device-side step count: valid under CUDA-graph replay
         ops_mod.invalidate_packs()                         # the kernel below rewrites the weights without bumping tensor versions
@@ -163,7 +191,7 @@ class FusedAdamW(torch.optim.Optimizer):
             for a, b in (subtract_spans(lo, hi, self._no_grad_spans) if self._no_grad_spans else [(lo, hi)]):
                 bf = fp.bf16[a:b] if fp.bf16 is not None else None
                 _lib.call('tfb_adamw_step', fp.flat[a:b], fp.grad[a:b], self._m[a:b], self._v[a:b], b - a, float(g['lr']), float(b1),
-                          float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0)
+                          float(b2), float(g['eps']), float(g['weight_decay']), self._step, self._step_dev, float(self.grad_scale), bf, 0, self._hp_dev)
 
 
     # ---- torch.optim.AdamW-compatible (de)serialisation: the reference saves / resumes optimizer_%d.pth (train.py:183, 384)
@@ -174,10 +202,11 @@ class FusedAdamW(torch.optim.Optimizer):
         ps = [p for g in self.param_groups for p in g['params']]
         off = {id(p): o for p, o in zip(fp.params, fp.offsets)}
         state = {}
-        if self._step > 0:
+        step = self.step_count()
+        if step > 0:
             for i, p in enumerate(ps):
                 o, n = off[id(p)], p.numel()
-                state[i] = dict(step=torch.tensor(float(self._step)),
+                state[i] = dict(step=torch.tensor(float(step)),
                                 exp_avg=self._m[o:o + n].view(p.shape).clone(), exp_avg_sq=self._v[o:o + n].view(p.shape).clone())
         groups, start = [], 0
         for g in self.param_groups:

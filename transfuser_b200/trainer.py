@@ -22,6 +22,13 @@ class Trainer:
         ops.manual_seed(1234 + seed)
         self.net = LidarCenterNet(cfg, device, backbone, 'regnety_032', 'regnety_032', use_velocity=False).train()
         self.flat = optim.flatten(self.net)
+        if self.world > 1:
+            # replicas start identical whatever the caller's RNG state: rank 0's parameters and buffers win (DDP does the same at
+            # construction, train.py:134)
+            dist.broadcast(self.flat.flat, 0)
+            for buf in self.net.buffers():
+                if buf.is_floating_point() or buf.dtype == torch.int64:
+                    dist.broadcast(buf, 0)
         if gemm_mode == 'bf16':
             gemm.attach_bf16_weights(self.flat)
         self.opt = optim.FusedAdamW(self.net.parameters(), lr=lr, grad_scale=1.0 / self.world)
@@ -79,6 +86,7 @@ class Trainer:
             self.static[k].copy_(batch[k], non_blocking=True)
 
     def replay(self):
+        self.opt.sync_hparams()       # lr / weight-decay edits of param_groups reach the captured AdamW kernel through device scalars
         self.graph.replay()
         ops.invalidate_packs()        # the replayed optimizer kernel changed the weights behind Python's back
         return self.static_loss
