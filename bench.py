@@ -20,6 +20,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE_TRAIN = 230.3e9   # 3 x 76.8 GFLOP forward (2*MAC)
+# BASELINE.json configs[1..4] -> (backbone, per-GPU batch, algorithmic train-step GFLOP per sample, label)
+CONFIGS = {2: ('transFuser', 10, 230.3e9, 'TransFuser RegNetY-3.2GF'), 3: ('transFuser', 12, 230.3e9, 'TransFuser RegNetY-3.2GF + all aux heads'),
+           4: ('geometric_fusion', 12, 109.1e9, 'GeometricFusion'), 5: ('late_fusion', 16, 93.1e9, 'LateFusion (conv-only)')}
 METRIC = 'training samples/sec (RGB+LiDAR pairs)'
 
 
@@ -63,10 +66,12 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def make_host_batch(B, seed, torch, np):
+def make_host_batch(B, seed, torch, np, backbone='transFuser'):
     """Synthetic inputs of SURVEY.md §8(d) in PINNED host memory (the e2e arm copies them every step)."""
     from oracle import bev_oracle, torch_oracle as O
     b = O.synthetic_batch(B, seed=seed)
+    if backbone == 'geometric_fusion':
+        b['bev_points'], b['cam_points'] = O.synthetic_correspondences(B, seed=seed)
     pts = np.stack([bev_oracle.synthetic_points(40000, 1000 * seed + i, np.float32, edge_cases=False) for i in range(B)])
     b['points'] = torch.from_numpy(pts)
     del b['lidar']
@@ -87,11 +92,12 @@ def run_b200(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's version / debug banner must not land on stdout (one JSON line)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
-    B = args.batch
+    backbone, cfg_batch, flop_per_sample, label = CONFIGS[args.config]
+    B = args.batch or cfg_batch
     cfg = TrainConfig()
     torch.manual_seed(0)
-    tr = Trainer(cfg, dev, gemm_mode=args.gemm, lr=1e-4, seed=rank)
-    host = make_host_batch(B, seed=100 + rank, torch=torch, np=np)
+    tr = Trainer(cfg, dev, gemm_mode=args.gemm, lr=1e-4, seed=rank, backbone=backbone)
+    host = make_host_batch(B, seed=100 + rank, torch=torch, np=np, backbone=backbone)
 
     def h2d():
         return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -171,15 +177,15 @@ def run_b200(args):
             'metric': METRIC, 'value': round(value, 3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': round(ms_dev / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.gemm == 'bf16' else 'fp32', 'data': 'synthetic',
-            'config': {'workload': 'TransFuser RegNetY-3.2GF LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
-                                   '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU' % B,
+            'config': {'workload': '%s LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
+                                   '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU (BASELINE configs[%d])' % (label, B, args.config - 1),
                        'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm, 'cuda_graph': tr.graph is not None, 'cuda_graph_error': tr.graph_error,
                        'l2': 'working set (672 MB weights + activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': round(e2e_v, 3), 'unit': 'samples/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
             'gpu_launches': launches, 'clocks': clocks,
-            'step_tensor_roofline': {'achieved_tflops': round(FLOP_PER_SAMPLE_TRAIN * value / 1e12, 2), 'peak_tflops': pk['bf16_tflops_sustained'],
-                                     'frac': round(FLOP_PER_SAMPLE_TRAIN * value / 1e12 / pk['bf16_tflops_sustained'], 4), 'of': how},
+            'step_tensor_roofline': {'achieved_tflops': round(flop_per_sample * value / 1e12, 2), 'peak_tflops': pk['bf16_tflops_sustained'],
+                                     'frac': round(flop_per_sample * value / 1e12 / pk['bf16_tflops_sustained'], 4), 'of': how},
             'roofline': roof,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -281,7 +287,9 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=10, help='samples per GPU (BASELINE configs[1]: 10)')
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS), help='BASELINE.json configs[] entry (1-based): 2 = TransFuser batch 10 '
+                    '(the headline), 3 = TransFuser batch 12, 4 = GeometricFusion batch 12, 5 = LateFusion batch 16')
+    ap.add_argument('--batch', type=int, default=0, help='samples per GPU (default: the batch of --config; configs[1]: 10)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'cpu_baseline'])
     ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

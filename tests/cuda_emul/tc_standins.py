@@ -6,7 +6,7 @@ kernels require (16-byte alignment, leading dimensions % 8) and compute in fp32 
 import torch
 import torch.nn.functional as F
 
-TC_NAMES = ('tfb_gemm_bf16_tc', 'tfb_conv3x3_tc', 'tfb_conv3x3_tc_strided', 'tfb_gemm_bf16_tc_wgrad_batched', 'tfb_attn_fwd_tc', 'tfb_attn_bwd_tc')
+TC_NAMES = ('tfb_gemm_bf16_tc', 'tfb_gemm_bf16_tc_stats', 'tfb_gemm_bf16_tc_out16', 'tfb_conv3x3_tc', 'tfb_conv3x3_tc_strided', 'tfb_gemm_bf16_tc_wgrad_batched', 'tfb_attn_fwd_tc', 'tfb_attn_bwd_tc')
 
 
 def _mat(t, rows, cols, ld):
@@ -28,6 +28,14 @@ def gemm_bf16_tc(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, bet
     out.copy_(r.clamp_min(0) if relu else r)
 
 
+def gemm_bf16_tc_stats(M, N, K, A, lda, B, ldb, C, ldc, stats):
+    gemm_bf16_tc(0, 1, M, N, K, A, lda, B, ldb, C, ldc, None, 0, 1.0, 0.0, 1)
+    out = torch.as_strided(C, (M, N), (ldc, 1)).double()
+    st = torch.as_strided(stats, (2, N), (N, 1))
+    st[0] += out.sum(0)
+    st[1] += (out * out).sum(0)
+
+
 def gemm_bf16_tc_wgrad_batched(M, N, K, A, lda, a_step, B, ldb, b_step, C, ldc, c_bstride, nbatch, splits):
     assert A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and lda % 8 == 0 and ldb % 8 == 0 and a_step % 8 == 0 and b_step % 8 == 0
     for b in range(nbatch):
@@ -37,10 +45,10 @@ def gemm_bf16_tc_wgrad_batched(M, N, K, A, lda, a_step, B, ldb, b_step, C, ldc, 
 
 
 def conv3x3_tc(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu):
-    conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1)
+    conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1, None)
 
 
-def conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, stride):
+def conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, stride, stats):
     """y = conv3x3(x16, packed weights; pad 1, stride 1 or 2): block gb reads channels gb*c_step + chunk*KC + kk, writes channels gb*nb_real + j; tap t
     multiplies the input pixel shifted by (t/3 - 1, t%3 - 1); out-of-image pixels and channels >= Cx read as zero."""
     assert x16.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16 and Cx % 8 == 0 and x16.data_ptr() % 16 == 0 and wp.data_ptr() % 16 == 0
@@ -61,6 +69,11 @@ def conv3x3_tc_strided(x16, wp, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunk
     out = out.clamp_min(0) if relu else out
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     torch.as_strided(y, (N, Ho, Wo, Cy), (Ho * Wo * Cy, Wo * Cy, Cy, 1)).copy_(out.permute(0, 2, 3, 1))
+    if stats is not None:
+        assert bias is None and not relu and Cy % 4 == 0 and nb_real % 4 == 0
+        st = torch.as_strided(stats, (2, Cy), (Cy, 1))
+        st[0] += out.double().sum((0, 2, 3))
+        st[1] += (out.double() ** 2).sum((0, 2, 3))
 
 
 def _attn_keep(seed_dev, seed_off, B, nh, T, p_drop):
@@ -96,8 +109,16 @@ def attn_fwd_tc(qkv, qkv_bf16, B, T, nh, hs, y32, y16, lse, scale, p_drop, seed_
         torch.as_strided(y16, (B * T, C), (C, 1)).copy_(y)
 
 
-def attn_bwd_tc(qkv, qkv_bf16, dy, dy_bf16, dy32, y32, lse, dsum, B, T, nh, hs, dqkv32, dqkv16, scale, p_drop, seed_dev, seed_off):
+def gemm_bf16_tc_out16(tb, M, N, K, A, lda, B, ldb, C16, ldc, bias, relu, alpha):
+    tmp = torch.empty(M, N)
+    gemm_bf16_tc(0, tb, M, N, K, A, lda, B, ldb, tmp, N, bias, relu, alpha, 0.0, 1)
+    assert C16.dtype == torch.bfloat16 and ldc % 4 == 0
+    torch.as_strided(C16, (M, N), (ldc, 1)).copy_(tmp)
+
+
+def attn_bwd_tc(qkv, qkv_bf16, dy32, y32, y_bf16, lse, dsum, dy16, B, T, nh, hs, dqkv32, dqkv16, scale, p_drop, seed_dev, seed_off):
     C = nh * hs
+    dy = dy32
     x = torch.as_strided(qkv, (B * T, 3 * C), (3 * C, 1)).bfloat16().float()
     q, k, v = (_heads(x[:, i * C:(i + 1) * C], B, T, nh, hs) for i in range(3))
     do = _heads(torch.as_strided(dy, (B * T, C), (C, 1)).bfloat16().float(), B, T, nh, hs)
@@ -122,7 +143,7 @@ class WithTensorCoreStandins:
         self.log = emul.log
         self.launches = 0
         self.profiler = None
-        self.fns = {'tfb_gemm_bf16_tc': gemm_bf16_tc, 'tfb_conv3x3_tc': conv3x3_tc, 'tfb_conv3x3_tc_strided': conv3x3_tc_strided, 'tfb_gemm_bf16_tc_wgrad_batched': gemm_bf16_tc_wgrad_batched,
+        self.fns = {'tfb_gemm_bf16_tc': gemm_bf16_tc, 'tfb_gemm_bf16_tc_stats': gemm_bf16_tc_stats, 'tfb_gemm_bf16_tc_out16': gemm_bf16_tc_out16, 'tfb_conv3x3_tc': conv3x3_tc, 'tfb_conv3x3_tc_strided': conv3x3_tc_strided, 'tfb_gemm_bf16_tc_wgrad_batched': gemm_bf16_tc_wgrad_batched,
                     'tfb_attn_fwd_tc': attn_fwd_tc, 'tfb_attn_bwd_tc': attn_bwd_tc}
 
     def call(self, name, *args):

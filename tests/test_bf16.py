@@ -9,6 +9,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-2
+BF16_ORACLE_ACT_TOL = 2e-2      # placeholder until the first hardware run; tightened to the measured level afterwards
+BF16_ORACLE_LOSS_TOL = 2e-2
 
 
 def rel(a, b):
@@ -213,8 +215,9 @@ def test_bf16_sidecars_do_not_change_the_step():
 
 @pytest.mark.parametrize('cfg', [(2, 40, 48, 72, 72, 3), (2, 20, 24, 216, 216, 9), (2, 32, 44, 3, 32, 1)])
 def test_conv3x3_stride2_bf16_mode(cfg):
-    """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward on the exact fp32 direct kernel; dgrad as the
-    stride-1 tensor-core dgrad of the zero-dilated dy; wgrad through im2col + the batched tensor-core GEMM."""
+    """Stride-2 3x3 convs (first block of every RegNetY stage, stems): forward on the tcgen05 implicit-GEMM kernel whose TMA map
+    steps two pixels per box element (the 3-channel stems stay on the exact fp32 direct kernel); dgrad as the stride-1
+    tensor-core dgrad of the zero-dilated dy; wgrad through im2col + the batched tensor-core GEMM."""
     from transfuser_b200 import ops
     N, H, W, Cin, Cout, g = cfg
     gen = torch.Generator(device='cuda').manual_seed(Cin)
@@ -224,7 +227,7 @@ def test_conv3x3_stride2_bf16_mode(cfg):
     xm = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_()
     wm = w.detach().clone().requires_grad_()
     out = ops.conv2d(xm, wm, None, 2, g, False)
-    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-4
+    assert rel(out.permute(0, 3, 1, 2), ref) < (TOL if (Cin % 8 == 0 and ops.CONV_S2_TC) else 1e-4)   # measured 2.4e-3 (bf16 operands)
     go = torch.randn_like(ref)
     mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
     rg = torch.autograd.grad(ref, [x, w], go)
@@ -247,3 +250,87 @@ def test_conv1x1_stride2_bf16_mode():
     mg = torch.autograd.grad(out, [xm, wm], go.permute(0, 2, 3, 1).contiguous())
     rg = torch.autograd.grad(ref, [x, w], go)
     assert rel(mg[0].permute(0, 3, 1, 2), rg[0]) < TOL and rel(mg[1], rg[1]) < TOL
+
+
+@pytest.mark.parametrize('cfg', [(2, 20, 24, 72, 216, 1, 1, 1), (3, 10, 12, 216, 216, 3, 9, 1), (2, 20, 24, 72, 72, 3, 3, 2), (2, 9, 11, 576, 576, 1, 1, 1)])
+def test_batchnorm_statistics_from_the_conv_epilogue(cfg):
+    """conv (1x1 GEMM / grouped 3x3 / stride-2 3x3 on the tensor cores) + training-mode BatchNorm(+ReLU): the per-channel sum and
+    sum of squares come out of the conv's epilogue (fp64 atomics into the per-step arena) and tfb_bn_fwd_stats normalises in one
+    launch. Against torch conv + batch_norm on the bf16-rounded operands, and against the same product path with the fusion off."""
+    from transfuser_b200 import _lib, ops
+    N, H, W, Cin, Cout, k, g, stride = cfg
+    gen = torch.Generator(device='cuda').manual_seed(Cin + Cout + k)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=gen) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin // g, k, k, device='cuda', generator=gen) / math.sqrt(Cin // g * k * k)
+    bn = torch.nn.BatchNorm2d(Cout).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=gen)
+        bn.bias.uniform_(-0.3, 0.3, generator=gen)
+    xr, wr = x.bfloat16().float(), w.bfloat16().float()
+    yc = F.conv2d(xr, wr, None, stride=stride, padding=k // 2, groups=g)
+    ref = F.relu(F.batch_norm(yc, None, None, bn.weight, bn.bias, True, 0.1, bn.eps))
+    xm = x.permute(0, 2, 3, 1).contiguous()
+    outs = {}
+    old = ops.BN_STATS_FUSED
+    try:
+        for fused in (True, False):
+            ops.BN_STATS_FUSED = fused
+            bn.running_mean.zero_(); bn.running_var.fill_(1.0)
+            ops.tick(x.device)
+            n0 = _lib.lib().launches
+            y = ops.conv2d(xm, w, None, stride, g, False, bn_stats=True)
+            assert (getattr(y, '_tfb_stats', None) is not None) == fused
+            o = ops.batch_norm(y, bn, True, True)
+            torch.cuda.synchronize()
+            outs[fused] = (o.permute(0, 3, 1, 2).clone(), bn.running_mean.clone(), bn.running_var.clone(), _lib.lib().launches - n0)
+    finally:
+        ops.BN_STATS_FUSED = old
+    assert rel(outs[True][0], ref) < 2e-3, rel(outs[True][0], ref)            # same bf16 operands, fp32 accumulation
+    assert rel(outs[True][0], outs[False][0]) < 1e-5
+    M = yc.numel() // Cout
+    assert rel(outs[True][1], 0.1 * yc.mean((0, 2, 3))) < 1e-4
+    assert rel(outs[True][2], 0.9 + 0.1 * yc.var((0, 2, 3), unbiased=True)) < 1e-4
+    assert rel(outs[True][1], outs[False][1]) < 1e-5 and rel(outs[True][2], outs[False][2]) < 1e-5
+    assert outs[True][3] < outs[False][3]                                    # one launch fewer (no reduction pass)
+
+
+def test_bf16_mode_matches_the_bf16_operand_oracle():
+    """Parity in the mode bench.py times. The fp32 CPU oracle is the wrong yardstick for a bf16-operand run at this (batch 2,
+    random weights) test point: ANY implementation that rounds the tensor-core operands to bf16 lands 24 % (stage 3) to 38 %
+    (stage 4) away from the fp32 activations — the oracle itself does when told to round the same operands
+    (oracle/torch_oracle.py BF16_OPERANDS: img_s3 0.240, img_s4 0.382 on the CPU; the CUDA path measures 0.240 / 0.383,
+    profiles/r2_bf16_vs_oracle.txt). So the bf16 mode is held to the oracle evaluated WITH the product's rounding points
+    (bf16 operands for every tcgen05 contraction, fp32 accumulation, everything else fp32): per-stage activations and all 11
+    losses, B = 2, dropout off."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_model import build, rel as relm, _oracle_run
+    from oracle import torch_oracle as O
+    net0 = build()
+    batch = O.synthetic_batch(2, seed=3)
+    O.BF16_OPERANDS[0] = True
+    try:
+        P16, ref16, taps16 = _oracle_run(net0, batch, torch.float32)
+    finally:
+        O.BF16_OPERANDS[0] = False
+    net = build().cuda().train()
+    cb = {k: v.cuda() for k, v in batch.items()}
+    mine = {}
+    feats, grid, fused = net._model.forward_nhwc(cb['rgb'], torch.cat((cb['lidar'], cb['target_point_image']), dim=1), taps=mine)
+    torch.cuda.synchronize()
+    errs = {k: relm(mine[k].permute(0, 3, 1, 2), taps16[k]) for k in sorted(mine)}
+    errs['p2'] = relm(feats[0].permute(0, 3, 1, 2), taps16['p2'])
+    errs['img_grid'] = relm(grid.permute(0, 3, 1, 2), taps16['img_grid'])
+    errs['fused'] = relm(fused, taps16['fused'])
+    print('bf16 mode vs bf16-operand oracle:', {k: float('%.2e' % v) for k, v in errs.items()})
+    net = build().cuda().train()
+    out = net(cb['rgb'], cb['lidar'], ego_waypoint=cb['ego_waypoint'], target_point=cb['target_point'],
+              target_point_image=cb['target_point_image'], ego_vel=cb['ego_vel'], bev=cb['bev'], label=cb['label'],
+              depth=cb['depth'], semantic=cb['semantic'])
+    lerr = {k: abs(out[k].item() - ref16[k].item()) / max(abs(ref16[k].item()), 1e-12) for k in ref16}
+    print('losses:', {k: float('%.2e' % v) for k, v in lerr.items()})
+    for k, v in errs.items():
+        assert v < BF16_ORACLE_ACT_TOL, (k, v)
+    for k, v in lerr.items():
+        assert v < BF16_ORACLE_LOSS_TOL, (k, v)

@@ -19,7 +19,7 @@ TOL = 3e-2     # forward, bf16 operands (8 mantissa bits) through a few layers w
 # with every host-side option of DESIGN.md 4b switched off (the configuration that passed `-m gpu` on the B200 earlier in the round).
 GRAD_TOL_VS_FP32 = 0.25
 TOL_VS_PLAIN_BF16 = 1e-3
-FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'SE_POOL_FUSED', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')
+FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'SE_POOL_FUSED', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')   # the numerically EQUIVALENT options (BN_STATS_FUSED, CONV_S2_TC, ATTN_FUSED change roundings: they stay on in both runs)
 
 
 def rel(a, b):
@@ -98,6 +98,9 @@ def test_conv_trunk_bf16_mode_matches_fp32_mode(lib):
     # the tensor cores were used for every conv flavour, and the bf16-only host paths were taken
     assert log1.count('tfb_conv3x3_tc') >= 6 and log1.count('tfb_gemm_bf16_tc') >= 12 and log1.count('tfb_gemm_bf16_tc_wgrad_batched') >= 4
     assert 'tfb_im2col3x3_bf16' in log1 and 'tfb_cast_bf16_pad' in log1
+    # BatchNorm statistics come out of the producing epilogues (1x1 GEMMs, grouped 3x3 incl. the stride-2 one): one BN launch, no reduction
+    assert log1.count('tfb_gemm_bf16_tc_stats') >= 5 and log1.count('tfb_conv3x3_tc_strided') >= 3 and log1.count('tfb_bn_fwd_stats') >= 8
+    assert log1.count('tfb_bn_fwd') == 0 and log1.count('tfb_conv2d_fwd') == 0
     # every weight gradient sits in its span of the flat buffer (the batched wgrad GEMM wrote PyTorch layout in place)
     grads = dict(zip([n for n, _ in net.named_parameters()], got[3:]))
     for (n, p), o in zip(((n, p) for n, p in net.named_parameters()), [dict(zip(map(id, fp.params), fp.offsets))[id(p)] for p in net.parameters()]):
@@ -164,7 +167,7 @@ def test_gpt_block_bf16_mode_matches_fp32_mode(lib):
             continue                                       # true gradient 0 (softmax shift invariance)
         assert rel(a, b) < (TOL if i == 0 else GRAD_TOL_VS_FP32), (n, rel(a, b))
     # q|k|v as one GEMM in forward, dgrad and wgrad (3) + proj (3) + two MLP layers (6); LayerNorm outputs reach them as sidecars
-    assert lib.log.count('tfb_gemm_bf16_tc') == 12
+    assert lib.log.count('tfb_gemm_bf16_tc') + lib.log.count('tfb_gemm_bf16_tc_out16') == 12 and lib.log.count('tfb_gemm_bf16_tc_out16') == 1
     assert lib.log.count('tfb_cast_bf16') == 1             # MLP hidden -> mlp.2 only: no LayerNorm-output casts, and the fused attention
     assert lib.log.count('tfb_attn_fwd_tc') == 1 and lib.log.count('tfb_attn_bwd_tc') == 1   # writes the bf16 copies of y and dqkv itself
     assert lib.log.count('tfb_colsum') == 1                # (the three bias gradients: one column reduction over dqkv)

@@ -23,7 +23,7 @@ def _nhwc(t):
 def torch_ops(monkeypatch):
     from transfuser_b200 import ops
 
-    def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
+    def conv2d(x, w, bias=None, stride=1, groups=1, relu=False, bn_stats=False):      # bn_stats: epilogue-statistics hint
         y = F.conv2d(_nchw(x), w, bias, stride=stride, padding=w.shape[2] // 2, groups=groups)
         return _nhwc(F.relu(y) if relu else y)
 

@@ -39,8 +39,9 @@ def run(B, T, nh, hs, p_drop=0.0, in_bf16=False, time_it=False):
         dqkv = torch.full((B * T, 3 * C), float('nan'), device='cuda')
         d16 = torch.empty((B * T, 3 * C), dtype=torch.bfloat16, device='cuda')
         dsum = torch.empty((B, nh, T), device='cuda')
-        dyin = dy.bfloat16() if in_bf16 else dy
-        _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dyin, int(in_bf16), dy, y, lse, dsum, B, T, nh, hs, dqkv, d16, scale, p_drop, seed, 7)
+        dy16 = torch.empty((B * T, C), dtype=torch.bfloat16, device='cuda')
+        yin = y16 if in_bf16 else y
+        _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dy, yin, int(in_bf16), lse, dsum, dy16, B, T, nh, hs, dqkv, d16, scale, p_drop, seed, 7)
         torch.cuda.synchronize()
         (gref,) = torch.autograd.grad(ref, qr, dy.bfloat16().float())
         for i, n in enumerate('qkv'):
@@ -58,7 +59,8 @@ def run(B, T, nh, hs, p_drop=0.0, in_bf16=False, time_it=False):
         # backward consistency: finite-difference-free check  <dy, d y/d v [dv]> = <dv_grad, dv>: y is linear in v for a fixed mask
         dqkv = torch.empty((B * T, 3 * C), device='cuda')
         dsum = torch.empty((B, nh, T), device='cuda')
-        _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dy, 0, dy, y, lse, dsum, B, T, nh, hs, dqkv, None, scale, p_drop, seed, 7)
+        dy16 = torch.empty((B * T, C), dtype=torch.bfloat16, device='cuda')
+        _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dy, y, 0, lse, dsum, dy16, B, T, nh, hs, dqkv, None, scale, p_drop, seed, 7)
         qkv2 = qkv.clone()
         dv = torch.randn(B * T, C, device='cuda', generator=g).bfloat16().float() * 0.5
         qkv2[:, 2 * C:] = (qkv[:, 2 * C:].bfloat16().float() + dv)
@@ -69,7 +71,7 @@ def run(B, T, nh, hs, p_drop=0.0, in_bf16=False, time_it=False):
         out['dv_linearity'] = abs(lhs - rhs) / max(abs(rhs), 1e-9)
     if time_it:
         for name, fn in (('fwd', lambda: _lib.call('tfb_attn_fwd_tc', qin, int(in_bf16), B, T, nh, hs, y, y16, lse, scale, p_drop, seed, 7)),
-                         ('bwd', lambda: _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dy, 0, dy, y, lse, dsum, B, T, nh, hs, dqkv, d16, scale, p_drop, seed, 7))):
+                         ('bwd', lambda: _lib.call('tfb_attn_bwd_tc', qin, int(in_bf16), dy, y, 0, lse, dsum, dy16, B, T, nh, hs, dqkv, d16, scale, p_drop, seed, 7))):
             if name == 'bwd' and p_drop > 0:
                 continue
             for _ in range(3):
@@ -88,7 +90,8 @@ if __name__ == '__main__':
     torch.manual_seed(0)
     for (B, T, nh, hs) in [(2, 174, 4, 18), (2, 174, 4, 54), (2, 174, 4, 144), (2, 174, 4, 378), (1, 100, 2, 64), (3, 192, 1, 130),
                            (10, 174, 4, 378), (10, 174, 4, 144), (10, 174, 4, 54), (10, 174, 4, 18)]:
-        r = run(B, T, nh, hs, time_it=(B == 10))
-        print('B%d T%d nh%d hs%d' % (B, T, nh, hs), {k: (float('%.3g' % v) if isinstance(v, float) else v) for k, v in r.items()}, flush=True)
+        for in16 in (False, True):
+            r = run(B, T, nh, hs, time_it=(B == 10), in_bf16=in16)
+            print('B%d T%d nh%d hs%d bf16_in=%d' % (B, T, nh, hs, in16), {k: (float('%.3g' % v) if isinstance(v, float) else v) for k, v in r.items()}, flush=True)
     print('bf16 inputs', run(2, 174, 4, 54, in_bf16=True), flush=True)
     print('dropout', run(2, 174, 4, 54, p_drop=0.1), run(10, 174, 4, 378, p_drop=0.1, time_it=True), flush=True)

@@ -43,8 +43,12 @@ if __name__ == '__main__':
     net0 = build()
     batch = O.synthetic_batch(2, seed=3)
     P, ref, taps = _oracle_run(net0, batch, torch.float32)
-    for mode in ('simt', 'bf16'):
-        acts, losses, g, cos = run(mode, net0, batch, P, ref, taps)
+    # the oracle with bf16-rounded tensor-core operands (oracle/torch_oracle.py BF16_OPERANDS): the product's rounding points on the CPU
+    O.BF16_OPERANDS[0] = True
+    P16, ref16, taps16 = _oracle_run(net0, batch, torch.float32)
+    O.BF16_OPERANDS[0] = False
+    for mode, (Pm, refm, tapsm) in (('simt', (P, ref, taps)), ('bf16', (P, ref, taps)), ('bf16 vs the bf16-operand oracle', (P16, ref16, taps16))):
+        acts, losses, g, cos = run(mode.split()[0], net0, batch, Pm, refm, tapsm)
         print('==== mode', mode)
         for k, v in acts.items():
             print('activation %-10s rel err %.3e' % (k, v))

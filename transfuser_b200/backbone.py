@@ -28,7 +28,7 @@ class _ConvBn(nn.Module):
     def run(self, x, emit16=False, residual=None, pool=False):
         """emit16: the output is the operand of a tensor-core GEMM / conv next (bf16 mode: BatchNorm writes its bf16 copy too).
         residual: relu(bn(conv(x)) + residual) — the Bottleneck tail, add and ReLU fused into the BatchNorm passes."""
-        y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups)
+        y = ops.conv2d(x, self.conv.weight, None, self.stride, self.groups, bn_stats=self.bn.training)
         # bwd16: this conv has no bias / ReLU of its own, so BatchNorm's dx is exactly the dy its tensor-core dgrad / wgrad read
         return ops.batch_norm(y, self.bn, self.act or residual is not None, self.bn.training, emit16,
                               bwd16=self.conv.in_channels % 8 == 0, residual=residual, pool=pool)

@@ -92,10 +92,57 @@ __device__ __forceinline__ void stage_chunk(uint8_t* dst, const TIn* __restrict_
   }
 }
 
+// bf16 source: the same chunk through cp.async (global -> shared without registers, many copies in flight per thread; the copies
+// of one call are NOT waited for here — cp_async_wait_all() before the proxy fence). VEC = bytes per copy (16 / 8 / 4): the largest
+// power of two that divides the source addresses (the head slices of the packed q|k|v rows are only 4-byte aligned in general).
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VEC>
+__device__ __forceinline__ void stage_chunk_async(uint8_t* dst, const __nv_bfloat16* __restrict__ src, int64_t ld, int64_t row0,
+                                                  int rows_valid, int rows_pad, int col0, int cols_valid, int tid, int nthreads) {
+  constexpr int PIECES = 16 / VEC, EPP = VEC / 2;      // copies per 16-byte unit, elements per copy
+  for (int idx = tid; idx < rows_pad * 8; idx += nthreads) {
+    const int r = idx >> 3, u = idx & 7;
+    uint8_t* d = dst + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4);
+    const int c = u * 8;
+    if (r < rows_valid && c < cols_valid) {
+      const __nv_bfloat16* p = src + (row0 + r) * ld + col0 + c;
+#pragma unroll
+      for (int j = 0; j < PIECES; ++j) {
+        if (c + (j + 1) * EPP <= cols_valid) {
+          const uint32_t da = tc::smem_u32(d + j * VEC);
+          if (VEC == 16)     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(p + j * EPP) : "memory");
+          else if (VEC == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(da), "l"(p + j * EPP) : "memory");
+          else               asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(da), "l"(p + j * EPP) : "memory");
+        } else {                                       // partially valid copy (VEC > 4 only): element pairs, the rest zero
+#pragma unroll
+          for (int e = 0; e < EPP; e += 2) {
+            uint32_t w = 0u;
+            if (c + j * EPP + e < cols_valid) w = *reinterpret_cast<const uint32_t*>(p + j * EPP + e);
+            *reinterpret_cast<uint32_t*>(d + j * VEC + e * 2) = w;
+          }
+        }
+      }
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// Issues the staging of one chunk; bf16 sources are asynchronous (see above), fp32 sources are converted synchronously.
 __device__ __forceinline__ void stage_any(uint8_t* dst, const void* src, int is_bf16, int64_t ld, int64_t row0, int rows_valid,
                                           int rows_pad, int col0, int cols_valid, int tid, int nthreads) {
-  if (is_bf16) stage_chunk<__nv_bfloat16>(dst, (const __nv_bfloat16*)src, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
-  else         stage_chunk<float>(dst, (const float*)src, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
+  if (is_bf16) {
+    const __nv_bfloat16* s16 = (const __nv_bfloat16*)src;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s16 + col0) | (uintptr_t)(ld * 2);
+    if ((a & 15) == 0)     stage_chunk_async<16>(dst, s16, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
+    else if ((a & 7) == 0) stage_chunk_async<8>(dst, s16, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
+    else                   stage_chunk_async<4>(dst, s16, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
+  } else {
+    stage_chunk<float>(dst, (const float*)src, ld, row0, rows_valid, rows_pad, col0, cols_valid, tid, nthreads);
+  }
 }
 
 // byte offset of element (row r, column j) of the 128 x 192 K-major bf16 matrix (3 chunks of 64 columns)
@@ -147,10 +194,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
   //   FWD / BWD_Q: X1 = Q tile, Y1 = K;  BWD_Q also X2 = dO tile, Y2 = V.   BWD_K: X1 = K tile, Y1 = Q, X2 = V tile, Y2 = dO.
   const int x1col = mode == MODE_BWD_K ? colk : colq, y1col = mode == MODE_BWD_K ? colq : colk;
   const int nchunks = (hs + 63) / 64;
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    if (c >= 2) { tc::mbar_wait(&bars[s], ph_stage[s]); ph_stage[s] ^= 1u; }   // the MMAs that read this stage have retired
-    uint8_t* st = smem + s * kStageBytes;
+  auto issue_loads = [&](int c) {
+    uint8_t* st = smem + (c & 1) * kStageBytes;
     const int cv = min(64, hs - c * 64);
     stage_any(st, p.qkv, p.in_bf16, ld3, tok0 + m0, rows_valid, kRowsX, x1col + c * 64, cv, tid, kThreads);
     stage_any(st + kXBytes, p.qkv, p.in_bf16, ld3, tok0, T, kRowsY, y1col + c * 64, cv, tid, kThreads);
@@ -161,6 +206,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
       stage_any(st + kXBytes + kYBytes, p.qkv, p.in_bf16, ld3, tok0 + m0, rows_valid, kRowsX, colv + c * 64, cv, tid, kThreads);
       stage_any(st + 2 * kXBytes + kYBytes, p.dy, p.dy_bf16, C, tok0, T, kRowsY, coly + c * 64, cv, tid, kThreads);
     }
+    cp_async_commit();
+  };
+  issue_loads(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    if (c + 1 < nchunks) {
+      // the copies of chunk c + 1 go out before chunk c is consumed: its stage was last read by the MMAs of chunk c - 1
+      if (c >= 1) { tc::mbar_wait(&bars[s ^ 1], ph_stage[s ^ 1]); ph_stage[s ^ 1] ^= 1u; }
+      issue_loads(c + 1);
+      cp_async_wait_group<1>();                        // everything but the newest group (chunk c + 1) has landed
+    } else {
+      cp_async_wait_all();
+    }
+    uint8_t* st = smem + s * kStageBytes;
+    const int cv = min(64, hs - c * 64);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -178,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
     }
   }
   // drain: every outstanding stage commit (at most two) is waited for exactly once, oldest first
+  // (iteration c waited for chunk c - 1 whenever it prefetched chunk c + 1: chunks 0 .. nchunks - 3 are done with)
   if (nchunks >= 2) { const int s = nchunks & 1; tc::mbar_wait(&bars[s], ph_stage[s]); ph_stage[s] ^= 1u; }
   { const int s = (nchunks - 1) & 1; tc::mbar_wait(&bars[s], ph_stage[s]); ph_stage[s] ^= 1u; }
   tc::fence_after_sync();
@@ -303,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
         const int cv = max(0, min(64, hs - q * 64));
         if (cv > 0) stage_any(smem + q * kYBytes, zsrc, z_bf16, zld, tok0, T, kRowsY, zcol + q * 64, cv, tid - 128, 128);
       }
+      cp_async_wait_all();
     }
     fence_async_smem();
     __syncthreads();
@@ -327,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
           const int cv = max(0, min(64, hs - (ps + 1) * 128 - q * 64));
           if (cv > 0) stage_any(zn + q * kYBytes, zsrc, z_bf16, zld, tok0, T, kRowsY, zcol + (ps + 1) * 128 + q * 64, cv, tid, kThreads);
         }
+        cp_async_wait_all();
         fence_async_smem();
       }
       tc::mbar_wait(&bars[2], ph_out); ph_out ^= 1u;
@@ -363,19 +426,32 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const Params p) {
   }
 }
 
-// D[b, h, i] = sum_d dO[b*T + i, h*hs + d] * O[b*T + i, h*hs + d]: one warp per (token row, head)
-__global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dsum,
-                                                        int B, int T, int nh, int hs) {
+// D[b, h, i] = sum_d dO[b*T + i, h*hs + d] * O[b*T + i, h*hs + d]: one warp per (token row, head); the same pass writes the bf16
+// copy of dO that the backward kernel stages with cp.async (hs even).
+template <typename TY>
+__global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict__ dy, const TY* __restrict__ y, float* __restrict__ dsum,
+                                                        __nv_bfloat16* __restrict__ dy16, int B, int T, int nh, int hs) {
   const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= (int64_t)B * T * nh) return;
   const int h = (int)(w % nh);
   const int64_t row = w / nh;
   const int b = (int)(row / T), i = (int)(row % T);
-  const float* a = dy + row * (int64_t)nh * hs + h * hs;
-  const float* c = y + row * (int64_t)nh * hs + h * hs;
+  const int64_t base = row * (int64_t)nh * hs + h * hs;
   float s = 0.f;
-  for (int d = lane; d < hs; d += 32) s = fmaf(a[d], c[d], s);
+  for (int d = lane * 2; d < hs; d += 64) {
+    const float2 g = *reinterpret_cast<const float2*>(dy + base + d);
+    float y0, y1;
+    if (sizeof(TY) == 4) {
+      const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(y) + base + d);
+      y0 = v.x; y1 = v.y;
+    } else {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(y) + base + d);
+      y0 = __low2float(v); y1 = __high2float(v);
+    }
+    s = fmaf(g.x, y0, fmaf(g.y, y1, s));
+    if (dy16) *reinterpret_cast<__nv_bfloat162*>(dy16 + base + d) = __floats2bfloat162_rn(g.x, g.y);
+  }
   s = warp_sum(s);
   if (lane == 0) dsum[((int64_t)b * nh + h) * T + i] = s;
 }
@@ -413,18 +489,21 @@ TFB_API int tfb_attn_fwd_tc(const void* qkv, int qkv_bf16, int B, int T, int nh,
   return launch_attn(p, stream);
 }
 
-// Backward of tfb_attn_fwd_tc: dqkv[B*T, 3C] (fp32 and / or bf16; every element written) from dy[B*T, C] (fp32 or bf16), the
-// forward's inputs, output y (fp32, for D = rowsum(dy * y)) and lse. dsum: [B, nh, T] fp32 scratch.
-TFB_API int tfb_attn_bwd_tc(const void* qkv, int qkv_bf16, const void* dy, int dy_bf16, const float* dy32, const float* y32, const float* lse,
-                            float* dsum, int B, int T, int nh, int hs, float* dqkv32, void* dqkv16, float scale, float p_drop,
+// Backward of tfb_attn_fwd_tc: dqkv[B*T, 3C] (fp32 and / or bf16; every element written) from dy[B*T, C] (fp32), the forward's
+// q|k|v input, its output y (fp32, or bf16 when y_bf16: for D = rowsum(dy * y)) and lse. Scratch: dsum [B, nh, T] fp32 and
+// dy16 [B*T, C] bf16 (the bf16 copy of dy the kernel stages; written by the pre-pass).
+TFB_API int tfb_attn_bwd_tc(const void* qkv, int qkv_bf16, const float* dy, const void* y, int y_bf16, const float* lse, float* dsum,
+                            void* dy16, int B, int T, int nh, int hs, float* dqkv32, void* dqkv16, float scale, float p_drop,
                             const uint64_t* seed_dev, uint64_t seed_off, cudaStream_t stream) {
-  TFB_REQUIRE(qkv && dy && dy32 && y32 && lse && dsum && (dqkv32 || dqkv16) && B > 0 && T > 0 && T <= kRowsY && nh > 0 && hs > 0 && hs % 2 == 0);
-  TFB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  TFB_REQUIRE(qkv && dy && y && lse && dsum && dy16 && (dqkv32 || dqkv16) && B > 0 && T > 0 && T <= kRowsY && nh > 0 && hs > 0 && hs % 2 == 0);
+  TFB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(dy16) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const int64_t warps = (int64_t)B * T * nh;
-  attn_dsum_kernel<<<(int)((warps + 7) / 8), 256, 0, stream>>>(dy32, y32, dsum, B, T, nh, hs);
+  if (y_bf16) attn_dsum_kernel<__nv_bfloat16><<<(int)((warps + 7) / 8), 256, 0, stream>>>(dy, (const __nv_bfloat16*)y, dsum, (__nv_bfloat16*)dy16, B, T, nh, hs);
+  else        attn_dsum_kernel<float><<<(int)((warps + 7) / 8), 256, 0, stream>>>(dy, (const float*)y, dsum, (__nv_bfloat16*)dy16, B, T, nh, hs);
   TFB_CHECK_LAUNCH();
   Params p{};
-  p.qkv = qkv; p.in_bf16 = qkv_bf16; p.dy = dy; p.dy_bf16 = dy_bf16; p.out32_a = dqkv32; p.out16_a = (__nv_bfloat16*)dqkv16;
+  p.qkv = qkv; p.in_bf16 = qkv_bf16; p.dy = dy16; p.dy_bf16 = 1; p.out32_a = dqkv32; p.out16_a = (__nv_bfloat16*)dqkv16;
   p.lse = const_cast<float*>(lse); p.dsum = dsum;
   p.seed_dev = seed_dev; p.seed_off = seed_off; p.B = B; p.T = T; p.nh = nh; p.hs = hs; p.C = nh * hs;
   p.scale = scale; p.p_drop = p_drop; p.mode = 1;

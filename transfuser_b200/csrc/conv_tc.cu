@@ -32,7 +32,7 @@ template <int KC, int NB, int STAGES>
 __global__ void __launch_bounds__(192)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, float* __restrict__ y,
                   const float* __restrict__ bias, int H, int W, int Cout, int tiles_w, int tiles_h, int c_step, int nchunks,
-                  int nb_real, int relu, int gblocks, int total_tiles, int stride) {
+                  int nb_real, int relu, int gblocks, int total_tiles, int stride, double* __restrict__ stats) {
   // H, W: OUTPUT height / width. stride 2: the activation map steps two pixels per box element, so tile pixel (h, w) reads the
   // input pixel (2h + dy, 2w + dx) of tap (dy, dx).
   // PERSISTENT: tile t = (spatial tile, channel block), channel block fastest (CTAs running together re-use the same activation
@@ -135,11 +135,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           const int cols_valid = nvalid - c0;
           if (cols_valid <= 0) break;
           tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
-                               [=](int row) -> float* {
+                               [=](int row) -> int64_t {
                                  const int r = q * 32 + row, h = h0 + r / TW, w = w0 + r % TW;
-                                 return (h < H && w < W) ? ytile + (((int64_t)n * H + h) * W + w) * Cout + c0 : nullptr;
+                                 return (h < H && w < W) ? (((int64_t)n * H + h) * W + w) * Cout + c0 : (int64_t)-1;
                                },
-                               cols_valid, bp ? bp + c0 : nullptr, 1.f, relu, lane);
+                               cols_valid, bp ? bp + c0 : nullptr, 1.f, relu, lane, ytile, nullptr,
+                               stats ? stats + gb * nb_real + c0 : nullptr, stats ? stats + Cout + gb * nb_real + c0 : nullptr);
         }
       } else {
         const int r = q * 32 + lane;
@@ -177,7 +178,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
 
 template <int KC, int NB>
 int launch_conv(const void* x16, const void* wpack, const float* bias, float* y, int N, int Hin, int Win, int Cx, int Cy, int c_step,
-                int nchunks, int nb_real, int gblocks, int relu, int stride, cudaStream_t stream) {
+                int nchunks, int nb_real, int gblocks, int relu, int stride, double* stats, cudaStream_t stream) {
   const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output size (kernel 3, pad 1)
   constexpr int STAGES = NB <= 64 ? 6 : 4;
   constexpr int STAGE = BM * KC * 2 + NB * KC * 2;
@@ -212,7 +213,7 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
   const int per_sm = (SMEM <= 110 * 1024) ? 2 : 1;
   const int64_t cap = (int64_t)tfb_num_sms() * per_sm;
   const int grid = (int)(total < cap ? total : cap);
-  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu, gblocks, (int)total, stride);
+  kern<<<grid, 192, SMEM, stream>>>(mx, mw, y, bias, H, W, Cy, tiles_w, tiles_h, c_step, nchunks, nb_real, relu, gblocks, (int)total, stride, stats);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
@@ -222,11 +223,15 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
 // y[N,Ho,Wo,Cy] (fp32) = conv3x3(x16[N,H,W,Cx] bf16, packed weights; pad 1, stride 1 or 2) (+bias) (ReLU), Ho = (H-1)/stride + 1.
 // Block gb reads channels [gb*c_step + chunk*KC, +KC) for chunk < nchunks and writes channels [gb*nb_real, +min(nb_real, Cy - gb*nb_real)).
 // stride 2 (first block of every RegNetY stage): the TMA map traverses the activation with element strides {1, 2, 2, 1}.
+// stats (optional, 2*Cy doubles, zeroed by the caller once per step): per-channel sum / sum of squares of y accumulated in the
+// epilogue (training-mode BatchNorm statistics without a pass over y); needs Cy % 4 == 0, nb_real % 4 == 0, no bias / ReLU.
 TFB_API int tfb_conv3x3_tc_strided(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
-                                   int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, int stride, cudaStream_t stream) {
+                                   int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, int stride, double* stats,
+                                   cudaStream_t stream) {
   TFB_REQUIRE(x16 && wpack && y && N > 0 && H > 0 && W > 0 && Cx > 0 && Cy > 0 && Cx % 8 == 0 && (stride == 1 || stride == 2));
+  TFB_REQUIRE(!stats || (Cy % 4 == 0 && nb_real % 4 == 0 && !bias && !relu && (reinterpret_cast<uintptr_t>(y) & 15) == 0));
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0);
-#define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stride, stream)
+#define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stride, stats, stream)
   CASE(64, 16); CASE(64, 32); CASE(64, 48); CASE(64, 64); CASE(64, 128);
   CASE(32, 16); CASE(32, 32); CASE(32, 64);
 #undef CASE
@@ -237,5 +242,5 @@ TFB_API int tfb_conv3x3_tc_strided(const void* x16, const void* wpack, const flo
 // Stride-1 form of tfb_conv3x3_tc_strided.
 TFB_API int tfb_conv3x3_tc(const void* x16, const void* wpack, const float* bias, float* y, int N, int H, int W, int Cx, int Cy,
                            int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, cudaStream_t stream) {
-  return tfb_conv3x3_tc_strided(x16, wpack, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1, stream);
+  return tfb_conv3x3_tc_strided(x16, wpack, bias, y, N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks, relu, 1, nullptr, stream);
 }

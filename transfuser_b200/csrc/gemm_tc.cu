@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, float* __restrict__ Cbase,
                int64_t ldc, int M, int N, int num_kb, int kb_per_split, const float* __restrict__ bias, float alpha, float beta,
                int relu, int atomic_out, int splits, int a_step, int b_step, int64_t c_bstride, int tiles_m, int tiles_n,
-               int total_tiles, int BN, int STAGES) {
+               int total_tiles, int BN, int STAGES, double* __restrict__ stats, __nv_bfloat16* __restrict__ C16) {
   // PERSISTENT: gridDim.x CTAs (<= one per SM) walk the tile list t = blockIdx.x, += gridDim.x. A tile is (m-tile, n-tile, z),
   // z = batch * splits + split; m fastest so that concurrently running CTAs share the same B (weight) tile in L2.
   // The TMEM accumulator is double buffered (2 x BN columns): the epilogue warps drain tile i while the MMA warp already
@@ -171,7 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       float* crow = Cbase + (int64_t)bz * c_bstride + (int64_t)m * ldc;
       const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols + ((uint32_t)(q * 32) << 16);
       float* cwarp = Cbase + (int64_t)bz * c_bstride + (int64_t)(m0 + q * 32) * ldc;   // first row of this warp's 32-row band
-      const bool fast = !atomic_out && beta == 0.f && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(cwarp + n0) & 15) == 0);
+      const bool fast = !atomic_out && beta == 0.f && (ldc & 3) == 0 &&
+                        (C16 ? (reinterpret_cast<uintptr_t>(C16) & 7) == 0 : (reinterpret_cast<uintptr_t>(cwarp + n0) & 15) == 0);
       if (fast) {
         // coalesced path: 32-column chunks through this warp's padded smem staging buffer
         float* stage = stage_out + q * (32 * 36);
@@ -180,10 +181,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int cols_valid = min(N - (n0 + c0), BN - c0);
           if (cols_valid <= 0) break;   // warp-uniform
-          float* dst = cwarp + n0 + c0;
+          const int64_t off0 = (int64_t)bz * c_bstride + (int64_t)(m0 + q * 32) * ldc + n0 + c0;
           tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
-                               [=](int row) -> float* { return row < rows_valid ? dst + (int64_t)row * ldc : nullptr; }, cols_valid,
-                               add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane);
+                               [=](int row) -> int64_t { return row < rows_valid ? off0 + (int64_t)row * ldc : (int64_t)-1; }, cols_valid,
+                               add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane, Cbase, C16, stats ? stats + n0 + c0 : nullptr,
+                               stats ? stats + N + n0 + c0 : nullptr);
         }
       } else {
 #pragma unroll 1
@@ -256,9 +258,15 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 template <typename T, bool A_MN, bool B_MN>
 int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
               int relu, float alpha, float beta, int splits, cudaStream_t stream, int nbatch = 1, int a_step = 0, int b_step = 0,
-              int64_t c_bstride = 0) {
+              int64_t c_bstride = 0, double* stats = nullptr, __nv_bfloat16* C16 = nullptr) {
   using E = Elem<T>;
+  if (C16) {     // bf16 output: coalesced epilogue path only
+    TFB_REQUIRE(splits <= 1 && beta == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C16) & 7) == 0);
+  }
   constexpr int BK = E::kPerRow;
+  if (stats) {   // the statistics come out of the coalesced epilogue path only: make sure the kernel takes it
+    TFB_REQUIRE(splits <= 1 && beta == 0.f && nbatch == 1 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && !relu);
+  }
   TFB_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && (!B_MN || BN % E::kPerRow == 0));
   const int stage_bytes = kABytes + BN * 128;
   int stages = (kSmemMax - kSmemFixed) / stage_bytes;
@@ -305,17 +313,21 @@ int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, 
   if (total > 0x7fffffff) { tfb_set_last_error("too many tiles"); return TFB_ERR_ARG; }
   const int grid = (int)(total < tfb_num_sms() ? total : tfb_num_sms());
   kern<<<grid, 192, smem_total, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
-                                          b_step, c_bstride, tiles_m, tiles_n, (int)total, BN, stages);
+                                          b_step, c_bstride, tiles_m, tiles_n, (int)total, BN, stages, stats, C16);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
 
 template <typename T>
 int dispatch_major(int BN, int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
-                   int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream) {
+                   int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream, double* stats = nullptr,
+                   __nv_bfloat16* C16 = nullptr) {
   // BLAS-style flags: op(A)[m][k] = transA ? A[k*lda+m] : A[m*lda+k];  op(B)[k][n] = transB ? B[n*ldb+k] : B[k*ldb+n]
   const bool a_mn = transA != 0, b_mn = transB == 0;
-  if (!a_mn && !b_mn) return launch_tc<T, false, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  if (!a_mn && !b_mn) return launch_tc<T, false, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream, 1, 0, 0, 0, stats, C16);
+  if (!a_mn && b_mn && C16) return launch_tc<T, false, true>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream, 1, 0, 0, 0, nullptr, C16);
+  if (C16) { tfb_set_last_error("bf16 output is wired for the forward / dgrad forms only"); return TFB_ERR_UNSUPPORTED; }
+  if (stats) { tfb_set_last_error("column statistics are produced by the y = x W^T form only"); return TFB_ERR_UNSUPPORTED; }
   if (!a_mn && b_mn)  return launch_tc<T, false, true>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
   if (a_mn && b_mn)   return launch_tc<T, true, true>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
   return launch_tc<T, true, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
@@ -347,15 +359,16 @@ int pick_bn(int M, int N, int zs, int step) {
 
 template <typename T>
 int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, float* C,
-                int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream) {
-  TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
+                int64_t ldc, const float* bias, int relu, float alpha, float beta, int splits, cudaStream_t stream, double* stats = nullptr,
+                __nv_bfloat16* C16 = nullptr) {
+  TFB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && (C || C16));
   // TMA: 16-byte aligned bases and leading dimensions.
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
   TFB_REQUIRE((lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0);
   const int step = transB == 0 ? Elem<T>::kPerRow : 16;
   const int num_kb = (K + Elem<T>::kPerRow - 1) / Elem<T>::kPerRow;
   const int zs = splits < 1 ? 1 : (splits > num_kb ? num_kb : splits);
-  return dispatch_major<T>(pick_bn(M, N, zs, step), transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
+  return dispatch_major<T>(pick_bn(M, N, zs, step), transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream, stats, C16);
 }
 
 }  // namespace
@@ -391,4 +404,25 @@ TFB_API int tfb_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const 
                              int splits, cudaStream_t stream) {
   return gemm_tc_any<__nv_bfloat16>(transA, transB, M, N, K, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, C, ldc,
                                     bias, relu, alpha, beta, splits, stream);
+}
+
+// y[M,N] (fp32) = x[M,K] W[N,K]^T (bf16 operands) as tfb_gemm_bf16_tc(0, 1, ...), and in the same epilogue the per-column
+// statistics of y: stats[n] += sum_m y[m][n], stats[N + n] += sum_m y[m][n]^2 (fp64 atomics; the caller zeroes stats once per
+// training step). The training-mode BatchNorm behind every 1x1 conv of the RegNetY trunks (timm BatchNormAct2d) then needs no
+// statistics pass of its own (tfb_bn_fwd_stats). ldc % 4 == 0, C 16-byte aligned.
+TFB_API int tfb_gemm_bf16_tc_stats(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                   double* stats, cudaStream_t stream) {
+  TFB_REQUIRE(stats != nullptr);
+  return gemm_tc_any<__nv_bfloat16>(0, 1, M, N, K, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f,
+                                    1, stream, stats);
+}
+
+// As tfb_gemm_bf16_tc with transA = 0 (forward y = x W^T or dgrad dx = dy W), but the result is written in bf16 (C16, leading
+// dimension ldc elements, ldc % 4 == 0): the operand of the next tensor-core GEMM / the fused attention needs no cast pass and
+// the epilogue writes half the bytes. No split-K, no beta.
+TFB_API int tfb_gemm_bf16_tc_out16(int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C16,
+                                   int64_t ldc, const float* bias, int relu, float alpha, cudaStream_t stream) {
+  TFB_REQUIRE(C16 != nullptr);
+  return gemm_tc_any<__nv_bfloat16>(0, transB, M, N, K, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, nullptr, ldc, bias, relu,
+                                    alpha, 0.f, 1, stream, nullptr, (__nv_bfloat16*)C16);
 }

@@ -256,6 +256,101 @@ bn_apply_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int HW,
   }
 }
 
+// ---- BatchNorm forward when the statistics were accumulated by the PRODUCER's epilogue (tfb_gemm_bf16_tc_stats, tfb_conv3x3_tc_strided):
+// stats = [sum x | sum x^2] in fp64. Every block derives scale / shift for all channels into shared memory (C doubles of math per
+// block: nothing next to the pass over x), block 0 also publishes save_mean / save_invstd and updates the running statistics.
+constexpr int kBnStatsMaxC = 2048;   // RegNetY-3.2GF: 1512 at most
+
+__device__ __forceinline__ void bn_params_from_stats(const double* __restrict__ stats, int C, int64_t M, float eps, float momentum,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* s_scale,
+                                                     float* s_shift, bool publish, float* __restrict__ save_mean,
+                                                     float* __restrict__ save_invstd, float* __restrict__ running_mean,
+                                                     float* __restrict__ running_var) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  for (int c = tid; c < C; c += nthr) {
+    const double mean = stats[c] / (double)M;
+    double var = stats[C + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    s_scale[c] = sc;
+    s_shift[c] = fmaf(-(float)mean, sc, beta[c]);
+    if (publish) {
+      save_mean[c] = (float)mean;
+      save_invstd[c] = invstd;
+      if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_stats_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total4, int C, int64_t M, const double* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, int relu,
+                      float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean,
+                      float* __restrict__ running_var, __nv_bfloat16* __restrict__ y16, const float* __restrict__ res) {
+  __shared__ __align__(16) float s_par[2 * kBnStatsMaxC];
+  float* s_scale = s_par;
+  float* s_shift = s_par + kBnStatsMaxC;
+  bn_params_from_stats(stats, C, M, eps, momentum, gamma, beta, s_scale, s_shift, blockIdx.x == 0, save_mean, save_invstd, running_mean, running_var);
+  const int C4 = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    if (res) {
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = o;
+    if (y16) tfb_store_bf16x4(y16, i, o.x, o.y, o.z, o.w);
+  }
+}
+
+// the pooling variant (thread mapping of bn_apply_pool_kernel); `pooled` must be zero on entry (the caller's per-step arena)
+__global__ void __launch_bounds__(256)
+bn_apply_pool_stats_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, int64_t M, const double* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, int relu,
+                           float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean,
+                           float* __restrict__ running_var, float* __restrict__ pooled, float inv_hw) {
+  __shared__ __align__(16) float s_par[2 * kBnStatsMaxC];
+  float* s_scale = s_par;
+  float* s_shift = s_par + kBnStatsMaxC;
+  bn_params_from_stats(stats, C, M, eps, momentum, gamma, beta, s_scale, s_shift, blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0,
+                       save_mean, save_invstd, running_mean, running_var);
+  __shared__ float4 sm[8][33];
+  const int n = blockIdx.y, c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+    const int64_t base = (int64_t)n * HW * C + c;
+    for (int p = blockIdx.z * 8 + threadIdx.y; p < HW; p += gridDim.z * 8) {
+      const float4 v = *reinterpret_cast<const float4*>(x + base + (int64_t)p * C);
+      float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(y + base + (int64_t)p * C) = o;
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 v = sm[j][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    float* o = pooled + (int64_t)n * C + c;
+    atomicAdd(o + 0, t.x * inv_hw); atomicAdd(o + 1, t.y * inv_hw); atomicAdd(o + 2, t.z * inv_hw); atomicAdd(o + 3, t.w * inv_hw);
+  }
+}
+
 // dx = gamma * invstd * (g - sum_g/M - xhat * sum_gx/M);  block 0 also writes dgamma = sum_gx, dbeta = sum_g.
 // 4 channels per thread (C % 4 == 0, 16-byte aligned rows).
 __global__ void __launch_bounds__(256)
@@ -467,6 +562,32 @@ TFB_API int tfb_bn_fwd(const float* x, float* y, int64_t M, int C, const float* 
   const int64_t total4 = M * C / 4;
   bn_apply_kernel<<<tfb_grid(total4, 256), 256, 0, stream>>>(x, y, total4, C / 4, save_mean, save_invstd, gamma, beta, relu,
                                                              (__nv_bfloat16*)y16_bf16, residual);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// Training-mode BatchNorm forward from statistics the producing conv / GEMM accumulated in its epilogue: stats = [sum x | sum x^2]
+// (2*C doubles, read only). One launch: no reduction pass over x. pooled (optional): must be ZERO on entry (it is accumulated).
+// Everything else as tfb_bn_fwd.
+TFB_API int tfb_bn_fwd_stats(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                             int relu, float* running_mean, float* running_var, float* save_mean, float* save_invstd, const double* stats,
+                             void* y16_bf16, const float* residual, float* pooled, int pool_batch, cudaStream_t stream) {
+  TFB_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && stats && M > 0 && C > 0 && C % 4 == 0 && C <= kBnStatsMaxC);
+  TFB_REQUIRE(!pooled || (pool_batch > 0 && M % pool_batch == 0 && !y16_bf16 && !residual));
+  if (pooled) {
+    const int HW = (int)(M / pool_batch);
+    int splits = (HW + 255) / 256;
+    if (splits > 32) splits = 32;
+    dim3 grid((C / 4 + 31) / 32, pool_batch, splits), block(32, 8);
+    bn_apply_pool_stats_kernel<<<grid, block, 0, stream>>>(x, y, HW, C, M, stats, gamma, beta, eps, momentum, relu, save_mean, save_invstd,
+                                                              running_mean, running_var, pooled, 1.f / (float)HW);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
+  const int64_t total4 = M * C / 4;
+  bn_apply_stats_kernel<<<tfb_grid(total4, 256, 4), 256, 0, stream>>>(x, y, total4, C, M, stats, gamma, beta, eps, momentum, relu, save_mean,
+                                                                         save_invstd, running_mean, running_var,
+                                                                         (__nv_bfloat16*)y16_bf16, residual);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

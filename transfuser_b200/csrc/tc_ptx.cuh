@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -125,13 +126,18 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Epilogue helper: one warp moves its 32 accumulator rows x 32 columns TMEM -> registers -> padded smem (row stride 36 floats:
-// conflict-free 16-byte accesses both ways) -> global memory with COALESCED 128-byte row segments (4 rows per instruction),
-// applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer. `row_ptr(row)` returns the
-// 16-byte aligned destination of accumulator row `row` (0..31) or nullptr for rows that must not be written; columns
-// >= cols_valid are not written.
-template <class RowPtr>
-__device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, RowPtr row_ptr, int cols_valid, const float* bias,
-                                                 float alpha, int relu, int lane) {
+// conflict-free 16-byte accesses both ways) -> global memory with COALESCED row segments (4 rows per instruction, 128 bytes of fp32
+// or 64 bytes of bf16 per row), applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer.
+// `row_off(row)` returns the ELEMENT offset of accumulator row `row` (0..31) in the output (a multiple of 4) or -1 for rows that
+// must not be written; columns >= cols_valid are not written. The result goes to out32 (fp32) or, when out16 is given, to out16
+// (bf16, round-to-nearest-even) at the same element offsets.
+// stat_sum / stat_sq (optional, fp64, this chunk's column 0): per-column sum and sum of squares of the values written (rows with
+// offset -1 contribute nothing) are added with one fp64 atomic per column and warp — the training-mode BatchNorm statistics
+// of a conv / GEMM output come out of its epilogue instead of a separate read pass over the tensor.
+template <class RowOff>
+__device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, RowOff row_off, int cols_valid, const float* bias,
+                                                 float alpha, int relu, int lane, float* out32, __nv_bfloat16* out16 = nullptr,
+                                                 double* stat_sum = nullptr, double* stat_sq = nullptr) {
   uint32_t r[32];
   tmem_ld16_nowait(taddr, r);
   tmem_ld16_nowait(taddr + 16, r + 16);
@@ -150,22 +156,54 @@ __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, R
     bv.z = c4 + 2 < cols_valid ? bias[c4 + 2] : 0.f;
     bv.w = c4 + 3 < cols_valid ? bias[c4 + 3] : 0.f;
   }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + rsub;
     float4 v = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
     v.x = fmaf(alpha, v.x, bv.x); v.y = fmaf(alpha, v.y, bv.y); v.z = fmaf(alpha, v.z, bv.z); v.w = fmaf(alpha, v.w, bv.w);
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    float* p = row_ptr(row);
-    if (p != nullptr) {
-      p += c4;
-      if (c4 + 3 < cols_valid) {
-        *reinterpret_cast<float4*>(p) = v;
-      } else {
-        if (c4 + 0 < cols_valid) p[0] = v.x;
-        if (c4 + 1 < cols_valid) p[1] = v.y;
-        if (c4 + 2 < cols_valid) p[2] = v.z;
+    const int64_t off = row_off(row);
+    if (off >= 0) {
+      if (stat_sum) {
+        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+        s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]); s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
       }
+      if (out16) {
+        __nv_bfloat16* p = out16 + off + c4;
+        if (c4 + 3 < cols_valid) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo);
+          o.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(p) = o;
+        } else {
+          if (c4 + 0 < cols_valid) p[0] = __float2bfloat16_rn(v.x);
+          if (c4 + 1 < cols_valid) p[1] = __float2bfloat16_rn(v.y);
+          if (c4 + 2 < cols_valid) p[2] = __float2bfloat16_rn(v.z);
+        }
+      } else {
+        float* p = out32 + off + c4;
+        if (c4 + 3 < cols_valid) {
+          *reinterpret_cast<float4*>(p) = v;
+        } else {
+          if (c4 + 0 < cols_valid) p[0] = v.x;
+          if (c4 + 1 < cols_valid) p[1] = v.y;
+          if (c4 + 2 < cols_valid) p[2] = v.z;
+        }
+      }
+    }
+  }
+  if (stat_sum) {   // warp-uniform: lanes with equal (lane & 7) hold the same 4 columns for different rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);  s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
+      s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c4 + q < cols_valid) { atomicAdd(stat_sum + c4 + q, (double)s1[q]); atomicAdd(stat_sq + c4 + q, (double)s2[q]); }
     }
   }
   __syncwarp();

@@ -34,9 +34,43 @@ def seed_state(device):
     return t
 
 
+# Per-step arena of accumulators that kernels ADD into (BatchNorm statistics written by conv / GEMM epilogues, squeeze-excite pooling
+# sums): one buffer per device, cleared by ONE memset at the start of the step (tick) and handed out in call order, so every step
+# (and a captured CUDA graph) uses the same addresses and no kernel needs a clearing pass or a last-block clean-up of its own.
+_ARENA = {}
+ARENA_BYTES = 8 << 20
+
+
+def _arena_take(device, nbytes, dtype):
+    """A zeroed [nbytes / itemsize] tensor of `dtype` out of the step arena, or None when the arena is exhausted / not armed."""
+    dev = torch.device(device)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    a = _ARENA.get(dev)
+    if a is None:
+        return None
+    off = (a['off'] + 15) // 16 * 16
+    if off + nbytes > ARENA_BYTES:
+        return None
+    a['off'] = off + nbytes
+    # an independent tensor on the arena's storage (set_, not a view): it does not share the arena's version counter, so clearing
+    # the arena at the next tick() never invalidates a tensor autograd saved from here
+    item = torch.empty(0, dtype=dtype).element_size()
+    return torch.empty(0, dtype=dtype, device=a['buf'].device).set_(a['buf'].untyped_storage(), off // item, (nbytes // item,))
+
+
 def tick(device):
     """Advance the device-side dropout seed (call once per training step)."""
     call('tfb_step_tick', seed_state(device), None)
+    dev = torch.device(device)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    a = _ARENA.get(dev)
+    if a is None:
+        a = _ARENA[dev] = dict(buf=torch.zeros(ARENA_BYTES, dtype=torch.uint8, device=dev), off=0, armed=True)
+    if a['off'] > 0:
+        a['buf'][:a['off']].zero_()          # what the last step handed out; everything beyond is still zero
+    a['off'] = 0
     _SEED['off'] = 0
     _BWD16.clear()
     _COL_CACHE.clear()
@@ -62,6 +96,7 @@ SE_POOL_FUSED = os.environ.get('TFB_SE_POOL_FUSED', '1') == '1'   # SE average p
 SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd (2 launches) instead of 8 small ones
 CONV_S2_TC = os.environ.get('TFB_CONV_S2_TC', '1') == '1'       # bf16 mode: stride-2 3x3 convs forward on the tcgen05 kernel (TMA element strides)
 WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: weight-gradient GEMMs on a third stream (they only feed AdamW)
+BN_STATS_FUSED = os.environ.get('TFB_BN_STATS_FUSED', '1') == '1'   # bf16 mode: BatchNorm statistics out of the producing conv / GEMM epilogue
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
@@ -292,7 +327,7 @@ class LinearFn(Function):
     forward / dgrad / wgrad all run on the tcgen05 kernel (K-major / MN-major operand descriptors, no transposes)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, relu):
+    def forward(ctx, x, w, bias, relu, want_stats=False):
         x = _c(x)
         w2 = w.view(w.shape[0], -1)
         M, K = x.shape
@@ -301,7 +336,14 @@ class LinearFn(Function):
         ctx.tc = G.tc_ok(M, N, K, K, N)
         if ctx.tc:
             xs = _as16(x)
-            G.gemm_bf16(xs, G.weight_bf16(w2), y, trans_b=True, bias=bias, relu=relu)
+            st = _arena_take(x.device, 2 * N * 8, torch.float64) if (want_stats and bias is None and not relu and N % 4 == 0) else None
+            if st is not None:
+                # training-mode BatchNorm follows: its per-channel sum / sum of squares come out of this GEMM's epilogue
+                wb = G.weight_bf16(w2)
+                call('tfb_gemm_bf16_tc_stats', M, N, K, xs, xs.stride(0), wb, wb.stride(0), y, N, st)
+                y._tfb_stats = st
+            else:
+                G.gemm_bf16(xs, G.weight_bf16(w2), y, trans_b=True, bias=bias, relu=relu)
         else:
             xs = x
             if M <= 16:
@@ -344,7 +386,7 @@ class LinearFn(Function):
                 call('tfb_conv2d_wgrad', xs, g, dw, None, 1, M, 1, K, N, 1, 1, 1)
             else:
                 gemm(g, xs, dw.view(w2.shape), trans_a=True, mode='simt')
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def linear(x, w, bias=None, relu=False):
@@ -357,7 +399,7 @@ class Conv2dFn(Function):
     """NHWC conv, k in {1,3}, pad k//2, stride {1,2}, groups. 1x1/stride-1/groups-1 goes to LinearFn instead."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, groups, relu):
+    def forward(ctx, x, w, bias, stride, groups, relu, want_stats=False):
         x = _c(x)
         N, H, W, Cin = x.shape
         Cout, ks = w.shape[0], w.shape[2]
@@ -365,7 +407,7 @@ class Conv2dFn(Function):
         plan = _conv_tc_plan(Cin, Cout, groups) if (G.MODE == 'bf16' and CONV_S2_TC and ks == 3 and stride == 2) else None
         if plan is not None:
             # stride 2 on the tensor cores: same implicit-GEMM kernel, the TMA map steps two pixels per box element
-            y = _conv_tc_run(_as16(x), w, bias, plan, 0, Cout, groups, relu, stride=2)
+            y = _conv_tc_run(_as16(x), w, bias, plan, 0, Cout, groups, relu, stride=2, want_stats=want_stats)
         else:
             y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
             call('tfb_conv2d_fwd', x, w, bias, y, N, H, W, Cin, Cout, ks, stride, groups, int(relu))
@@ -401,7 +443,7 @@ class Conv2dFn(Function):
                 dw = _gbuf(w)
                 db = _gbuf(bias_p) if has_bias else None
                 call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def _conv_tc_plan(c_read, c_write, groups):
@@ -490,7 +532,7 @@ def _prepack_all(device):
         e.epoch, e.version = _PACK_STATE['epoch'], w._version
 
 
-def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu, stride=1):
+def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu, stride=1, want_stats=False):
     N, H, W, c_read = x16.shape
     Cout, Cin = (w.shape[0], w.shape[1] * groups)
     e = _packed_weights(w, plan, mode, groups)
@@ -498,12 +540,17 @@ def _conv_tc_run(x16, w, bias, plan, mode, c_write, groups, relu, stride=1):
         call('tfb_conv3x3_pack_weights', w, e.wp, Cout, Cin, groups, mode, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'],
              plan['nb_real'], plan['gblocks'])
     y = torch.empty((N, (H - 1) // stride + 1, (W - 1) // stride + 1, c_write), dtype=torch.float32, device=x16.device)
-    if stride == 1:
+    st = None
+    if want_stats and bias is None and not relu and c_write % 4 == 0 and plan['nb_real'] % 4 == 0:
+        st = _arena_take(x16.device, 2 * c_write * 8, torch.float64)
+    if stride == 1 and st is None:
         call('tfb_conv3x3_tc', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'], plan['nb_real'],
              plan['gblocks'], int(relu))
     else:
         call('tfb_conv3x3_tc_strided', x16, e.wp, bias, y, N, H, W, c_read, c_write, plan['NB'], plan['KC'], plan['c_step'], plan['nchunks'],
-             plan['nb_real'], plan['gblocks'], int(relu), stride)
+             plan['nb_real'], plan['gblocks'], int(relu), stride, st)
+    if st is not None:
+        y._tfb_stats = st
     return y
 
 
@@ -561,10 +608,10 @@ class Conv3x3TCFn(Function):
     TMA tap-shifted NHWC tiles, no im2col); wgrad on the fp32 direct kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, groups, relu):
+    def forward(ctx, x, w, bias, groups, relu, want_stats=False):
         x = _c(x)
         Cout, Cin = w.shape[0], w.shape[1] * groups
-        y = _conv_tc_run(_as16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu)
+        y = _conv_tc_run(_as16(x), w, bias, _conv_tc_plan(Cin, Cout, groups), 0, Cout, groups, relu, want_stats=want_stats)
         ctx.save_for_backward(x, w, y if relu else None, bias)
         ctx.cfg = (groups, relu, bias is not None)
         return y
@@ -612,7 +659,7 @@ class Conv3x3TCFn(Function):
                 dw = _gbuf(w)
                 db = (_gbuf(bias_p) if db is None else db) if has_bias else None
                 call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, 3, 1, groups)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class Subsample2Fn(Function):
@@ -636,15 +683,23 @@ class Subsample2Fn(Function):
         return dx
 
 
-def conv2d(x, w, bias=None, stride=1, groups=1, relu=False):
+def conv2d(x, w, bias=None, stride=1, groups=1, relu=False, bn_stats=False):
+    """bn_stats: a training-mode BatchNorm consumes the result next — on the tensor-core paths (bf16 mode) the producing kernel's
+    epilogue then accumulates the per-channel sum / sum of squares (y._tfb_stats) and batch_norm skips its statistics pass."""
+    bn_stats = bn_stats and BN_STATS_FUSED and G.MODE == 'bf16' and bias is None and not relu
     if w.shape[2] == 1 and stride == 2 and groups == 1 and G.MODE == 'bf16':
         x, stride = Subsample2Fn.apply(x), 1
     if w.shape[2] == 1 and stride == 1 and groups == 1:
         N, H, W, C = x.shape
-        return LinearFn.apply(_view16(x, x.reshape(-1, C)), w, bias, relu).view(N, H, W, w.shape[0])
+        y2 = LinearFn.apply(_view16(x, x.reshape(-1, C)), w, bias, relu, bn_stats)
+        y = y2.view(N, H, W, w.shape[0])
+        st = getattr(y2, '_tfb_stats', None)
+        if st is not None:
+            y._tfb_stats = st
+        return y
     if G.MODE == 'bf16' and w.shape[2] == 3 and stride == 1 and _conv_tc_plan(w.shape[1] * groups, w.shape[0], groups) is not None:
-        return Conv3x3TCFn.apply(x, w, bias, groups, relu)
-    return Conv2dFn.apply(x, w, bias, stride, groups, relu)
+        return Conv3x3TCFn.apply(x, w, bias, groups, relu, bn_stats)
+    return Conv2dFn.apply(x, w, bias, stride, groups, relu, bn_stats)
 
 
 # ------------------------------------------------------------------ normalisation
@@ -652,7 +707,7 @@ class BatchNormTrainFn(Function):
     """BatchNorm2d in training mode (+ fused ReLU): batch statistics, running-stat update (momentum, unbiased var)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False, bwd16=False, pool=False):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, emit16=False, bwd16=False, pool=False, stats=None):
         x = _c(x)
         C = x.shape[-1]
         M = x.numel() // C
@@ -661,11 +716,23 @@ class BatchNormTrainFn(Function):
         y16 = _emit16(y, emit16 and not pool)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        ws = _ws(x.device)
         # pool: the squeeze-excite average pool of the output comes out of the normalise pass (SEFn picks it up from y._tfb_pooled)
-        pooled = torch.empty((x.shape[0], C), dtype=torch.float32, device=x.device) if pool else None
-        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd, ws,
-             y16, None, pooled, x.shape[0] if pool else 0)
+        pooled = None
+        if stats is not None and pool:
+            pooled = _arena_take(x.device, x.shape[0] * C * 4, torch.float32)      # accumulated into: must start at zero
+            if pooled is None:
+                stats = None
+            else:
+                pooled = pooled.view(x.shape[0], C)
+        if stats is not None:
+            # the conv / GEMM that produced x already accumulated sum x, sum x^2 per channel in its epilogue: one launch, one pass
+            call('tfb_bn_fwd_stats', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd,
+                 stats, y16, None, pooled, x.shape[0] if pool else 0)
+        else:
+            if pool:
+                pooled = torch.empty((x.shape[0], C), dtype=torch.float32, device=x.device)
+            call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), int(relu), running_mean, running_var, mean, invstd,
+                 _ws(x.device), y16, None, pooled, x.shape[0] if pool else 0)
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.relu, ctx.bwd16 = relu, bwd16
         if pool:
@@ -686,7 +753,7 @@ class BatchNormTrainFn(Function):
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, int(ctx.relu), dg, db, ws, dx16, None, None)
         if dx16 is not None:
             _offer16(dx, dx16)
-        return dx, dg, db, None, None, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None, None, None
 
 
 class BatchNormAddReluFn(Function):
@@ -695,7 +762,7 @@ class BatchNormAddReluFn(Function):
     passes — two launches and four passes over the block-sized activation fewer than BatchNorm, add+ReLU, ReLU', BatchNorm'."""
 
     @staticmethod
-    def forward(ctx, x, res, weight, bias, running_mean, running_var, momentum, eps, emit16=False, bwd16=False):
+    def forward(ctx, x, res, weight, bias, running_mean, running_var, momentum, eps, emit16=False, bwd16=False, stats=None):
         x, res = _c(x), _c(res)
         C = x.shape[-1]
         M = x.numel() // C
@@ -703,8 +770,12 @@ class BatchNormAddReluFn(Function):
         y16 = _emit16(y, emit16)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
-             _ws(x.device), y16, res, None, 0)
+        if stats is not None:
+            call('tfb_bn_fwd_stats', x, y, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
+                 stats, y16, res, None, 0)
+        else:
+            call('tfb_bn_fwd', x, y, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
+                 _ws(x.device), y16, res, None, 0)
         ctx.save_for_backward(x, weight, bias, mean, invstd, y)
         ctx.bwd16 = bwd16
         return _attach16(y, y16)
@@ -721,7 +792,7 @@ class BatchNormAddReluFn(Function):
         call('tfb_bn_bwd', x, dy, dx, M, C, weight, bias, mean, invstd, 0, dg, db, _ws(x.device), dx16, y, g)
         if dx16 is not None:
             _offer16(dx, dx16)
-        return dx, g, dg, db, None, None, None, None, None, None
+        return dx, g, dg, db, None, None, None, None, None, None, None
 
 
 def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None, pool=False):
@@ -732,11 +803,14 @@ def batch_norm(x, bn, relu, training, emit16=False, bwd16=False, residual=None, 
     if residual is not None and not (relu and BN_ADD_FUSED):
         return add(batch_norm(x, bn, False, training, False, bwd16), residual, relu=relu, emit16=emit16)
     if training:
+        stats = getattr(x, '_tfb_stats', None)        # accumulated by the producing conv / GEMM epilogue (conv2d(..., bn_stats=True))
+        if stats is not None and (stats.numel() != 2 * x.shape[-1] or x.shape[-1] > 2048):
+            stats = None
         if residual is not None:
             return BatchNormAddReluFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, emit16,
-                                            bwd16)
+                                            bwd16, stats)
         return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, emit16, bwd16,
-                                      pool)
+                                      pool, stats)
     if torch.is_grad_enabled() and x.requires_grad:
         raise RuntimeError('eval-mode BatchNorm backward is not implemented (training path only)')
     C = x.shape[-1]
@@ -933,14 +1007,19 @@ class AttentionFn(Function):
         C = h.shape[1]
         hs = C // nh
         dev = h.device
-        qkv = torch.empty((B * T, 3 * C), dtype=torch.float32, device=dev)
         tc = G.tc_ok(B * T, C, C, C)
-        hs_ = _as16(h) if tc else h
+        fused = tc and ATTN_FUSED and T <= 192 and hs % 2 == 0
         w3, b3 = (_pack3(wq, wk, wv), _pack3(bq, bk, bv)) if QKV_FUSED else (None, None)
         packed = w3 is not None and b3 is not None
+        q16 = fused and packed          # q|k|v straight out of the GEMM epilogue in bf16: the fused attention stages it with cp.async
+        qkv = torch.empty((B * T, 3 * C), dtype=torch.bfloat16 if q16 else torch.float32, device=dev)
+        hs_ = _as16(h) if tc else h
         if packed:
             # the three projections as ONE GEMM on the [3C, C] weight the flat parameter buffer holds contiguously
-            if tc:
+            if q16:
+                wb = G.weight_bf16(w3)
+                call('tfb_gemm_bf16_tc_out16', 1, B * T, 3 * C, C, hs_, hs_.stride(0), wb, wb.stride(0), qkv, 3 * C, b3, 0, 1.0)
+            elif tc:
                 G.gemm_bf16(hs_, G.weight_bf16(w3), qkv, trans_b=True, bias=b3)
             else:
                 gemm(h, w3, qkv, trans_b=True, bias=b3, mode='simt')
@@ -951,14 +1030,13 @@ class AttentionFn(Function):
                 else:
                     gemm(h, w_, qkv[:, i * C:(i + 1) * C], trans_b=True, bias=b_, mode='simt')
         scale = 1.0 / (hs ** 0.5)
-        fused = tc and ATTN_FUSED and T <= 192 and hs % 2 == 0
         if fused:
             # one launch: scores in TMEM, softmax on the TMEM lanes, probabilities through shared memory (csrc/attn_tc.cu)
             y = torch.empty((B * T, C), dtype=torch.float32, device=dev)
             y16 = _emit16(y, True)                           # the output feeds the proj GEMM
             lse = torch.empty((B, nh, T), dtype=torch.float32, device=dev)
-            call('tfb_attn_fwd_tc', qkv, 0, B, T, nh, hs, y, y16, lse, scale, float(p_drop), seed_state(dev), seed)
-            ctx.save_for_backward(hs_, wq, wk, wv, qkv, y, lse, bq, bk, bv)
+            call('tfb_attn_fwd_tc', qkv, int(q16), B, T, nh, hs, y, y16, lse, scale, float(p_drop), seed_state(dev), seed)
+            ctx.save_for_backward(hs_, wq, wk, wv, qkv, y, lse, bq, bk, bv)      # y in fp32: D = rowsum(dy * y) keeps full precision
             ctx.cfg = (B, T, nh, p_drop, seed, scale, tc, packed, True)
             return _attach16(y, y16)
         S = torch.empty((B, nh, T, T), dtype=torch.float32, device=dev)
@@ -980,14 +1058,16 @@ class AttentionFn(Function):
         C = h.shape[1]
         hs = C // nh
         dev = h.device
-        dqkv = torch.empty_like(qkv)
+        dqkv = torch.empty(qkv.shape, dtype=torch.float32, device=dev)
         dq, dk, dv = dqkv[:, 0:C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
         d16 = None
         if fused:
-            y, lse = P, Pd                                   # (saved in their place by the fused forward)
+            y, lse = P, Pd                                   # (saved in their place by the fused forward; y fp32 or its bf16 copy)
             d16 = torch.empty(dqkv.shape, dtype=torch.bfloat16, device=dev)
             dsum = torch.empty((B, nh, T), dtype=torch.float32, device=dev)
-            call('tfb_attn_bwd_tc', qkv, 0, dy, 0, dy, y, lse, dsum, B, T, nh, hs, dqkv, d16, scale, float(p_drop), seed_state(dev), seed)
+            dy16 = torch.empty((B * T, C), dtype=torch.bfloat16, device=dev)
+            call('tfb_attn_bwd_tc', qkv, int(qkv.dtype == torch.bfloat16), dy, y, int(y.dtype == torch.bfloat16), lse, dsum, dy16,
+                 B, T, nh, hs, dqkv, d16, scale, float(p_drop), seed_state(dev), seed)
         else:
             q, k, v = qkv[:, 0:C], qkv[:, C:2 * C], qkv[:, 2 * C:]
             sP, sQ, sY = (nh * T * T, T * T), (T * 3 * C, hs), (T * C, hs)
