@@ -104,8 +104,15 @@ class Profiler:
     """Per-entry-point CUDA-event timing (events recorded on the launching stream around every C-ABI call) plus the
     algorithmic FLOPs / bytes of each call, used by bench.py for the live roofline of the dominant kernel."""
 
-    def __init__(self):
+    # entry points that launch the same kernel: their times are added up when the dominant KERNEL of the step is picked
+    FAMILY = {'tfb_gemm_bf16_tc': 'gemm_tc_kernel', 'tfb_gemm_bf16_tc_stats': 'gemm_tc_kernel', 'tfb_gemm_bf16_tc_out16': 'gemm_tc_kernel',
+              'tfb_gemm_bf16_tc_wgrad_batched': 'gemm_tc_kernel', 'tfb_conv3x3_tc': 'conv3x3_tc_kernel', 'tfb_conv3x3_tc_strided': 'conv3x3_tc_kernel',
+              'tfb_bn_fwd': 'bn_fwd (colreduce4 + bn_apply)', 'tfb_bn_fwd_stats': 'bn_apply_stats_kernel', 'tfb_attn_fwd_tc': 'attn_tc_kernel',
+              'tfb_attn_bwd_tc': 'attn_tc_kernel'}
+
+    def __init__(self, keep_calls=False):
         self.records = []
+        self.calls = [] if keep_calls else None     # (name, args) of every call, tensors kept alive: replayed by bench.py's graph timing
 
     def timed(self, name, args, thunk):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -113,6 +120,8 @@ class Profiler:
         rc = thunk()
         e1.record()
         self.records.append((name, self._work(name, args), e0, e1, self._key(name, args)))
+        if self.calls is not None:
+            self.calls.append((name, args))
         return rc
 
     @staticmethod
@@ -121,6 +130,15 @@ class Profiler:
             return '%s tb%d M%d N%d K%d' % (name, a[0], a[1], a[2], a[3])
         if name == 'tfb_gemm_bf16_tc_wgrad_batched':
             return '%s M%d N%d K%d batch%d splits%d' % (name, a[0], a[1], a[2], a[12], a[13])
+        if name == 'tfb_gemm_bf16_tc_stats':
+            return '%s M%d N%d K%d' % (name, a[0], a[1], a[2])
+        if name == 'tfb_gemm_bf16_tc_out16':
+            return '%s tb%d M%d N%d K%d' % (name, a[0], a[1], a[2], a[3])
+        if name in ('tfb_attn_fwd_tc', 'tfb_attn_bwd_tc'):
+            i0 = 2 if name.endswith('fwd_tc') else 8
+            return '%s B%d T%d nh%d hs%d' % ((name,) + tuple(a[i0:i0 + 4]))
+        if name == 'tfb_conv3x3_tc_strided':
+            return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d s%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14], a[16])
         if name == 'tfb_conv3x3_tc':
             return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14])
         if name.startswith('tfb_gemm'):
@@ -137,11 +155,24 @@ class Profiler:
             return 2.0 * a[1] * a[2] * a[3], 4.0 * (a[1] * a[3] + a[2] * a[3] + a[1] * a[2])
         if name == 'tfb_gemm_bf16_tc_wgrad_batched':
             return 2.0 * a[0] * a[1] * a[2] * a[12], 2.0 * a[2] * a[12] * (a[0] + a[1]) + 4.0 * a[0] * a[1] * a[12]
-        if name == 'tfb_conv3x3_tc':
+        if name == 'tfb_gemm_bf16_tc_stats':
+            return 2.0 * a[0] * a[1] * a[2], 2.0 * (a[0] * a[2] + a[1] * a[2]) + 4.0 * a[0] * a[1]
+        if name == 'tfb_gemm_bf16_tc_out16':
+            return 2.0 * a[1] * a[2] * a[3], 2.0 * (a[1] * a[3] + a[2] * a[3]) + 2.0 * a[1] * a[2]
+        if name == 'tfb_gemm_bf16_tc':
+            return 2.0 * a[2] * a[3] * a[4], 2.0 * (a[2] * a[4] + a[3] * a[4]) + 4.0 * a[2] * a[3]
+        if name in ('tfb_attn_fwd_tc', 'tfb_attn_bwd_tc'):
+            i0 = 2 if name.endswith('fwd_tc') else 8
+            B, T, nh, hs = a[i0:i0 + 4]
+            mult = 1.0 if name.endswith('fwd_tc') else 2.5     # forward: S and PV; backward: S, dP, dV, dQ, dK
+            return 4.0 * B * nh * T * T * hs * mult, 4.0 * B * T * nh * hs * 4 * mult
+        if name in ('tfb_conv3x3_tc', 'tfb_conv3x3_tc_strided'):
             N, H, W, Cx, Cy, NB, KC, c_step, nchunks, nb_real, gblocks = a[4:15]
             # algorithmic (useful) MACs: each written channel contracts over its group's channels only
             cin_eff = Cx if c_step == 0 else 24
-            return 2.0 * N * H * W * Cy * cin_eff * 9, 2.0 * N * H * W * Cx + 4.0 * N * H * W * Cy
+            st = a[16] if name == 'tfb_conv3x3_tc_strided' else 1
+            Ho, Wo = (H - 1) // st + 1, (W - 1) // st + 1
+            return 2.0 * N * Ho * Wo * Cy * cin_eff * 9, 2.0 * N * H * W * Cx + 4.0 * N * Ho * Wo * Cy
         if name.startswith('tfb_gemm'):
             M, N, K = a[2], a[3], a[4]
             nb = a[15] * a[16] if name.endswith('simt') else 1
@@ -169,8 +200,16 @@ class Profiler:
             d[2] += by
             d[3] += 1
         total = sum(v[0] for v in agg.values()) or 1.0
-        top = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        fam = {}
+        for name, v in agg.items():
+            f = fam.setdefault(self.FAMILY.get(name, name), [0.0, 0.0, 0.0, 0, []])
+            for i in range(4):
+                f[i] += v[i]
+            f[4].append(name)
+        self.families = fam
+        top = sorted(((k, v[:4]) for k, v in fam.items()), key=lambda kv: -kv[1][0])
         name, (ms, fl, by, n) = top[0]
+        self.top_entry_points = fam[name][4]
         tensor = fl > 0
         if tensor:
             ach, peak, unit = fl / (ms * 1e-3) / 1e12, pk['bf16_tflops_sustained'], 'TFLOP/s'

@@ -333,27 +333,43 @@ int dispatch_major(int BN, int transA, int transB, int M, int N, int K, const T*
   return launch_tc<T, true, false>(BN, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream);
 }
 
-// Tile width for a [M, N] output with `zs` independent K-splits / batches. The kernel is bound by the bytes each CTA pulls from L2
-// per k-block ((128 + BN) * 128 B against ~42 B/clk per SM), so the cost of a tile is ~ (128 + BN) plus a fixed prologue / epilogue
-// share; the persistent grid runs ceil(tiles / SMs) waves. step = 16 (K-major B) or 64 (MN-major B: whole 128-byte swizzle rows).
-int pick_bn(int M, int N, int zs, int step) {
+// Tile width (and, when auto_split, the split-K factor) for a [M, N] output with `nbatch` independent batches and num_kb k-blocks.
+// The kernel is bound by the bytes each CTA pulls from L2 per k-block ((128 + BN) * 128 B against ~42 B/clk per SM), so one CTA
+// costs ~ kb_per_split * (128 + BN) plus a fixed prologue / epilogue share (kFixed, in the same unit: ~6 k-blocks of a 128 x 128
+// tile) plus, for split-K, the fp32 atomics of its 128 x BN partial tile; the persistent grid runs ceil(CTAs / SMs) waves.
+// step = 16 (K-major B) or 64 (MN-major B: whole 128-byte swizzle rows). auto_split: the number of splits that fills one wave of
+// SMs while leaving >= 4 k-blocks per CTA (weight gradients: long contraction, few output tiles).
+int pick_bn(int M, int N, int zs, int step, int num_kb = 0, bool auto_split = false, int* splits_out = nullptr) {
   static int force_bn = -1, model_c = -2;
   if (force_bn < 0) { const char* e = getenv("TFB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
   if (model_c == -2) { const char* e = getenv("TFB_GEMM_TILE_MODEL"); model_c = e ? atoi(e) : 64; }
   const int nmax = ((N + step - 1) / step) * step;                 // one tile covers all of N
-  if (force_bn > 0) { int bn = ((force_bn + step - 1) / step) * step; if (bn > 256) bn = 256; return bn < nmax ? bn : (nmax > 256 ? 256 : nmax); }
   const int64_t mt = (M + BM - 1) / BM;
   const int sms = tfb_num_sms();
-  int best_bn = 0;
+  int best_bn = 0, best_s = 1;
   int64_t best = -1;
   for (int bn = step < 32 ? 32 : step; bn <= 256; bn += step) {
-    const int use = bn < nmax ? bn : nmax;                         // never wider than the problem
+    int use = bn < nmax ? bn : nmax;                               // never wider than the problem
+    if (force_bn > 0) { use = ((force_bn + step - 1) / step) * step; if (use > 256) use = 256; if (use > nmax) use = nmax > 256 ? 256 : nmax; }
     if (use > 256) continue;
     const int64_t tiles = mt * ((N + use - 1) / use) * zs;
-    const int64_t cost = ((tiles + sms - 1) / sms) * (128 + use + model_c);
-    if (best < 0 || cost < best || (cost == best && use > best_bn)) { best = cost; best_bn = use; }
-    if (use == nmax) break;
+    int64_t cost;
+    int s = 1;
+    if (auto_split && num_kb > 0) {
+      s = (int)(sms / tiles);
+      if (s > num_kb / 4) s = num_kb / 4;
+      if (s < 1) s = 1;
+      const int kbs = (num_kb + s - 1) / s;
+      s = (num_kb + kbs - 1) / kbs;
+      const int64_t waves = (tiles * s + sms - 1) / sms;
+      cost = waves * ((int64_t)kbs * (128 + use) + 6 * 256 + (s > 1 ? 4 * use : 0));
+    } else {
+      cost = ((tiles + sms - 1) / sms) * (128 + use + model_c);
+    }
+    if (best < 0 || cost < best || (cost == best && use > best_bn)) { best = cost; best_bn = use; best_s = s; }
+    if (use == nmax || force_bn > 0) break;
   }
+  if (splits_out) *splits_out = best_s;
   return best_bn;
 }
 
@@ -367,6 +383,10 @@ int gemm_tc_any(int transA, int transB, int M, int N, int K, const T* A, int64_t
   TFB_REQUIRE((lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0);
   const int step = transB == 0 ? Elem<T>::kPerRow : 16;
   const int num_kb = (K + Elem<T>::kPerRow - 1) / Elem<T>::kPerRow;
+  if (splits <= 0 && !stats && !C16 && !relu && (beta == 0.f || beta == 1.f)) {      // auto split-K (weight gradients)
+    const int bn = pick_bn(M, N, 1, step, num_kb, true, &splits);
+    return dispatch_major<T>(bn, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream, stats, C16);
+  }
   const int zs = splits < 1 ? 1 : (splits > num_kb ? num_kb : splits);
   return dispatch_major<T>(pick_bn(M, N, zs, step), transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, alpha, beta, splits, stream, stats, C16);
 }
@@ -384,6 +404,10 @@ TFB_API int tfb_gemm_bf16_tc_wgrad_batched(int M, int N, int K, const void* A, i
   TFB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_step % 8 == 0 && b_step % 8 == 0);
   using T = __nv_bfloat16;
   const int num_kb = (K + 63) / 64;
+  if (splits <= 0) {                                                                  // auto split-K
+    const int bn = pick_bn(M, N, nbatch, 64, num_kb, true, &splits);
+    return launch_tc<T, true, true>(bn, M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
+  }
   const int zs = (splits < 1 ? 1 : (splits > num_kb ? num_kb : splits)) * nbatch;
   return launch_tc<T, true, true>(pick_bn(M, N, zs, 64), M, N, K, (const T*)A, lda, (const T*)B, ldb, C, ldc, nullptr, 0, 1.f, 0.f, splits, stream, nbatch, a_step, b_step, c_bstride);
 }

@@ -97,6 +97,7 @@ SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd
 CONV_S2_TC = os.environ.get('TFB_CONV_S2_TC', '1') == '1'       # bf16 mode: stride-2 3x3 convs forward on the tcgen05 kernel (TMA element strides)
 WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: weight-gradient GEMMs on a third stream (they only feed AdamW)
 BN_STATS_FUSED = os.environ.get('TFB_BN_STATS_FUSED', '1') == '1'   # bf16 mode: BatchNorm statistics out of the producing conv / GEMM epilogue
+WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '1') == '1'   # split-K of the weight-gradient GEMMs chosen by the library
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
@@ -317,6 +318,8 @@ def _relu_bwd(y, dy):
 # ------------------------------------------------------------------ dense layers (GEMM) and convolutions
 def _wgrad_splits(M, N, K):
     """split-K factor for dW[N,K] = dy^T x with a long contraction (M rows): aim for >= 2 waves of 128x128 tiles."""
+    if WGRAD_AUTO_SPLIT:
+        return 0          # the library picks tile width and split factor together (csrc/gemm_tc.cu pick_bn: one wave of SMs, >= 4 k-blocks per CTA)
     tiles = ((N + 127) // 128) * ((K + 127) // 128)
     return max(1, min(64, (296 + tiles - 1) // tiles, M // 2048 if M >= 4096 else 1))
 
@@ -595,7 +598,7 @@ def _conv_wgrad_tc(x, g16, w, groups, stride):
                 _COL_CACHE[key] = (x, col, x._version)
         dwp = dw.view(Cout, 9 * Cig) if rows == Cout else torch.empty((rows, 9 * Cig), dtype=torch.float32, device=x.device)
         ntiles = groups * ((9 * Cig + 127) // 128)
-        splits = max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
+        splits = 0 if WGRAD_AUTO_SPLIT else max(1, min(128, (2 * 148 + ntiles - 1) // ntiles, M // 256))
         call('tfb_gemm_bf16_tc_wgrad_batched', Cog if groups > 1 else rows, 9 * Cig, M, g16, ldg, Cog if groups > 1 else 0, col, 9 * Cin,
              9 * Cig if groups > 1 else 0, dwp, 9 * Cig, Cog * 9 * Cig, groups, splits)
         if rows != Cout:
