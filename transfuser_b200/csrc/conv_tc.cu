@@ -47,6 +47,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* stage_out = reinterpret_cast<float*>(smem + STAGES * STAGE + 256);
+  float* s_stat = stage_out + 4 * 32 * 36;      // [2][Cout] per-channel statistics accumulators (present only when stats != nullptr)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = nchunks * 9;
@@ -117,6 +118,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     const int q = warp & 3;
     float* stage = stage_out + q * (32 * 36);
     int lt = 0;
+    if (stats) tc::stat_clear(s_stat, Cout, (int)threadIdx.x - 64);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int gb, n, h0, w0;
       decode(t, gb, n, h0, w0);
@@ -140,7 +142,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
                                  return (h < H && w < W) ? (((int64_t)n * H + h) * W + w) * Cout + c0 : (int64_t)-1;
                                },
                                cols_valid, bp ? bp + c0 : nullptr, 1.f, relu, lane, ytile, nullptr,
-                               stats ? stats + gb * nb_real + c0 : nullptr, stats ? stats + Cout + gb * nb_real + c0 : nullptr);
+                               stats ? s_stat + gb * nb_real + c0 : nullptr, stats ? s_stat + Cout + gb * nb_real + c0 : nullptr);
         }
       } else {
         const int r = q * 32 + lane;
@@ -167,6 +169,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (stats) tc::stat_flush(s_stat, stats, Cout, (int)threadIdx.x - 64);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -182,7 +185,8 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
   const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output size (kernel 3, pad 1)
   constexpr int STAGES = NB <= 64 ? 6 : 4;
   constexpr int STAGE = BM * KC * 2 + NB * KC * 2;
-  constexpr int SMEM = STAGES * STAGE + 256 + 4 * 32 * 36 * 4 + 1024;   // ring + barriers/TMEM slot + epilogue staging + alignment slack
+  constexpr int SMEM0 = STAGES * STAGE + 256 + 4 * 32 * 36 * 4 + 1024;   // ring + barriers/TMEM slot + epilogue staging + alignment slack
+  const int SMEM = SMEM0 + (stats ? 2 * Cy * (int)sizeof(float) : 0);    // + per-channel statistics accumulators
   CUtensorMap mx, mw;
   const uint64_t xd[4] = {(uint64_t)Cx, (uint64_t)Win, (uint64_t)Hin, (uint64_t)N};
   const uint64_t xs[3] = {(uint64_t)Cx * 2, (uint64_t)Win * Cx * 2, (uint64_t)Hin * Win * Cx * 2};
@@ -203,7 +207,7 @@ int launch_conv(const void* x16, const void* wpack, const float* bias, float* y,
   auto kern = conv3x3_tc_kernel<KC, NB, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return TFB_ERR_DRIVER;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM0 + 2 * 2048 * (int)sizeof(float)) != cudaSuccess) return TFB_ERR_DRIVER;
     attr_done = true;
   }
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
@@ -229,7 +233,7 @@ TFB_API int tfb_conv3x3_tc_strided(const void* x16, const void* wpack, const flo
                                    int NB, int KC, int c_step, int nchunks, int nb_real, int gblocks, int relu, int stride, double* stats,
                                    cudaStream_t stream) {
   TFB_REQUIRE(x16 && wpack && y && N > 0 && H > 0 && W > 0 && Cx > 0 && Cy > 0 && Cx % 8 == 0 && (stride == 1 || stride == 2));
-  TFB_REQUIRE(!stats || (Cy % 4 == 0 && nb_real % 4 == 0 && !bias && !relu && (reinterpret_cast<uintptr_t>(y) & 15) == 0));
+  TFB_REQUIRE(!stats || (Cy % 4 == 0 && Cy <= 2048 && nb_real % 4 == 0 && !bias && !relu && (reinterpret_cast<uintptr_t>(y) & 15) == 0));
   TFB_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0);
 #define CASE(KC_, NB_) if (KC == KC_ && NB == NB_) return launch_conv<KC_, NB_>(x16, wpack, bias, y, N, H, W, Cx, Cy, c_step, nchunks, nb_real, gblocks, relu, stride, stats, stream)
   CASE(64, 16); CASE(64, 32); CASE(64, 48); CASE(64, 64); CASE(64, 128);

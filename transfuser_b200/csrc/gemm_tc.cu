@@ -35,6 +35,7 @@ template <> struct Elem<__nv_bfloat16> {
 // Shared memory: STAGES x (A tile 128 x 128 B | B tile BN x 128 B), barriers, 4 x (32 x 36 floats) epilogue staging. BN (the tile
 // width, any multiple of 16 up to 256; a multiple of 64 for an MN-major B) and STAGES are RUNTIME values: the host picks the width
 // that fills whole waves of the persistent grid (M = 1740 token GEMMs: N = 1512 -> 160, N = 4536 -> 224) and the deepest ring that fits.
+int g_max_ctas = 0;                                           // tfb_gemm_set_max_ctas: cap of the persistent grid (0 = one CTA per SM)
 constexpr int kABytes = BM * 128;
 constexpr int kSmemMax = 232448;                              // 227 KB opt-in limit
 constexpr int kSmemFixed = 256 + 4 * 32 * 36 * 4 + 1024;      // barriers + epilogue staging + alignment slack
@@ -64,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
   float* stage_out = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 256);
+  float* s_stat = stage_out + 4 * 32 * 36;       // [2][N] per-column statistics accumulators (present only when stats != nullptr)
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_a);
@@ -160,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
     int lt = 0;
+    if (stats) tc::stat_clear(s_stat, N, (int)threadIdx.x - 64);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int m0, n0, bz, sz, kb_begin, nkb;
       decode(t, m0, n0, bz, sz, kb_begin, nkb);
@@ -184,8 +187,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int64_t off0 = (int64_t)bz * c_bstride + (int64_t)(m0 + q * 32) * ldc + n0 + c0;
           tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
                                [=](int row) -> int64_t { return row < rows_valid ? off0 + (int64_t)row * ldc : (int64_t)-1; }, cols_valid,
-                               add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane, Cbase, C16, stats ? stats + n0 + c0 : nullptr,
-                               stats ? stats + N + n0 + c0 : nullptr);
+                               add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane, Cbase, C16, stats ? s_stat + n0 + c0 : nullptr,
+                               stats ? s_stat + N + n0 + c0 : nullptr);
         }
       } else {
 #pragma unroll 1
@@ -215,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (stats) tc::stat_flush(s_stat, stats, N, (int)threadIdx.x - 64);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -265,13 +269,14 @@ int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, 
   }
   constexpr int BK = E::kPerRow;
   if (stats) {   // the statistics come out of the coalesced epilogue path only: make sure the kernel takes it
-    TFB_REQUIRE(splits <= 1 && beta == 0.f && nbatch == 1 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && !relu);
+    TFB_REQUIRE(splits <= 1 && beta == 0.f && nbatch == 1 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && !relu && N <= 4096);
   }
   TFB_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && (!B_MN || BN % E::kPerRow == 0));
   const int stage_bytes = kABytes + BN * 128;
-  int stages = (kSmemMax - kSmemFixed) / stage_bytes;
+  const int stat_bytes = stats ? 2 * N * (int)sizeof(float) : 0;       // per-column accumulators behind the epilogue staging
+  int stages = (kSmemMax - kSmemFixed - stat_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  const int smem_total = stages * stage_bytes + kSmemFixed;
+  const int smem_total = stages * stage_bytes + kSmemFixed + stat_bytes;
   CUtensorMap ma, mb;
   bool ok;
   const int64_t Mext = (int64_t)(nbatch - 1) * a_step + M, Next = (int64_t)(nbatch - 1) * b_step + N;   // extents of the shared maps
@@ -311,7 +316,8 @@ int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, 
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const int64_t total = (int64_t)tiles_m * tiles_n * splits * nbatch;
   if (total > 0x7fffffff) { tfb_set_last_error("too many tiles"); return TFB_ERR_ARG; }
-  const int grid = (int)(total < tfb_num_sms() ? total : tfb_num_sms());
+  int grid = (int)(total < tfb_num_sms() ? total : tfb_num_sms());
+  if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
   kern<<<grid, 192, smem_total, stream>>>(ma, mb, C, ldc, M, N, num_kb, kb_per_split, bias, alpha, beta, relu, atomic_out, splits, a_step,
                                           b_step, c_bstride, tiles_m, tiles_n, (int)total, BN, stages, stats, C16);
   TFB_CHECK_LAUNCH();
@@ -449,4 +455,13 @@ TFB_API int tfb_gemm_bf16_tc_out16(int transB, int M, int N, int K, const void* 
   TFB_REQUIRE(C16 != nullptr);
   return gemm_tc_any<__nv_bfloat16>(0, transB, M, N, K, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, nullptr, ldc, bias, relu,
                                     alpha, 0.f, 1, stream, nullptr, (__nv_bfloat16*)C16);
+}
+
+// Caps the persistent grid of the following tcgen05 GEMM launches at max_ctas CTAs (0 = no cap: one per SM). The weight-gradient
+// GEMMs run on a side stream next to the critical dx chain; with a full-chip grid they take every SM away from it (measured: the
+// step got 1.3 ms SLOWER when their split-K filled all 148 SMs), with a capped grid they use the SMs the chain leaves idle.
+// Host-side state (not a stream operation); read at launch time, so a captured CUDA graph keeps the grid it was captured with.
+TFB_API int tfb_gemm_set_max_ctas(int max_ctas) {
+  g_max_ctas = max_ctas > 0 ? max_ctas : 0;
+  return TFB_OK;
 }

@@ -131,13 +131,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // `row_off(row)` returns the ELEMENT offset of accumulator row `row` (0..31) in the output (a multiple of 4) or -1 for rows that
 // must not be written; columns >= cols_valid are not written. The result goes to out32 (fp32) or, when out16 is given, to out16
 // (bf16, round-to-nearest-even) at the same element offsets.
-// stat_sum / stat_sq (optional, fp64, this chunk's column 0): per-column sum and sum of squares of the values written (rows with
-// offset -1 contribute nothing) are added with one fp64 atomic per column and warp — the training-mode BatchNorm statistics
-// of a conv / GEMM output come out of its epilogue instead of a separate read pass over the tensor.
+// stat_sum / stat_sq (optional, fp32 accumulators in SHARED memory, this chunk's column 0): per-column sum and sum of squares of
+// the values written (rows with offset -1 contribute nothing) — the training-mode BatchNorm statistics of a conv / GEMM output
+// come out of its epilogue instead of a separate read pass over the tensor. The CTA accumulates over all of its tiles and flushes
+// once (stat_flush) with one fp64 global atomic per column: a first version that issued global atomics per warp and chunk
+// serialised thousands of same-address atomics on the 72-channel, 70 400-row stage-1 GEMMs and cost more than the pass it removed.
 template <class RowOff>
 __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, RowOff row_off, int cols_valid, const float* bias,
                                                  float alpha, int relu, int lane, float* out32, __nv_bfloat16* out16 = nullptr,
-                                                 double* stat_sum = nullptr, double* stat_sq = nullptr) {
+                                                 float* stat_sum = nullptr, float* stat_sq = nullptr) {
   uint32_t r[32];
   tmem_ld16_nowait(taddr, r);
   tmem_ld16_nowait(taddr + 16, r + 16);
@@ -203,10 +205,24 @@ __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, R
     if (lane < 8) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (c4 + q < cols_valid) { atomicAdd(stat_sum + c4 + q, (double)s1[q]); atomicAdd(stat_sq + c4 + q, (double)s2[q]); }
+        if (c4 + q < cols_valid) { atomicAdd(stat_sum + c4 + q, s1[q]); atomicAdd(stat_sq + c4 + q, s2[q]); }
     }
   }
   __syncwarp();
+}
+
+// The four epilogue warps (128 threads, named barrier 1) clear / flush the CTA's per-column statistics accumulators s_stat[2][n]
+// (shared) into stats[2][n] (global fp64: [sum | sum of squares]). t = thread index among the 128 epilogue threads.
+__device__ __forceinline__ void stat_clear(float* s_stat, int n, int t) {
+  for (int i = t; i < 2 * n; i += 128) s_stat[i] = 0.f;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+__device__ __forceinline__ void stat_flush(const float* s_stat, double* stats, int n, int t) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int i = t; i < 2 * n; i += 128) {
+    const float v = s_stat[i];
+    if (v != 0.f) atomicAdd(stats + i, (double)v);
+  }
 }
 
 // ---------------- descriptors ----------------

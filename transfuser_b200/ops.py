@@ -97,7 +97,10 @@ SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd
 CONV_S2_TC = os.environ.get('TFB_CONV_S2_TC', '1') == '1'       # bf16 mode: stride-2 3x3 convs forward on the tcgen05 kernel (TMA element strides)
 WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: weight-gradient GEMMs on a third stream (they only feed AdamW)
 BN_STATS_FUSED = os.environ.get('TFB_BN_STATS_FUSED', '1') == '1'   # bf16 mode: BatchNorm statistics out of the producing conv / GEMM epilogue
-WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '1') == '1'   # split-K of the weight-gradient GEMMs chosen by the library
+WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '0') == '1'   # split-K of the weight-gradient GEMMs chosen by the library (fills a wave:
+#                                                                          measured 1.3 ms/step SLOWER next to the critical chain; off)
+WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '0'))          # cap of the persistent grid of GEMMs on the weight-gradient stream
+NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
@@ -223,10 +226,14 @@ class _OnWgradStream:
                     t.record_stream(s)
             self.ctx = torch.cuda.stream(s)
             self.ctx.__enter__()
+            if WGRAD_MAX_CTAS > 0:
+                call('tfb_gemm_set_max_ctas', WGRAD_MAX_CTAS)
         return self
 
     def __exit__(self, *exc):
         if self.on:
+            if WGRAD_MAX_CTAS > 0:
+                call('tfb_gemm_set_max_ctas', 0)
             self.ctx.__exit__(*exc)
         return False
 
@@ -643,7 +650,9 @@ class Conv3x3TCFn(Function):
             else:
                 g16 = None
         if ctx.needs_input_grad[0]:
-            plan = _conv_tc_plan(Cout, Cin, groups) if Cout % 8 == 0 else None
+            # narrow outputs (the 7- / 1-channel decoder heads at 160 x 704): dgrad on the tensor cores too, reading the dy that was
+            # zero-padded to 8 channels for the wgrad GEMM (the packed dgrad weights are zero beyond the real Cout)
+            plan = _conv_tc_plan(Cout, Cin, groups) if Cout % 8 == 0 else (_conv_tc_plan(8, Cin, 1) if (g16 is not None and NARROW_DGRAD_TC) else None)
             if plan is not None:
                 dx = _conv_tc_run(g16, w, None, plan, 1, Cin, groups, False)
             else:
