@@ -90,5 +90,8 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert abs(s0 - s1) <= 1e-5 * s0
     # after 3 AdamW steps parameters moved by ~lr per step; eager and graph moved them the same way. (Adam's first updates are
     # ~lr*sign(g): noise-level gradients whose sign depends on the fp32 atomic accumulation order account for the residual.)
+    # Batch 1 with batch-statistics BatchNorm in bf16 mode is the noisiest configuration there is: round 2 moved the attention and the
+    # stride-2 convs onto bf16 operands as well and the residual grew from < 0.1 to 0.24 of the distance moved while the losses of
+    # the two paths still agree to 2e-3 (above). The bound separates "same trajectory up to sign noise" from "different step" (>= 1).
     moved = (p0 - i0).norm().item()
-    assert moved > 0 and (p0 - p1).norm().item() <= 0.1 * moved
+    assert moved > 0 and (p0 - p1).norm().item() <= 0.4 * moved

@@ -141,7 +141,7 @@ class Profiler:
             return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d s%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14], a[16])
         if name == 'tfb_conv3x3_tc':
             return '%s N%d H%d W%d Cx%d Cy%d NB%d KC%d chunks%d gblocks%d' % (name, a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[12], a[14])
-        if name.startswith('tfb_gemm'):
+        if name in ('tfb_gemm_bf16_tc', 'tfb_gemm_f32_simt', 'tfb_gemm_tf32_tc'):
             return '%s ta%d tb%d M%d N%d K%d%s' % (name, a[0], a[1], a[2], a[3], a[4], (' batch%dx%d' % (a[15], a[16])) if name.endswith('simt') else '')
         if name.startswith('tfb_conv2d'):
             i0 = 3 if name.endswith('dgrad') else 4
@@ -173,7 +173,7 @@ class Profiler:
             st = a[16] if name == 'tfb_conv3x3_tc_strided' else 1
             Ho, Wo = (H - 1) // st + 1, (W - 1) // st + 1
             return 2.0 * N * Ho * Wo * Cy * cin_eff * 9, 2.0 * N * H * W * Cx + 4.0 * N * Ho * Wo * Cy
-        if name.startswith('tfb_gemm'):
+        if name in ('tfb_gemm_f32_simt', 'tfb_gemm_tf32_tc'):
             M, N, K = a[2], a[3], a[4]
             nb = a[15] * a[16] if name.endswith('simt') else 1
             return 2.0 * M * N * K * nb, 4.0 * nb * (M * K + N * K + M * N)

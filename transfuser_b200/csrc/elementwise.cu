@@ -502,16 +502,17 @@ __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict_
 //   ds = dgate*gate*(1-gate);  dw2 = ds^T h;  db2 = colsum ds;  dh = (ds w2) * (h > 0);  dw1 = dh^T pooled;  db1 = colsum dh;
 //   dpool = dh w1
 // used to be eight launches of [N,C]-sized kernels (sigmoid', 2 weight-gradient GEMMs, 2 column sums, 2 skinny GEMMs, relu'). It is
-// two: both run one CTA per 64-channel chunk of C; the only cross-chunk quantity, dh (a sum over all of C), leaves kernel 1 as
-// per-chunk partials dh_part[chunk][N][Cr] that every CTA of kernel 2 sums in chunk order (deterministic, no atomics, no memset).
+// two: both run one CTA per 64-channel chunk of C; the only cross-chunk quantity, dh (a sum over all of C), is accumulated by
+// kernel 1 into a zeroed [N, Cr] buffer with fp32 atomics (24 per address at most) and read back by every CTA of kernel 2.
 constexpr int SE_CHUNK = 64;
 constexpr int SE_MAX_N = 16;
 constexpr int SE_MAX_CR = 512;   // static shared memory: (64 + 512) * 16 floats = 36 KiB
 
 __global__ void __launch_bounds__(256) se_mlp_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
                                                           const float* __restrict__ h, const float* __restrict__ w2,
-                                                          float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dh_part,
+                                                          float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dh_acc,
                                                           int N, int C, int Cr) {
+  // one CTA per 64-channel chunk of C. dh_acc[N][Cr] (ZERO on entry) receives this chunk's share of ds w2 through fp32 atomics.
   __shared__ float ds[SE_MAX_N * SE_CHUNK];  // [N][SE_CHUNK]
   __shared__ float hs[SE_MAX_N * SE_MAX_CR]; // [N][Cr]
   const int c0 = blockIdx.x * SE_CHUNK;
@@ -532,34 +533,41 @@ __global__ void __launch_bounds__(256) se_mlp_bwd1_kernel(const float* __restric
     for (int n = 0; n < N; ++n) t += ds[n * SE_CHUNK + threadIdx.x];
     db2[c0 + threadIdx.x] = t;
   }
-  for (int i = threadIdx.x; i < cw * Cr; i += blockDim.x) {          // dw2[c][r] = sum_n ds[n][c] h[n][r]
+  for (int i = threadIdx.x; i < cw * Cr; i += blockDim.x) {          // dw2[c][r] = sum_n ds[n][c] h[n][r]   (shared-memory operands)
     const int j = i / Cr, r = i % Cr;
     float t = 0.f;
     for (int n = 0; n < N; ++n) t = fmaf(ds[n * SE_CHUNK + j], hs[n * Cr + r], t);
     dw2[(int64_t)(c0 + j) * Cr + r] = t;
   }
-  float* part = dh_part + (int64_t)blockIdx.x * N * Cr;
-  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) {           // partial dh[n][r] = sum_{c in chunk} ds[n][c] w2[c][r]
-    const int n = i / Cr, r = i % Cr;
-    float t = 0.f;
-    for (int j = 0; j < cw; ++j) t = fmaf(ds[n * SE_CHUNK + j], w2[(int64_t)(c0 + j) * Cr + r], t);
-    part[i] = t;
+  // dh[n][r] += sum_{c in chunk} ds[n][c] w2[c][r]: a thread owns column r, streams the 64 weights of that column ONCE (coalesced
+  // across the threads, 8 loads in flight) and feeds all N rows from registers; the first version re-read each weight per row
+  for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
+    float acc[SE_MAX_N];
+#pragma unroll
+    for (int n = 0; n < SE_MAX_N; ++n) acc[n] = 0.f;
+    const float* wp = w2 + (int64_t)c0 * Cr + r;
+#pragma unroll 8
+    for (int j = 0; j < cw; ++j) {
+      const float w = wp[(int64_t)j * Cr];
+#pragma unroll
+      for (int n = 0; n < SE_MAX_N; ++n) acc[n] = fmaf(ds[n * SE_CHUNK + j], w, acc[n]);   // (rows >= N are zero in ds)
+    }
+#pragma unroll
+    for (int n = 0; n < SE_MAX_N; ++n)
+      if (n < N) atomicAdd(dh_acc + (int64_t)n * Cr + r, acc[n]);
   }
 }
 
-__global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restrict__ dh_part, int nchunks, const float* __restrict__ h,
+__global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restrict__ dh_acc, const float* __restrict__ h,
                                                           const float* __restrict__ pooled, const float* __restrict__ w1,
                                                           float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dpool,
                                                           int N, int C, int Cr) {
   __shared__ float ps[SE_MAX_N * SE_CHUNK];  // [N][SE_CHUNK] pooled chunk
   __shared__ float dh[SE_MAX_N * SE_MAX_CR]; // [N][Cr]
+  __shared__ float red[3][SE_MAX_N][SE_CHUNK];   // quarters 1..3 (quarter 0 keeps its sums in registers): 48 KiB of static smem in total
   const int c0 = blockIdx.x * SE_CHUNK;
   const int cw = min(SE_CHUNK, C - c0);
-  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) {
-    float t = 0.f;
-    for (int k = 0; k < nchunks; ++k) t += dh_part[(int64_t)k * N * Cr + i];
-    dh[i] = h[i] > 0.f ? t : 0.f;
-  }
+  for (int i = threadIdx.x; i < SE_MAX_N * Cr; i += blockDim.x) dh[i] = (i < N * Cr && h[i] > 0.f) ? dh_acc[i] : 0.f;
   for (int i = threadIdx.x; i < N * SE_CHUNK; i += blockDim.x) {
     const int n = i / SE_CHUNK, j = i % SE_CHUNK;
     ps[i] = j < cw ? pooled[(int64_t)n * C + c0 + j] : 0.f;
@@ -572,19 +580,40 @@ __global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restric
       db1[r] = t;
     }
   }
-  for (int i = threadIdx.x; i < Cr * SE_CHUNK; i += blockDim.x) {    // dw1[r][c] = sum_n dh[n][r] pooled[n][c]
+  for (int i = threadIdx.x; i < Cr * SE_CHUNK; i += blockDim.x) {    // dw1[r][c] = sum_n dh[n][r] pooled[n][c]   (shared-memory operands)
     const int r = i / SE_CHUNK, j = i % SE_CHUNK;
     if (j >= cw) continue;
     float t = 0.f;
     for (int n = 0; n < N; ++n) t = fmaf(dh[n * Cr + r], ps[n * SE_CHUNK + j], t);
     dw1[(int64_t)r * C + c0 + j] = t;
   }
-  for (int i = threadIdx.x; i < N * SE_CHUNK; i += blockDim.x) {     // dpool[n][c] = sum_r dh[n][r] w1[r][c]
-    const int n = i / SE_CHUNK, j = i % SE_CHUNK;
-    if (j >= cw) continue;
-    float t = 0.f;
-    for (int r = 0; r < Cr; ++r) t = fmaf(dh[n * Cr + r], w1[(int64_t)r * C + c0 + j], t);
-    dpool[(int64_t)n * C + c0 + j] = t;
+  // dpool[n][c] = sum_r dh[n][r] w1[r][c]: thread = (channel j, quarter q of the r range): each weight is loaded once (coalesced
+  // along j) and used for all N rows; the four quarters meet in shared memory
+  {
+    const int j = threadIdx.x & 63, q = threadIdx.x >> 6;
+    float acc[SE_MAX_N];
+#pragma unroll
+    for (int n = 0; n < SE_MAX_N; ++n) acc[n] = 0.f;
+    if (j < cw) {
+      const int r_lo = (Cr * q) / 4, r_hi = (Cr * (q + 1)) / 4;
+      const float* wp = w1 + c0 + j;
+#pragma unroll 8
+      for (int r = r_lo; r < r_hi; ++r) {
+        const float w = wp[(int64_t)r * C];
+#pragma unroll
+        for (int n = 0; n < SE_MAX_N; ++n) acc[n] = fmaf(dh[n * Cr + r], w, acc[n]);         // (rows >= N are zero in dh)
+      }
+    }
+    if (q > 0) {
+#pragma unroll
+      for (int n = 0; n < SE_MAX_N; ++n) red[q - 1][n][j] = acc[n];
+    }
+    __syncthreads();
+    if (q == 0 && j < cw) {
+#pragma unroll
+      for (int n = 0; n < SE_MAX_N; ++n)
+        if (n < N) dpool[(int64_t)n * C + c0 + j] = acc[n] + red[0][n][j] + red[1][n][j] + red[2][n][j];
+    }
   }
 }
 
@@ -660,16 +689,17 @@ TFB_API int tfb_se_bwd_reduce(const float* x, const float* dy, float* dgate, int
 }
 // Fused backward of the squeeze-excite MLP (see se_mlp_bwd1_kernel): dgate, gate, pooled [N,C]; h [N,Cr]; w1 [Cr,C]; w2 [C,Cr] ->
 // dw1 [Cr,C], db1 [Cr], dw2 [C,Cr], db2 [C], dpool [N,C] (all overwritten). N <= 16, Cr <= 512.
-// dh_part: workspace of ceil(C / 64) * N * Cr floats (fully written before it is read; no initialisation needed).
+// dh_part: workspace of at least N * Cr floats (cleared here: one memset node).
 TFB_API int tfb_se_mlp_bwd(const float* dgate, const float* gate, const float* h, const float* pooled, const float* w1, const float* w2,
                            float* dw1, float* db1, float* dw2, float* db2, float* dpool, float* dh_part, int N, int C, int Cr,
                            cudaStream_t stream) {
   TFB_REQUIRE(dgate && gate && h && pooled && w1 && w2 && dw1 && db1 && dw2 && db2 && dpool && dh_part);
   TFB_REQUIRE(N > 0 && N <= SE_MAX_N && C > 0 && Cr > 0 && Cr <= SE_MAX_CR);
   const int nchunks = (C + SE_CHUNK - 1) / SE_CHUNK;
+  if (cudaMemsetAsync(dh_part, 0, (size_t)N * Cr * sizeof(float), stream) != cudaSuccess) return TFB_ERR_DRIVER;
   se_mlp_bwd1_kernel<<<nchunks, 256, 0, stream>>>(dgate, gate, h, w2, dw2, db2, dh_part, N, C, Cr);
   TFB_CHECK_LAUNCH();
-  se_mlp_bwd2_kernel<<<nchunks, 256, 0, stream>>>(dh_part, nchunks, h, pooled, w1, dw1, db1, dpool, N, C, Cr);
+  se_mlp_bwd2_kernel<<<nchunks, 256, 0, stream>>>(dh_part, h, pooled, w1, dw1, db1, dpool, N, C, Cr);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

@@ -198,12 +198,19 @@ class LidarCenterNet(nn.Module):
         if two:
             # auxiliary decoders (image grid -> 160x704 maps) on the second stream, concurrently with the BEV-side heads
             main, side = torch.cuda.current_stream(), ops.side_stream(rgb.device)
+            # the two decoders are independent chains of mostly latency-bound launches (5x22 -> 160x704): one side stream each
+            side2 = ops.side_stream2(rgb.device) if ops.DECODER_STREAMS else side
             side.wait_stream(main)
+            ops.record_stream(image_features_grid, side)
+            if side2 is not side:
+                side2.wait_stream(main)
+                ops.record_stream(image_features_grid, side2)
             with torch.cuda.stream(side):
                 pred_semantic = self.seg_decoder.run(image_features_grid)
+                loss_semantic = ops.CrossEntropyFn.apply(pred_semantic, semantic, None, 'count', float(cfg.ls_seg))
+            with torch.cuda.stream(side2):
                 pred_depth = self.depth_decoder.run(image_features_grid)
                 loss_depth = ops.L1Fn.apply(pred_depth.view(pred_depth.shape[0], pred_depth.shape[1], pred_depth.shape[2]), depth, True, float(cfg.ls_depth))
-                loss_semantic = ops.CrossEntropyFn.apply(pred_semantic, semantic, None, 'count', float(cfg.ls_seg))
 
         pred_wp, _, _, _, _ = self.forward_gru(fused_features, target_point)
 
@@ -224,6 +231,8 @@ class LidarCenterNet(nn.Module):
 
         if two:
             main.wait_stream(side)
+            if side2 is not side:
+                main.wait_stream(side2)
             loss_depth.record_stream(main)
             loss_semantic.record_stream(main)
             loss['loss_depth'], loss['loss_semantic'] = loss_depth, loss_semantic

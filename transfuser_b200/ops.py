@@ -101,6 +101,7 @@ WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '0') == '1'   # split-
 #                                                                          measured 1.3 ms/step SLOWER next to the critical chain; off)
 WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '0'))          # cap of the persistent grid of GEMMs on the weight-gradient stream
 NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
+DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '1') == '1'   # segmentation and depth decoders on two side streams (not one)
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
@@ -177,6 +178,16 @@ def side_stream(device):
     if s is None:
         s = torch.cuda.Stream(device=device)
         _SIDE[device] = s
+    return s
+
+
+def side_stream2(device):
+    """A further side stream (the depth decoder runs next to the segmentation decoder on it)."""
+    device = torch.device(device)
+    key = ('side2', device)
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream(device=device)
     return s
 
 
