@@ -66,7 +66,7 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def make_host_batch(B, seed, torch, np, backbone='transFuser'):
+def make_host_batch(B, seed, torch, np, backbone='transFuser', raw=False):
     """Synthetic inputs of SURVEY.md §8(d) in PINNED host memory (the e2e arm copies them every step)."""
     from oracle import bev_oracle, torch_oracle as O
     b = O.synthetic_batch(B, seed=seed)
@@ -75,6 +75,20 @@ def make_host_batch(B, seed, torch, np, backbone='transFuser'):
     pts = np.stack([bev_oracle.synthetic_points(40000, 1000 * seed + i, np.float32, edge_cases=False) for i in range(B)])
     b['points'] = torch.from_numpy(pts)
     del b['lidar']
+    if raw:
+        # the compact form of the same batch (what the dataset holds on disk): uint8 camera / depth / semantic frames, the pose
+        # transform of align() (identity: no second LiDAR sweep in the synthetic batch), the float64 target point; the expanded
+        # fp32 / int64 tensors they replace are built on the GPU by pipeline.InputPipeline inside the step
+        g = torch.Generator().manual_seed(4000 + seed)
+        b['rgb_u8'] = b.pop('rgb').permute(0, 2, 3, 1).contiguous().to(torch.uint8)
+        b['depth_u8'] = torch.randint(0, 256, (B, 160, 704, 3), dtype=torch.uint8, generator=g)
+        b['depth_u8'][..., 0] = torch.randint(0, 13, (B, 160, 704), dtype=torch.uint8, generator=g)   # 24-bit depth code, mostly inside the 0.05 clip
+        b['seg_u8'] = torch.randint(0, 28, (B, 160, 704), dtype=torch.uint8, generator=g)
+        b['crop_shift'] = torch.zeros(B, dtype=torch.int32)
+        b['transforms'] = torch.eye(4, dtype=torch.float64).reshape(1, 4, 4).repeat(B, 1, 1)
+        b['target_point64'] = b.pop('target_point').double()
+        for k in ('depth', 'semantic', 'target_point_image'):
+            del b[k]
     return {k: v.pin_memory() for k, v in b.items()}
 
 
@@ -96,8 +110,9 @@ def run_b200(args):
     B = args.batch or cfg_batch
     cfg = TrainConfig()
     torch.manual_seed(0)
-    tr = Trainer(cfg, dev, gemm_mode=args.gemm, lr=1e-4, seed=rank, backbone=backbone)
-    host = make_host_batch(B, seed=100 + rank, torch=torch, np=np, backbone=backbone)
+    raw = bool(args.raw_inputs)
+    tr = Trainer(cfg, dev, gemm_mode=args.gemm, lr=1e-4, seed=rank, backbone=backbone, raw_inputs=raw)
+    host = make_host_batch(B, seed=100 + rank, torch=torch, np=np, backbone=backbone, raw=raw)
 
     def h2d():
         return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -184,7 +199,9 @@ def run_b200(args):
             'dtype': 'bf16' if args.gemm == 'bf16' else 'fp32', 'data': 'synthetic',
             'config': {'workload': '%s LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
                                    '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU (BASELINE configs[%d])' % (label, B, args.config - 1),
-                       'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm, 'cuda_graph': tr.graph is not None, 'cuda_graph_error': tr.graph_error,
+                       'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm,
+                       'inputs': ('raw (uint8 frames, points, pose transform, target point): model inputs built by the GPU input pipeline inside the step'
+                                  if raw else 'expanded fp32 / int64 tensors as the reference DataLoader ships them; LiDAR points -> BEV histogram on the GPU'), 'cuda_graph': tr.graph is not None, 'cuda_graph_error': tr.graph_error,
                        'l2': 'working set (672 MB weights + activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': round(e2e_v, 3), 'unit': 'samples/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
@@ -377,6 +394,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'cpu_baseline'])
     ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--raw-inputs', type=int, default=int(os.environ.get('TFB_RAW_INPUTS', '1')),
+                    help='1: feed the step with what is on disk (uint8 frames, raw points, pose transform; 1.6 MB per sample over PCIe) and '
+                         'build the model inputs on the GPU inside the step; 0: the expanded fp32 / int64 tensors of the reference DataLoader (3.8 MB)')
     ap.add_argument('--graph', type=int, default=1, help='1: capture the whole step (incl. the NCCL gradient all-reduce when N > 1) in a CUDA graph; 0: eager')
     args = ap.parse_args()
     if args.impl == 'cpu_baseline':

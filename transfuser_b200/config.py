@@ -65,6 +65,8 @@ class TrainConfig:
     gpt_linear_layer_init_mean = 0.0
     gpt_linear_layer_init_std = 0.02
     gpt_layer_norm_init_weight = 1.0
+    # CARLA semantic tag -> the 7 training classes (config.py:88-117), used by the GPU input pipeline's class LUT
+    converter = [0, 0, 0, 0, 4, 0, 5, 2, 6, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 3, 0, 0, 5]
 
     def __init__(self, **kwargs):
         for k, v in kwargs.items():

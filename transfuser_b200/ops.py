@@ -99,7 +99,7 @@ WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: wei
 BN_STATS_FUSED = os.environ.get('TFB_BN_STATS_FUSED', '1') == '1'   # bf16 mode: BatchNorm statistics out of the producing conv / GEMM epilogue
 WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '0') == '1'   # split-K of the weight-gradient GEMMs chosen by the library (fills a wave:
 #                                                                          measured 1.3 ms/step SLOWER next to the critical chain; off)
-WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '0'))          # cap of the persistent grid of GEMMs on the weight-gradient stream
+WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '96'))          # cap of the persistent grid of GEMMs on the weight-gradient stream
 NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
 DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '1') == '1'   # segmentation and depth decoders on two side streams (not one)
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
@@ -189,6 +189,12 @@ def side_stream2(device):
     if s is None:
         s = _SIDE[key] = torch.cuda.Stream(device=device)
     return s
+
+
+def side_streams(device):
+    """All side streams created so far on `device`."""
+    device = torch.device(device)
+    return [s for s in _SIDE.values() if s.device == device or (device.index is None and s.device.type == device.type)]
 
 
 def join_side_streams():

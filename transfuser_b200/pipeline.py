@@ -78,11 +78,19 @@ class InputPipeline:
         rgb = self._dev(raw['rgb'], torch.uint8)
         B, H, W, _ = rgb.shape
         ch, cw = self.crop
-        shift_host = torch.as_tensor(raw.get('crop_shift', torch.zeros(B, dtype=torch.int32))).to('cpu', torch.int32)
-        x0 = W // 2 - cw // 2 + shift_host
-        if ch > H or cw > W or int(x0.min()) < 0 or int(x0.max()) + cw > W:
-            raise ValueError('crop %s with shifts %s leaves the %dx%d frame' % (self.crop, shift_host.tolist(), H, W))
-        shift = shift_host.to(self.device, non_blocking=True)
+        cs = raw.get('crop_shift')
+        if isinstance(cs, torch.Tensor) and cs.is_cuda:
+            # device-resident shifts (the static inputs of a captured training step): validated on the host when they were produced
+            # (no device -> host read here: it would synchronise, and is illegal inside a CUDA-graph capture)
+            if ch > H or cw > W or cs.dtype != torch.int32:
+                raise ValueError('crop %s does not fit the %dx%d frame / crop_shift must be int32' % (self.crop, H, W))
+            shift = cs.contiguous()
+        else:
+            shift_host = torch.as_tensor(cs if cs is not None else torch.zeros(B, dtype=torch.int32)).to('cpu', torch.int32)
+            x0 = W // 2 - cw // 2 + shift_host
+            if ch > H or cw > W or int(x0.min()) < 0 or int(x0.max()) + cw > W:
+                raise ValueError('crop %s with shifts %s leaves the %dx%d frame' % (self.crop, shift_host.tolist(), H, W))
+            shift = shift_host.to(self.device, non_blocking=True)
         depth = self._dev(raw['depth'], torch.uint8) if raw.get('depth') is not None else None
         seg = self._dev(raw['seg'], torch.uint8) if raw.get('seg') is not None else None
         if seg is not None and not self.has_lut:

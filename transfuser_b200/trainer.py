@@ -9,14 +9,27 @@ import torch.distributed as dist
 from . import _lib, bev, gemm, ops, optim
 from .model import LidarCenterNet
 
+import os
+
+OVERLAP_ADAMW = os.environ.get('TFB_OVERLAP_ADAMW', '1') == '1'   # AdamW per gradient span from inside backward (captured step only)
+
 INPUT_KEYS = ('rgb', 'points', 'target_point_image', 'target_point', 'ego_vel', 'ego_waypoint', 'bev', 'semantic', 'depth', 'label')
+# raw_inputs=True: what is on disk instead of the expanded tensors (uint8 frames, raw points, one pose transform, the target point);
+# the GPU input pipeline (pipeline.InputPipeline, csrc/input_prep.cu) builds the model inputs inside the step — 1.6 MB instead of
+# 3.8 MB per sample over PCIe
+RAW_KEYS = ('rgb_u8', 'depth_u8', 'seg_u8', 'crop_shift', 'points', 'transforms', 'target_point64', 'ego_vel', 'ego_waypoint', 'bev', 'label')
 
 
 class Trainer:
-    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=8, backbone='transFuser'):
+    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=int(os.environ.get('TFB_GRAD_CHUNKS', '24')), backbone='transFuser',
+                 raw_inputs=False):
         self.cfg, self.device = cfg, device
         # the geometric-fusion backbone consumes two more inputs per sample (train.py:279-288)
-        self.input_keys = INPUT_KEYS + (('bev_points', 'cam_points') if backbone == 'geometric_fusion' else ())
+        self.raw_inputs = raw_inputs
+        self.input_keys = (RAW_KEYS if raw_inputs else INPUT_KEYS) + (('bev_points', 'cam_points') if backbone == 'geometric_fusion' else ())
+        if raw_inputs:
+            from .pipeline import InputPipeline
+            self.pipe = InputPipeline(cfg, device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         gemm.set_mode(gemm_mode)
         ops.manual_seed(1234 + seed)
@@ -32,7 +45,7 @@ class Trainer:
         if gemm_mode == 'bf16':
             gemm.attach_bf16_weights(self.flat)
         self.opt = optim.FusedAdamW(self.net.parameters(), lr=lr, grad_scale=1.0 / self.world)
-        self.reducer = optim.GradAllReducer(self.flat, n_chunks=n_chunks)
+        self.reducer = optim.GradAllReducer(self.flat, n_chunks=n_chunks, opt=self.opt if OVERLAP_ADAMW else None)
         self.weights = dict(zip(cfg.detailed_losses, cfg.detailed_losses_weights))
         self.graph = None
         self.static = None
@@ -42,8 +55,18 @@ class Trainer:
 
     def step(self, d):
         """Eager step on device-resident inputs `d` (dict with INPUT_KEYS). Returns the weighted total loss (0-dim tensor)."""
-        lidar = bev.lidar_to_histogram_features_batched(d['points'])
+        if self.raw_inputs:
+            # crop + CHW / normalise, depth decode, class LUT, align + BEV histogram, target-point map: three launches on the raw batch
+            p = self.pipe.prepare(dict(rgb=d['rgb_u8'], depth=d['depth_u8'], seg=d['seg_u8'], crop_shift=d['crop_shift'], points=d['points'],
+                                       transforms=d['transforms'], target_point=d['target_point64']), normalized_nhwc=True)
+            d = dict(d, rgb=p['rgb'], depth=p['depth'], semantic=p['semantic'], target_point=p['target_point'],
+                     target_point_image=p['target_point_image'])
+            lidar = p['lidar']
+        else:
+            lidar = bev.lidar_to_histogram_features_batched(d['points'])
         self.opt.zero_grad()
+        if self.reducer.pipeline:
+            self.opt.begin_step()        # AdamW spans are launched from the backward pass (optim.FusedAdamW.step_span)
         losses = self.net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
                           target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
                           depth=d['depth'], semantic=d['semantic'], bev_points=d.get('bev_points'), cam_points=d.get('cam_points'))
@@ -69,6 +92,7 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.opt.check_grads = False
+            self.reducer.pipeline = OVERLAP_ADAMW    # every gradient is known to land in the flat buffer: update spans as they complete
             g = torch.cuda.CUDAGraph()
             l0 = _lib.lib().launches
             with torch.cuda.graph(g):
