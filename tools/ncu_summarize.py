@@ -4,7 +4,7 @@ utilisation, achieved occupancy, registers — the per-kernel evidence table com
 import csv
 import sys
 
-rows = list(csv.reader(open(sys.argv[1])))
+rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))      # (ncu's ==PROF== banner lines precede the table)
 hdr = rows[0]
 units = rows[1]
 want = {

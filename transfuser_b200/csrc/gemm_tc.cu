@@ -351,7 +351,8 @@ int pick_bn(int M, int N, int zs, int step, int num_kb = 0, bool auto_split = fa
   if (model_c == -2) { const char* e = getenv("TFB_GEMM_TILE_MODEL"); model_c = e ? atoi(e) : 64; }
   const int nmax = ((N + step - 1) / step) * step;                 // one tile covers all of N
   const int64_t mt = (M + BM - 1) / BM;
-  const int sms = tfb_num_sms();
+  // the grid this launch may use: all SMs, or the cap set for launches on the weight-gradient stream (tfb_gemm_set_max_ctas)
+  const int sms = (g_max_ctas > 0 && g_max_ctas < tfb_num_sms()) ? g_max_ctas : tfb_num_sms();
   int best_bn = 0, best_s = 1;
   int64_t best = -1;
   for (int bn = step < 32 ? 32 : step; bn <= 256; bn += step) {

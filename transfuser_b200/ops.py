@@ -115,6 +115,7 @@ def _emit16(x, want):
 def _attach16(y, y16):
     if y16 is not None:
         y._tfb16, y._tfb16v = y16, y._version       # version stamp: an in-place edit of y afterwards invalidates the sidecar (_as16)
+        y._tfb16e = None                            # written by y's own producer kernel: whoever may read y may read the sidecar
     return y
 
 
@@ -122,10 +123,25 @@ def _as16(x):
     """bf16 copy of the contiguous fp32 tensor x: its sidecar when the producer wrote one, else a cast pass."""
     s = getattr(x, '_tfb16', None)
     if s is not None and s.shape == x.shape and getattr(x, '_tfb16v', x._version) == x._version:
+        evt = getattr(x, '_tfb16e', None)
+        if evt is not None and x.is_cuda:
+            # the copy was made lazily by an earlier consumer, possibly on ANOTHER stream (the image grid feeds the segmentation
+            # decoder on one side stream and the depth decoder on a second one): order this stream behind that cast. Without it the
+            # second decoder read the bf16 copy before it was written whenever the streams really ran concurrently (graph replay):
+            # loss_depth came out doubled under CUDA-graph replay — found by tools/graph_vs_eager.py in round 2.
+            cur = torch.cuda.current_stream(x.device)
+            if cur.cuda_stream != evt[0]:
+                cur.wait_event(evt[1])
+                s.record_stream(cur)
         return s
     s = G.to_bf16(x)
     if SIDECARS:
         x._tfb16, x._tfb16v = s, x._version      # a tensor with several tensor-core consumers (p2 -> 8 head convs) is cast once
+        if x.is_cuda:
+            cur = torch.cuda.current_stream(x.device)
+            evt = torch.cuda.Event()
+            evt.record(cur)
+            x._tfb16e = (cur.cuda_stream, evt)
     return s
 
 
@@ -162,7 +178,7 @@ def _view16(x, v):
     """v = a view (reshape) of x: carries x's sidecar over to v under the same reshape."""
     s = getattr(x, '_tfb16', None)
     if s is not None and v.is_contiguous() and x.is_contiguous():
-        v._tfb16 = s.view(v.shape)
+        v._tfb16, v._tfb16e = s.view(v.shape), getattr(x, '_tfb16e', None)
     return v
 
 
@@ -191,10 +207,20 @@ def side_stream2(device):
     return s
 
 
+def _capturing(stream):
+    with torch.cuda.stream(stream):
+        return torch.cuda.is_current_stream_capturing()
+
+
 def side_streams(device):
-    """All side streams created so far on `device`."""
+    """The side streams on `device` that the caller may wait for: all of them normally; while the current stream is being captured
+    into a CUDA graph only those that were forked into the same capture (waiting for an event of a stream outside the capture
+    invalidates it — a stream created by an earlier model / configuration and not used by this step is simply skipped)."""
     device = torch.device(device)
-    return [s for s in _SIDE.values() if s.device == device or (device.index is None and s.device.type == device.type)]
+    out = [s for s in _SIDE.values() if s.device == device or (device.index is None and s.device.type == device.type)]
+    if out and torch.cuda.is_current_stream_capturing():
+        out = [s for s in out if _capturing(s)]
+    return out
 
 
 def join_side_streams():
@@ -202,9 +228,8 @@ def join_side_streams():
     if not _SIDE:
         return
     cur = torch.cuda.current_stream()
-    for s in _SIDE.values():
-        if s.device == cur.device:
-            cur.wait_stream(s)
+    for s in side_streams(cur.device):
+        cur.wait_stream(s)
 
 
 

@@ -302,6 +302,7 @@ class GradAllReducer:
         self.fp = fp
         self.opt = opt            # FusedAdamW to update each span as soon as it is complete (pipelined mode), or None
         self.pipeline = False     # switched on by Trainer once the set of gradient producers is known to be complete
+        self._launch_stream = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         per = (fp.total + n_chunks - 1) // n_chunks
         per = (per + ALIGN - 1) // ALIGN * ALIGN
@@ -321,6 +322,23 @@ class GradAllReducer:
                 p.register_post_accumulate_grad_hook(self._make_hook(ids))
         self.reset()
 
+    def _all_reduce(self, lo, hi):
+        """Async SUM all-reduce of grad[lo:hi]. The gradients of the span were produced on several streams (critical chain, LiDAR
+        trunk / decoders, weight-gradient stream): the collective is issued from a launch stream that waits for all of them, so the
+        critical chain itself is never made to wait for the side streams here (NCCL orders its kernel after the issuing stream)."""
+        g = self.fp.grad[lo:hi]
+        if not g.is_cuda:
+            return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+        dev = g.device
+        if self._launch_stream is None:
+            self._launch_stream = torch.cuda.Stream(device=dev)
+        ls = self._launch_stream
+        ls.wait_stream(torch.cuda.current_stream(dev))
+        for s_ in ops_mod.side_streams(dev):
+            ls.wait_stream(s_)
+        with torch.cuda.stream(ls):
+            return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+
     def reset(self):
         self.pending = list(self.counts)
         self.works = [None] * len(self.spans)
@@ -332,8 +350,7 @@ class GradAllReducer:
                 if self.pending[c] == 0:
                     lo, hi = self.spans[c]
                     if self.world > 1:
-                        ops_mod.join_side_streams()   # gradients of the LiDAR branch / decoders are produced on the second stream
-                        self.works[c] = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+                        self.works[c] = self._all_reduce(lo, hi)
                     if self.pipeline and self.opt is not None and self.fp.grad.is_cuda:
                         self.opt.step_span(lo, hi, self.works[c])
         return hook
@@ -344,8 +361,7 @@ class GradAllReducer:
         for c, (lo, hi) in enumerate(self.spans):
             w = self.works[c]
             if w is None and self.world > 1:
-                ops_mod.join_side_streams()
-                w = dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+                w = self._all_reduce(lo, hi)
             out.append((lo, hi, w))
         self.reset()
         return out

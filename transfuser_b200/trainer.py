@@ -70,6 +70,7 @@ class Trainer:
         losses = self.net(d['rgb'], lidar, ego_waypoint=d['ego_waypoint'], target_point=d['target_point'],
                           target_point_image=d['target_point_image'], ego_vel=d['ego_vel'], bev=d['bev'], label=d['label'],
                           depth=d['depth'], semantic=d['semantic'], bev_points=d.get('bev_points'), cam_points=d.get('cam_points'))
+        self.last_losses = losses          # the 11 scalars of this step (device tensors; static buffers under graph replay)
         loss = None
         for k, v in losses.items():
             loss = v * self.weights[k] if loss is None else loss + v * self.weights[k]
