@@ -52,9 +52,35 @@ class Trainer:
         self.static_loss = None
         self.graph_launches = 0
         self.graph_error = None
+        self._stream = None
 
     def step(self, d):
-        """Eager step on device-resident inputs `d` (dict with INPUT_KEYS). Returns the weighted total loss (0-dim tensor)."""
+        """Eager step on device-resident inputs `d` (dict with INPUT_KEYS). Returns the weighted total loss (0-dim tensor).
+
+        Never runs on the legacy default stream: autograd pins every parameter's AccumulateGrad node to the stream of its first
+        backward, the gradient hooks keep those nodes alive, and a later CUDA-graph capture cannot fork the legacy stream
+        (cudaErrorStreamCaptureImplicit — the round-1 "AccumulateGrad node's stream does not match" warning, fatal once the hooks
+        also drive the pipelined AdamW). When called on the default stream the step runs on a stream of the trainer's own, ordered
+        after the caller's work, and the caller's stream is ordered after the step."""
+        dev = self.device
+        if torch.device(dev).type == 'cuda' and not torch.cuda.is_current_stream_capturing():
+            cur = torch.cuda.current_stream(dev)
+            if cur == torch.cuda.default_stream(dev):
+                if self._stream is None:
+                    self._stream = torch.cuda.Stream(device=dev)
+                own = self._stream
+                own.wait_stream(cur)
+                for t in d.values():
+                    if isinstance(t, torch.Tensor) and t.is_cuda:
+                        t.record_stream(own)
+                with torch.cuda.stream(own):
+                    loss = self._step(d)
+                cur.wait_stream(own)
+                loss.record_stream(cur)
+                return loss
+        return self._step(d)
+
+    def _step(self, d):
         if self.raw_inputs:
             # crop + CHW / normalise, depth decode, class LUT, align + BEV histogram, target-point map: three launches on the raw batch
             p = self.pipe.prepare(dict(rgb=d['rgb_u8'], depth=d['depth_u8'], seg=d['seg_u8'], crop_shift=d['crop_shift'], points=d['points'],
@@ -101,7 +127,11 @@ class Trainer:
             self.graph, self.graph_launches = g, _lib.lib().launches - l0
             return True
         except Exception as e:  # noqa: BLE001 — keep the eager path, report why
+            import traceback
             self.graph, self.graph_error = None, repr(e)[:300]
+            self.graph_traceback = traceback.format_exc()
+            if os.environ.get('TFB_CAPTURE_DEBUG') == '1':
+                print(self.graph_traceback, flush=True)
             torch.cuda.synchronize()
             return False
 
