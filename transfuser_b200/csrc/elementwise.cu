@@ -382,6 +382,51 @@ upsample_bwd_gather_kernel(const float* __restrict__ dy, float* __restrict__ dx,
   }
 }
 
+// ---- float4 forms of the GPT upsample-add (forward, and the gather backward) and of the zero-dilation: the same 32-bit index
+// arithmetic / 16-byte access pattern as upsample4_kernel below. The token slab keeps the reference's view quirk (channel c of cell p
+// sits at slab[c * G + p]), so the four slab values of a channel quad are gathered separately (the slab is tiny and L1 resident).
+__global__ void __launch_bounds__(256) gpt_up_add4_kernel(const float4* __restrict__ feat, const float* __restrict__ tok, float4* __restrict__ out,
+                                                          int N, int H, int W, int C4, int gh, int gw, int t_off, int T,
+                                                          __nv_bfloat16* __restrict__ out16) {
+  const uint32_t total = (uint32_t)N * H * W * C4;
+  const int G = gh * gw, C = C4 * 4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t c4 = i % (uint32_t)C4, pix = i / (uint32_t)C4;
+    const int x = (int)(pix % (uint32_t)W);
+    const uint32_t t = pix / (uint32_t)W;
+    const int y = (int)(t % (uint32_t)H), n = (int)(t / (uint32_t)H);
+    const Lerp ly = lerp_coord(y, gh, H, 0), lx = lerp_coord(x, gw, W, 0);
+    const float* slab = tok + ((int64_t)n * T + t_off) * C + (int64_t)(c4 * 4) * G;
+    const int i00 = ly.i0 * gw + lx.i0, i01 = ly.i0 * gw + lx.i1, i10 = ly.i1 * gw + lx.i0, i11 = ly.i1 * gw + lx.i1;
+    const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* sq = slab + q * G;
+      v[q] = w00 * sq[i00] + w01 * sq[i01] + w10 * sq[i10] + w11 * sq[i11];
+    }
+    const float4 f = feat[i];
+    const float4 o = make_float4(f.x + v[0], f.y + v[1], f.z + v[2], f.w + v[3]);
+    out[i] = o;
+    if (out16) tfb_store_bf16x4(out16, i, o.x, o.y, o.z, o.w);
+  }
+}
+
+// MODE 1 of stride2_kernel (zero-dilation of a [N, Ho, Wo, C] map into [N, H, W, C], bf16 output), four channels per thread
+__global__ void __launch_bounds__(256) dilate2_bf16x4_kernel(const float4* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int H, int W,
+                                                             int Ho, int Wo, int C4) {
+  const uint32_t total = (uint32_t)N * H * W * C4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t c4 = i % (uint32_t)C4, pix = i / (uint32_t)C4;
+    const int w = (int)(pix % (uint32_t)W);
+    const uint32_t t = pix / (uint32_t)W;
+    const int h = (int)(t % (uint32_t)H), n = (int)(t / (uint32_t)H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (((h | w) & 1) == 0 && h / 2 < Ho && w / 2 < Wo) v = src[(((int64_t)n * Ho + h / 2) * Wo + w / 2) * C4 + c4];
+    tfb_store_bf16x4(dst, i, v.x, v.y, v.z, v.w);
+  }
+}
+
 // ---- 4-channel (float4) forms of the two kernels above for C % 4 == 0 and < 2^31 quads: 32-bit index arithmetic, one set of
 // interpolation weights per 16 bytes, 16-byte loads / stores and an 8-byte bf16 store. The scalar forward kernel was instruction-bound
 // (three 64-bit divisions, four scalar loads and a 2-byte store per ELEMENT: 719 us for the 160x704x64 decoder map, 7 % of the HBM
@@ -833,6 +878,13 @@ TFB_API int tfb_gpt_up_add_fwd(const float* feat, const float* tok, float* out, 
                                int T, void* out16_bf16, cudaStream_t stream) {
   TFB_REQUIRE(feat && tok && out && N > 0);
   const int64_t total = (int64_t)N * H * W * C;
+  if (C % 4 == 0 && total / 4 < 0x7fffffffLL && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+      (!out16_bf16 || (reinterpret_cast<uintptr_t>(out16_bf16) & 7) == 0)) {
+    gpt_up_add4_kernel<<<tfb_grid(total / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(feat), tok, reinterpret_cast<float4*>(out), N, H, W,
+                                                                    C / 4, gh, gw, t_off, T, (__nv_bfloat16*)out16_bf16);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   gpt_up_add_kernel<0><<<tfb_grid(total, 256), 256, 0, stream>>>(feat, const_cast<float*>(tok), out, N, H, W, C, gh, gw, t_off, T,
                                                                  (__nv_bfloat16*)out16_bf16);
   TFB_CHECK_LAUNCH();
@@ -935,6 +987,13 @@ TFB_API int tfb_dilate2(const float* src, void* dst, int N, int H, int W, int C,
   TFB_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0);
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int grid = tfb_grid((int64_t)N * H * W * C, 256);
+  if (out_bf16 && C % 4 == 0 && (int64_t)N * H * W * C / 4 < 0x7fffffffLL && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    dilate2_bf16x4_kernel<<<tfb_grid((int64_t)N * H * W * C / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(src), (__nv_bfloat16*)dst, N, H, W,
+                                                                                        Ho, Wo, C / 4);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   if (out_bf16) stride2_kernel<1, __nv_bfloat16><<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, N, H, W, Ho, Wo, C, nullptr);
   else          stride2_kernel<1, float><<<grid, 256, 0, stream>>>(src, (float*)dst, N, H, W, Ho, Wo, C, nullptr);
   TFB_CHECK_LAUNCH();

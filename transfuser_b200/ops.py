@@ -97,11 +97,14 @@ SE_FUSED_BWD = os.environ.get('TFB_SE_FUSED_BWD', '1') == '1'   # tfb_se_mlp_bwd
 CONV_S2_TC = os.environ.get('TFB_CONV_S2_TC', '1') == '1'       # bf16 mode: stride-2 3x3 convs forward on the tcgen05 kernel (TMA element strides)
 WGRAD_STREAM = os.environ.get('TFB_WGRAD_STREAM', '1') == '1'   # bf16 mode: weight-gradient GEMMs on a third stream (they only feed AdamW)
 BN_STATS_FUSED = os.environ.get('TFB_BN_STATS_FUSED', '1') == '1'   # bf16 mode: BatchNorm statistics out of the producing conv / GEMM epilogue
-WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '0') == '1'   # split-K of the weight-gradient GEMMs chosen by the library (fills a wave:
-#                                                                          measured 1.3 ms/step SLOWER next to the critical chain; off)
-WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '96'))          # cap of the persistent grid of GEMMs on the weight-gradient stream
+# Weight-gradient GEMMs run on a side stream next to the critical dx chain. Measured on a B200 (profiles/r2_bench_ab_*.json): letting
+# their split-K fill all 148 SMs made the step 1.3 ms SLOWER (they starve the chain); capping their persistent grid at 64 CTAs and
+# letting the library pick tile width + split factor for THAT grid (csrc/gemm_tc.cu pick_bn) is the fastest combination (-0.5 ms).
+WGRAD_AUTO_SPLIT = os.environ.get('TFB_WGRAD_AUTO_SPLIT', '1') == '1'
+WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '64'))
 NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
-DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '1') == '1'   # segmentation and depth decoders on two side streams (not one)
+DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '0') == '1'   # segmentation and depth decoders on two side streams (measured: no gain once
+#                                                                        the upsample kernels were vectorised; off)
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
