@@ -82,7 +82,8 @@ def test_conv2d(cfg):
     check_grads([xm, wm] + ([bm] if has_b else []), [x, w] + ([b] if has_b else []), out, ref)
 
 
-@pytest.mark.parametrize('shape,relu', [((3, 10, 12, 72), True), ((2, 6, 7, 216), False), ((1, 5, 22, 1512), True)])
+@pytest.mark.parametrize('shape,relu', [((3, 10, 12, 72), True), ((2, 6, 7, 216), False), ((1, 5, 22, 1512), True),
+                                        ((2, 48, 44, 72), True), ((2, 40, 56, 216), False), ((1, 80, 64, 32), True)])   # M >= 4096: the flat column reduction
 def test_batchnorm_train(shape, relu):
     from transfuser_b200 import ops
     N, H, W, C = shape
@@ -101,7 +102,7 @@ def test_batchnorm_train(shape, relu):
     check_grads([xm, bn2.weight, bn2.bias], [x, bn.weight, bn.bias], out, ref)
 
 
-@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 6, 7, 216), (1, 5, 22, 1512)])
+@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 6, 7, 216), (1, 5, 22, 1512), (2, 48, 44, 72)])
 def test_batchnorm_add_relu_fused(shape):
     """relu(bn(x) + shortcut) — the Bottleneck tail — as ONE BatchNorm call (add + ReLU inside the normalise pass; ReLU mask and the
     shortcut's gradient inside the backward passes) against torch and against the unfused product path (eval mode too)."""
@@ -212,9 +213,10 @@ def test_attention(C, nh, packed):
         assert rel(a, b_) < TOL
 
 
-def test_se_add_pool():
+@pytest.mark.parametrize('dims', [(3, 6, 9, 72, 8), (2, 32, 36, 72, 8), (2, 32, 34, 216, 18)])     # HW >= 1024: the flat SE reduction
+def test_se_add_pool(dims):
     from transfuser_b200 import ops
-    N, H, W, C, Cr = 3, 6, 9, 72, 8
+    N, H, W, C, Cr = dims
     x = rnd(N, C, H, W, seed=1).requires_grad_()
     w1, b1 = rnd(Cr, C, 1, 1, seed=2, scale=0.2).requires_grad_(), rnd(Cr, seed=3, scale=0.1).requires_grad_()
     w2, b2 = rnd(C, Cr, 1, 1, seed=4, scale=0.3).requires_grad_(), rnd(C, seed=5, scale=0.1).requires_grad_()

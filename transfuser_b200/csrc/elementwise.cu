@@ -68,6 +68,38 @@ __global__ void __launch_bounds__(256) pool_hw_kernel(const float* __restrict__ 
   }
 }
 
+// pool_hw_kernel for narrow maps (C / 4 <= 128 channel quads): a block covers 256 / C4 whole pixel rows of ONE sample per iteration,
+// consecutive threads read consecutive 16-byte quads (every lane busy: the 32-quad slabs above idle 44 % of the lanes at C = 72);
+// grid (splits over the pixels, n).
+template <int MODE>
+__global__ void __launch_bounds__(256) pool_hw_flat_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out,
+                                                           int HW, int C, float scale) {
+  const int C4 = C / 4, RPB = 256 / C4;
+  const int t = threadIdx.x, q = t % C4, rr = t / C4, n = blockIdx.y;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rr < RPB) {
+    const float* xp = x + (int64_t)n * HW * C + q * 4;
+    const float* zp = MODE == 1 ? z + (int64_t)n * HW * C + q * 4 : nullptr;
+    for (int p = blockIdx.x * RPB + rr; p < HW; p += gridDim.x * RPB) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + (int64_t)p * C);
+      if (MODE == 0) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      else {
+        const float4 w = *reinterpret_cast<const float4*>(zp + (int64_t)p * C);
+        a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+      }
+    }
+  }
+  __shared__ float4 sm[256];
+  sm[t] = rr < RPB ? a : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (t < C4) {
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < RPB; ++j) { const float4 v = sm[j * C4 + t]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+    float* o = out + (int64_t)n * C + t * 4;
+    atomicAdd(o + 0, s4.x * scale); atomicAdd(o + 1, s4.y * scale); atomicAdd(o + 2, s4.z * scale); atomicAdd(o + 3, s4.w * scale);
+  }
+}
+
 // y[n][p][c] = x[n][p][c] * gate[n][c]  (+ add[n][c] * add_scale); VEC = 4 when C % 4 == 0 (16-byte accesses)
 template <int VEC>
 __global__ void __launch_bounds__(256) scale_nc_kernel(const float* __restrict__ x, const float* __restrict__ gate,
@@ -805,6 +837,16 @@ TFB_API int tfb_se_bwd_reduce(const float* x, const float* dy, float* dgate, int
   int splits = (HW + 255) / 256;
   if (splits > 32) splits = 32;
   dim3 grid((C / 4 + 31) / 32, N, splits), block(32, 8);
+  if (C / 4 <= 128 && HW >= 1024) {
+    const int rpb = 256 / (C / 4);
+    int sp = (HW + rpb * 16 - 1) / (rpb * 16);                      // >= 16 pixel rows per thread
+    const int cap = (4 * tfb_num_sms() + N - 1) / N;
+    if (sp > cap) sp = cap;
+    if (sp < 1) sp = 1;
+    pool_hw_flat_kernel<1><<<dim3(sp, N), 256, 0, stream>>>(x, dy, dgate, HW, C, 1.f);
+    TFB_CHECK_LAUNCH();
+    return TFB_OK;
+  }
   pool_hw_kernel<1><<<grid, block, 0, stream>>>(x, dy, dgate, HW, C, 1.f);
   TFB_CHECK_LAUNCH();
   return TFB_OK;

@@ -190,6 +190,76 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   finalize_last_block(out, C, fin);
 }
 
+// Narrow matrices (C / 4 <= 128 channel quads: the 32-, 72- and 216-channel maps of the stem / stage 1 / stage 2, i.e. the LARGEST
+// tensors of the trunks): the 32-quad slabs of colreduce4_kernel leave 44 % (C = 72) of the lanes idle. Here a block of 256 threads
+// covers RPB = 256 / C4 whole rows per iteration — consecutive threads read consecutive 16-byte quads of consecutive rows, every lane
+// busy (252 of 256 for C = 72) — each thread owns ONE quad column, and the RPB row phases meet in shared memory. Same MODE /
+// Finalize semantics as colreduce4_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_flat_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin) {
+  const int C4 = C / 4, RPB = 256 / C4;
+  const int t = threadIdx.x, q = t % C4, rr = t / C4;
+  const bool active = rr < RPB;
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+  if (active) {
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f}, ga[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { mu[k] = mean[q * 4 + k]; is[k] = invstd[q * 4 + k]; ga[k] = gamma[q * 4 + k]; be[k] = beta[q * 4 + k]; }
+    }
+    int cnt = 0;
+    const int64_t step = (int64_t)gridDim.x * RPB;
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rr; r < M; r += step) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * C + q * 4);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a0[k] += xv[k]; a1[k] = fmaf(xv[k], xv[k], a1[k]); }
+      } else {
+        const float4 g4 = *reinterpret_cast<const float4*>(dy + r * C + q * 4);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        float mv[4] = {1.f, 1.f, 1.f, 1.f};
+        if (ymask) {
+          const float4 m4 = *reinterpret_cast<const float4*>(ymask + r * C + q * 4);
+          mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xh = (xv[k] - mu[k]) * is[k];
+          float g = gv[k];
+          if (ymask) { if (!(mv[k] > 0.f)) g = 0.f; }
+          else if (relu && !(fmaf(xh, ga[k], be[k]) > 0.f)) g = 0.f;
+          a0[k] += g; a1[k] = fmaf(g, xh, a1[k]);
+        }
+      }
+      if (++cnt == 64) {           // bound the fp32 partial length
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { d0[k] += a0[k]; d1[k] += a1[k]; a0[k] = a1[k] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { d0[k] += a0[k]; d1[k] += a1[k]; }
+  }
+  __shared__ double sd[256][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sd[t][k] = active ? d0[k] : 0.0; sd[t][4 + k] = active ? d1[k] : 0.0; }
+  __syncthreads();
+  // thread (q, value v): sum the RPB row phases of quad q; 8 values per quad
+  for (int i = t; i < C4 * 8; i += 256) {
+    const int qq = i >> 3, v = i & 7;
+    double sum = 0.0;
+    for (int j = 0; j < RPB; ++j) sum += sd[j * C4 + qq][v];
+    if (v < 4) atomicAdd(&out[qq * 4 + v], sum);
+    else if (fin.nsums > C) atomicAdd(&out[C + qq * 4 + v - 4], sum);
+  }
+  finalize_last_block(out, C, fin);
+}
+
 // y = (x - mean) * invstd * gamma + beta (ReLU); 4 channels per thread (C % 4 == 0).
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total4, int C4, const float* __restrict__ mean,
@@ -522,6 +592,16 @@ int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, in
   const bool vec = C % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!dy || (reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                    (!ymask || (reinterpret_cast<uintptr_t>(ymask) & 15) == 0);
   dim3 block(32, 8);
+  if (vec && C / 4 <= 128 && ldx == C && M >= 4096) {
+    // narrow and tall: whole rows per block, every lane busy (see colreduce_flat_kernel)
+    const int rpb = 256 / (C / 4);
+    int64_t blocks = ceil_div64(M, (int64_t)rpb * 8);              // >= 8 rows per thread
+    const int64_t cap = (int64_t)tfb_num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    colreduce_flat_kernel<MODE><<<(int)blocks, 256, 0, stream>>>(x, dy, M, C, out, mean, invstd, gamma, beta, relu, ymask, fin);
+    return 0;
+  }
   if (vec) {
     const int slabs = (C / 4 + 31) / 32;
     dim3 grid(slabs, colreduce_splits(M, slabs));
