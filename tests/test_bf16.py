@@ -341,3 +341,29 @@ def test_bf16_mode_matches_the_bf16_operand_oracle():
     _, _, taps32 = _oracle_run(net0, batch, torch.float32)
     for k in ('img_s1', 'lid_s1', 'img_s2', 'lid_s2'):
         assert errs[k] < 0.7 * relm(mine[k].permute(0, 3, 1, 2), taps32[k]), k
+
+
+@pytest.mark.parametrize('cfg', [(2, 40, 44, 72), (2, 24, 48, 216), (3, 10, 12, 576)])
+def test_batchnorm_from_epilogue_statistics_with_se_pool(cfg):
+    """The conv2.bn -> SE hand-off in bf16 mode: statistics from the conv epilogue, normalise + ReLU + the squeeze-excite average pool in
+    ONE launch (the flat kernel for the narrow / tall maps, the slab kernel otherwise); pooled must equal the mean of the output."""
+    from transfuser_b200 import ops
+    N, H, W, C = cfg
+    gen = torch.Generator(device='cuda').manual_seed(C + H)
+    x = torch.randn(N, C, H, W, device='cuda', generator=gen) + 0.2
+    w = torch.randn(C, C, 1, 1, device='cuda', generator=gen) / math.sqrt(C)
+    bn = torch.nn.BatchNorm2d(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=gen)
+        bn.bias.uniform_(-0.3, 0.3, generator=gen)
+    yc = F.conv2d(x.bfloat16().float(), w.bfloat16().float())
+    ref = F.relu(F.batch_norm(yc, None, None, bn.weight, bn.bias, True, 0.1, bn.eps))
+    ops.tick(x.device)
+    y = ops.conv2d(x.permute(0, 2, 3, 1).contiguous(), w, None, 1, 1, False, bn_stats=True)
+    assert getattr(y, '_tfb_stats', None) is not None
+    o = ops.batch_norm(y, bn, True, True, pool=True)
+    torch.cuda.synchronize()
+    assert rel(o.permute(0, 3, 1, 2), ref) < 2e-3
+    pooled = getattr(o, '_tfb_pooled', None)
+    assert pooled is not None and rel(pooled, ref.mean((2, 3))) < 2e-3
+    assert rel(pooled, o.mean((1, 2))) < 1e-5

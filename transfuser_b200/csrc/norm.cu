@@ -421,6 +421,44 @@ bn_apply_pool_stats_kernel(const float* __restrict__ x, float* __restrict__ y, i
   }
 }
 
+// bn_apply_pool_stats_kernel for narrow maps (C / 4 <= 128): whole pixel rows of one sample per block iteration, every lane busy
+// (same mapping as colreduce_flat_kernel); grid (splits over the pixels, n).
+__global__ void __launch_bounds__(256)
+bn_apply_pool_stats_flat_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, int64_t M, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, int relu,
+                                float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean,
+                                float* __restrict__ running_var, float* __restrict__ pooled, float inv_hw) {
+  __shared__ __align__(16) float s_par[2 * 512];
+  float* s_scale = s_par;
+  float* s_shift = s_par + 512;
+  bn_params_from_stats(stats, C, M, eps, momentum, gamma, beta, s_scale, s_shift, blockIdx.x == 0 && blockIdx.y == 0, save_mean, save_invstd,
+                       running_mean, running_var);
+  const int C4 = C / 4, RPB = 256 / C4;
+  const int t = threadIdx.x, q = t % C4, rr = t / C4, n = blockIdx.y;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rr < RPB) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + q * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + q * 4);
+    const int64_t base = (int64_t)n * HW * C + q * 4;
+    for (int p = blockIdx.x * RPB + rr; p < HW; p += gridDim.x * RPB) {
+      const float4 v = *reinterpret_cast<const float4*>(x + base + (int64_t)p * C);
+      float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(y + base + (int64_t)p * C) = o;
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+  }
+  __shared__ float4 sm[256];
+  sm[t] = rr < RPB ? a : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (t < C4) {
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < RPB; ++j) { const float4 v = sm[j * C4 + t]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+    float* o = pooled + (int64_t)n * C + t * 4;
+    atomicAdd(o + 0, s4.x * inv_hw); atomicAdd(o + 1, s4.y * inv_hw); atomicAdd(o + 2, s4.z * inv_hw); atomicAdd(o + 3, s4.w * inv_hw);
+  }
+}
+
 // dx = gamma * invstd * (g - sum_g/M - xhat * sum_gx/M);  block 0 also writes dgamma = sum_gx, dbeta = sum_g.
 // 4 channels per thread (C % 4 == 0, 16-byte aligned rows).
 __global__ void __launch_bounds__(256)
@@ -658,6 +696,17 @@ TFB_API int tfb_bn_fwd_stats(const float* x, float* y, int64_t M, int C, const f
     const int HW = (int)(M / pool_batch);
     int splits = (HW + 255) / 256;
     if (splits > 32) splits = 32;
+    if (C / 4 <= 128 && HW >= 1024) {
+      const int rpb = 256 / (C / 4);
+      int sp = (HW + rpb * 16 - 1) / (rpb * 16);
+      const int cap = (4 * tfb_num_sms() + pool_batch - 1) / pool_batch;
+      if (sp > cap) sp = cap;
+      if (sp < 1) sp = 1;
+      bn_apply_pool_stats_flat_kernel<<<dim3(sp, pool_batch), 256, 0, stream>>>(x, y, HW, C, M, stats, gamma, beta, eps, momentum, relu, save_mean,
+                                                                               save_invstd, running_mean, running_var, pooled, 1.f / (float)HW);
+      TFB_CHECK_LAUNCH();
+      return TFB_OK;
+    }
     dim3 grid((C / 4 + 31) / 32, pool_batch, splits), block(32, 8);
     bn_apply_pool_stats_kernel<<<grid, block, 0, stream>>>(x, y, HW, C, M, stats, gamma, beta, eps, momentum, relu, save_mean, save_invstd,
                                                               running_mean, running_var, pooled, 1.f / (float)HW);
