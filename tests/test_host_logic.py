@@ -114,6 +114,12 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'GptUpAddFn', _Apply(gpt_up_add))
     monkeypatch.setattr(ops, 'layer_norm', lambda x, ln, emit16=False: F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps))
     monkeypatch.setattr(ops, 'dropout', lambda x, p, training: x)       # the tests run with all dropout probabilities at 0
+
+    def add_dropout_ln(res, x, p, training, ln, emit16=False):
+        xnew = res + x
+        return xnew, F.layer_norm(xnew, (xnew.shape[-1],), ln.weight, ln.bias, ln.eps)
+
+    monkeypatch.setattr(ops, 'add_dropout_ln', add_dropout_ln)
     monkeypatch.setattr(ops, 'next_seed', lambda: 0)
     return ops
 

@@ -176,6 +176,42 @@ def test_layernorm_linear_dropout():
     assert ops.add_dropout(res, yb, 0.1, False).equal(res + yb) and ops.add_dropout(res, yb, 0.0, True).equal(res + yb)
 
 
+@pytest.mark.parametrize('p', [0.0, 0.1])
+def test_residual_dropout_layernorm_fused(p):
+    """ops.add_dropout_ln == add_dropout followed by layer_norm: same mask (same seed), both outputs and all five gradients, with the
+    residual stream consumed twice (by the LayerNorm and by the next residual connection) as in the GPT block."""
+    from transfuser_b200 import ops
+    C = 216
+    ln = torch.nn.LayerNorm(C).to(DEV)
+    ln.weight.data = rnd(C, seed=2) * 0.2 + 1
+    ln.bias.data = rnd(C, seed=3) * 0.1
+    w = rnd(LN_ROWS, C, seed=6)
+    outs = {}
+    old = ops.ADD_LN_FUSED
+    try:
+        for fused in (False, True):
+            ops.ADD_LN_FUSED = fused
+            res, x = rnd(LN_ROWS, C, seed=4).requires_grad_(), rnd(LN_ROWS, C, seed=5).requires_grad_()
+            ln.zero_grad()
+            ops._SEED['off'] = 0x70000000
+            xnew, h = ops.add_dropout_ln(res, x, p, True, ln, emit16=False)
+            loss = (h * w).sum() + (xnew * xnew).sum() * 0.5
+            g = torch.autograd.grad(loss, (res, x, ln.weight, ln.bias))
+            outs[fused] = (xnew.detach(), h.detach()) + tuple(g)
+            # the LayerNorm output alone / the residual stream alone
+            xnew, h = ops.add_dropout_ln(res, x, 0.0, True, ln)
+            (g1,) = torch.autograd.grad(xnew.sum(), res)
+            assert torch.equal(g1, torch.ones_like(g1))
+    finally:
+        ops.ADD_LN_FUSED = old
+    assert torch.equal(outs[True][0], outs[False][0])
+    for a, b in zip(outs[True][1:], outs[False][1:]):
+        assert rel(a, b) < 1e-5
+    if p == 0.0:
+        res, x = rnd(LN_ROWS, C, seed=4), rnd(LN_ROWS, C, seed=5)
+        assert rel(outs[True][1], F.layer_norm(res + x, (C,), ln.weight, ln.bias, ln.eps)) < TOL
+
+
 @pytest.mark.parametrize('packed', [False, True])
 @pytest.mark.parametrize('C,nh', [(72, 4), (216, 4)])
 def test_attention(C, nh, packed):

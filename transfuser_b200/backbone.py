@@ -147,16 +147,25 @@ class Block(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(n_embd, block_exp * n_embd), nn.ReLU(True), nn.Linear(block_exp * n_embd, n_embd),
                                  nn.Dropout(resid_pdrop))
 
-    def run(self, x, B, T):
+    def _first_half(self, x, h, B, T):
+        """h = ln1(x) -> (x + attn(h), mlp[0](ln2(x + attn(h))))."""
         a, training = self.attn, self.training
-        h = ops.layer_norm(x, self.ln1, emit16=True)
         p_att = a.attn_pdrop if training else 0.0
         y = ops.AttentionFn.apply(h, a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
                                   B, T, a.n_head, p_att, ops.next_seed())
-        x = ops.add_dropout(x, ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training)
-        h = ops.layer_norm(x, self.ln2, emit16=True)
-        h = ops.linear(h, self.mlp[0].weight, self.mlp[0].bias, relu=True)
-        return ops.add_dropout(x, ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), a.resid_pdrop, training)
+        x, h = ops.add_dropout_ln(x, ops.linear(y, a.proj.weight, a.proj.bias), a.resid_pdrop, training, self.ln2, emit16=True)
+        return x, ops.linear(h, self.mlp[0].weight, self.mlp[0].bias, relu=True)
+
+    def run(self, x, B, T):
+        x, h = self._first_half(x, ops.layer_norm(x, self.ln1, emit16=True), B, T)
+        return ops.add_dropout(x, ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), self.attn.resid_pdrop, self.training)
+
+    def run_chained(self, x, h, B, T, next_ln, next_emit16):
+        """As run(), with the LayerNorms moved onto the residual connections in front of them: x is the residual stream and
+        h = ln1(x); returns the new residual stream and next_ln of it (the next block's ln1, or ln_f after the last block)."""
+        x, h = self._first_half(x, h, B, T)
+        return ops.add_dropout_ln(x, ops.linear(h, self.mlp[2].weight, self.mlp[2].bias), self.attn.resid_pdrop, self.training, next_ln,
+                                  emit16=next_emit16)
 
 
 class GPT(nn.Module):
@@ -194,9 +203,12 @@ class GPT(nn.Module):
         p = self.embd_pdrop if self.training else 0.0
         tok = ops.TokensFn.apply(img, lid, self.pos_emb, ghi, gwi, ghl, gwl, p, ops.next_seed())
         x = tok.view(B * T, self.n_embd)
-        for blk in self.blocks:
-            x = blk.run(x, B, T)
-        x = ops.layer_norm(x, self.ln_f).view(B, T, self.n_embd)
+        blocks = list(self.blocks)
+        h = ops.layer_norm(x, blocks[0].ln1, emit16=True)
+        for i, blk in enumerate(blocks):
+            last = i + 1 == len(blocks)
+            x, h = blk.run_chained(x, h, B, T, self.ln_f if last else blocks[i + 1].ln1, not last)
+        x = h.view(B, T, self.n_embd)
         return ops.GptUpAddFn.apply(img, lid, x, ghi, gwi, ghl, gwl)
 
 

@@ -656,11 +656,12 @@ __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict_
 //   ds = dgate*gate*(1-gate);  dw2 = ds^T h;  db2 = colsum ds;  dh = (ds w2) * (h > 0);  dw1 = dh^T pooled;  db1 = colsum dh;
 //   dpool = dh w1
 // used to be eight launches of [N,C]-sized kernels (sigmoid', 2 weight-gradient GEMMs, 2 column sums, 2 skinny GEMMs, relu'). It is
-// two: both run one CTA per 64-channel chunk of C; the only cross-chunk quantity, dh (a sum over all of C), is accumulated by
-// kernel 1 into a zeroed [N, Cr] buffer with fp32 atomics (24 per address at most) and read back by every CTA of kernel 2.
-constexpr int SE_CHUNK = 64;
+// two: both run one CTA per 16-channel chunk of C; the only cross-chunk quantity, dh (a sum over all of C), is accumulated by
+// kernel 1 into a zeroed [N, Cr] buffer with fp32 atomics (C / 16 <= 95 per address) and read back by every CTA of kernel 2.
+constexpr int SE_CHUNK = 16;    // channels of C per CTA: C / 16 CTAs (36 for the 576-channel stage) — these kernels are latency-bound
+constexpr int SE_SLICES = 256 / SE_CHUNK;   // se_mlp_bwd2: slices of the Cr range that share one channel
 constexpr int SE_MAX_N = 16;
-constexpr int SE_MAX_CR = 512;   // static shared memory: (64 + 512) * 16 floats = 36 KiB
+constexpr int SE_MAX_CR = 512;   // static shared memory: (16 + 512) * 16 floats = 33 KiB (+ 15 KiB of partial sums in kernel 2)
 
 __global__ void __launch_bounds__(256) se_mlp_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
                                                           const float* __restrict__ h, const float* __restrict__ w2,
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(256) se_mlp_bwd1_kernel(const float* __restric
     for (int n = 0; n < N; ++n) t = fmaf(ds[n * SE_CHUNK + j], hs[n * Cr + r], t);
     dw2[(int64_t)(c0 + j) * Cr + r] = t;
   }
-  // dh[n][r] += sum_{c in chunk} ds[n][c] w2[c][r]: a thread owns column r, streams the 64 weights of that column ONCE (coalesced
+  // dh[n][r] += sum_{c in chunk} ds[n][c] w2[c][r]: a thread owns column r, streams the chunk's weights of that column ONCE (coalesced
   // across the threads, 8 loads in flight) and feeds all N rows from registers; the first version re-read each weight per row
   for (int r = threadIdx.x; r < Cr; r += blockDim.x) {
     float acc[SE_MAX_N];
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restric
                                                           int N, int C, int Cr) {
   __shared__ float ps[SE_MAX_N * SE_CHUNK];  // [N][SE_CHUNK] pooled chunk
   __shared__ float dh[SE_MAX_N * SE_MAX_CR]; // [N][Cr]
-  __shared__ float red[3][SE_MAX_N][SE_CHUNK];   // quarters 1..3 (quarter 0 keeps its sums in registers): 48 KiB of static smem in total
+  __shared__ float red[SE_SLICES - 1][SE_MAX_N][SE_CHUNK];   // slices 1.. (slice 0 keeps its sums in registers): 48 KiB of static smem in total
   const int c0 = blockIdx.x * SE_CHUNK;
   const int cw = min(SE_CHUNK, C - c0);
   for (int i = threadIdx.x; i < SE_MAX_N * Cr; i += blockDim.x) dh[i] = (i < N * Cr && h[i] > 0.f) ? dh_acc[i] : 0.f;
@@ -741,15 +742,15 @@ __global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restric
     for (int n = 0; n < N; ++n) t = fmaf(dh[n * Cr + r], ps[n * SE_CHUNK + j], t);
     dw1[(int64_t)r * C + c0 + j] = t;
   }
-  // dpool[n][c] = sum_r dh[n][r] w1[r][c]: thread = (channel j, quarter q of the r range): each weight is loaded once (coalesced
-  // along j) and used for all N rows; the four quarters meet in shared memory
+  // dpool[n][c] = sum_r dh[n][r] w1[r][c]: thread = (channel j, slice q of the r range): each weight is loaded once and used for
+  // all N rows; the slices meet in shared memory
   {
-    const int j = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int j = threadIdx.x % SE_CHUNK, q = threadIdx.x / SE_CHUNK;
     float acc[SE_MAX_N];
 #pragma unroll
     for (int n = 0; n < SE_MAX_N; ++n) acc[n] = 0.f;
     if (j < cw) {
-      const int r_lo = (Cr * q) / 4, r_hi = (Cr * (q + 1)) / 4;
+      const int r_lo = (Cr * q) / SE_SLICES, r_hi = (Cr * (q + 1)) / SE_SLICES;
       const float* wp = w1 + c0 + j;
 #pragma unroll 8
       for (int r = r_lo; r < r_hi; ++r) {
@@ -766,7 +767,12 @@ __global__ void __launch_bounds__(256) se_mlp_bwd2_kernel(const float* __restric
     if (q == 0 && j < cw) {
 #pragma unroll
       for (int n = 0; n < SE_MAX_N; ++n)
-        if (n < N) dpool[(int64_t)n * C + c0 + j] = acc[n] + red[0][n][j] + red[1][n][j] + red[2][n][j];
+        if (n < N) {
+          float t = acc[n];
+#pragma unroll
+          for (int k = 0; k < SE_SLICES - 1; ++k) t += red[k][n][j];
+          dpool[(int64_t)n * C + c0 + j] = t;
+        }
     }
   }
 }

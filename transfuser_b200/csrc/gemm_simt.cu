@@ -173,31 +173,51 @@ TFB_API int tfb_gemm_f32_simt(int transA, int transB, int M, int N, int K, const
 // over n. A (<= 16 x K) is read through L1. act: 0 none, 1 ReLU, 2 sigmoid.
 namespace {
 
+// transB: a block of 8 warps covers 8 / KS output columns, KS warps sharing the K range of one column (KS = 1, 2, 4, 8 picked by the
+// host so that a lane walks <= ~6 k steps: these products are latency-bound — a few hundred KB of weights read once — so the loads
+// of a column are spread over more warps and unrolled rather than walked by one warp). Lanes read consecutive k (coalesced rows of
+// A and B); the warp sums meet in shared memory.
+template <int KS>
 __global__ void __launch_bounds__(256)
 small_m_tb_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                   float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (n >= N) return;
+  constexpr int COLS = 8 / KS;
+  __shared__ float red[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = warp / KS, slice = warp % KS;
+  const int n = blockIdx.x * COLS + col;
   float acc[16];
 #pragma unroll
   for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-  const float* b = B + (int64_t)n * ldb;
-  for (int k = lane; k < K; k += 32) {
-    const float bv = b[k];
+  if (n < N) {
+    const float* b = B + (int64_t)n * ldb;
+#pragma unroll 4
+    for (int k = slice * 32 + lane; k < K; k += 32 * KS) {
+      const float bv = b[k];
 #pragma unroll
-    for (int m = 0; m < 16; ++m)
-      if (m < M) acc[m] = fmaf(A[(int64_t)m * lda + k], bv, acc[m]);
+      for (int m = 0; m < 16; ++m)
+        if (m < M) acc[m] = fmaf(A[(int64_t)m * lda + k], bv, acc[m]);
+    }
   }
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     if (m < M) {
-      float v = warp_sum(acc[m]);
-      if (lane == 0) {
-        if (bias) v += bias[n];
-        if (act == 1) v = fmaxf(v, 0.f);
-        else if (act == 2) v = 1.f / (1.f + expf(-v));
-        C[(int64_t)m * ldc + n] = v;
-      }
+      const float v = warp_sum(acc[m]);
+      if (lane == 0) red[warp][m] = v;
+    }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;                 // thread (column c, row m) finishes one output
+  if (t < COLS * 16) {
+    const int c = t >> 4, m = t & 15, nn = blockIdx.x * COLS + c;
+    if (m < M && nn < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) v += red[c * KS + j][m];
+      if (bias) v += bias[nn];
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = 1.f / (1.f + expf(-v));
+      C[(int64_t)m * ldc + nn] = v;
     }
   }
 }
@@ -246,7 +266,13 @@ small_m_nt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
 TFB_API int tfb_gemm_small_m(int transB, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                              int64_t ldc, const float* bias, int act, cudaStream_t stream) {
   TFB_REQUIRE(A && B && C && M >= 1 && M <= 16 && N >= 1 && K >= 1);
-  if (transB) small_m_tb_kernel<<<(N + 7) / 8, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+  if (transB) {
+    const int ks = K > 32 * 6 * 4 ? 8 : K > 32 * 6 * 2 ? 4 : K > 32 * 6 ? 2 : 1;      // <= 6 k steps per lane (K <= 1536)
+    if (ks == 8)      small_m_tb_kernel<8><<<N, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+    else if (ks == 4) small_m_tb_kernel<4><<<(N + 1) / 2, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+    else if (ks == 2) small_m_tb_kernel<2><<<(N + 3) / 4, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+    else              small_m_tb_kernel<1><<<(N + 7) / 8, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+  }
   else        small_m_nt_kernel<<<(N + 31) / 32, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act);
   TFB_CHECK_LAUNCH();
   return TFB_OK;

@@ -3,6 +3,7 @@
 // and nn.LayerNorm in Block / GPT.ln_f (transfuser.py:533-534, 321).
 //   BN fwd : stats (per-channel sum, sum of squares; fp32 partials combined in fp64) -> normalise (+ReLU) + running stats
 //   BN bwd : reduce (sum g, sum g*xhat with the ReLU mask recomputed from x) -> dx, dgamma, dbeta
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -552,6 +553,68 @@ ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
   }
 }
 
+// ---- GPT block glue fused (transfuser.py:546-547 followed by the next LayerNorm, transfuser.py:533-534 / 321):
+//   xnew = res + dropout(x, p)          (the residual connection)          h = LayerNorm(xnew)   (+ bf16 copy for the next GEMM)
+// one CTA per token row, three passes over the L1-resident row (as ln_fwd_kernel); dropout mask = tfb_dropout_scale(seed, flat index).
+__global__ void __launch_bounds__(256)
+add_dropout_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ x, float* __restrict__ xnew, float* __restrict__ h, int C,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float p,
+                          const uint64_t* __restrict__ seed_dev, uint64_t seed_off, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                          __nv_bfloat16* __restrict__ h16) {
+  __shared__ float red[32];
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
+  const int64_t r = blockIdx.x;
+  const float* rr = res + r * C;
+  const float* xr = x + r * C;
+  float* nr = xnew + r * C;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = rr[c] + xr[c] * tfb_dropout_scale(seed, (uint64_t)(r * C + c), p);
+    nr[c] = v;
+    s += v;
+  }
+  const float mean = block_sum(s, red) / (float)C;
+  float q = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { const float d = nr[c] - mean; q = fmaf(d, d, q); }   // (own writes: same thread)
+  const float rstd = rsqrtf(block_sum(q, red) / (float)C + eps);
+  float* hr = h + r * C;
+  __nv_bfloat16* h16r = h16 ? h16 + r * C : nullptr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float o = fmaf((nr[c] - mean) * rstd, gamma[c], beta[c]);
+    hr[c] = o;
+    if (h16r) h16r[c] = __float2bfloat16_rn(o);
+  }
+  if (threadIdx.x == 0) { save_mean[r] = mean; save_rstd[r] = rstd; }
+}
+
+// backward: total = gx (gradient reaching xnew from its other consumer, may be null) + LayerNorm'(dh);  dres = total;  dx = total * mask
+__global__ void __launch_bounds__(256)
+add_dropout_ln_bwd_kernel(const float* __restrict__ xnew, const float* __restrict__ dh, const float* __restrict__ gx, float* __restrict__ dres,
+                          float* __restrict__ dx, int C, const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                          const float* __restrict__ save_rstd, float p, const uint64_t* __restrict__ seed_dev, uint64_t seed_off) {
+  __shared__ float red[32];
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + seed_off;
+  const int64_t r = blockIdx.x;
+  const float mean = save_mean[r], rstd = save_rstd[r];
+  const float* xr = xnew + r * C;
+  const float* gr = dh + r * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gg = gr[c] * gamma[c];
+    s1 += gg;
+    s2 = fmaf(gg, (xr[c] - mean) * rstd, s2);
+  }
+  const float m1 = block_sum(s1, red) / (float)C;
+  const float m2 = block_sum(s2, red) / (float)C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float xh = (xr[c] - mean) * rstd;
+    float t = rstd * (gr[c] * gamma[c] - m1 - xh * m2);
+    if (gx) t += gx[r * C + c];
+    dres[r * C + c] = t;
+    dx[r * C + c] = t * tfb_dropout_scale(seed, (uint64_t)(r * C + c), p);
+  }
+}
+
 // dgamma[c] = sum_r dy*xhat, dbeta[c] = sum_r dy  (column reduction; rows are few thousand). Partial sums meet in the self-cleaning
 // fp64 workspace (sums = [sum dy | sum dy*xhat]) and the last block writes dbeta / dgamma: no memsets of the outputs.
 __global__ void __launch_bounds__(256)
@@ -615,9 +678,15 @@ template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
                      const float* gamma, const float* beta, int relu, const float* ymask, Finalize fin, cudaStream_t stream);
 
+int colreduce_min_rows() {           // rows per thread below which a column reduction is not split further
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TFB_COLREDUCE_ROWS"); v = e ? atoi(e) : 16; if (v < 1) v = 1; }
+  return v;
+}
+
 int colreduce_splits(int64_t M, int slabs) {
   int64_t want = (4LL * tfb_num_sms() + slabs - 1) / slabs;
-  int64_t maxs = ceil_div64(M, 8 * 16);  // at least 16 rows per thread
+  int64_t maxs = ceil_div64(M, 8 * colreduce_min_rows());
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
@@ -795,6 +864,36 @@ TFB_API int tfb_layernorm_bwd(const float* x, const float* dy, float* dx, int64_
   dim3 grid(slabs, splits), block(32, 8);
   Finalize fin = {2, 2 * C, R, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
   ln_bwd_param_kernel<<<grid, block, 0, stream>>>(x, dy, R, C, save_mean, save_rstd, sums_ws, fin);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// xnew = res + dropout(x, p);  h = LayerNorm(xnew) (gamma, beta, eps);  h16 (optional): bf16 copy of h. One launch. [R, C] row-major.
+TFB_API int tfb_add_dropout_ln_fwd(const float* res, const float* x, float* xnew, float* h, int64_t R, int C, const float* gamma, const float* beta,
+                                   float eps, float p, const uint64_t* seed_dev, uint64_t seed_off, float* save_mean, float* save_rstd,
+                                   void* h16_bf16, cudaStream_t stream) {
+  TFB_REQUIRE(res && x && xnew && h && gamma && beta && save_mean && save_rstd && R > 0 && C > 0 && p >= 0.f && p < 1.f);
+  add_dropout_ln_fwd_kernel<<<(unsigned)R, 256, 0, stream>>>(res, x, xnew, h, C, gamma, beta, eps, p, seed_dev, seed_off, save_mean, save_rstd,
+                                                             (__nv_bfloat16*)h16_bf16);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
+// Backward of tfb_add_dropout_ln_fwd: dres, dx (both overwritten) from dh (gradient of h) and gx (gradient of xnew from its other consumer,
+// may be null); dgamma / dbeta overwritten (sums_ws as for tfb_layernorm_bwd). Two launches (row kernel + parameter reduction).
+TFB_API int tfb_add_dropout_ln_bwd(const float* xnew, const float* dh, const float* gx, float* dres, float* dx, int64_t R, int C, const float* gamma,
+                                   const float* save_mean, const float* save_rstd, float p, const uint64_t* seed_dev, uint64_t seed_off,
+                                   float* dgamma, float* dbeta, double* sums_ws, cudaStream_t stream) {
+  TFB_REQUIRE(xnew && dh && dres && dx && gamma && save_mean && save_rstd && dgamma && dbeta && sums_ws && R > 0 && C > 0);
+  add_dropout_ln_bwd_kernel<<<(unsigned)R, 256, 0, stream>>>(xnew, dh, gx, dres, dx, C, gamma, save_mean, save_rstd, p, seed_dev, seed_off);
+  TFB_CHECK_LAUNCH();
+  const int slabs = (C + 31) / 32;
+  int splits = (int)ceil_div64(R, 8 * 8);
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  dim3 grid(slabs, splits), block(32, 8);
+  Finalize fin = {2, 2 * C, R, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
+  ln_bwd_param_kernel<<<grid, block, 0, stream>>>(xnew, dh, R, C, save_mean, save_rstd, sums_ws, fin);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

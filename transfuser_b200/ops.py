@@ -105,6 +105,7 @@ WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '64'))
 NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
 DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '0') == '1'   # segmentation and depth decoders on two side streams (measured: no gain once
 #                                                                        the upsample kernels were vectorised; off)
+ADD_LN_FUSED = os.environ.get('TFB_ADD_LN_FUSED', '1') == '1'   # GPT: residual add + dropout + the next LayerNorm in one launch
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
 
@@ -1051,6 +1052,59 @@ def add_dropout(res, x, p, training):
     if not training or p <= 0.0:
         return add(res, x)
     return AddDropoutFn.apply(res, x, p, next_seed())
+
+
+class AddDropoutLNFn(Function):
+    """(xnew, h) = (res + dropout(x, p), LayerNorm(xnew)) in one launch — a GPT residual connection together with the LayerNorm
+    that reads it (transfuser.py:546-547, then 533/321). Backward: one row kernel takes the gradient of h and the gradient
+    reaching xnew from the next residual connection and writes d res and d x (mask regenerated), plus the parameter reduction."""
+
+    @staticmethod
+    def forward(ctx, res, x, p, seed, weight, bias, eps, emit16):
+        res, x = _c(res), _c(x)
+        C = x.shape[-1]
+        R = x.numel() // C
+        xnew = torch.empty_like(x)
+        h = torch.empty_like(x)
+        h16 = _emit16(h, emit16)
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        call('tfb_add_dropout_ln_fwd', res, x, xnew, h, R, C, weight, bias, float(eps), float(p), seed_state(x.device), seed, mean, rstd, h16)
+        ctx.save_for_backward(xnew, weight, mean, rstd, bias)
+        ctx.p, ctx.seed = p, seed
+        ctx.set_materialize_grads(False)
+        return xnew, _attach16(h, h16)
+
+    @staticmethod
+    def backward(ctx, gx, dh):
+        xnew, weight, mean, rstd, bias = ctx.saved_tensors
+        C = xnew.shape[-1]
+        R = xnew.numel() // C
+        if dh is None:                                      # LayerNorm output unused: only the residual connection's gradient
+            if gx is None:
+                return (None,) * 8
+            gx = _c(gx)
+            dx = torch.empty_like(gx)
+            call('tfb_dropout', gx, dx, gx.numel(), float(ctx.p), seed_state(gx.device), ctx.seed, None)
+            return gx, dx, None, None, None, None, None, None
+        dh = _c(dh)
+        gx = _c(gx) if gx is not None else None
+        dres = torch.empty_like(xnew)
+        dx = torch.empty_like(xnew)
+        dg = _gbuf(weight)
+        db = _gbuf(bias)
+        call('tfb_add_dropout_ln_bwd', xnew, dh, gx, dres, dx, R, C, weight, mean, rstd, float(ctx.p), seed_state(xnew.device), ctx.seed,
+             dg, db, _ws(xnew.device))
+        return dres, dx, None, None, dg, db, None, None
+
+
+def add_dropout_ln(res, x, p, training, ln, emit16=False):
+    """(res + dropout(x, p), ln(res + dropout(x, p))): fused unless TFB_ADD_LN_FUSED=0."""
+    if not ADD_LN_FUSED:
+        xnew = add_dropout(res, x, p, training)
+        return xnew, layer_norm(xnew, ln, emit16=emit16)
+    p = float(p) if training else 0.0
+    return AddDropoutLNFn.apply(res, x, p, next_seed() if p > 0.0 else 0, ln.weight, ln.bias, ln.eps, emit16)
 
 
 # ------------------------------------------------------------------ attention (SelfAttention.forward, transfuser.py:510-527)
