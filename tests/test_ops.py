@@ -417,6 +417,22 @@ def test_losses():
     assert rel(torch.autograd.grad(out, xm)[0], torch.autograd.grad(ref, x)[0]) < 1e-5
 
 
+@pytest.mark.parametrize('M,N,K', [(10, 37, 100), (10, 54, 216), (16, 145, 576), (3, 9, 1000), (10, 33, 1512)])
+def test_small_m_gemm(M, N, K):
+    """tfb_gemm_small_m (the squeeze-excite fc layers on pooled [B, C] vectors): every K-slice variant of the transB kernel (1, 2, 4, 8
+    warps per output column), ragged N, both activations, and the !transB form."""
+    from transfuser_b200._lib import call
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    for act, fn in ((0, lambda t: t), (1, F.relu), (2, torch.sigmoid)):
+        out = torch.empty(M, N, device=DEV)
+        call('tfb_gemm_small_m', 1, M, N, K, a, K, w, K, out, N, b, act)
+        assert rel(out, fn(a @ w.t() + b)) < TOL
+    wt = w.t().contiguous()
+    out = torch.empty(M, N, device=DEV)
+    call('tfb_gemm_small_m', 0, M, N, K, a, K, wt, N, out, N, None, 0)
+    assert rel(out, a @ wt) < TOL
+
+
 def test_gru_waypoints():
     from transfuser_b200 import ops
     B = 5

@@ -569,7 +569,7 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict
   float* nr = xnew + r * C;
   float s = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float v = rr[c] + xr[c] * tfb_dropout_scale(seed, (uint64_t)(r * C + c), p);
+    const float v = __fadd_rn(rr[c], __fmul_rn(xr[c], tfb_dropout_scale(seed, (uint64_t)(r * C + c), p)));   // (no FMA: as tfb_dropout + add)
     nr[c] = v;
     s += v;
   }
