@@ -643,6 +643,23 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     y[i] = __float2bfloat16_rn(x[i]);
 }
 
+// x = hi + lo + O(2^-17 |x|): hi = bf16(x), lo = bf16(x - hi). The operands of the 3 x bf16 tensor-core parity mode.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                         __nv_bfloat16* __restrict__ hi16, __nv_bfloat16* __restrict__ lo16,
+                                                         float* __restrict__ hi32, float* __restrict__ lo32) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[(i / cols) * ldx + (i % cols)];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float hf = __bfloat162float(h);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - hf);
+    if (hi16) hi16[i] = h;
+    if (lo16) lo16[i] = l;
+    if (hi32) hi32[i] = hf;
+    if (lo32) lo32[i] = __bfloat162float(l);
+  }
+}
+
 // y = x * (*s) * k  (device-resident scalar: no host sync)  /  y += ...
 __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s, float k,
                                                         float* __restrict__ y, int64_t n, int accumulate) {
@@ -1010,6 +1027,17 @@ TFB_API int tfb_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t strea
   TFB_REQUIRE(x && y && n >= 0);
   if (n == 0) return TFB_OK;
   cast_bf16_kernel<<<tfb_grid(n / 4 + 1, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y, n);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+// The two bf16 terms of x[rows, cols] (row stride ldx): hi = bf16(x), lo = bf16(x - hi), written contiguously as bf16 (hi16 / lo16)
+// and / or as the same values in fp32 (hi32 / lo32); any output may be null. x ~ hi + lo to 2^-17 relative: three bf16 tensor-core
+// products hi*hi + hi*lo + lo*hi reproduce an fp32 product to ~2e-5 (the "bf16x3" parity mode of gemm.py).
+TFB_API int tfb_split_bf16(const float* x, int64_t ldx, int64_t rows, int cols, void* hi16, void* lo16, float* hi32, float* lo32,
+                           cudaStream_t stream) {
+  TFB_REQUIRE(x && rows >= 0 && cols > 0 && ldx >= cols);
+  if (rows == 0) return TFB_OK;
+  split_bf16_kernel<<<tfb_grid(rows * cols, 256), 256, 0, stream>>>(x, ldx, rows, cols, (__nv_bfloat16*)hi16, (__nv_bfloat16*)lo16, hi32, lo32);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

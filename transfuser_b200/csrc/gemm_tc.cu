@@ -174,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       float* crow = Cbase + (int64_t)bz * c_bstride + (int64_t)m * ldc;
       const uint32_t acc_addr = tmem_base + (uint32_t)as * kAccCols + ((uint32_t)(q * 32) << 16);
       float* cwarp = Cbase + (int64_t)bz * c_bstride + (int64_t)(m0 + q * 32) * ldc;   // first row of this warp's 32-row band
-      const bool fast = !atomic_out && beta == 0.f && (ldc & 3) == 0 &&
+      const bool fast = (atomic_out || beta == 0.f) && (ldc & 3) == 0 &&
                         (C16 ? (reinterpret_cast<uintptr_t>(C16) & 7) == 0 : (reinterpret_cast<uintptr_t>(cwarp + n0) & 15) == 0);
       if (fast) {
         // coalesced path: 32-column chunks through this warp's padded smem staging buffer
@@ -188,7 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tc::epilogue_chunk32(acc_addr + (uint32_t)c0, stage,
                                [=](int row) -> int64_t { return row < rows_valid ? off0 + (int64_t)row * ldc : (int64_t)-1; }, cols_valid,
                                add_bias ? bias + n0 + c0 : nullptr, alpha, relu, lane, Cbase, C16, stats ? s_stat + n0 + c0 : nullptr,
-                               stats ? s_stat + N + n0 + c0 : nullptr);
+                               stats ? s_stat + N + n0 + c0 : nullptr, atomic_out);
         }
       } else {
 #pragma unroll 1

@@ -125,12 +125,17 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fp32 vector reduction into global memory (sm_90+): four consecutive floats, 16-byte aligned, one L2 transaction per lane instead of 4
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // Epilogue helper: one warp moves its 32 accumulator rows x 32 columns TMEM -> registers -> padded smem (row stride 36 floats:
 // conflict-free 16-byte accesses both ways) -> global memory with COALESCED row segments (4 rows per instruction, 128 bytes of fp32
 // or 64 bytes of bf16 per row), applying o = alpha*acc + bias (ReLU). `stage` is this warp's private 32 x 36 float buffer.
 // `row_off(row)` returns the ELEMENT offset of accumulator row `row` (0..31) in the output (a multiple of 4) or -1 for rows that
 // must not be written; columns >= cols_valid are not written. The result goes to out32 (fp32) or, when out16 is given, to out16
-// (bf16, round-to-nearest-even) at the same element offsets.
+// (bf16, round-to-nearest-even) at the same element offsets. atomic: the fp32 values are ADDED to out32 (split-K partial tiles).
 // stat_sum / stat_sq (optional, fp32 accumulators in SHARED memory, this chunk's column 0): per-column sum and sum of squares of
 // the values written (rows with offset -1 contribute nothing) — the training-mode BatchNorm statistics of a conv / GEMM output
 // come out of its epilogue instead of a separate read pass over the tensor. The CTA accumulates over all of its tiles and flushes
@@ -139,7 +144,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <class RowOff>
 __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, RowOff row_off, int cols_valid, const float* bias,
                                                  float alpha, int relu, int lane, float* out32, __nv_bfloat16* out16 = nullptr,
-                                                 float* stat_sum = nullptr, float* stat_sq = nullptr) {
+                                                 float* stat_sum = nullptr, float* stat_sq = nullptr, int atomic = 0) {
   uint32_t r[32];
   tmem_ld16_nowait(taddr, r);
   tmem_ld16_nowait(taddr + 16, r + 16);
@@ -186,7 +191,15 @@ __device__ __forceinline__ void epilogue_chunk32(uint32_t taddr, float* stage, R
         }
       } else {
         float* p = out32 + off + c4;
-        if (c4 + 3 < cols_valid) {
+        if (atomic) {                 // split-K partial tile: one 16-byte vector reduction per lane (coalesced 128-byte row segments)
+          if (c4 + 3 < cols_valid) {
+            red_add_v4(p, v);
+          } else {
+            if (c4 + 0 < cols_valid) atomicAdd(p + 0, v.x);
+            if (c4 + 1 < cols_valid) atomicAdd(p + 1, v.y);
+            if (c4 + 2 < cols_valid) atomicAdd(p + 2, v.z);
+          }
+        } else if (c4 + 3 < cols_valid) {
           *reinterpret_cast<float4*>(p) = v;
         } else {
           if (c4 + 0 < cols_valid) p[0] = v.x;
