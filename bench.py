@@ -196,7 +196,9 @@ def run_b200(args):
         line = {
             'metric': METRIC, 'value': round(value, 3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': round(ms_dev / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16' if args.gemm == 'bf16' else 'fp32', 'data': 'synthetic',
+            'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (fp32 operands as two bf16 terms, three tensor-core products, fp32 accumulate)',
+                      'bf16x6': 'bf16x6 (fp32 operands as three bf16 terms, six tensor-core products, fp32 accumulate)'}.get(args.gemm, 'fp32'),
+            'data': 'synthetic',
             'config': {'workload': '%s LidarCenterNet full train step (fwd+bwd+AdamW), all aux heads, dropout 0.1, '
                                    '160x704 RGB + 40k-point LiDAR->BEV, batch %d per GPU (BASELINE configs[%d])' % (label, B, args.config - 1),
                        'global_batch': total, 'parallelism': 'dp%d' % world, 'gemm_mode': args.gemm,
@@ -392,7 +394,9 @@ def main():
                     '(the headline), 3 = TransFuser batch 12, 4 = GeometricFusion batch 12, 5 = LateFusion batch 16')
     ap.add_argument('--batch', type=int, default=0, help='samples per GPU (default: the batch of --config; configs[1]: 10)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'cpu_baseline'])
-    ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16'])
+    ap.add_argument('--gemm', default=os.environ.get('TFB_GEMM', 'bf16'), choices=['simt', 'bf16', 'bf16x3', 'bf16x6'],
+                    help="bf16: tcgen05 bf16 operands (the benched mode); bf16x6 / bf16x3: the tensor-core parity modes (fp32 operands as three / two bf16 terms, six / three "
+                         "tcgen05 products per fp32 product); simt: exact fp32 on the CUDA cores")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--raw-inputs', type=int, default=int(os.environ.get('TFB_RAW_INPUTS', '1')),
                     help='1: feed the step with what is on disk (uint8 frames, raw points, pose transform; 1.6 MB per sample over PCIe) and '

@@ -643,20 +643,26 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     y[i] = __float2bfloat16_rn(x[i]);
 }
 
-// x = hi + lo + O(2^-17 |x|): hi = bf16(x), lo = bf16(x - hi). The operands of the 3 x bf16 tensor-core parity mode.
+// x = t0 + t1 (+ t2) with t0 = bf16(x), t1 = bf16(x - t0), t2 = bf16(x - t0 - t1): 16 (24) mantissa bits of x in bf16 terms.
+// The operands of the multi-term tensor-core parity modes.
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
-                                                         __nv_bfloat16* __restrict__ hi16, __nv_bfloat16* __restrict__ lo16,
-                                                         float* __restrict__ hi32, float* __restrict__ lo32) {
+                                                         __nv_bfloat16* __restrict__ a16, __nv_bfloat16* __restrict__ b16,
+                                                         __nv_bfloat16* __restrict__ c16, float* __restrict__ a32,
+                                                         float* __restrict__ b32, float* __restrict__ c32) {
   const int64_t n = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[(i / cols) * ldx + (i % cols)];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float hf = __bfloat162float(h);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - hf);
-    if (hi16) hi16[i] = h;
-    if (lo16) lo16[i] = l;
-    if (hi32) hi32[i] = hf;
-    if (lo32) lo32[i] = __bfloat162float(l);
+    const __nv_bfloat16 t0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(t0);                 // exact (Sterbenz / the residual fits in fp32)
+    const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(t1);
+    const __nv_bfloat16 t2 = __float2bfloat16_rn(r2);
+    if (a16) a16[i] = t0;
+    if (b16) b16[i] = t1;
+    if (c16) c16[i] = t2;
+    if (a32) a32[i] = __bfloat162float(t0);
+    if (b32) b32[i] = __bfloat162float(t1);
+    if (c32) c32[i] = __bfloat162float(t2);
   }
 }
 
@@ -1030,14 +1036,16 @@ TFB_API int tfb_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t strea
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
-// The two bf16 terms of x[rows, cols] (row stride ldx): hi = bf16(x), lo = bf16(x - hi), written contiguously as bf16 (hi16 / lo16)
-// and / or as the same values in fp32 (hi32 / lo32); any output may be null. x ~ hi + lo to 2^-17 relative: three bf16 tensor-core
-// products hi*hi + hi*lo + lo*hi reproduce an fp32 product to ~2e-5 (the "bf16x3" parity mode of gemm.py).
-TFB_API int tfb_split_bf16(const float* x, int64_t ldx, int64_t rows, int cols, void* hi16, void* lo16, float* hi32, float* lo32,
-                           cudaStream_t stream) {
+// The bf16 terms of x[rows, cols] (row stride ldx): t0 = bf16(x), t1 = bf16(x - t0), t2 = bf16(x - t0 - t1), written contiguously as
+// bf16 (t0_16 / t1_16 / t2_16) and / or as the same values in fp32 (t0_32 / ...); any output may be null. Two terms carry 16 mantissa
+// bits of x, three terms all 24: the tensor-core parity modes of gemm.py multiply term by term ("bf16x3": 3 products of 2 terms,
+// ~1e-5 relative; "bf16x6": 6 products of 3 terms, fp32-grade) with fp32 accumulation.
+TFB_API int tfb_split_bf16(const float* x, int64_t ldx, int64_t rows, int cols, void* t0_16, void* t1_16, void* t2_16, float* t0_32,
+                           float* t1_32, float* t2_32, cudaStream_t stream) {
   TFB_REQUIRE(x && rows >= 0 && cols > 0 && ldx >= cols);
   if (rows == 0) return TFB_OK;
-  split_bf16_kernel<<<tfb_grid(rows * cols, 256), 256, 0, stream>>>(x, ldx, rows, cols, (__nv_bfloat16*)hi16, (__nv_bfloat16*)lo16, hi32, lo32);
+  split_bf16_kernel<<<tfb_grid(rows * cols, 256), 256, 0, stream>>>(x, ldx, rows, cols, (__nv_bfloat16*)t0_16, (__nv_bfloat16*)t1_16,
+                                                                   (__nv_bfloat16*)t2_16, t0_32, t1_32, t2_32);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

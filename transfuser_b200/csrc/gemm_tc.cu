@@ -291,7 +291,10 @@ int launch_tc(int BN, int M, int N, int K, const T* A, int64_t lda, const T* B, 
   if (splits > num_kb) splits = num_kb;
   int kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per_split - 1) / kb_per_split;
-  const int atomic_out = splits > 1 ? 1 : 0;
+  // beta == 1 without an activation (accumulating a further term into C: the multi-term parity modes, q/k/v dgrad sums): the
+  // reduction epilogue adds into C with coalesced vector reductions instead of the scalar read-modify-write path
+  const bool accumulate = beta == 1.f && !relu && !stats && !C16 && nbatch == 1;
+  const int atomic_out = (splits > 1 || accumulate) ? 1 : 0;
   if (atomic_out) {
     if (relu) { tfb_set_last_error("split-K cannot fuse ReLU"); return TFB_ERR_ARG; }
     if (beta == 0.f) {

@@ -437,7 +437,7 @@ class LinearFn(Function):
             if ctx.tc:
                 with _OnWgradStream(dy.device, gb, xs, dw):
                     G.gemm_bf16(gb, xs, dw.view(w2.shape), trans_a=True, splits=_wgrad_splits(M, N, K))
-            elif M >= 4096:
+            elif M >= 4096 and not (G.multi_term() and G.x3_ok(N, K, M, True, False)):
                 # long contraction, narrow output (head 1x1 convs): the pixel-split direct-conv wgrad kernel (k = 1)
                 call('tfb_conv2d_wgrad', xs, g, dw, None, 1, M, 1, K, N, 1, 1, 1)
             else:
@@ -461,7 +461,12 @@ class Conv2dFn(Function):
         Cout, ks = w.shape[0], w.shape[2]
         Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
         plan = _conv_tc_plan(Cin, Cout, groups) if (G.MODE == 'bf16' and CONV_S2_TC and ks == 3 and stride == 2) else None
-        if plan is not None:
+        ctx.x3 = _conv_x3_ok(x.shape, Cout, ks, stride, groups)
+        if ctx.x3:
+            # tensor-core parity mode, dense 3x3: im2col of the two bf16 terms of x, then the three-term GEMM against the split weights
+            y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+            G.gemm_x3(_im2col_x3(x), G.split_bf16(w.view(Cout, Cin * 9)), y.view(-1, Cout), trans_b=True, bias=bias, relu=relu)
+        elif plan is not None:
             # stride 2 on the tensor cores: same implicit-GEMM kernel, the TMA map steps two pixels per box element
             y = _conv_tc_run(_as16(x), w, bias, plan, 0, Cout, groups, relu, stride=2, want_stats=want_stats)
         else:
@@ -478,6 +483,18 @@ class Conv2dFn(Function):
         dy = _c(dy)
         g = _relu_bwd(y, dy) if relu else dy
         dx = dw = db = None
+        if ctx.x3:
+            g = _c(g)
+            if ctx.needs_input_grad[0]:
+                # dgrad = the 3x3 conv of g with the transposed, tap-flipped weights: w'[ci][co][kh][kw] = w[co][ci][2-kh][2-kw]
+                wt = w.detach().flip(2, 3).transpose(0, 1).contiguous().view(Cin, Cout * 9)
+                dx = torch.empty_like(x)
+                G.gemm_x3(_im2col_x3(g), G.split_bf16(wt), dx.view(-1, Cin), trans_b=True)
+            if ctx.needs_input_grad[1]:
+                dw = _gbuf(w)
+                G.gemm_x3(G.split_bf16(g.view(-1, Cout)), _im2col_x3(x), dw.view(Cout, Cin * 9), trans_a=True)
+                db = _colsum(g.view(-1, Cout), _gbuf(bias_p)) if has_bias else None
+            return dx, dw, db, None, None, None, None
         if ctx.needs_input_grad[0]:
             plan = _conv_tc_plan(Cout, Cin, groups) if (G.MODE == 'bf16' and ks == 3 and stride == 2) else None
             if plan is not None:
@@ -500,6 +517,29 @@ class Conv2dFn(Function):
                 db = _gbuf(bias_p) if has_bias else None
                 call('tfb_conv2d_wgrad', x, g, dw, db, N, H, W, Cin, Cout, ks, stride, groups)
         return dx, dw, db, None, None, None, None
+
+
+def _conv_x3_ok(x_shape, Cout, ks, stride, groups):
+    """Dense 3x3 / stride-1 convs the 'bf16x3' parity mode runs on the tensor cores (im2col + three-term GEMM, forward, dgrad and
+    wgrad); grouped 3x3 convs (24 channels per group: few FLOPs), the 3-channel stems and outputs narrower than 16 channels stay
+    on the exact fp32 direct kernels."""
+    N, H, W, Cin = x_shape
+    return (G.multi_term() and ks == 3 and stride == 1 and groups == 1 and Cin % 8 == 0 and Cout % 8 == 0 and Cin >= 16 and Cout >= 16
+            and N * H * W >= 32)
+
+
+def _im2col_x3(x):
+    """bf16 im2col matrices [N*H*W, 9*C] ((channel, tap) column order) of the 2 / 3 bf16 terms of the NHWC fp32 tensor x."""
+    N, H, W, C = x.shape
+    terms = G.MULTI_TERM[G.MODE]
+    t32 = [torch.empty_like(x) for _ in range(terms)]
+    call('tfb_split_bf16', x, C, N * H * W, C, None, None, None, t32[0], t32[1], t32[2] if terms > 2 else None)
+    cols = []
+    for t in t32:                    # (exactly bf16-representable fp32 values: the cast inside the im2col kernel is exact)
+        col = torch.empty((N * H * W, 9 * C), dtype=torch.bfloat16, device=x.device)
+        call('tfb_im2col3x3_bf16', t, col, N, H, W, C, 1, 1)
+        cols.append(col)
+    return tuple(cols)
 
 
 def _conv_tc_plan(c_read, c_write, groups):
@@ -745,7 +785,7 @@ def conv2d(x, w, bias=None, stride=1, groups=1, relu=False, bn_stats=False):
     """bn_stats: a training-mode BatchNorm consumes the result next — on the tensor-core paths (bf16 mode) the producing kernel's
     epilogue then accumulates the per-channel sum / sum of squares (y._tfb_stats) and batch_norm skips its statistics pass."""
     bn_stats = bn_stats and BN_STATS_FUSED and G.MODE == 'bf16' and bias is None and not relu
-    if w.shape[2] == 1 and stride == 2 and groups == 1 and G.MODE == 'bf16':
+    if w.shape[2] == 1 and stride == 2 and groups == 1 and (G.MODE == 'bf16' or G.multi_term()):
         x, stride = Subsample2Fn.apply(x), 1
     if w.shape[2] == 1 and stride == 1 and groups == 1:
         N, H, W, C = x.shape

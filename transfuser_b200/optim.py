@@ -4,6 +4,8 @@
 gradient buffer), which turns the optimizer step into a single HBM-bound kernel over 168 M elements and the DDP
 exchange into a few large NCCL all-reduces that are issued from autograd hooks while backward is still running
 (reference: torch.optim.AdamW + DistributedDataParallel, train.py:134,142,312-314)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -293,6 +295,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 raise ValueError('amsgrad=True is not implemented (train.py:142 uses the default)')
 
 
+_SKIP_ALLREDUCE = os.environ.get('TFB_NO_ALLREDUCE', '0') == '1'
+
+
 class GradAllReducer:
     """Data-parallel exchange: SUM all-reduce of the flat gradient buffer in `n_chunks` spans. Each span is launched (async,
     NCCL stream) from a post-accumulate-grad hook as soon as the last parameter of that span has its gradient, so the
@@ -327,6 +332,8 @@ class GradAllReducer:
         trunk / decoders, weight-gradient stream): the collective is issued from a launch stream that waits for all of them, so the
         critical chain itself is never made to wait for the side streams here (NCCL orders its kernel after the issuing stream)."""
         g = self.fp.grad[lo:hi]
+        if _SKIP_ALLREDUCE:
+            return None          # measurement only (TFB_NO_ALLREDUCE=1): the step WITHOUT the exchange, to attribute its cost; results are wrong
         if not g.is_cuda:
             return dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
         dev = g.device
