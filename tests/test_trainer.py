@@ -30,7 +30,17 @@ def _ddp_worker(rank, world, port, out):
     assert len(red.spans) >= 3
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(16, 37, generator=g)
-    for it in range(2):                        # second iteration checks that the per-step bookkeeping resets
+    for it in range(3):                        # later iterations check that the per-step bookkeeping resets; the spans are re-planned
+        if it == 1:                            # from the gradient completion order seen in the first backward pass (rank 0's plan)
+            n0 = len(red.spans)
+            assert red.replan(late_frac=0.34) and not red.replan()
+            # the first Linear's gradients complete last: its weight / bias got spans of their own, every span boundary is shared
+            assert len(red.spans) > n0 and red.spans[0][0] == 0 and red.spans[-1][1] == fp.total
+            assert all(a[1] == b[0] for a, b in zip(red.spans[:-1], red.spans[1:]))
+            plan = torch.tensor([v for sp in red.spans for v in sp] + [0] * (64 - 2 * len(red.spans)), dtype=torch.int64)
+            both = [torch.zeros_like(plan) for _ in range(world)]
+            dist.all_gather(both, plan)
+            assert torch.equal(both[0], both[1])
         fp.grad.zero_()
         model(x * (it + 1)).square().mean().backward()
         local = fp.grad.clone()                # NOTE: spans already reduced by hooks are not local any more -> recompute below

@@ -296,6 +296,7 @@ class FusedAdamW(torch.optim.Optimizer):
 
 
 _SKIP_ALLREDUCE = os.environ.get('TFB_NO_ALLREDUCE', '0') == '1'
+SPLIT_LATE_SPANS = os.environ.get('TFB_SPLIT_LATE_SPANS', '1') == '1'     # readiness-aware exchange spans (GradAllReducer.replan)
 
 
 class GradAllReducer:
@@ -309,23 +310,68 @@ class GradAllReducer:
         self.pipeline = False     # switched on by Trainer once the set of gradient producers is known to be complete
         self._launch_stream = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_chunks = n_chunks
+        self._fired = []          # parameter indices in the order their gradients completed (first backward pass: see replan())
+        self._record = SPLIT_LATE_SPANS
+        self.replanned = False
         per = (fp.total + n_chunks - 1) // n_chunks
         per = (per + ALIGN - 1) // ALIGN * ALIGN
-        self.spans = [(lo, min(fp.total, lo + per)) for lo in range(0, fp.total, per)]
-        self.pending = [0] * len(self.spans)
-        self.counts = [0] * len(self.spans)
-        self.works = [None] * len(self.spans)
+        self._set_spans([(lo, min(fp.total, lo + per)) for lo in range(0, fp.total, per)])
+        if self.world > 1 or opt is not None:
+            for i, p in enumerate(fp.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _set_spans(self, spans):
+        fp = self.fp
+        self.spans = spans
+        starts = [lo for lo, _ in spans]
+        self.counts = [0] * len(spans)
         self.param_chunks = []
+        import bisect
         for p, o in zip(fp.params, fp.offsets):
-            first = o // per
-            last = (o + max(p.numel(), 1) - 1) // per
+            first = bisect.bisect_right(starts, o) - 1
+            last = bisect.bisect_right(starts, o + max(p.numel(), 1) - 1) - 1
             ids = list(range(first, last + 1))
             self.param_chunks.append(ids)
             for c in ids:
                 self.counts[c] += 1
-            if self.world > 1 or opt is not None:
-                p.register_post_accumulate_grad_hook(self._make_hook(ids))
         self.reset()
+
+    def replan(self, late_frac=0.2):
+        """Readiness-aware spans. Uniform spans in flat-buffer (registration) order complete when their LAST gradient does — and the
+        flat order starts each encoder with its stem, whose gradient is the last of the whole backward pass: the spans holding
+        stem / stage 1 / stage 2 (a few MB of parameters) drag tens of MB of long-finished stage-3 gradients into an exchange that can
+        only start when backward ends, fully exposed. After the first backward pass the order in which gradients completed is known;
+        every uniform span is cut wherever it changes between `late` parameters (the last `late_frac` of that order) and the rest, so
+        the exposed tail of the step carries only the late parameters' bytes. The plan comes from rank 0 (all ranks must issue the same
+        collectives). Call between steps (Trainer does, once, before capturing the step)."""
+        n = len(self._fired)
+        fp = self.fp
+        if self.replanned or n == 0:
+            return False
+        rank_of = {i: r for r, i in enumerate(self._fired)}
+        late = [rank_of.get(i, -1) >= (1.0 - late_frac) * n for i in range(len(fp.params))]
+        cuts = set()
+        prev = None
+        for i, o in enumerate(fp.offsets):
+            if prev is not None and late[i] != prev:
+                cuts.add(o)
+            prev = late[i]
+        per = (fp.total + self.n_chunks - 1) // self.n_chunks
+        per = (per + ALIGN - 1) // ALIGN * ALIGN
+        bounds = sorted(set(range(0, fp.total, per)) | cuts | {fp.total})
+        if self.world > 1:                                  # one plan for every rank
+            t = torch.zeros(256, dtype=torch.int64, device=fp.grad.device)
+            if dist.get_rank() == 0:
+                assert len(bounds) <= 255
+                t[0] = len(bounds)
+                t[1:1 + len(bounds)] = torch.tensor(bounds, dtype=torch.int64)
+            dist.broadcast(t, 0)
+            t = t.cpu()
+            bounds = [int(v) for v in t[1:1 + int(t[0])]]
+        self._set_spans([(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a])
+        self._record, self.replanned = False, True
+        return True
 
     def _all_reduce(self, lo, hi):
         """Async SUM all-reduce of grad[lo:hi]. The gradients of the span were produced on several streams (critical chain, LiDAR
@@ -350,9 +396,11 @@ class GradAllReducer:
         self.pending = list(self.counts)
         self.works = [None] * len(self.spans)
 
-    def _make_hook(self, ids):
+    def _make_hook(self, i):
         def hook(_p):
-            for c in ids:
+            if self._record:
+                self._fired.append(i)
+            for c in self.param_chunks[i]:
                 self.pending[c] -= 1
                 if self.pending[c] == 0:
                     lo, hi = self.spans[c]

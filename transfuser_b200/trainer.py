@@ -21,7 +21,7 @@ RAW_KEYS = ('rgb_u8', 'depth_u8', 'seg_u8', 'crop_shift', 'points', 'transforms'
 
 
 class Trainer:
-    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=int(os.environ.get('TFB_GRAD_CHUNKS', '24')), backbone='transFuser',
+    def __init__(self, cfg, device, gemm_mode='bf16', lr=1e-4, seed=0, n_chunks=int(os.environ.get('TFB_GRAD_CHUNKS', '8')), backbone='transFuser',
                  raw_inputs=False):
         self.cfg, self.device = cfg, device
         # the geometric-fusion backbone consumes two more inputs per sample (train.py:279-288)
@@ -102,6 +102,8 @@ class Trainer:
             loss = v * self.weights[k] if loss is None else loss + v * self.weights[k]
         loss.backward()
         self.opt.step(chunks=self.reducer.chunks())
+        if not self.reducer.replanned and self.graph is None and not torch.cuda.is_current_stream_capturing():
+            self.reducer.replan()       # once, after the first backward pass showed the order in which gradients complete
         return loss
 
     def capture(self, example):
