@@ -18,7 +18,7 @@ TOL = 3e-2     # forward, bf16 operands (8 mantissa bits) through a few layers w
 # "wrong layout" (a permuted tap / channel order gives a relative error >= 1). The tight gradient check is bf16-mode against bf16-mode
 # with every host-side option of DESIGN.md 4b switched off (the configuration that passed `-m gpu` on the B200 earlier in the round).
 GRAD_TOL_VS_FP32 = 0.25
-TOL_VS_PLAIN_BF16 = 1e-3
+TOL_VS_PLAIN_BF16 = 3e-3    # (the fused BatchNorm + squeeze-excite backward forms dy*gate + dpool/HW with one fma inside BatchNorm's passes: 1e-7 differences, a few flipped bf16 roundings downstream)
 FLAGS = ('SIDECARS', 'SE_FUSED_BWD', 'SE_POOL_FUSED', 'QKV_FUSED', 'BN_ADD_FUSED', 'PACK_BATCHED')   # the numerically EQUIVALENT options (BN_STATS_FUSED, CONV_S2_TC, ATTN_FUSED change roundings: they stay on in both runs)
 
 

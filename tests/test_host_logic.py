@@ -109,6 +109,7 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'GRUFn', _Apply(gru))
     monkeypatch.setattr(ops, 'centernet_decode', decode)
     monkeypatch.setattr(ops, 'TWO_STREAMS', False)
+    monkeypatch.setattr(ops, 'BN_SE_FUSED', False)      # (the Bottleneck then goes through ops.batch_norm + ops.SEFn, stubbed above)
     monkeypatch.setattr(ops, 'TokensFn', _Apply(tokens))
     monkeypatch.setattr(ops, 'AttentionFn', _Apply(attention))
     monkeypatch.setattr(ops, 'GptUpAddFn', _Apply(gpt_up_add))

@@ -83,7 +83,8 @@ def test_conv2d(cfg):
 
 
 @pytest.mark.parametrize('shape,relu', [((3, 10, 12, 72), True), ((2, 6, 7, 216), False), ((1, 5, 22, 1512), True),
-                                        ((2, 48, 44, 72), True), ((2, 40, 56, 216), False), ((1, 80, 64, 32), True)])   # M >= 4096: the flat column reduction
+                                        ((2, 48, 44, 72), True), ((2, 40, 56, 216), False), ((1, 80, 64, 32), True),      # M >= 4096: the flat column reduction
+                                        ((2, 10, 22, 576), True), ((3, 9, 7, 1512), False)])                            # the stage-3 / stage-4 widths
 def test_batchnorm_train(shape, relu):
     from transfuser_b200 import ops
     N, H, W, C = shape
@@ -102,7 +103,7 @@ def test_batchnorm_train(shape, relu):
     check_grads([xm, bn2.weight, bn2.bias], [x, bn.weight, bn.bias], out, ref)
 
 
-@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 6, 7, 216), (1, 5, 22, 1512), (2, 48, 44, 72)])
+@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 6, 7, 216), (1, 5, 22, 1512), (2, 48, 44, 72), (2, 10, 22, 576)])
 def test_batchnorm_add_relu_fused(shape):
     """relu(bn(x) + shortcut) — the Bottleneck tail — as ONE BatchNorm call (add + ReLU inside the normalise pass; ReLU mask and the
     shortcut's gradient inside the backward passes) against torch and against the unfused product path (eval mode too)."""
@@ -304,6 +305,38 @@ def test_batchnorm_with_se_pool(shape):
         assert 'tfb_pool_hw_fwd' not in _calls()[n0:]
     assert rel(nchw(out), ref) < TOL
     check_grads([xm, bn2.weight, bn2.bias] + ps, [x, bn.weight, bn.bias, w1, b1, w2, b2], out, ref)
+
+
+@pytest.mark.parametrize('shape', [(3, 10, 12, 72), (2, 48, 44, 72), (2, 10, 22, 576), (2, 5, 22, 1512), (2, 40, 56, 216)])
+def test_batchnorm_squeeze_excite_one_node(shape):
+    """ops.bn_se (BatchNorm + ReLU + squeeze-excite as one autograd node, the SE gradient folded into BatchNorm's backward kernels:
+    tfb_bn_bwd_se) against torch, forward and all seven gradients. Shapes: small narrow / wide maps (slab column reduction), tall narrow
+    maps (M >= 4096, C <= 512: the flat column reduction)."""
+    from transfuser_b200 import ops
+    N, H, W, C = shape
+    Cr = 8
+    x = (rnd(N, C, H, W, seed=1) * 2 + 0.3).requires_grad_()
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    bn.weight.data = rnd(C, seed=2) * 0.3 + 1
+    bn.bias.data = rnd(C, seed=3) * 0.2
+    bn2 = torch.nn.BatchNorm2d(C).to(DEV)
+    bn2.load_state_dict(bn.state_dict())
+    fc1, fc2 = torch.nn.Conv2d(C, Cr, 1).to(DEV), torch.nn.Conv2d(Cr, C, 1).to(DEV)
+    fc1.weight.data, fc1.bias.data = rnd(Cr, C, 1, 1, seed=4, scale=0.1), rnd(Cr, seed=5, scale=0.1)
+    fc2.weight.data, fc2.bias.data = rnd(C, Cr, 1, 1, seed=6, scale=0.3), rnd(C, seed=7, scale=0.1)
+    w1, b1, w2, b2 = [t.detach().clone().requires_grad_() for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    yb = F.relu(bn(x))
+    ref = yb * torch.sigmoid(F.conv2d(F.relu(F.conv2d(yb.mean((2, 3), keepdim=True), w1, b1)), w2, b2))
+    xm = nhwc(x.detach()).requires_grad_()
+    assert ops.bn_se_ok(xm, bn2, fc1)
+    n0 = len(_calls())
+    out = ops.bn_se(xm, bn2, fc1, fc2)
+    assert rel(nchw(out), ref) < TOL
+    assert rel(bn2.running_mean, bn.running_mean) < TOL and rel(bn2.running_var, bn.running_var) < TOL
+    check_grads([xm, bn2.weight, bn2.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias], [x, bn.weight, bn.bias, w1, b1, w2, b2], out, ref)
+    if _calls() is not _NOLOG:
+        log = _calls()[n0:]
+        assert 'tfb_bn_bwd_se' in log and 'tfb_se_bwd_apply' not in log and 'tfb_pool_hw_fwd' not in log
 
 
 @pytest.mark.parametrize('N,C,Cr', [(10, 1512, 144), (10, 576, 54), (16, 216, 18), (2, 72, 8), (1, 80, 3)])

@@ -57,7 +57,14 @@ class _Bottleneck(nn.Module):
 
     def run(self, x, emit16=True):
         """emit16: the block output feeds a 1x1 conv next (the following block's conv1, or the channel-change conv)."""
-        y = self.se.run(self.conv2.run(self.conv1.run(x, emit16=self.conv2.stride == 1), pool=True))   # SE pool inside conv2.bn
+        y1 = self.conv1.run(x, emit16=self.conv2.stride == 1)
+        c2 = self.conv2
+        if ops.bn_se_ok(y1, c2.bn, self.se.fc1):
+            # conv2.bn (+ReLU, + SE average pool) and the squeeze-excite module as one autograd node (ops.BNSEFn)
+            t = ops.conv2d(y1, c2.conv.weight, None, c2.stride, c2.groups, bn_stats=True)
+            y = ops.bn_se(t, c2.bn, self.se.fc1, self.se.fc2, bwd16=c2.conv.in_channels % 8 == 0)
+        else:
+            y = self.se.run(c2.run(y1, pool=True))            # SE pool inside conv2.bn
         sc = self.downsample.run(x) if self.downsample is not None else x
         return self.conv3.run(y, emit16=emit16, residual=sc)      # relu(conv3.bn(conv3(y)) + shortcut)
 

@@ -69,6 +69,15 @@ __device__ __forceinline__ void finalize_last_block(double* sums, int C, const F
   if (tid == 0) *reinterpret_cast<unsigned int*>(sums + f.nsums) = 0u;
 }
 
+// Gradient entering a BatchNorm whose output feeds a squeeze-excite gate (y = bn_out * gate[n][c]): with dy the gradient of the SE
+// OUTPUT, the gradient of the BatchNorm output is dy * gate[n][c] + dpool[n][c] / HW (dpool: gradient of the pooled vector through the
+// SE MLP). Folding it into the BatchNorm backward kernels removes the separate se_bwd_apply pass (one write + one read of the map).
+__device__ __forceinline__ void se_grad4(float g[4], const float* __restrict__ gate, const float* __restrict__ dpool, int64_t nc, float inv_hw) {
+  const float4 ga = *reinterpret_cast<const float4*>(gate + nc), dp = *reinterpret_cast<const float4*>(dpool + nc);
+  g[0] = fmaf(g[0], ga.x, dp.x * inv_hw); g[1] = fmaf(g[1], ga.y, dp.y * inv_hw);
+  g[2] = fmaf(g[2], ga.z, dp.z * inv_hw); g[3] = fmaf(g[3], ga.w, dp.w * inv_hw);
+}
+
 // ---------------- per-channel column reductions over a [M, C] matrix ----------------
 // block (32, 8): threadIdx.x -> channel inside a 32-wide slab, threadIdx.y -> row phase. grid (slabs, row splits).
 // MODE 0: (sum x, sum x^2)            MODE 1: BN backward (sum g, sum g*xhat), g = dy * relu_mask
@@ -120,7 +129,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin) {
+                  const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin,
+                  const float* __restrict__ se_gate = nullptr, const float* __restrict__ se_dpool = nullptr, int hw = 1) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
   double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
@@ -147,7 +157,11 @@ colreduce4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
         }
       }
       const float xv[2][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}};
-      const float gv[2][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}};
+      float gv[2][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}};
+      if (MODE == 1 && se_gate) {
+        se_grad4(gv[0], se_gate, se_dpool, (int64_t)((int)r / hw) * C + c, 1.f / (float)hw);
+        if (two) se_grad4(gv[1], se_gate, se_dpool, (int64_t)((int)(r + step) / hw) * C + c, 1.f / (float)hw);
+      }
       const float mv[2][4] = {{m0.x, m0.y, m0.z, m0.w}, {m1.x, m1.y, m1.z, m1.w}};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -200,7 +214,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_flat_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t M, int C, double* __restrict__ out,
                       const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin) {
+                      const float* __restrict__ beta, int relu, const float* __restrict__ ymask, Finalize fin,
+                      const float* __restrict__ se_gate = nullptr, const float* __restrict__ se_dpool = nullptr, int hw = 1) {
   const int C4 = C / 4, RPB = 256 / C4;
   const int t = threadIdx.x, q = t % C4, rr = t / C4;
   const bool active = rr < RPB;
@@ -222,7 +237,8 @@ colreduce_flat_kernel(const float* __restrict__ x, const float* __restrict__ dy,
         for (int k = 0; k < 4; ++k) { a0[k] += xv[k]; a1[k] = fmaf(xv[k], xv[k], a1[k]); }
       } else {
         const float4 g4 = *reinterpret_cast<const float4*>(dy + r * C + q * 4);
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        if (MODE == 1 && se_gate) se_grad4(gv, se_gate, se_dpool, (int64_t)((int)r / hw) * C + q * 4, 1.f / (float)hw);
         float mv[4] = {1.f, 1.f, 1.f, 1.f};
         if (ymask) {
           const float4 m4 = *reinterpret_cast<const float4*>(ymask + r * C + q * 4);
@@ -467,7 +483,8 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
                     const double* __restrict__ sums, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, const float* __restrict__ dgamma,
                     const float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx16, const float* __restrict__ ymask,
-                    float* __restrict__ gout) {
+                    float* __restrict__ gout, const float* __restrict__ se_gate = nullptr, const float* __restrict__ se_dpool = nullptr,
+                    int hw = 1) {
   const int C4 = C / 4;
   const int64_t total4 = M * C4;
   const double invM = 1.0 / (double)M;
@@ -479,7 +496,9 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
     const float4 is = *reinterpret_cast<const float4*>(invstd + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
     const float4 be = *reinterpret_cast<const float4*>(beta + c);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    if (se_gate) se_grad4(gs, se_gate, se_dpool, (int64_t)((int)(i / C4) / hw) * C + c, 1.f / (float)hw);
     const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, iss[4] = {is.x, is.y, is.z, is.w};
     const float gas[4] = {ga.x, ga.y, ga.z, ga.w}, bes[4] = {be.x, be.y, be.z, be.w};
     float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -678,6 +697,21 @@ template <int MODE>
 int launch_colreduce(const float* x, int64_t ldx, const float* dy, int64_t M, int C, double* out, const float* mean, const float* invstd,
                      const float* gamma, const float* beta, int relu, const float* ymask, Finalize fin, cudaStream_t stream);
 
+// d[n, hw, c] = dy * gate[n][c] + dpool[n][c] * inv_hw  (float4 per thread; C % 4 == 0)
+__global__ void __launch_bounds__(256) scale_gate_kernel(const float* __restrict__ dy, const float* __restrict__ gate,
+                                                         const float* __restrict__ dpool, float inv_hw, float* __restrict__ d, int64_t total4,
+                                                         int hw, int C) {
+  const int C4 = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(dy)[i];
+    float g[4] = {v.x, v.y, v.z, v.w};
+    se_grad4(g, gate, dpool, (int64_t)((int)(i / C4) / hw) * C + (int)(i % C4) * 4, inv_hw);
+    reinterpret_cast<float4*>(d)[i] = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int colreduce_min_rows() {           // rows per thread below which a column reduction is not split further
   static int v = -1;
   if (v < 0) { const char* e = getenv("TFB_COLREDUCE_ROWS"); v = e ? atoi(e) : 16; if (v < 1) v = 1; }
@@ -801,23 +835,73 @@ TFB_API int tfb_bn_apply(const float* x, float* y, int64_t M, int C, const float
   return TFB_OK;
 }
 
+// Common body of tfb_bn_bwd / tfb_bn_bwd_se: column reduction (sum g, sum g*xhat per channel) + apply pass.
+static int bn_bwd_impl(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
+                       const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
+                       void* dx16_bf16, const float* ymask, float* gmasked, const float* se_gate, const float* se_dpool, int hw,
+                       cudaStream_t stream) {
+  Finalize fin = {2, 2 * C, M, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
+  const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx) && (!ymask || aligned16(ymask)) && (!se_gate || (aligned16(se_gate) && aligned16(se_dpool)));
+  if (se_gate && !vec) {
+    // unaligned operands (never the case for the trunks' maps): the squeeze-excite gradient as its own pass (into dx, which the
+    // BatchNorm passes then read as dy and overwrite element by element)
+    const int64_t total = M * C;
+    scale_gate_kernel<<<tfb_grid(total / 4, 256), 256, 0, stream>>>(dy, se_gate, se_dpool, 1.f / (float)hw, dx, total / 4, hw, C);
+    TFB_CHECK_LAUNCH();
+    dy = dx;
+    se_gate = se_dpool = nullptr;
+  }
+  if (se_gate) {
+    if (C / 4 <= 128 && M >= 4096) {            // as launch_colreduce picks
+      const int rpb = 256 / (C / 4);
+      int64_t blocks = ceil_div64(M, (int64_t)rpb * 8);
+      const int64_t cap = (int64_t)tfb_num_sms() * 4;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      colreduce_flat_kernel<1><<<(int)blocks, 256, 0, stream>>>(x, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, ymask, fin,
+                                                               se_gate, se_dpool, hw);
+    } else {
+      const int slabs = (C / 4 + 31) / 32;
+      dim3 grid(slabs, colreduce_splits(M, slabs)), block(32, 8);
+      colreduce4_kernel<1><<<grid, block, 0, stream>>>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, ymask, fin, se_gate,
+                                                       se_dpool, hw);
+    }
+  } else {
+    launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, ymask, fin, stream);
+  }
+  TFB_CHECK_LAUNCH();
+  bn_bwd_apply_kernel<<<tfb_grid(M * C / 4, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
+                                                                dgamma, dbeta, (__nv_bfloat16*)dx16_bf16, ymask, gmasked, se_gate, se_dpool, hw);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+
 // sums_ws: as for tfb_bn_fwd. dx16_bf16 (optional): bf16 copy of dx written in the same pass (operand of the tensor-core dgrad /
 // wgrad of the convolution in front of this BatchNorm).
 // ymask / gmasked (optional, [M, C]): backward of y = relu(bn(x) + residual) (tfb_bn_fwd with a residual): the ReLU mask is
 // (ymask > 0) with ymask = that y, the masked gradient g = dy * mask drives the BatchNorm backward (pass relu = 0) and is also
 // written to gmasked — it is the gradient of the residual branch.
+// Training-mode BatchNorm backward (timm BatchNormAct2d behind transfuser.py:136-184): dx, dgamma, dbeta (overwritten).
 TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
                        const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
                        void* dx16_bf16, const float* ymask, float* gmasked, cudaStream_t stream) {
   TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0 && C % 4 == 0);
-  Finalize fin = {2, 2 * C, M, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr};
   TFB_REQUIRE(!gmasked || ymask);
-  launch_colreduce<1>(x, C, dy, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu, ymask, fin, stream);
-  TFB_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<tfb_grid(M * C / 4, 256), 256, 0, stream>>>(x, dy, dx, M, C, sums_ws, save_mean, save_invstd, gamma, beta, relu,
-                                                                dgamma, dbeta, (__nv_bfloat16*)dx16_bf16, ymask, gmasked);
-  TFB_CHECK_LAUNCH();
-  return TFB_OK;
+  return bn_bwd_impl(x, dy, dx, M, C, gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta, sums_ws, dx16_bf16, ymask, gmasked,
+                     nullptr, nullptr, 1, stream);
+}
+
+// tfb_bn_bwd for a BatchNorm whose output feeds a squeeze-excite gate (the Bottleneck's conv2.bn -> se): dy is the gradient of the SE
+// OUTPUT [M = batch * hw, C]; the gradient of the BatchNorm output, dy * se_gate[n][c] + se_dpool[n][c] / hw, is formed inside the
+// two BatchNorm passes (se_gate: the sigmoid gate [batch, C]; se_dpool: gradient of the pooled vector [batch, C], tfb_se_mlp_bwd),
+// replacing tfb_se_bwd_apply (one launch, one write and one read of the map fewer).
+TFB_API int tfb_bn_bwd_se(const float* x, const float* dy, float* dx, int64_t M, int C, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_invstd, int relu, float* dgamma, float* dbeta, double* sums_ws,
+                          void* dx16_bf16, const float* se_gate, const float* se_dpool, int hw, cudaStream_t stream) {
+  TFB_REQUIRE(x && dy && dx && gamma && beta && save_mean && save_invstd && dgamma && dbeta && sums_ws && M > 0 && C > 0 && C % 4 == 0);
+  TFB_REQUIRE(se_gate && se_dpool && hw > 0 && M % hw == 0 && M < (int64_t)1 << 31);
+  return bn_bwd_impl(x, dy, dx, M, C, gamma, beta, save_mean, save_invstd, relu, dgamma, dbeta, sums_ws, dx16_bf16, nullptr, nullptr,
+                     se_gate, se_dpool, hw, stream);
 }
 
 // out[c] = sum_r x[r][c]  (bias gradients of Linear / 1x1 conv layers)

@@ -105,6 +105,7 @@ WGRAD_MAX_CTAS = int(os.environ.get('TFB_WGRAD_MAX_CTAS', '64'))
 NARROW_DGRAD_TC = os.environ.get('TFB_NARROW_DGRAD_TC', '1') == '1'   # dgrad of 3x3 convs with < 8 output channels on the tensor cores (padded dy)
 DECODER_STREAMS = os.environ.get('TFB_DECODER_STREAMS', '0') == '1'   # segmentation and depth decoders on two side streams (measured: no gain once
 #                                                                        the upsample kernels were vectorised; off)
+BN_SE_FUSED = os.environ.get('TFB_BN_SE_FUSED', '1') == '1'     # Bottleneck conv2.bn + squeeze-excite as one autograd node (SE gradient folded into BatchNorm backward)
 ADD_LN_FUSED = os.environ.get('TFB_ADD_LN_FUSED', '1') == '1'   # GPT: residual add + dropout + the next LayerNorm in one launch
 ATTN_FUSED = os.environ.get('TFB_ATTN_FUSED', '1') == '1'       # bf16 mode: fused tcgen05 attention (csrc/attn_tc.cu), no T x T tensor in HBM
 
@@ -1016,6 +1017,78 @@ class SEFn(Function):
         dx = torch.empty_like(x)
         call('tfb_se_bwd_apply', dy, gate, dpool, dx, N, H * W, C)
         return dx, dw1, db1, dw2, db2, None
+
+
+class BNSEFn(Function):
+    """relu(BatchNorm2d(x)) followed by the squeeze-excite module it feeds (timm Bottleneck: conv2.bn -> se), training mode, as ONE
+    autograd node: forward = BatchNormTrainFn(pool=True) + SEFn, launch for launch; backward folds the squeeze-excite gradient
+    dy * gate + dpool / HW into BatchNorm's backward passes (tfb_bn_bwd_se) instead of materialising it (tfb_se_bwd_apply): one
+    launch, one write and one read of the block-sized map fewer per bottleneck."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, w1, b1, w2, b2, bwd16, stats):
+        x = _c(x)
+        N, H, W, C = x.shape
+        M, Cr, dev = N * H * W, w1.shape[0], x.device
+        y2 = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        pooled = None
+        if stats is not None:
+            pooled = _arena_take(dev, N * C * 4, torch.float32)               # accumulated into: must start at zero
+            pooled = pooled.view(N, C) if pooled is not None else None
+        if stats is not None and pooled is not None:
+            call('tfb_bn_fwd_stats', x, y2, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
+                 stats, None, None, pooled, N)
+        else:
+            pooled = torch.empty((N, C), dtype=torch.float32, device=dev)
+            call('tfb_bn_fwd', x, y2, M, C, weight, bias, float(eps), float(momentum), 1, running_mean, running_var, mean, invstd,
+                 _ws(dev), None, None, pooled, N)
+        h = torch.empty((N, Cr), dtype=torch.float32, device=dev)
+        gate = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call('tfb_gemm_small_m', 1, N, Cr, C, pooled, C, w1, C, h, Cr, b1, 1)
+        call('tfb_gemm_small_m', 1, N, C, Cr, h, Cr, w2, Cr, gate, C, b2, 2)
+        y = torch.empty_like(x)
+        y16 = _emit16(y, True)                               # the gated output always feeds the 1x1 conv3 GEMM
+        call('tfb_se_scale_fwd', y2, gate, y, N, H * W, C, y16)
+        ctx.save_for_backward(x, weight, bias, mean, invstd, y2, w1, w2, pooled, h, gate, b1, b2)
+        ctx.bwd16 = bwd16
+        return _attach16(y, y16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, invstd, y2, w1, w2, pooled, h, gate, b1, b2 = ctx.saved_tensors
+        dy = _c(dy)
+        N, H, W, C = x.shape
+        M, Cr, dev = N * H * W, w1.shape[0], x.device
+        dgate = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call('tfb_se_bwd_reduce', y2, dy, dgate, N, H * W, C)
+        dw2, db2, dw1, db1 = _gbuf(w2), _gbuf(b2), _gbuf(w1), _gbuf(b1)
+        dpool = torch.empty((N, C), dtype=torch.float32, device=dev)
+        part = torch.empty((N, Cr), dtype=torch.float32, device=dev)
+        call('tfb_se_mlp_bwd', dgate, gate, h, pooled, w1, w2, dw1, db1, dw2, db2, dpool, part, N, C, Cr)
+        dx = torch.empty_like(x)
+        dg, db = _gbuf(weight), _gbuf(bias)
+        dx16 = _emit16(dx, ctx.bwd16)
+        call('tfb_bn_bwd_se', x, dy, dx, M, C, weight, bias, mean, invstd, 1, dg, db, _ws(dev), dx16, gate, dpool, H * W)
+        if dx16 is not None:
+            _offer16(dx, dx16)
+        return dx, dg, db, None, None, None, None, dw1, db1, dw2, db2, None, None
+
+
+def bn_se_ok(x, bn, fc1):
+    """The fused BatchNorm + squeeze-excite node covers the training step's configuration (batch <= 16 per GPU, fused SE backward)."""
+    return (BN_SE_FUSED and bn.training and SE_POOL_FUSED and SE_FUSED_BWD and x.dim() == 4 and x.shape[0] <= 16 and fc1.weight.shape[0] <= 512
+            and x.shape[-1] % 4 == 0 and x.numel() < (1 << 31))
+
+
+def bn_se(x, bn, fc1, fc2, bwd16=False):
+    """relu(bn(x)) -> squeeze-excite(fc1, fc2), training mode (see BNSEFn)."""
+    stats = getattr(x, '_tfb_stats', None)
+    if stats is not None and (stats.numel() != 2 * x.shape[-1] or x.shape[-1] > 2048):
+        stats = None
+    return BNSEFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, fc1.weight, fc1.bias, fc2.weight,
+                        fc2.bias, bwd16, stats)
 
 
 class AddFn(Function):
