@@ -172,10 +172,11 @@ def run_b200(args):
     roof = None
     prof = _lib.Profiler(keep_calls=True) if rank == 0 else None
     _lib.lib().profiler = prof
-    torch.cuda.nvtx.range_push('tfb_profiled_step')   # `ncu --nvtx --nvtx-include "tfb_profiled_step/"` captures exactly this eager step
-    step(h2d())                      # every rank runs it (it contains the gradient all-reduce); only rank 0 instruments
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures exactly this eager step (process-wide: the backward
+    step(h2d())                      # kernels are launched by the autograd thread, which a per-thread NVTX range would miss).
+    torch.cuda.synchronize()         # Every rank runs the step (it contains the gradient all-reduce); only rank 0 instruments.
+    torch.cuda.profiler.stop()
     _lib.lib().profiler = None
     if rank == 0:
         roof = prof.summary(peaks())

@@ -1,7 +1,7 @@
 """Condenses `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` of ONE eager training step
-(bench.py's NVTX range `tfb_profiled_step`) into a per-kernel table and the DRAM-traffic JSON bench.py reads for `roofline.traffic`.
+(bench.py brackets its instrumented step with cudaProfilerStart / Stop) into a per-kernel table and the DRAM-traffic JSON bench.py reads for `roofline.traffic`.
 
-    ncu --nvtx --nvtx-include "tfb_profiled_step/" --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \\
+    ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \\
         --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --graph 0 --no-cpu-baseline
     python tools/ncu_step_summary.py gpurun_out/launches.csv profiles/rN_ncu_launch_summary.txt profiles/rN_ncu_traffic.json
 """
@@ -27,7 +27,7 @@ def main(src, out_txt, out_json):
     tot = sum(v[1] for v in agg.values())
     with open(out_txt, 'w') as f:
         f.write('one eager training step (batch 10, bf16 mode) under ncu --metrics gpu__time_duration.sum,dram__bytes_* (serialised, cold caches; '
-                'NVTX range tfb_profiled_step): %d launches, %.2f ms of kernel time\n' % (sum(v[0] for v in agg.values()), tot / 1e3))
+                'cudaProfilerStart/Stop around the step): %d launches, %.2f ms of kernel time\n' % (sum(v[0] for v in agg.values()), tot / 1e3))
         for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('%9.1f us %5.1f%% x%-5d %9.2f MB DRAM/launch  %s\n' % (us, 100 * us / tot, n, by / max(n, 1) / 1e6, k))
     g = [(k, v) for k, v in agg.items() if 'gemm_tc_kernel' in k]
