@@ -1036,6 +1036,8 @@ TFB_API int tfb_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t strea
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }
+// (No reference counterpart: operand preparation of the tensor-core parity modes, which replace cuBLAS fp32 behind nn.Linear / 1x1 /
+// dense 3x3 nn.Conv2d — transfuser.py:498-506, 538-543, 214-281, model.py:93-99.)
 // The bf16 terms of x[rows, cols] (row stride ldx): t0 = bf16(x), t1 = bf16(x - t0), t2 = bf16(x - t0 - t1), written contiguously as
 // bf16 (t0_16 / t1_16 / t2_16) and / or as the same values in fp32 (t0_32 / ...); any output may be null. Two terms carry 16 mantissa
 // bits of x, three terms all 24: the tensor-core parity modes of gemm.py multiply term by term ("bf16x3": 3 products of 2 terms,

@@ -891,7 +891,8 @@ TFB_API int tfb_bn_bwd(const float* x, const float* dy, float* dx, int64_t M, in
                      nullptr, nullptr, 1, stream);
 }
 
-// tfb_bn_bwd for a BatchNorm whose output feeds a squeeze-excite gate (the Bottleneck's conv2.bn -> se): dy is the gradient of the SE
+// tfb_bn_bwd for a BatchNorm whose output feeds a squeeze-excite gate (timm Bottleneck conv2.bn -> se inside the RegNetY trunks,
+// reference team_code_transfuser/transfuser.py:136-184 via timm.create_model at :382-384): dy is the gradient of the SE
 // OUTPUT [M = batch * hw, C]; the gradient of the BatchNorm output, dy * se_gate[n][c] + se_dpool[n][c] / hw, is formed inside the
 // two BatchNorm passes (se_gate: the sigmoid gate [batch, C]; se_dpool: gradient of the pooled vector [batch, C], tfb_se_mlp_bwd),
 // replacing tfb_se_bwd_apply (one launch, one write and one read of the map fewer).
@@ -952,7 +953,9 @@ TFB_API int tfb_layernorm_bwd(const float* x, const float* dy, float* dx, int64_
   return TFB_OK;
 }
 
-// xnew = res + dropout(x, p);  h = LayerNorm(xnew) (gamma, beta, eps);  h16 (optional): bf16 copy of h. One launch. [R, C] row-major.
+// Replaces the GPT Block's residual connection and the LayerNorm that reads it (reference team_code_transfuser/transfuser.py:546-547, then
+// :533-534 of the same / next Block, or ln_f at :321): xnew = res + dropout(x, p);  h = LayerNorm(xnew) (gamma, beta, eps);  h16 (optional):
+// bf16 copy of h. One launch. [R, C] row-major.
 TFB_API int tfb_add_dropout_ln_fwd(const float* res, const float* x, float* xnew, float* h, int64_t R, int C, const float* gamma, const float* beta,
                                    float eps, float p, const uint64_t* seed_dev, uint64_t seed_off, float* save_mean, float* save_rstd,
                                    void* h16_bf16, cudaStream_t stream) {
