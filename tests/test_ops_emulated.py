@@ -8,7 +8,7 @@ import pytest
 
 import test_ops as T
 from cuda_emul import loader
-from test_ops import (test_attention, test_batchnorm_add_relu_fused, test_batchnorm_squeeze_excite_one_node, test_batchnorm_train, test_batchnorm_with_se_pool, test_conv2d, test_gpt_tokens_and_view_quirk, test_gru_waypoints,  # noqa: F401
+from test_ops import (test_attention, test_batchnorm_add_relu_fused, test_batchnorm_squeeze_excite_one_node, test_batchnorm_train, test_batchnorm_with_se_pool, test_conv2d, test_gpt_tokens_and_view_quirk, test_gpt_with_velocity_embedding, test_gru_waypoints,  # noqa: F401
                       test_image_prep_and_layout, test_layernorm_linear_dropout, test_losses, test_se_add_pool, test_residual_dropout_layernorm_fused, test_se_fused_mlp_backward, test_small_m_gemm,
                       test_upsample)
 

@@ -181,11 +181,11 @@ class GPT(nn.Module):
     def __init__(self, n_embd, n_head, block_exp, n_layer, img_vert_anchors, img_horz_anchors, lidar_vert_anchors,
                  lidar_horz_anchors, seq_len, embd_pdrop, attn_pdrop, resid_pdrop, config, use_velocity=True):
         super().__init__()
-        if use_velocity:
-            raise RuntimeError('use_velocity=True is not implemented (train.py:54 default is 0)')
-        self.n_embd, self.seq_len, self.config, self.use_velocity = n_embd, 1, config, use_velocity
+        self.n_embd, self.seq_len, self.config, self.use_velocity = n_embd, 1, config, bool(use_velocity)
         self.grid = (img_vert_anchors, img_horz_anchors, lidar_vert_anchors, lidar_horz_anchors)
         self.pos_emb = nn.Parameter(torch.zeros(1, img_vert_anchors * img_horz_anchors + lidar_vert_anchors * lidar_horz_anchors, n_embd))
+        if self.use_velocity:
+            self.vel_emb = nn.Linear(self.seq_len, n_embd)          # transfuser.py:306-309 (registered between pos_emb and the blocks)
         self.embd_pdrop = embd_pdrop
         self.drop = nn.Dropout(embd_pdrop)
         self.blocks = nn.Sequential(*[Block(n_embd, n_head, block_exp, attn_pdrop, resid_pdrop) for _ in range(n_layer)])
@@ -202,13 +202,21 @@ class GPT(nn.Module):
             module.bias.data.zero_()
             module.weight.data.fill_(self.config.gpt_layer_norm_init_weight)
 
-    def run(self, img, lid):
-        """img / lid: NHWC stage features -> the same features with the upsampled GPT output added."""
+    def run(self, img, lid, velocity=None):
+        """img / lid: NHWC stage features -> the same features with the upsampled GPT output added. velocity [B, 1]: the ego speed
+        (only read with use_velocity: its embedding is added to every token before the embedding dropout, transfuser.py:352-355)."""
         ghi, gwi, ghl, gwl = self.grid
         B = img.shape[0]
         T = ghi * gwi + ghl * gwl
         p = self.embd_pdrop if self.training else 0.0
-        tok = ops.TokensFn.apply(img, lid, self.pos_emb, ghi, gwi, ghl, gwl, p, ops.next_seed())
+        if self.use_velocity:
+            if velocity is None:
+                raise RuntimeError('GPT(use_velocity=True) needs the velocity input')
+            tok = ops.TokensFn.apply(img, lid, self.pos_emb, ghi, gwi, ghl, gwl, 0.0, 0)
+            ve = ops.linear(velocity.reshape(B, self.seq_len).to(self.vel_emb.weight.dtype), self.vel_emb.weight, self.vel_emb.bias)
+            tok = ops.dropout(ops.BcastAddTokensFn.apply(tok, ve), self.embd_pdrop, self.training)
+        else:
+            tok = ops.TokensFn.apply(img, lid, self.pos_emb, ghi, gwi, ghl, gwl, p, ops.next_seed())
         x = tok.view(B * T, self.n_embd)
         blocks = list(self.blocks)
         h = ops.layer_norm(x, blocks[0].ln1, emit16=True)
@@ -256,9 +264,9 @@ class TransfuserBackbone(nn.Module):
             object.__setattr__(self, '_bn_cache', [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)])
         return self._bn_cache
 
-    def forward_nhwc(self, image, lidar, taps=None):
+    def forward_nhwc(self, image, lidar, taps=None, velocity=None):
         """image: NCHW 0..255, lidar: NCHW -> (p2..p5 NHWC), image grid NHWC, fused [B,512]. `taps` (optional dict) receives the
-        per-stage fused feature maps (NHWC) for layer-by-layer parity checks."""
+        per-stage fused feature maps (NHWC) for layer-by-layer parity checks. velocity [B, 1]: read by the GPTs with use_velocity."""
         if self.training:
             torch._foreach_add_([m.num_batches_tracked for m in self._bn_modules()], 1)
             ops.tick(image.device)
@@ -271,7 +279,7 @@ class TransfuserBackbone(nn.Module):
             for i in range(1, 5):
                 x = getattr(ie, 's%d' % i).run(x, last16=False)
                 l = getattr(le, 's%d' % i).run(l, last16=False)
-                x, l = getattr(self, 'transformer%d' % i).run(x, l)
+                x, l = getattr(self, 'transformer%d' % i).run(x, l, velocity)
                 if taps is not None:
                     taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
         else:
@@ -290,7 +298,7 @@ class TransfuserBackbone(nn.Module):
                 x = getattr(ie, 's%d' % i).run(x, last16=False)
                 main.wait_stream(side)
                 ops.record_stream(l, main)
-                x, l = getattr(self, 'transformer%d' % i).run(x, l)
+                x, l = getattr(self, 'transformer%d' % i).run(x, l, velocity)
                 if taps is not None:
                     taps['img_s%d' % i], taps['lid_s%d' % i] = x, l
                 if i < 4:
@@ -308,7 +316,7 @@ class TransfuserBackbone(nn.Module):
         return (p2, p3, p4, p5), x, fused
 
     def forward(self, image, lidar, velocity):
-        feats, grid, fused = self.forward_nhwc(image, lidar)
+        feats, grid, fused = self.forward_nhwc(image, lidar, velocity=velocity)
         return tuple(ops.nhwc_to_nchw(f) for f in feats), ops.nhwc_to_nchw(grid), fused
 
 
@@ -534,6 +542,6 @@ class latentTFBackbone(TransfuserBackbone):
             object.__setattr__(self, '_grid_key', key)
         return self._grid_buf
 
-    def forward_nhwc(self, image, lidar, taps=None):
+    def forward_nhwc(self, image, lidar, taps=None, velocity=None):
         lidar = torch.cat((self._grid(lidar).expand(lidar.shape[0], -1, -1, -1), lidar[:, 2:]), dim=1)
-        return super().forward_nhwc(image, lidar, taps)
+        return super().forward_nhwc(image, lidar, taps, velocity)

@@ -666,6 +666,14 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
+// y[n][t][c] = x[n][t][c] + v[n][c]: a per-sample vector added to every token (the GPT velocity embedding, transfuser.py:352-355)
+__global__ void __launch_bounds__(256) bcast_add_nc_kernel(const float* __restrict__ x, const float* __restrict__ v, float* __restrict__ y,
+                                                           int64_t total, int T, int C) {
+  const int64_t tc = (int64_t)T * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] + v[(i / tc) * C + i % C];
+}
+
 // y = x * (*s) * k  (device-resident scalar: no host sync)  /  y += ...
 __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s, float k,
                                                         float* __restrict__ y, int64_t n, int accumulate) {
@@ -1048,6 +1056,15 @@ TFB_API int tfb_split_bf16(const float* x, int64_t ldx, int64_t rows, int cols, 
   if (rows == 0) return TFB_OK;
   split_bf16_kernel<<<tfb_grid(rows * cols, 256), 256, 0, stream>>>(x, ldx, rows, cols, (__nv_bfloat16*)t0_16, (__nv_bfloat16*)t1_16,
                                                                    (__nv_bfloat16*)t2_16, t0_32, t1_32, t2_32);
+  TFB_CHECK_LAUNCH();
+  return TFB_OK;
+}
+// y[N, T, C] = x[N, T, C] + v[N, C] broadcast over T — GPT.forward with use_velocity (reference team_code_transfuser/transfuser.py:352-355:
+// pos_emb + token_embeddings + velocity_embeddings.unsqueeze(1)); the gradient of v is the sum of dy over T (tfb_pool_hw_fwd x T).
+TFB_API int tfb_bcast_add_nc(const float* x, const float* v, float* y, int N, int T, int C, cudaStream_t stream) {
+  TFB_REQUIRE(x && v && y && N > 0 && T > 0 && C > 0);
+  const int64_t total = (int64_t)N * T * C;
+  bcast_add_nc_kernel<<<tfb_grid(total, 256), 256, 0, stream>>>(x, v, y, total, T, C);
   TFB_CHECK_LAUNCH();
   return TFB_OK;
 }

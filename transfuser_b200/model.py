@@ -145,11 +145,13 @@ class LidarCenterNet(nn.Module):
                                   self.pred_len, float(self.config.lidar_pos[0]))
         return pred_wp, None, None, None, None
 
-    def _run_backbone(self, rgb, lidar_bev, bev_points, cam_points):
+    def _run_backbone(self, rgb, lidar_bev, bev_points, cam_points, ego_vel=None):
         if self.backbone == 'geometric_fusion':
             if bev_points is None or cam_points is None:
                 raise RuntimeError('the geometric_fusion backbone needs bev_points and cam_points (train.py:281-288)')
             return self._model.forward_nhwc(rgb, lidar_bev, bev_points, cam_points)
+        if self.backbone in ('transFuser', 'latentTF') and self._model.transformer1.use_velocity:   # (latentTF.py:144-195: same GPTs)
+            return self._model.forward_nhwc(rgb, lidar_bev, velocity=ego_vel)      # model.py:753 passes ego_vel to the backbone
         return self._model.forward_nhwc(rgb, lidar_bev)
 
     def get_bbox_local_metric(self, bbox):
@@ -179,7 +181,7 @@ class LidarCenterNet(nn.Module):
             raise RuntimeError('forward_ego(debug=True) visualisation is out of scope')
         if self.use_target_point_image:
             lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
-        features, _, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points)
+        features, _, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points, ego_vel)
         pred_wp, _, _, _, _ = self.forward_gru(fused_features, target_point)
         bboxes, _ = self.head.get_bboxes_nhwc(self.head.run(features[0]))[0]
         bboxes = bboxes[bboxes[:, -1] > self.config.bb_confidence_threshold]
@@ -193,7 +195,7 @@ class LidarCenterNet(nn.Module):
         loss = {}
         if self.use_target_point_image:
             lidar_bev = torch.cat((lidar_bev, target_point_image), dim=1)
-        features, image_features_grid, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points)
+        features, image_features_grid, fused_features = self._run_backbone(rgb, lidar_bev, bev_points, cam_points, ego_vel)
         two = ops.TWO_STREAMS and cfg.multitask
         if two:
             # auxiliary decoders (image grid -> 160x704 maps) on the second stream, concurrently with the BEV-side heads

@@ -1141,6 +1141,28 @@ def dropout(x, p, training):
     return DropoutFn.apply(x, p, next_seed())
 
 
+class BcastAddTokensFn(Function):
+    """tok[B, T, C] + v[B, C] for every token: the velocity embedding of GPT.forward (transfuser.py:352-355, use_velocity=True)."""
+
+    @staticmethod
+    def forward(ctx, tok, v):
+        tok, v = _c(tok), _c(v)
+        B, T, C = tok.shape
+        y = torch.empty_like(tok)
+        call('tfb_bcast_add_nc', tok, v, y, B, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        B, T, C = dy.shape
+        mean = torch.empty((B, C), dtype=torch.float32, device=dy.device)
+        call('tfb_pool_hw_fwd', dy, mean, B, T, C)
+        dv = torch.empty_like(mean)
+        call('tfb_scale_dev', mean, None, float(T), dv, mean.numel(), 0)
+        return dy, dv
+
+
 class AddDropoutFn(Function):
     """res + dropout(x) in one pass (the GPT block's residual connections, transfuser.py:546-547); backward regenerates the mask."""
 
