@@ -405,57 +405,6 @@ def test_gpt_tokens_and_view_quirk(C, hw):
     assert rel(mg[0], rg[0]) < 1e-5 and rel(nchw(mg[1]), rg[1]) < 1e-5 and rel(nchw(mg[2]), rg[2]) < 1e-5
 
 
-def test_gpt_with_velocity_embedding():
-    """GPT.forward with use_velocity=True (transfuser.py:346-364): tokens + pos_emb + vel_emb(velocity) for every token, one Block,
-    ln_f, the view quirk and the upsample-add — the product module (kernels through the C-ABI) against the same nn.Parameters driven
-    through plain torch ops, outputs and gradients incl. vel_emb's."""
-    from transfuser_b200.backbone import GPT
-
-    class Cfg:
-        gpt_linear_layer_init_mean, gpt_linear_layer_init_std, gpt_layer_norm_init_weight = 0.0, 0.02, 1.0
-    C, B, nh = 32, 2, 4
-    torch.manual_seed(0)
-    g = GPT(C, nh, 4, 1, 2, 3, 2, 2, 1, 0.0, 0.0, 0.0, Cfg, use_velocity=True).to(DEV).train()
-    with torch.no_grad():
-        g.pos_emb.copy_(rnd(1, 10, C, seed=1, scale=0.1))
-        g.vel_emb.weight.copy_(rnd(C, 1, seed=2, scale=0.3))
-        g.vel_emb.bias.copy_(rnd(C, seed=3, scale=0.1))
-        for i, p in enumerate(g.blocks.parameters()):
-            if p.dim() == 2:
-                p.copy_(rnd(*p.shape, seed=10 + i, scale=p.shape[1] ** -0.5))
-    img, lid, vel = rnd(B, C, 4, 6, seed=4), rnd(B, C, 4, 4, seed=5), rnd(B, 1, seed=6).abs() * 5
-    im, lm = nhwc(img).requires_grad_(), nhwc(lid).requires_grad_()
-    oi, ol = g.run(im, lm, vel)
-    # the same parameters through torch
-    ir, lr = img.clone().requires_grad_(), lid.clone().requires_grad_()
-    tok = torch.cat((F.adaptive_avg_pool2d(ir, (2, 3)).permute(0, 2, 3, 1).reshape(B, -1, C),
-                     F.adaptive_avg_pool2d(lr, (2, 2)).permute(0, 2, 3, 1).reshape(B, -1, C)), dim=1)
-    x = g.pos_emb + tok + g.vel_emb(vel).unsqueeze(1)
-    blk = g.blocks[0]
-    a = blk.attn
-    h = blk.ln1(x)
-    T = 10
-    q, k, v = [f(h).view(B, T, nh, C // nh).transpose(1, 2) for f in (a.query, a.key, a.value)]
-    att = F.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(C // nh)), dim=-1)
-    x = x + a.proj((att @ v).transpose(1, 2).reshape(B, T, C))
-    x = x + blk.mlp(blk.ln2(x))
-    x = g.ln_f(x)
-    ref_i = ir + F.interpolate(x[:, :6, :].contiguous().view(B, -1, 2, 3), size=(4, 6), mode='bilinear', align_corners=False)
-    ref_l = lr + F.interpolate(x[:, 6:, :].contiguous().view(B, -1, 2, 2), size=(4, 4), mode='bilinear', align_corners=False)
-    assert rel(nchw(oi), ref_i) < TOL and rel(nchw(ol), ref_l) < TOL
-    params = [g.vel_emb.weight, g.vel_emb.bias, g.pos_emb, a.proj.weight, blk.mlp[0].weight, g.ln_f.weight]
-    gi, gl = rnd(B, C, 4, 6, seed=7), rnd(B, C, 4, 4, seed=8)
-    want = torch.autograd.grad([ref_i, ref_l], [ir, lr] + params, [gi, gl])
-    got = torch.autograd.grad([oi, ol], [im, lm] + params, [nhwc(gi), nhwc(gl)])
-    assert rel(nchw(got[0]), want[0]) < TOL and rel(nchw(got[1]), want[1]) < TOL
-    for name, x1, x2 in zip(('vel_emb.weight', 'vel_emb.bias', 'pos_emb', 'proj.weight', 'mlp.0.weight', 'ln_f.weight'), got[2:], want[2:]):
-        assert rel(x1, x2) < TOL, (name, rel(x1, x2))
-    # without the input the module refuses to run; the default module has no such parameter
-    with pytest.raises(RuntimeError):
-        g.run(im, lm)
-    assert not hasattr(GPT(C, nh, 4, 1, 2, 3, 2, 2, 1, 0.0, 0.0, 0.0, Cfg, use_velocity=False), 'vel_emb')
-
-
 @pytest.mark.parametrize('cfg', [(2, 8, 8, 64, 16, 16, False), (2, 64, 64, 3, 160, 160, True), (1, 5, 22, 64, 40, 176, False),
                                  (1, 40, 176, 8, 160, 704, False)])
 def test_upsample(cfg):
